@@ -1,0 +1,167 @@
+"""The oracle against the reference's OWN known-answer tests.
+
+Each test names the reference test it transcribes (paths relative to
+/root/reference/safe_learning/tests).  These pin the numpy restatement before it
+is trusted as the checker for the CUDA path.
+"""
+import numpy as np
+import pytest
+from numpy.testing import assert_allclose, assert_equal
+
+import oracle as O
+
+
+def test_gp_golden_vector():
+    """test_functions.py:237-261 (Testgpflow.test_new_data): RBF(2) defaults, noise 1, beta 2."""
+    x = np.array([[1, 0], [0, 1]], dtype=float)
+    y = np.array([[0], [1]], dtype=float)
+    gp = O.GPRCached(x, y, O.RBF(2), noise_variance=1.0)
+    ufun = O.GaussianProcess(gp)
+    ufun.add_data_point(np.array([[1.2, 2.3]]), np.array([[2.4]]))
+    assert_allclose(ufun.X, np.array([[1, 0], [0, 1], [1.2, 2.3]]))
+    assert_allclose(ufun.Y, np.array([[0], [1], [2.4]]))
+    a1, b1 = ufun(np.array([[0.9, 0.1], [3., 2]]))
+    assert_allclose(a1, np.array([[0.16371139], [0.22048311]]))
+    assert_allclose(b1, np.array([[1.37678679], [1.98183191]]))
+
+
+def test_gp_input_concatenation():
+    """test_functions.py:216-235: GaussianProcess(x) == GaussianProcess(x[:, 0], x[:, 1])."""
+    gp = O.GPRCached(np.array([[1, 0], [0, 1.]]), np.array([[0], [1.]]), O.RBF(2))
+    ufun = O.GaussianProcess(gp, beta=3.0)
+    pts = np.array([[0.9, 0.1], [3., 2]])
+    m1, e1 = ufun(pts)
+    m2, e2 = ufun(pts[:, [0]], pts[:, [1]])
+    assert_allclose(m1, m2)
+    assert_allclose(e1, e2)
+
+
+def test_gp_cached_equals_uncached_algebra():
+    """test_functions.py:164-199: cached predict == textbook (uncached gpflow GPR) posterior,
+    including scale != 1 (functions.py:399-405, :438-456)."""
+    rng = np.random.default_rng(0)
+    X = rng.uniform(-1, 1, (12, 3))
+    Y = rng.normal(size=(12, 1))
+    kern = O.RBF(3, variance=0.7, lengthscales=[0.8, 1.1, 1.4])
+    xs = rng.uniform(-1, 1, (5, 3))
+    K = kern.K(X) + 0.01 * np.eye(12)
+    mean_ref = kern.K(xs, X) @ np.linalg.solve(K, Y)
+    var_ref = kern.Kdiag(xs) - np.einsum('ij,ji->i', kern.K(xs, X), np.linalg.solve(K, kern.K(X, xs)))
+    for scale in (1.0, 3.5):
+        gp = O.GPRCached(X, Y, kern, noise_variance=0.01, scale=scale)
+        m, v = gp.build_predict(xs)
+        assert_allclose(m, mean_ref, rtol=1e-9)
+        assert_allclose(v[:, 0], var_ref, rtol=1e-7)
+
+
+def test_quadratic_function():
+    """test_functions.py:264-282."""
+    points = np.array([[0, 0], [0, 1], [1, 0], [1, 1]], dtype=float)
+    quad = O.QuadraticFunction(np.array([[1., 0.1], [0.2, 2.]]))
+    assert_allclose(quad(points), np.array([[0., 2., 1., 3.3]]).T)
+
+
+def test_gridworld_round_trips():
+    """test_functions.py:313-367 (TestGridworld)."""
+    grid = O.GridWorld([[-1.1, 1.5], [2.2, 2.4]], [7, 8])
+    with pytest.raises(O.DimensionError):
+        grid._check_dimensions(np.array([[1, 2, 3]]))
+    with pytest.raises(O.DimensionError):
+        grid._check_dimensions(np.array([[1]]))
+    idx = np.arange(grid.nindex)
+    states = grid.index_to_state(idx)
+    assert_equal(idx, grid.state_to_index(states))
+    assert_equal(states, grid.all_points)           # linspace grid == ijk*unit+offset bitwise here
+    rect = np.arange(grid.nrectangles)
+    rstates = grid.rectangle_to_state(rect)
+    assert_equal(rect, grid.state_to_rectangle(rstates + grid.unit_maxes / 2))
+    assert_equal(grid.state_to_rectangle(100 * np.ones((1, 2))), grid.nrectangles - 1)
+    assert_equal(grid.state_to_rectangle(-100 * np.ones((1, 2))), 0)
+    assert_equal(grid.rectangle_corner_index(rect), grid.state_to_index(rstates))
+    assert_equal(grid.state_to_index(np.array([[-1.2, 2.]])), 0)
+    assert_equal(O.GridWorld([[1, 2], [3, 4]], 2).num_points, np.array([2, 2]))
+    g1 = O.GridWorld([[0, 1]], 3)
+    test = np.array([[0.1, 0.4, 0.9]]).T
+    assert_allclose(g1.state_to_index(test), np.array([0, 1, 2]))
+    assert_allclose(g1.state_to_rectangle(test), np.array([0, 0, 1]))
+    assert_allclose(g1.rectangle_to_state(np.array([0, 0, 1])), np.array([0, 0, 1])[:, None] * 0.5)
+    with pytest.raises(O.DimensionError):
+        O.GridWorld([[0, 1]], 1)
+
+
+def _lyap_1d(eps):
+    grid = O.GridWorld([[-1, 1]], 3)
+    lyap_fun = O.QuadraticFunction(np.array([[1.0]]))        # sum(x^2, keep_dims)
+    policy = O.LinearSystem(np.array([[-.1]]))                # lambda x: -.1 * x
+    dynamics = O.LinearSystem(np.array([[1, 1.]]))
+    return O.Lyapunov(grid, lyap_fun, dynamics, 0.4, 0.3, eps, policy, initial_set=[1])
+
+
+def test_update_safe_set_known_answers():
+    """test_lyapunov.py:48-74 (TestLyapunov.test_update)."""
+    lyap = _lyap_1d(0.5)
+    lyap.update_safe_set()
+    assert_equal(lyap.safe_set, np.array([False, True, False]))
+    assert lyap.c_max == 0.0
+    lyap = _lyap_1d(0.0)
+    lyap.update_safe_set()
+    assert_equal(lyap.safe_set, np.ones(3, dtype=bool))
+    assert lyap.c_max == 1.0        # the -1 index quirk
+
+
+def test_safe_set_init():
+    """test_lyapunov.py:24-46."""
+    grid = O.GridWorld([[0, 1], [0, 1]], 3)
+    lyap_fun = O.QuadraticFunction(np.eye(2))
+    dynamics = O.LinearSystem(np.array([[1, 0.01], [0., 1.]]))
+    policy = O.LinearSystem(np.zeros((2, 2)))
+    O.Lyapunov(grid, lyap_fun, lambda x, u: dynamics(x), 0.4, 0.3, 0.5, policy)
+    lyap = O.Lyapunov(grid, lyap_fun, lambda x, u: dynamics(x), 0.4, 0.3, 0.5, policy,
+                      initial_set=[1, 3])
+    assert_equal(lyap.safe_set,
+                 np.array([False, True, False, True, False, False, False, False, False]))
+
+
+def test_dlqr_golden():
+    """test_utilities.py:17-28: scalar system, k = 0.618..., p = 1.618... (golden ratio)."""
+    k, p = O.dlqr(1., 1., 1., 1.)
+    assert_allclose(k, 0.5 * (np.sqrt(5) - 1), rtol=1e-10)
+    assert_allclose(p, 0.5 * (np.sqrt(5) + 1), rtol=1e-10)
+
+
+def test_future_values_r_plus_gamma_v():
+    """test_rl.py:145-172 (mock plumbing): future_values == rewards + gamma * V(dynamics)."""
+    grid = O.GridWorld([[-1, 1]], 5)
+    vf = O.Triangulation(grid, np.arange(5.0)[:, None] ** 2, project=True)
+    dynamics = O.LinearSystem(np.array([[0.9, 0.1]]))
+    reward = O.QuadraticFunction(-np.eye(2))
+    policy = O.LinearSystem(np.array([[-0.5]]))
+    rl = O.PolicyIteration(policy, dynamics, reward, vf, gamma=0.9)
+    states = grid.all_points
+    u = policy(states)
+    expect = reward(states, u) + 0.9 * vf(dynamics(states, u))
+    assert_allclose(rl.future_values(states), expect, rtol=0, atol=0)
+
+
+def test_prefix_rule_matches_batch_loop():
+    """the sort-free closed form == the batch loop as written (random ties,
+    random batch sizes, random initial sets)."""
+    rng = np.random.default_rng(7)
+    old = O.config.gp_batch_size
+    try:
+        for _ in range(300):
+            n = int(rng.integers(2, 40))
+            grid = O.GridWorld([[-1, 1]], n)
+            values = rng.integers(0, 6, n).astype(float)
+            neg = rng.random(n) < 0.8
+            init = rng.random(n) < 0.2
+            lyap = O.Lyapunov(grid, lambda x: np.zeros((len(x), 1)), None, 0., 0., 0.,
+                              None, initial_set=init)
+            lyap.values = values
+            lyap.negative = lambda states, g=grid, nn=neg: nn[g.state_to_index(states)]
+            O.config.gp_batch_size = int(rng.integers(1, 24))
+            lyap.update_safe_set()
+            safe, p = O.prefix_rule(values, neg | init, init)
+            assert_equal(lyap.safe_set, safe)
+    finally:
+        O.config.gp_batch_size = old
