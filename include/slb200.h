@@ -1,0 +1,241 @@
+/*
+ * slb200.h -- C ABI of libslb200.so: the B200 (sm_100a) implementation of the
+ * safe_learning region-of-attraction hot path.
+ *
+ * The reference (befelix/safe_learning @ f1aad5a) has no FFI: the path sits behind
+ * Python classes that build a TF1 graph and call Session.run once per 10 000-point
+ * batch.  The entry points below are what a binding for that path would bind; each
+ * cites the reference code it replaces (paths relative to /root/reference).  The
+ * Python host side (safe_learning_b200/) loads this library with ctypes -- see
+ * INTEGRATION.md for the stub a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - plain C: pointers, sizes, POD structs passed by pointer; no torch/C++ types.
+ *   - every `*_dev` / `const double*` inside a struct is a DEVICE pointer (fp64,
+ *     row-major, contiguous) owned by the caller; the library never allocates or frees.
+ *   - `stream` is a cudaStream_t (CUstream) cast to void*; calls enqueue and return.
+ *   - return 0 on success, non-zero on error; slb_last_error() gives the message.
+ *     There is NO CPU fallback: without a CUDA device every compute call fails.
+ *   - fp64 everywhere (safe_learning/configuration.py:16); flags are uint8; flat grid
+ *     indices int64 with the last dimension fastest (functions.py:622-638).
+ */
+#ifndef SLB200_H
+#define SLB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SLB_ABI_VERSION 1
+#define SLB_MAX_DIM 6   /* state dimension d                         */
+#define SLB_MAX_IN  8   /* GP input dimension d_in = d + m           */
+#define SLB_MAX_OUT 6   /* stacked one-output GPs (FunctionStack)    */
+#define SLB_MAX_ACT 2   /* action dimension m                        */
+#define SLB_TILE_POINTS 64  /* grid points per CTA tile of the GP kernels */
+
+/* ---- GridWorld (functions.py:579-817) ------------------------------------------- */
+typedef struct slb_grid {
+    int32_t ndim;
+    int32_t _pad;
+    int64_t nindex;                    /* prod(num_points)                              */
+    int64_t num_points[SLB_MAX_DIM];
+    double  offset[SLB_MAX_DIM];       /* limits[:, 0]                  (:604)          */
+    double  unit_maxes[SLB_MAX_DIM];   /* (hi - lo) / (n - 1)           (:605-606)      */
+    double  upper[SLB_MAX_DIM];        /* limits[:, 1]                                  */
+    const double* discrete_points;     /* device, concatenated np.linspace values per dim
+                                          (:612-614); needed only by SLB_FN_TRIANGULATION */
+} slb_grid;
+
+/* ---- function objects fused into the kernels (functions.py, examples/utilities.py) -- */
+enum slb_fn_kind {
+    SLB_FN_NONE = 0,
+    SLB_FN_CONSTANT = 1,       /* ConstantFunction            functions.py:241-251          */
+    SLB_FN_LINEAR = 2,         /* LinearSystem  y = x A^T      functions.py:1546-1583        */
+    SLB_FN_QUADRATIC = 3,      /* QuadraticFunction sum((xP)*x) functions.py:1513-1539       */
+    SLB_FN_TRIANGULATION = 4,  /* Triangulation               functions.py:1103-1158,1442-1499 */
+    SLB_FN_PENDULUM = 5,       /* InvertedPendulum            examples/utilities.py:144-289 */
+    SLB_FN_CARTPOLE = 6,       /* CartPole                    examples/utilities.py:292-437 */
+    SLB_FN_LYAPUNOV_NN = 7     /* LyapunovNetwork             examples/utilities.py:48-104  */
+};
+/* post-ops, applied in this order: saturate -> abs -> norm1 -> out_scale */
+#define SLB_FLAG_SATURATE 1u   /* Saturation  functions.py:349-354                     */
+#define SLB_FLAG_ABS      2u   /* tf.abs(fun(x))     (notebook Lipschitz lambdas)      */
+#define SLB_FLAG_NORM1    4u   /* tf.norm(., ord=1, axis=1, keepdims=True)             */
+#define SLB_FLAG_PROJECT  8u   /* Triangulation(project=True) functions.py:1479-1485  */
+#define SLB_FLAG_SCALE   16u   /* multiply by out_scale (MultipliedFunction / __neg__) */
+
+typedef struct slb_function {
+    int32_t kind;
+    int32_t in_dim;
+    int32_t out_dim;            /* before NORM1 (which reduces to 1 column)            */
+    uint32_t flags;
+    double  out_scale;
+    double  lower, upper;       /* saturation bounds                                   */
+    double  cparams[24];        /* CONSTANT: value; PENDULUM/CARTPOLE: plant constants
+                                   (see safe_learning_b200/functions.py); NN: layer dims */
+    const double*  matrix;      /* LINEAR [out,in]; QUADRATIC [in,in]; TRIANGULATION
+                                   vertex values [nindex,out]; LYAPUNOV_NN packed kernels */
+    const double*  hyperplanes; /* TRIANGULATION [nsimplex, d, d]  (functions.py:1090-1101) */
+    const int64_t* unit_simplices; /* TRIANGULATION [nsimplex, d+1] (functions.py:1064-1088) */
+    const int32_t* corner_simplex; /* TRIANGULATION [2^d] or NULL: Qhull's find_simplex answer for
+                                      a query clipped in EVERY dimension (bit c set = clipped to
+                                      the upper limit); such points sit on a unit-cell corner
+                                      where several simplices meet and extrapolation differs  */
+    int32_t nsimplex;
+    int32_t _pad;
+    slb_grid grid;              /* TRIANGULATION discretization                        */
+} slb_function;
+
+/* ---- GP stack: FunctionStack of GaussianProcess(GPRCached) (functions.py:254-546) ---- */
+typedef struct slb_gp_factor {
+    int32_t M;                  /* training points                                      */
+    int32_t nrb;                /* ceil(M / 8) row blocks of the packed factor          */
+    const double* Xs;           /* device [M, d_in]: X / lengthscales (gpflow RBF)      */
+    const double* Wpack;        /* device: L^-1 in DMMA fragment order (slb_pack_factor);
+                                   L = chol(scale^2 (K + noise I))  functions.py:399-408 */
+    double lengthscales[SLB_MAX_IN];
+    double variance;            /* RBF variance (Kdiag)                                 */
+    double scale;               /* GPRCached _scale                functions.py:392     */
+    double kss;                 /* (scale**2) * variance           functions.py:450     */
+} slb_gp_factor;
+
+typedef struct slb_gp_output {
+    int32_t factor;             /* index into factors[] (outputs sharing X, kernel and
+                                   noise share one factor)                              */
+    int32_t _pad;
+    double  beta;               /* GaussianProcess.beta            functions.py:487,514 */
+    const double* alpha;        /* device [8*nrb]: L^-1 scale (Y - m(X)), zero padded
+                                                                    functions.py:405-409 */
+    const double* gamma;        /* device [M]: L^-T alpha (mean-only Bellman path)      */
+    const double* prior_mean;   /* device [d_in] linear prior-mean row, or NULL         */
+} slb_gp_output;
+
+typedef struct slb_gp_stack {
+    int32_t num_outputs;        /* D; 0 => dynamics are deterministic                   */
+    int32_t num_factors;        /* D' distinct Cholesky factors                         */
+    int32_t input_dim;          /* d_in                                                 */
+    int32_t _pad;
+    slb_gp_factor factors[SLB_MAX_OUT];
+    slb_gp_output outputs[SLB_MAX_OUT];
+} slb_gp_stack;
+
+/* ---- one Lyapunov sweep: the graph of lyapunov.py:433-441 ----------------------------- */
+typedef struct slb_sweep {
+    slb_grid     grid;          /* discretization                                       */
+    slb_function policy;        /* x -> u                       lyapunov.py:436         */
+    slb_function dynamics;      /* deterministic [x,u] -> x+ when gp.num_outputs == 0   */
+    slb_gp_stack gp;            /* uncertain dynamics           lyapunov.py:437         */
+    slb_function lyapunov;      /* V                            lyapunov.py:351-352     */
+    slb_function lipschitz_v;   /* L_V(.) as a function, or kind NONE => lv_const       */
+    double lv_const;            /* scalar lipschitz_lyapunov    lyapunov.py:246-263     */
+    double lf_const;            /* scalar lipschitz_dynamics    lyapunov.py:227-244     */
+    double tau;                 /* discretization constant      lyapunov.py:195         */
+} slb_sweep;
+
+/* ---- one Bellman sweep: PolicyIteration.future_values (reinforcement_learning.py:65-114) */
+typedef struct slb_bellman {
+    slb_grid     grid;          /* value_function.discretization (state space, :58-59)  */
+    slb_function policy;        /* ignored when fixed_action != 0                       */
+    slb_function dynamics;      /* deterministic dynamics when gp.num_outputs == 0      */
+    slb_gp_stack gp;            /* GP dynamics: mean only               (:98-99)        */
+    slb_function reward;        /* r([x,u])                             (:95)           */
+    slb_function value;         /* V as Triangulation (vertex table = `matrix`) (:101)  */
+    double gamma;               /*                                      (:104)          */
+    int32_t fixed_action;       /* 1 => use `action` for every state (:266-270)         */
+    int32_t _pad;
+    double action[SLB_MAX_ACT];
+} slb_bellman;
+
+/* ---- result of the first-fail reduction (sort-free form of lyapunov.py:512-587) ------- */
+typedef struct slb_fail_key {
+    uint64_t key_value;   /* order-preserving bits of V at the first failing point in stable
+                             V-order, or UINT64_MAX if no point fails                     */
+    int64_t  key_index;   /* its flat grid index, or INT64_MAX                            */
+    int64_t  n_ok;        /* number of points with negative | initial                     */
+    int64_t  _pad;
+} slb_fail_key;
+
+typedef struct slb_prefix_stats {
+    int64_t  n_safe;        /* |{key < k*} U initial|                                     */
+    int64_t  n_below;       /* |{key < k*}| = sorted position p* of the first failure     */
+    uint64_t max_below;     /* order-preserving bits of max{V_i : key_i < k*} (0 if none) */
+    uint64_t max_all;       /* order-preserving bits of max V over the range              */
+} slb_prefix_stats;
+
+/* ---- library ---------------------------------------------------------------------------- */
+int         slb_abi_version(void);
+const char* slb_last_error(void);
+/* number of CUDA devices visible, or <0 with slb_last_error set */
+int         slb_device_count(void);
+/* sizeof() of the ABI structs in declaration order (grid, function, gp_factor, gp_output,
+   gp_stack, sweep, bellman, fail_key, prefix_stats); returns how many there are */
+int         slb_struct_sizes(int64_t* out, int32_t n);
+/* kernels this library has launched since load (bench.py's gpu_launches) */
+int64_t     slb_launch_count(void);
+
+/* ---- GP factor packing (after GPRCached.update_cache, functions.py:395-415) ------------ */
+/* doubles needed for the packed L^-1 of an M-point GP */
+int64_t slb_packed_len(int32_t M);
+/* Linv_dev [M,M] row-major lower-triangular -> Wpack_dev (slb_packed_len(M) doubles) */
+int slb_pack_factor(void* stream, const double* Linv_dev, int32_t M, double* Wpack_dev);
+
+/* ---- GP posterior on an explicit point list: GaussianProcess.__call__ / FunctionStack
+ *      (functions.py:278-291, 417-458, 507-515).  points_dev [n, d_in] (already [x,u]
+ *      concatenated, utilities.py:143); mean_dev, err_dev [n, D];
+ *      err = beta*sqrt(var) (want_var == 0) or the latent variance (want_var != 0). ------- */
+int slb_gp_predict(void* stream, const slb_gp_stack* gp, const double* points_dev, int64_t n,
+                   double* mean_dev, double* err_dev, int32_t want_var);
+
+/* ---- the fused Lyapunov sweep over flat grid indices [idx_begin, idx_end):
+ *      index -> x (functions.py:714-731) -> u = policy(x) -> [x,u] -> GP mean / beta*sigma
+ *      (or deterministic dynamics) -> V(x), V(mu), L_V(mu) . e -> decrease < threshold
+ *      (lyapunov.py:265-288, 324-376, 436-441).  Outputs are arrays of length
+ *      idx_end - idx_begin; any of values/decrease/threshold/mean/err may be NULL. -------- */
+int slb_lyapunov_sweep(void* stream, const slb_sweep* cfg, int64_t idx_begin, int64_t idx_end,
+                       uint8_t* negative_dev, double* values_dev, double* decrease_dev,
+                       double* threshold_dev, double* mean_dev, double* err_dev);
+/* same on an explicit state list states_dev [n, d] (get_safe_sample-style callers) */
+int slb_lyapunov_points(void* stream, const slb_sweep* cfg, const double* states_dev, int64_t n,
+                        uint8_t* negative_dev, double* values_dev, double* decrease_dev,
+                        double* threshold_dev, double* mean_dev, double* err_dev);
+
+/* ---- prefix rule without sorting (lyapunov.py:500-606):
+ *      k* = min over failing points of key (V_i, i); safe_i = key_i < k* | initial_i.
+ *      workspace_dev: >= slb_first_fail_workspace(n) bytes.  result_dev: one slb_fail_key
+ *      in device memory (the caller all-reduces it across ranks, then applies).           */
+int64_t slb_first_fail_workspace(int64_t n);
+int slb_first_fail(void* stream, const double* values_dev, const uint8_t* negative_dev,
+                   const uint8_t* initial_dev /* may be NULL */, int64_t n, int64_t idx_begin,
+                   void* workspace_dev, slb_fail_key* result_dev);
+int slb_apply_prefix(void* stream, const double* values_dev, const uint8_t* initial_dev,
+                     int64_t n, int64_t idx_begin, const slb_fail_key* key_dev,
+                     uint8_t* safe_dev, void* workspace_dev, slb_prefix_stats* stats_dev);
+
+/* ---- generic evaluation of a fused function object on explicit points:
+ *      DeterministicFunction.__call__, Lyapunov.update_values (lyapunov.py:305-322).
+ *      points_dev [n, fn->in_dim] -> out_dev [n, out columns]. ---------------------------- */
+int slb_eval_function(void* stream, const slb_function* fn, const double* points_dev, int64_t n,
+                      double* out_dev);
+/* grid coordinates for flat indices [idx_begin, idx_end): GridWorld.index_to_state */
+int slb_index_to_state(void* stream, const slb_grid* grid, int64_t idx_begin, int64_t idx_end,
+                       double* states_dev);
+
+/* ---- Bellman sweep (reinforcement_learning.py:65-114, 135-140, 213-279) ---------------- */
+/* out_dev[i] = r(x_i,u_i) + gamma * V(mean f(x_i,u_i)) for flat indices [idx_begin, idx_end) */
+int slb_bellman_sweep(void* stream, const slb_bellman* cfg, int64_t idx_begin, int64_t idx_end,
+                      double* out_dev);
+/* discrete_policy_optimization: actions_dev [n_actions, m]; constraint_dev [n_actions, n] or
+ * NULL (value < 0 => -inf, :272-275); best_dev[i] = first argmax over actions (:278) */
+int slb_bellman_argmax(void* stream, const slb_bellman* cfg, int64_t idx_begin, int64_t idx_end,
+                       const double* actions_dev, int32_t n_actions, const double* constraint_dev,
+                       int32_t* best_dev, double* best_value_dev);
+/* max_i |a_i - b_i| into result_dev[0] (value-iteration convergence test, test_rl.py:66-69) */
+int slb_max_abs_diff(void* stream, const double* a_dev, const double* b_dev, int64_t n,
+                     double* result_dev);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SLB200_H */

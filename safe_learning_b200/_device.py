@@ -1,0 +1,77 @@
+"""Device plumbing: torch owns device memory, streams and (optionally) torch.distributed.
+
+Nothing here computes on the hot path; it moves numpy arrays to HBM once and hands raw
+pointers + the current CUDA stream to libslb200.
+"""
+
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import _native
+
+
+def device():
+    _native.require_device()
+    if not torch.cuda.is_available():
+        raise _native.NativeLibraryError("torch sees no CUDA device; safe_learning_b200 has no "
+                                         "CPU fallback")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def to_device(array, dtype=torch.float64):
+    """numpy (or tensor) -> contiguous device tensor of `dtype`."""
+    if isinstance(array, torch.Tensor):
+        return array.to(device=device(), dtype=dtype).contiguous()
+    np_dtype = {torch.float64: np.float64, torch.int64: np.int64, torch.uint8: np.uint8,
+                torch.int32: np.int32}[dtype]
+    host = np.ascontiguousarray(np.asarray(array), dtype=np_dtype)
+    return torch.from_numpy(host).to(device())
+
+
+def empty(shape, dtype=torch.float64):
+    return torch.empty(shape, dtype=dtype, device=device())
+
+
+def zeros(shape, dtype=torch.float64):
+    return torch.zeros(shape, dtype=dtype, device=device())
+
+
+def stream():
+    """The current CUDA stream as the void* libslb200 expects."""
+    return torch.cuda.current_stream().cuda_stream
+
+
+def ptr(tensor):
+    return None if tensor is None else tensor.data_ptr()
+
+
+# ---- torch.distributed (one process per GPU; NCCL on GPUs, gloo in the CPU tests) ----------
+def dist_info():
+    """(rank, world_size) -- (0, 1) when torch.distributed is not initialised."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+def shard_range(nindex, rank=None, world=None):
+    """Contiguous flat-index range [begin, end) of this rank."""
+    if rank is None or world is None:
+        rank, world = dist_info()
+    per = -(-nindex // world)
+    begin = min(rank * per, nindex)
+    return begin, min(begin + per, nindex)
+
+
+def allgather_rows(row):
+    """All-gather one small 1-D tensor per rank -> [world, len] (device of `row`); a view of the
+    input when torch.distributed is not initialised.  The only collective of a Lyapunov sweep."""
+    rank, world = dist_info()
+    if world == 1:
+        return row.view(1, -1)
+    import torch.distributed as dist
+    out = torch.empty((world, row.numel()), dtype=row.dtype, device=row.device)
+    dist.all_gather_into_tensor(out, row.view(1, -1).contiguous())
+    return out

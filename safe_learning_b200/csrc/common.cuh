@@ -1,0 +1,311 @@
+// common.cuh -- shared device code of libslb200: error plumbing, GridWorld coordinates,
+// the fused function objects (policy / V / Lipschitz / plants / reward / Triangulation),
+// the Lyapunov decision formula and the order-preserving V key.
+//
+// Reference citations are relative to /root/reference (befelix/safe_learning @ f1aad5a).
+// Bit-parity rule: the cheap element-wise pieces use __dmul_rn/__dadd_rn (never contracted
+// into FMA) in the left-to-right order that oracle/reference_path.py writes out, so grid
+// coordinates, linear maps, quadratic forms and barycentric weights are bit-identical to
+// the CPU oracle.  Only the GP contraction (DMMA) and libm calls (exp/sin/cos/sqrt is exact)
+// differ in rounding.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math.h>
+
+#include "../../include/slb200.h"
+
+// ----------------------------------------------------------------------------- host side
+void slb_set_error(const char* fmt, ...);
+extern long long g_slb_launches;
+
+#define SLB_CHECK(cond, ...)                                                     \
+    do {                                                                         \
+        if (!(cond)) { slb_set_error(__VA_ARGS__); return 1; }                   \
+    } while (0)
+
+#define SLB_CUDA(call)                                                           \
+    do {                                                                         \
+        cudaError_t e__ = (call);                                                \
+        if (e__ != cudaSuccess) {                                                \
+            slb_set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), \
+                          __FILE__, __LINE__);                                   \
+            return 2;                                                            \
+        }                                                                        \
+    } while (0)
+
+#define SLB_LAUNCH_CHECK()                                                       \
+    do {                                                                         \
+        ++g_slb_launches;                                                        \
+        SLB_CUDA(cudaGetLastError());                                            \
+    } while (0)
+
+int slb_validate_function(const slb_function* f, const char* what, int expect_in /* <=0: any */);
+int slb_validate_gp(const slb_gp_stack* gp);
+int slb_validate_grid(const slb_grid* g, bool need_points);
+
+// ----------------------------------------------------------------------------- device side
+#define SLB_DEV __device__ __forceinline__
+
+SLB_DEV double f64mul(double a, double b) { return __dmul_rn(a, b); }
+SLB_DEV double f64add(double a, double b) { return __dadd_rn(a, b); }
+SLB_DEV double f64sub(double a, double b) { return __dsub_rn(a, b); }
+
+// Order-preserving map double -> uint64 (ascending).  -0.0 is canonicalised to +0.0 first
+// so that it ties with +0.0 like np.argsort sees it (lyapunov.py:512).
+SLB_DEV uint64_t value_key(double v) {
+    if (v == 0.0) v = 0.0;
+    uint64_t b = (uint64_t)__double_as_longlong(v);
+    return (b & 0x8000000000000000ull) ? ~b : (b | 0x8000000000000000ull);
+}
+SLB_DEV double key_value(uint64_t k) {
+    uint64_t b = (k & 0x8000000000000000ull) ? (k & 0x7fffffffffffffffull) : ~k;
+    return __longlong_as_double((long long)b);
+}
+
+// GridWorld.index_to_state (functions.py:714-731): ijk * unit_maxes + offset, two roundings.
+SLB_DEV void grid_index_to_state(const slb_grid& g, int64_t idx, double* x) {
+#pragma unroll
+    for (int c = SLB_MAX_DIM - 1; c >= 0; --c) {
+        if (c < g.ndim) {
+            const int64_t n = g.num_points[c];
+            const int64_t i = idx % n;
+            idx /= n;
+            x[c] = f64add(f64mul((double)i, g.unit_maxes[c]), g.offset[c]);
+        }
+    }
+}
+
+// ---- Triangulation (functions.py:1103-1158 lookup, :1473-1499 evaluation) ----------------
+SLB_DEV void eval_triangulation(const slb_function& f, const double* xin, double* out) {
+    const slb_grid& g = f.grid;
+    const int d = g.ndim;
+    const double eps = 2.220446049250313e-16;
+    double unit[SLB_MAX_DIM];
+    int64_t corner = 0;
+    int poff = 0;
+    int pattern = 0;
+    bool all_clipped = true;
+    for (int c = 0; c < d; ++c) {
+        const double* pts = g.discrete_points + poff;
+        const int n = (int)g.num_points[c];
+        poff += n;
+        const double xc = xin[c];
+        // np.digitize(x, pts) - 1 clipped to [0, n-2]   (functions.py:771-773)
+        int k = (int)floor((xc - g.offset[c]) / g.unit_maxes[c]);
+        k = k < 0 ? 0 : (k > n - 1 ? n - 1 : k);
+        while (k + 1 <= n - 1 && pts[k + 1] <= xc) ++k;
+        while (k >= 0 && pts[k] > xc) --k;            // k = -1 when x < pts[0]
+        k = k < 0 ? 0 : (k > n - 2 ? n - 2 : k);
+        corner = corner * g.num_points[c] + k;        // rectangle_corner_index (:800-817)
+        // _center_states(clip=True) % unit_maxes          (:691-712, :1120-1123)
+        double cen = f64sub(xc, g.offset[c]);
+        const double lo = 2.0 * eps;
+        const double hi = f64sub(f64sub(g.upper[c], g.offset[c]), 2.0 * eps);
+        if (cen < lo) cen = lo;
+        else if (cen > hi) { cen = hi; pattern |= 1 << c; }
+        else all_clipped = false;
+        unit[c] = fmod(cen, g.unit_maxes[c]);
+    }
+    // simplex inside the unit cell: first simplex whose barycentric weights are all >= -tol
+    int best = 0;
+    double best_min = -1e300;
+    const bool tabled = all_clipped && f.corner_simplex != nullptr;
+    if (tabled) best = f.corner_simplex[pattern];
+    for (int s = 0; s < f.nsimplex && !tabled; ++s) {
+        const int64_t v0 = f.unit_simplices[s * (d + 1)];
+        double o[SLB_MAX_DIM];
+        int64_t t = v0;
+        for (int c = d - 1; c >= 0; --c) {
+            o[c] = (double)(t % g.num_points[c]) * g.unit_maxes[c];
+            t /= g.num_points[c];
+        }
+        const double* H = f.hyperplanes + (size_t)s * d * d;
+        double wsum = 0.0, wmin = 1e300;
+        for (int c = 0; c < d; ++c) {
+            double w = 0.0;
+            for (int k = 0; k < d; ++k) w += (unit[k] - o[k]) * H[k * d + c];
+            wsum += w;
+            wmin = fmin(wmin, w);
+        }
+        wmin = fmin(wmin, 1.0 - wsum);
+        if (wmin > best_min) { best_min = wmin; best = s; }
+        if (wmin >= -1e-12) break;
+    }
+    // weights with the ORIGINAL (optionally projected) point   (:1479-1491)
+    const int64_t* simp = f.unit_simplices + (size_t)best * (d + 1);
+    const double* H = f.hyperplanes + (size_t)best * d * d;
+    double origin[SLB_MAX_DIM], off[SLB_MAX_DIM];
+    grid_index_to_state(g, simp[0] + corner, origin);
+    for (int c = 0; c < d; ++c) {
+        double xc = xin[c];
+        if (f.flags & SLB_FLAG_PROJECT) xc = fmin(fmax(xc, g.offset[c]), g.upper[c]);
+        off[c] = f64sub(xc, origin[c]);
+    }
+    double w[SLB_MAX_DIM + 1];
+    for (int c = 0; c < d; ++c) {
+        double acc = f64mul(off[0], H[c]);
+        for (int k = 1; k < d; ++k) acc = f64add(acc, f64mul(off[k], H[k * d + c]));
+        w[c + 1] = acc;
+    }
+    double acc = w[1];
+    for (int c = 2; c <= d; ++c) acc = f64add(acc, w[c]);
+    w[0] = f64sub(1.0, acc);
+    // gather vertex values and combine  (:1494-1499)
+    const int od = f.out_dim;
+    for (int o = 0; o < od; ++o) {
+        double v = f64mul(w[0], f.matrix[(simp[0] + corner) * od + o]);
+        for (int k = 1; k <= d; ++k)
+            v = f64add(v, f64mul(w[k], f.matrix[(simp[k] + corner) * od + o]));
+        out[o] = v;
+    }
+}
+
+// ---- plants (examples/utilities.py:242-289 pendulum, :387-437 cart-pole) -----------------
+// cparams layout is written by safe_learning_b200/functions.py (InvertedPendulum/CartPole).
+SLB_DEV void eval_pendulum(const slb_function& f, const double* in, double* out) {
+    const double* p = f.cparams;
+    const double g_l = p[0], inertia = p[1], fric_i = p[2], dt = p[3];
+    const bool has_norm = p[9] != 0.0, has_fric = p[10] != 0.0;
+    double th = in[0], om = in[1], u = in[2];
+    if (has_norm) { th = f64mul(th, p[4]); om = f64mul(om, p[5]); u = f64mul(u, p[6]); }
+    const double ui = u / inertia;
+    for (int i = 0; i < 10; ++i) {
+        double acc = f64add(f64mul(g_l, sin(th)), ui);
+        if (has_fric) acc = f64sub(acc, f64mul(fric_i, om));
+        const double th_n = f64add(th, f64mul(dt, om));
+        const double om_n = f64add(om, f64mul(dt, acc));
+        th = th_n; om = om_n;
+    }
+    if (has_norm) { th = f64mul(th, p[7]); om = f64mul(om, p[8]); }
+    out[0] = th; out[1] = om;
+}
+
+SLB_DEV void eval_cartpole(const slb_function& f, const double* in, double* out) {
+    const double* p = f.cparams;
+    const double m = p[0], M = p[1], L = p[2], b = p[3], g = p[4], dt = p[5];
+    const bool has_norm = p[15] != 0.0;
+    double s[4] = {in[0], in[1], in[2], in[3]};
+    double u = in[4];
+    if (has_norm) { for (int c = 0; c < 4; ++c) s[c] = f64mul(s[c], p[6 + c]); u = f64mul(u, p[10]); }
+    for (int i = 0; i < 10; ++i) {
+        const double th = s[1], v = s[2], om = s[3];
+        const double st = sin(th), ct = cos(th), s2t = sin(2.0 * th);
+        const double det = L * (M + m * (st * st));
+        const double v_dot = (u - m * L * (om * om) * st - b * om * ct + 0.5 * m * g * L * s2t) * L / det;
+        const double om_dot = (u * ct - 0.5 * m * L * (om * om) * s2t - b * (m + M) * om / (m * L)
+                               + (m + M) * g * st) / det;
+        s[0] = f64add(s[0], f64mul(dt, v));
+        s[1] = f64add(s[1], f64mul(dt, om));
+        s[2] = f64add(s[2], f64mul(dt, v_dot));
+        s[3] = f64add(s[3], f64mul(dt, om_dot));
+    }
+    if (has_norm) for (int c = 0; c < 4; ++c) s[c] = f64mul(s[c], p[11 + c]);
+    for (int c = 0; c < 4; ++c) out[c] = s[c];
+}
+
+// Evaluate a fused function object. `in` has f.in_dim entries, `out` receives the result
+// columns; returns the number of columns (1 after NORM1).
+SLB_DEV int eval_fn(const slb_function& f, const double* in, double* out) {
+    int od = f.out_dim;
+    switch (f.kind) {
+    case SLB_FN_CONSTANT:
+        for (int o = 0; o < od; ++o) out[o] = f.cparams[o];
+        break;
+    case SLB_FN_LINEAR:       // functions.py:1583   y_o = sum_k x_k A[o,k]
+        for (int o = 0; o < od; ++o) {
+            const double* row = f.matrix + o * f.in_dim;
+            double acc = f64mul(in[0], row[0]);
+            for (int k = 1; k < f.in_dim; ++k) acc = f64add(acc, f64mul(in[k], row[k]));
+            out[o] = acc;
+        }
+        break;
+    case SLB_FN_QUADRATIC: {  // functions.py:1537-1539   sum_c (sum_r x_r P[r,c]) * x_c
+        const int n = f.in_dim;
+        double total = 0.0;
+        for (int c = 0; c < n; ++c) {
+            double lin = f64mul(in[0], f.matrix[c]);
+            for (int r = 1; r < n; ++r) lin = f64add(lin, f64mul(in[r], f.matrix[r * n + c]));
+            const double prod = f64mul(lin, in[c]);
+            total = (c == 0) ? prod : f64add(total, prod);
+        }
+        out[0] = total;
+        od = 1;
+        break;
+    }
+    case SLB_FN_TRIANGULATION:
+        eval_triangulation(f, in, out);
+        break;
+    case SLB_FN_PENDULUM:
+        eval_pendulum(f, in, out); od = 2;
+        break;
+    case SLB_FN_CARTPOLE:
+        eval_cartpole(f, in, out); od = 4;
+        break;
+    default:
+        for (int o = 0; o < od; ++o) out[o] = __longlong_as_double(0x7ff8000000000000ll);
+        break;
+    }
+    if (f.flags & SLB_FLAG_SATURATE)
+        for (int o = 0; o < od; ++o) out[o] = fmin(fmax(out[o], f.lower), f.upper);
+    if (f.flags & (SLB_FLAG_ABS | SLB_FLAG_NORM1))
+        for (int o = 0; o < od; ++o) out[o] = fabs(out[o]);
+    if (f.flags & SLB_FLAG_NORM1) {
+        double acc = out[0];
+        for (int o = 1; o < od; ++o) acc = f64add(acc, out[o]);
+        out[0] = acc;
+        od = 1;
+    }
+    if (f.flags & SLB_FLAG_SCALE)
+        for (int o = 0; o < od; ++o) out[o] = f64mul(out[o], f.out_scale);
+    return od;
+}
+
+// The Lyapunov decision for one state (lyapunov.py:265-288, 324-376, 441).
+//   x [d]; mu [d] predicted mean; err [d] error bounds (beta*sigma) or nullptr when the
+//   dynamics are deterministic.  Returns negative = decrease < threshold (false on NaN).
+struct slb_decision { double vx, decrease, threshold; bool negative; };
+
+SLB_DEV slb_decision lyapunov_decide(const slb_sweep& cfg, const double* x, const double* mu,
+                                     const double* err) {
+    const int d = cfg.grid.ndim;
+    double tmp[SLB_MAX_OUT];
+    slb_decision r;
+    double vx[1], vm[1];
+    eval_fn(cfg.lyapunov, x, vx);
+    eval_fn(cfg.lyapunov, mu, vm);
+    r.vx = vx[0];
+    const double v_dec = f64sub(vm[0], vx[0]);                 // :351-352
+    double bound = 0.0;
+    if (err != nullptr) {                                    // :344-347, lv at the MEAN
+        if (cfg.lipschitz_v.kind != SLB_FN_NONE) {
+            const int nl = eval_fn(cfg.lipschitz_v, mu, tmp);
+            if (nl == 1) {
+                bound = f64mul(tmp[0], err[0]);
+                for (int j = 1; j < d; ++j) bound = f64add(bound, f64mul(tmp[0], err[j]));
+            } else {
+                bound = f64mul(tmp[0], err[0]);
+                for (int j = 1; j < d; ++j) bound = f64add(bound, f64mul(tmp[j], err[j]));
+            }
+        } else {
+            bound = f64mul(cfg.lv_const, err[0]);
+            for (int j = 1; j < d; ++j) bound = f64add(bound, f64mul(cfg.lv_const, err[j]));
+        }
+    }
+    r.decrease = f64add(v_dec, bound);                         // :376
+    double lvx;
+    if (cfg.lipschitz_v.kind != SLB_FN_NONE) {               // :284-286 (1-norm of a vector lv)
+        const int nl = eval_fn(cfg.lipschitz_v, x, tmp);
+        lvx = tmp[0];
+        if (nl > 1) {
+            lvx = fabs(tmp[0]);
+            for (int j = 1; j < nl; ++j) lvx = f64add(lvx, fabs(tmp[j]));
+        }
+    } else {
+        lvx = cfg.lv_const;
+    }
+    r.threshold = f64mul(f64mul(-lvx, f64add(1.0, cfg.lf_const)), cfg.tau);   // :288
+    r.negative = r.decrease < r.threshold;                   // :441 strict, NaN -> false
+    return r;
+}

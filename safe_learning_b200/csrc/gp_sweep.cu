@@ -1,0 +1,453 @@
+// gp_sweep.cu -- the dominant kernel: GP posterior (mean + variance) of a 64-point tile and,
+// in sweep mode, the fused Lyapunov decision.
+//
+// Replaces, per 10 000-point Session.run of the reference (paths relative to /root/reference):
+//   gpflow kern.K(X, Xnew)                       functions.py:438   -> k-row generation phase
+//   tf.matrix_triangular_solve(L, Kx)            functions.py:441   -> a = L^-1 k as DMMA GEMM
+//   a^T alpha (+ prior mean), Kdiag - sum a^2    functions.py:442,450-451 -> panel epilogue
+//   beta * sqrt(var)                             functions.py:514
+//   FunctionStack concat                         functions.py:278-291
+//   v_decrease_bound < threshold                 lyapunov.py:436-441 -> tile epilogue
+//
+// Design (B200, fp64 pipe bound -- see DESIGN.md):
+//   * one CTA = 64 grid points x all M training points, 8 warps, 1 CTA/SM (181 KB smem).
+//   * W = L^-1 (lower triangular) is pre-packed in DMMA.8x8x4 A-fragment order
+//     (slb_pack_factor); each warp streams ITS rows of W straight from L2 into registers
+//     with coalesced 256 B loads, software-pipelined two k-steps ahead -- W is used by
+//     exactly one warp per CTA, so it never needs shared memory.
+//   * the k-row tile K[j, p] = s^2 exp(-|z_p - X_j|^2/2) is generated once per 256-row
+//     j-panel into shared memory ([j][68] doubles: conflict-free B-fragment reads).
+//   * a 256-row i-panel of a = W k lives in registers (32 rows x 64 points per warp =
+//     64 fp64 accumulators per thread); rows are dealt to warps round-robin from the bottom
+//     of the panel so the triangular work is balanced.  sum a^2 and a.alpha are reduced in
+//     the panel epilogue, so `a` is never stored.
+#include "common.cuh"
+
+namespace {
+
+constexpr int TP = SLB_TILE_POINTS;   // points per CTA
+constexpr int PANEL = 256;            // rows per i-panel, columns per j-panel
+constexpr int KSTR = TP + 4;          // Ks row stride: (r*68 + c) mod 16 distinct for r,c in 0..3
+constexpr int NW = 8;
+constexpr int NT = NW * 32;
+constexpr int NRED = 1 + SLB_MAX_OUT;
+
+constexpr size_t SMEM_KS = (size_t)PANEL * KSTR * sizeof(double);
+constexpr size_t SMEM_Z = (size_t)SLB_MAX_IN * TP * sizeof(double);
+constexpr size_t SMEM_RED = (size_t)NW * TP * NRED * sizeof(double);
+constexpr size_t SMEM_TOT = (size_t)NRED * TP * sizeof(double);
+constexpr size_t SMEM_POST = (size_t)2 * SLB_MAX_OUT * TP * sizeof(double);
+constexpr size_t SMEM_TOTAL = SMEM_KS + SMEM_Z + SMEM_RED + SMEM_TOT + SMEM_POST;
+
+enum { MODE_SWEEP_GRID = 0, MODE_SWEEP_STATES = 1, MODE_PREDICT = 2 };
+
+struct gp_args {
+    const double* points;   // MODE_SWEEP_STATES: [n, d]; MODE_PREDICT: [n, d_in]
+    int64_t n;
+    int64_t idx_begin;
+    int32_t mode;
+    int32_t want_var;
+    uint8_t* negative;
+    double* values;
+    double* decrease;
+    double* threshold;
+    double* mean;
+    double* err;
+};
+
+SLB_DEV double ldg_stream(const double* p) {
+    double v;
+    asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    return v;
+}
+
+SLB_DEV void dmma884(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+// k-steps [k0, k1) of the current j-panel for row blocks q >= Q0 of this warp.
+template <int Q0>
+SLB_DEV void mma_run(double (&acc)[4][8][2], const double* const (&ap)[4], int k0, int k1,
+                     const double* ks_lane) {
+    double a_cur[4], a_nxt[4];
+    const int k1m = k1 - 1;
+    const int kn = min(k0 + 1, k1m);
+#pragma unroll
+    for (int q = Q0; q < 4; ++q) {
+        a_cur[q] = ldg_stream(ap[q] + k0 * 32);
+        a_nxt[q] = ldg_stream(ap[q] + kn * 32);
+    }
+#pragma unroll 1
+    for (int kk = k0; kk < k1; ++kk) {
+        const int k2 = min(kk + 2, k1m);
+        double a_pre[4];
+#pragma unroll
+        for (int q = Q0; q < 4; ++q) a_pre[q] = ldg_stream(ap[q] + k2 * 32);
+        const double* kb = ks_lane + kk * (4 * KSTR);
+        double b[8];
+#pragma unroll
+        for (int nb = 0; nb < 8; ++nb) b[nb] = kb[nb * 8];
+#pragma unroll
+        for (int q = Q0; q < 4; ++q) {
+#pragma unroll
+            for (int nb = 0; nb < 8; ++nb) dmma884(acc[q][nb][0], acc[q][nb][1], a_cur[q], b[nb]);
+        }
+#pragma unroll
+        for (int q = Q0; q < 4; ++q) { a_cur[q] = a_nxt[q]; a_nxt[q] = a_pre[q]; }
+    }
+}
+
+template <int DIN>
+__global__ void __launch_bounds__(NT, 1)
+gp_tile_kernel(const __grid_constant__ slb_sweep cfg, const gp_args a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double* Ks = reinterpret_cast<double*>(smem_raw);
+    double* zraw = Ks + PANEL * KSTR;                 // [SLB_MAX_IN][TP]
+    double* red = zraw + SLB_MAX_IN * TP;             // [NW][TP][NRED]
+    double* tot = red + NW * TP * NRED;               // [NRED][TP]
+    double* post = tot + NRED * TP;                   // mean [MAX_OUT][TP], err [MAX_OUT][TP]
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t tile0 = (int64_t)blockIdx.x * TP;
+    const int D = cfg.gp.num_outputs;
+
+    // ---- stage 1: query points z = [x, policy(x)]  (lyapunov.py:436-437, utilities.py:143)
+    if (tid < TP) {
+        int64_t rel = tile0 + tid;
+        if (rel > a.n - 1) rel = a.n - 1;
+        double z[SLB_MAX_IN];
+        if (a.mode == MODE_PREDICT) {
+#pragma unroll
+            for (int c = 0; c < DIN; ++c) z[c] = a.points[rel * DIN + c];
+        } else {
+            const int d = cfg.grid.ndim;
+            double x[SLB_MAX_DIM];
+            if (a.mode == MODE_SWEEP_GRID) {
+                grid_index_to_state(cfg.grid, a.idx_begin + rel, x);
+            } else {
+                for (int c = 0; c < d; ++c) x[c] = a.points[rel * d + c];
+            }
+            double u[SLB_MAX_OUT];
+            const int m = eval_fn(cfg.policy, x, u);
+            for (int c = 0; c < d; ++c) z[c] = x[c];
+            for (int c = 0; c < m; ++c) z[d + c] = u[c];
+        }
+#pragma unroll
+        for (int c = 0; c < DIN; ++c) zraw[c * TP + tid] = z[c];
+    }
+    __syncthreads();
+
+    const int p_gen = tid & (TP - 1);
+    const int jg = tid >> 6;                          // 0..3
+    const double* ks_lane = Ks + (lane & 3) * KSTR + (lane >> 2);
+
+    for (int f = 0; f < cfg.gp.num_factors; ++f) {
+        const slb_gp_factor& F = cfg.gp.factors[f];
+        const int M = F.M, nrb = F.nrb;
+        const int nk4 = (M + 3) >> 2;
+        const int npan = (nrb + 31) >> 5;
+        const double s2 = f64mul(F.scale, F.scale);
+        const double variance = F.variance;
+        const double* __restrict__ Xs = F.Xs;
+
+        double zs[DIN];
+#pragma unroll
+        for (int c = 0; c < DIN; ++c) zs[c] = zraw[c * TP + p_gen] / F.lengthscales[c];
+        if (tid < TP) {
+#pragma unroll
+            for (int r = 0; r < NRED; ++r) tot[r * TP + tid] = 0.0;
+        }
+        int resident = -1;
+
+        for (int ip = 0; ip < npan; ++ip) {
+            double acc[4][8][2];
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+#pragma unroll
+                for (int nb = 0; nb < 8; ++nb) { acc[q][nb][0] = 0.0; acc[q][nb][1] = 0.0; }
+
+            const int pbeg = 32 * ip;
+            const int pend = min(pbeg + 32, nrb);
+            int bq[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) bq[q] = pend - 1 - warp - 8 * (3 - q);
+
+            for (int jp = 0; jp <= ip; ++jp) {
+                const int nkp = min(64, nk4 - 64 * jp);
+                if (jp != resident) {
+                    // ---- generation phase: K[j, p] for j in this panel (functions.py:438)
+                    __syncthreads();
+                    const int j0 = PANEL * jp;
+                    const int nj = min(PANEL, M - j0);
+                    for (int j = jg; j < nkp * 4; j += 4) {
+                        double k = 0.0;
+                        if (j < nj) {
+                            const double* xr = Xs + (size_t)(j0 + j) * DIN;
+                            double t2 = 0.0;
+#pragma unroll
+                            for (int c = 0; c < DIN; ++c) {
+                                const double df = zs[c] - __ldg(xr + c);
+                                t2 = fma(df, df, t2);
+                            }
+                            k = s2 * (variance * exp(-0.5 * t2));
+                        }
+                        Ks[j * KSTR + p_gen] = k;
+                    }
+                    resident = jp;
+                    __syncthreads();
+                }
+                // ---- contraction phase: acc[rows of this warp, 64 points] += W[rows, panel] K
+                int kend[4];
+                const double* ap[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const bool valid = bq[q] >= pbeg;
+                    int ke = valid ? nkp : 0;
+                    if (valid && jp == ip) ke = min(nkp, 2 * (bq[q] - pbeg) + 2);
+                    kend[q] = ke;
+                    const int64_t b = valid ? bq[q] : 0;
+                    ap[q] = F.Wpack + (b * (b + 1) + 64 * jp) * 32 + lane;
+                }
+                int kprev = 0;
+                if (kend[0] > kprev) { mma_run<0>(acc, ap, kprev, kend[0], ks_lane); kprev = kend[0]; }
+                if (kend[1] > kprev) { mma_run<1>(acc, ap, kprev, kend[1], ks_lane); kprev = kend[1]; }
+                if (kend[2] > kprev) { mma_run<2>(acc, ap, kprev, kend[2], ks_lane); kprev = kend[2]; }
+                if (kend[3] > kprev) { mma_run<3>(acc, ap, kprev, kend[3], ks_lane); kprev = kend[3]; }
+            }
+
+            // ---- panel epilogue: sum_i a_i^2 and sum_i a_i alpha_i   (functions.py:442, 451)
+            int qty = 0;
+            for (int o = -1; o < D; ++o) {
+                double al[4] = {0.0, 0.0, 0.0, 0.0};
+                if (o >= 0) {
+                    if (cfg.gp.outputs[o].factor != f) continue;
+                    const double* alpha = cfg.gp.outputs[o].alpha;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+                        if (bq[q] >= pbeg) al[q] = __ldg(alpha + 8 * bq[q] + (lane >> 2));
+                }
+#pragma unroll
+                for (int nb = 0; nb < 8; ++nb) {
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        double v = 0.0;
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const double x = acc[q][nb][e];
+                            v = fma(x, (o < 0) ? x : al[q], v);
+                        }
+                        v += __shfl_xor_sync(0xffffffffu, v, 4);
+                        v += __shfl_xor_sync(0xffffffffu, v, 8);
+                        v += __shfl_xor_sync(0xffffffffu, v, 16);
+                        if (lane < 4) red[(warp * TP + nb * 8 + 2 * lane + e) * NRED + qty] = v;
+                    }
+                }
+                ++qty;
+            }
+            __syncthreads();
+            if (tid < TP) {
+                for (int r = 0; r < qty; ++r) {
+                    double s = 0.0;
+#pragma unroll
+                    for (int w = 0; w < NW; ++w) s += red[(w * TP + tid) * NRED + r];
+                    tot[r * TP + tid] += s;
+                }
+            }
+            __syncthreads();
+        }
+
+        // ---- factor epilogue: mean and error bound of the outputs on this factor
+        if (tid < TP) {
+            int qty = 1;
+            for (int o = 0; o < D; ++o) {
+                const slb_gp_output& G = cfg.gp.outputs[o];
+                if (G.factor != f) continue;
+                double mx = 0.0;                                   // functions.py:439
+                if (G.prior_mean != nullptr) {
+                    mx = f64mul(zraw[tid], G.prior_mean[0]);
+                    for (int c = 1; c < DIN; ++c)
+                        mx = f64add(mx, f64mul(zraw[c * TP + tid], G.prior_mean[c]));
+                    mx = f64mul(F.scale, mx);
+                }
+                const double fmean = f64add(tot[qty * TP + tid], mx) / F.scale;   // :442, :455
+                const double fvar = f64sub(F.kss, tot[tid]) / s2;                  // :450-451, :456
+                post[o * TP + tid] = fmean;
+                post[(SLB_MAX_OUT + o) * TP + tid] =
+                    a.want_var ? fvar : f64mul(G.beta, sqrt(fvar));               // :514
+                ++qty;
+            }
+        }
+        __syncthreads();
+    }
+
+    // ---- tile epilogue
+    if (tid < TP && tile0 + tid < a.n) {
+        const int64_t rel = tile0 + tid;
+        double mu[SLB_MAX_OUT], er[SLB_MAX_OUT];
+        for (int o = 0; o < D; ++o) {
+            mu[o] = post[o * TP + tid];
+            er[o] = post[(SLB_MAX_OUT + o) * TP + tid];
+        }
+        if (a.mean != nullptr) for (int o = 0; o < D; ++o) a.mean[rel * D + o] = mu[o];
+        if (a.err != nullptr) for (int o = 0; o < D; ++o) a.err[rel * D + o] = er[o];
+        if (a.mode != MODE_PREDICT) {
+            double x[SLB_MAX_DIM];
+            for (int c = 0; c < cfg.grid.ndim; ++c) x[c] = zraw[c * TP + tid];
+            const slb_decision r = lyapunov_decide(cfg, x, mu, er);
+            a.negative[rel] = r.negative ? 1 : 0;
+            if (a.values != nullptr) a.values[rel] = r.vx;
+            if (a.decrease != nullptr) a.decrease[rel] = r.decrease;
+            if (a.threshold != nullptr) a.threshold[rel] = r.threshold;
+        }
+    }
+}
+
+__global__ void pack_factor_kernel(const double* __restrict__ Linv, int M, int nrb,
+                                   double* __restrict__ W, int64_t total) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= total) return;
+    const int64_t blk = e >> 5;
+    const int lane = (int)(e & 31);
+    int64_t b = (int64_t)((sqrt(4.0 * (double)blk + 1.0) - 1.0) * 0.5);
+    while (b * (b + 1) > blk) --b;
+    while ((b + 1) * (b + 2) <= blk) ++b;
+    const int64_t kb4 = blk - b * (b + 1);
+    const int64_t row = 8 * b + (lane >> 2);
+    const int64_t col = 4 * kb4 + (lane & 3);
+    W[e] = (row < M && col <= row) ? Linv[row * M + col] : 0.0;
+}
+
+template <int DIN>
+int launch_gp_tile(cudaStream_t st, const slb_sweep& cfg, const gp_args& a) {
+    static bool configured = false;
+    if (!configured) {
+        SLB_CUDA(cudaFuncSetAttribute(gp_tile_kernel<DIN>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)SMEM_TOTAL));
+        configured = true;
+    }
+    const int64_t tiles = (a.n + TP - 1) / TP;
+    gp_tile_kernel<DIN><<<(unsigned)tiles, NT, SMEM_TOTAL, st>>>(cfg, a);
+    SLB_LAUNCH_CHECK();
+    return 0;
+}
+
+int dispatch_gp_tile(cudaStream_t st, const slb_sweep& cfg, const gp_args& a) {
+    if (a.n <= 0) return 0;
+    SLB_CHECK(a.n <= (int64_t)0x7fffffff * TP, "too many points for one launch");
+    switch (cfg.gp.input_dim) {
+    case 1: return launch_gp_tile<1>(st, cfg, a);
+    case 2: return launch_gp_tile<2>(st, cfg, a);
+    case 3: return launch_gp_tile<3>(st, cfg, a);
+    case 4: return launch_gp_tile<4>(st, cfg, a);
+    case 5: return launch_gp_tile<5>(st, cfg, a);
+    case 6: return launch_gp_tile<6>(st, cfg, a);
+    default:
+        slb_set_error("GP input_dim %d not compiled (1..6)", cfg.gp.input_dim);
+        return 1;
+    }
+}
+
+}  // namespace
+
+// implemented in light.cu
+int slb_launch_det_sweep(cudaStream_t st, const slb_sweep& cfg, const double* states, int64_t n,
+                         int64_t idx_begin, uint8_t* negative, double* values, double* decrease,
+                         double* threshold, double* mean);
+
+extern "C" {
+
+int64_t slb_packed_len(int32_t M) {
+    if (M <= 0) return 0;
+    const int64_t nrb = (M + 7) / 8;
+    return nrb * (nrb + 1) * 32;
+}
+
+int slb_pack_factor(void* stream, const double* Linv_dev, int32_t M, double* Wpack_dev) {
+    SLB_CHECK(Linv_dev != nullptr && Wpack_dev != nullptr, "slb_pack_factor: null pointer");
+    SLB_CHECK(M > 0, "slb_pack_factor: M must be positive (got %d)", M);
+    const int nrb = (M + 7) / 8;
+    const int64_t total = slb_packed_len(M);
+    const int threads = 256;
+    const int64_t blocks = (total + threads - 1) / threads;
+    pack_factor_kernel<<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(Linv_dev, M, nrb,
+                                                                              Wpack_dev, total);
+    SLB_LAUNCH_CHECK();
+    return 0;
+}
+
+int slb_gp_predict(void* stream, const slb_gp_stack* gp, const double* points_dev, int64_t n,
+                   double* mean_dev, double* err_dev, int32_t want_var) {
+    SLB_CHECK(gp != nullptr, "slb_gp_predict: null gp");
+    if (slb_validate_gp(gp)) return 1;
+    SLB_CHECK(gp->num_outputs > 0, "slb_gp_predict: GP stack has no outputs");
+    SLB_CHECK(n >= 0, "slb_gp_predict: negative n");
+    SLB_CHECK(n == 0 || (points_dev && mean_dev && err_dev), "slb_gp_predict: null buffer");
+    slb_sweep cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gp = *gp;
+    gp_args a;
+    memset(&a, 0, sizeof(a));
+    a.points = points_dev; a.n = n; a.mode = MODE_PREDICT; a.want_var = want_var;
+    a.mean = mean_dev; a.err = err_dev;
+    return dispatch_gp_tile((cudaStream_t)stream, cfg, a);
+}
+
+static int sweep_common(void* stream, const slb_sweep* cfg, const double* states, int64_t n,
+                        int64_t idx_begin, uint8_t* negative, double* values, double* decrease,
+                        double* threshold, double* mean, double* err) {
+    SLB_CHECK(cfg != nullptr, "lyapunov sweep: null config");
+    SLB_CHECK(n >= 0, "lyapunov sweep: negative point count");
+    if (n == 0) return 0;
+    SLB_CHECK(negative != nullptr, "lyapunov sweep: negative_dev is required");
+    if (slb_validate_grid(&cfg->grid, false)) return 1;
+    const int d = cfg->grid.ndim;
+    if (slb_validate_function(&cfg->policy, "policy", d)) return 1;
+    SLB_CHECK(cfg->policy.kind != SLB_FN_NONE, "lyapunov sweep: a policy is required");
+    if (slb_validate_function(&cfg->lyapunov, "lyapunov_function", d)) return 1;
+    SLB_CHECK(cfg->lyapunov.kind != SLB_FN_NONE, "lyapunov sweep: a Lyapunov function is required");
+    if (slb_validate_function(&cfg->lipschitz_v, "lipschitz_lyapunov", d)) return 1;
+    const int m = (cfg->policy.flags & SLB_FLAG_NORM1) ? 1 : cfg->policy.out_dim;
+    SLB_CHECK(m >= 1 && m <= SLB_MAX_ACT, "policy output dim %d unsupported", m);
+    if (cfg->gp.num_outputs > 0) {
+        if (slb_validate_gp(&cfg->gp)) return 1;
+        SLB_CHECK(cfg->gp.num_outputs == d,
+                  "GP stack has %d outputs but the state has %d dims", cfg->gp.num_outputs, d);
+        SLB_CHECK(cfg->gp.input_dim == d + m, "GP input_dim %d != state %d + action %d",
+                  cfg->gp.input_dim, d, m);
+        gp_args a;
+        memset(&a, 0, sizeof(a));
+        a.points = states; a.n = n; a.idx_begin = idx_begin;
+        a.mode = states ? MODE_SWEEP_STATES : MODE_SWEEP_GRID;
+        a.negative = negative; a.values = values; a.decrease = decrease; a.threshold = threshold;
+        a.mean = mean; a.err = err;
+        return dispatch_gp_tile((cudaStream_t)stream, *cfg, a);
+    }
+    if (slb_validate_function(&cfg->dynamics, "dynamics", d + m)) return 1;
+    SLB_CHECK(cfg->dynamics.kind != SLB_FN_NONE, "lyapunov sweep: no dynamics given");
+    SLB_CHECK(err == nullptr, "deterministic dynamics have no error bounds (err_dev must be NULL)");
+    return slb_launch_det_sweep((cudaStream_t)stream, *cfg, states, n, idx_begin, negative, values,
+                                decrease, threshold, mean);
+}
+
+int slb_lyapunov_sweep(void* stream, const slb_sweep* cfg, int64_t idx_begin, int64_t idx_end,
+                       uint8_t* negative_dev, double* values_dev, double* decrease_dev,
+                       double* threshold_dev, double* mean_dev, double* err_dev) {
+    SLB_CHECK(cfg != nullptr, "slb_lyapunov_sweep: null config");
+    SLB_CHECK(idx_begin >= 0 && idx_end >= idx_begin && idx_end <= cfg->grid.nindex,
+              "slb_lyapunov_sweep: index range [%lld, %lld) outside the grid (nindex %lld)",
+              (long long)idx_begin, (long long)idx_end, (long long)cfg->grid.nindex);
+    return sweep_common(stream, cfg, nullptr, idx_end - idx_begin, idx_begin, negative_dev,
+                        values_dev, decrease_dev, threshold_dev, mean_dev, err_dev);
+}
+
+int slb_lyapunov_points(void* stream, const slb_sweep* cfg, const double* states_dev, int64_t n,
+                        uint8_t* negative_dev, double* values_dev, double* decrease_dev,
+                        double* threshold_dev, double* mean_dev, double* err_dev) {
+    SLB_CHECK(n == 0 || states_dev != nullptr, "slb_lyapunov_points: null states");
+    return sweep_common(stream, cfg, states_dev, n, 0, negative_dev, values_dev, decrease_dev,
+                        threshold_dev, mean_dev, err_dev);
+}
+
+}  // extern "C"

@@ -1,0 +1,563 @@
+// light.cu -- the bandwidth-/latency-bound kernels around the GP sweep, plus library plumbing:
+//   deterministic-dynamics Lyapunov sweep      lyapunov.py:436-441 with a DeterministicFunction
+//   first-fail reduction + prefix application   lyapunov.py:500-606 (sort-free)
+//   generic function evaluation                 Function.__call__, Lyapunov.update_values :305-322
+//   GridWorld.index_to_state                    functions.py:714-731
+//   Bellman sweep / argmax / max|dV|            reinforcement_learning.py:65-114,135-140,213-279
+#include "common.cuh"
+
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+// ----------------------------------------------------------------------------- plumbing
+static thread_local char g_err[512] = "";
+long long g_slb_launches = 0;
+
+void slb_set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int slb_validate_grid(const slb_grid* g, bool need_points) {
+    SLB_CHECK(g->ndim >= 1 && g->ndim <= SLB_MAX_DIM, "grid ndim %d outside 1..%d", g->ndim,
+              SLB_MAX_DIM);
+    int64_t n = 1;
+    for (int c = 0; c < g->ndim; ++c) {
+        SLB_CHECK(g->num_points[c] >= 2, "grid needs >= 2 points per dimension (dim %d has %lld)",
+                  c, (long long)g->num_points[c]);
+        n *= g->num_points[c];
+    }
+    SLB_CHECK(n == g->nindex, "grid nindex %lld != prod(num_points) %lld", (long long)g->nindex,
+              (long long)n);
+    SLB_CHECK(!need_points || g->discrete_points != nullptr,
+              "grid.discrete_points is required for a Triangulation");
+    return 0;
+}
+
+int slb_validate_function(const slb_function* f, const char* what, int expect_in) {
+    switch (f->kind) {
+    case SLB_FN_NONE:
+        return 0;
+    case SLB_FN_CONSTANT:
+        SLB_CHECK(f->out_dim >= 1 && f->out_dim <= SLB_MAX_OUT, "%s: constant out_dim %d", what,
+                  f->out_dim);
+        return 0;
+    case SLB_FN_LINEAR:
+        SLB_CHECK(f->matrix != nullptr, "%s: LinearSystem without matrix", what);
+        SLB_CHECK(f->out_dim >= 1 && f->out_dim <= SLB_MAX_OUT && f->in_dim >= 1 &&
+                  f->in_dim <= SLB_MAX_IN, "%s: LinearSystem shape [%d,%d] unsupported", what,
+                  f->out_dim, f->in_dim);
+        break;
+    case SLB_FN_QUADRATIC:
+        SLB_CHECK(f->matrix != nullptr, "%s: QuadraticFunction without matrix", what);
+        SLB_CHECK(f->in_dim >= 1 && f->in_dim <= SLB_MAX_IN, "%s: quadratic dim %d unsupported",
+                  what, f->in_dim);
+        break;
+    case SLB_FN_TRIANGULATION:
+        if (slb_validate_grid(&f->grid, true)) return 1;
+        SLB_CHECK(f->matrix && f->hyperplanes && f->unit_simplices && f->nsimplex >= 1,
+                  "%s: Triangulation tables missing", what);
+        SLB_CHECK(f->in_dim == f->grid.ndim, "%s: Triangulation in_dim %d != grid ndim %d", what,
+                  f->in_dim, f->grid.ndim);
+        SLB_CHECK(f->out_dim >= 1 && f->out_dim <= SLB_MAX_OUT, "%s: Triangulation out_dim %d",
+                  what, f->out_dim);
+        break;
+    case SLB_FN_PENDULUM:
+        SLB_CHECK(f->in_dim == 3 && f->out_dim == 2, "%s: pendulum must map 3 -> 2", what);
+        break;
+    case SLB_FN_CARTPOLE:
+        SLB_CHECK(f->in_dim == 5 && f->out_dim == 4, "%s: cart-pole must map 5 -> 4", what);
+        break;
+    default:
+        slb_set_error("%s: function kind %d is not implemented in this build", what, f->kind);
+        return 1;
+    }
+    SLB_CHECK(expect_in <= 0 || f->in_dim == expect_in, "%s: expects %d inputs, function takes %d",
+              what, expect_in, f->in_dim);
+    return 0;
+}
+
+int slb_validate_gp(const slb_gp_stack* gp) {
+    if (gp->num_outputs == 0) return 0;
+    SLB_CHECK(gp->num_outputs >= 1 && gp->num_outputs <= SLB_MAX_OUT, "GP outputs %d outside 1..%d",
+              gp->num_outputs, SLB_MAX_OUT);
+    SLB_CHECK(gp->num_factors >= 1 && gp->num_factors <= gp->num_outputs,
+              "GP factors %d inconsistent with %d outputs", gp->num_factors, gp->num_outputs);
+    SLB_CHECK(gp->input_dim >= 1 && gp->input_dim <= SLB_MAX_IN, "GP input_dim %d unsupported",
+              gp->input_dim);
+    for (int f = 0; f < gp->num_factors; ++f) {
+        const slb_gp_factor& F = gp->factors[f];
+        SLB_CHECK(F.M >= 1 && F.nrb == (F.M + 7) / 8, "GP factor %d: bad M/nrb (%d/%d)", f, F.M,
+                  F.nrb);
+        SLB_CHECK(F.Xs != nullptr && F.Wpack != nullptr, "GP factor %d: null table", f);
+        SLB_CHECK(F.scale > 0.0, "GP factor %d: scale must be positive", f);
+        for (int c = 0; c < gp->input_dim; ++c)
+            SLB_CHECK(F.lengthscales[c] > 0.0, "GP factor %d: lengthscale[%d] must be positive", f, c);
+    }
+    for (int o = 0; o < gp->num_outputs; ++o) {
+        const slb_gp_output& G = gp->outputs[o];
+        SLB_CHECK(G.factor >= 0 && G.factor < gp->num_factors, "GP output %d: bad factor index", o);
+        SLB_CHECK(G.alpha != nullptr, "GP output %d: null alpha", o);
+    }
+    return 0;
+}
+
+// ----------------------------------------------------------------------------- kernels
+namespace {
+
+constexpr int LT = 256;
+
+__global__ void __launch_bounds__(LT)
+det_sweep_kernel(const __grid_constant__ slb_sweep cfg, const double* __restrict__ states, int64_t n,
+                 int64_t idx_begin, uint8_t* __restrict__ negative, double* __restrict__ values,
+                 double* __restrict__ decrease, double* __restrict__ threshold,
+                 double* __restrict__ mean) {
+    const int64_t i = (int64_t)blockIdx.x * LT + threadIdx.x;
+    if (i >= n) return;
+    const int d = cfg.grid.ndim;
+    double z[SLB_MAX_IN], u[SLB_MAX_OUT], mu[SLB_MAX_OUT];
+    if (states != nullptr) {
+        for (int c = 0; c < d; ++c) z[c] = states[i * d + c];
+    } else {
+        grid_index_to_state(cfg.grid, idx_begin + i, z);
+    }
+    const int m = eval_fn(cfg.policy, z, u);
+    for (int c = 0; c < m; ++c) z[d + c] = u[c];
+    eval_fn(cfg.dynamics, z, mu);
+    const slb_decision r = lyapunov_decide(cfg, z, mu, nullptr);
+    negative[i] = r.negative ? 1 : 0;
+    if (values != nullptr) values[i] = r.vx;
+    if (decrease != nullptr) decrease[i] = r.decrease;
+    if (threshold != nullptr) threshold[i] = r.threshold;
+    if (mean != nullptr) for (int c = 0; c < d; ++c) mean[i * d + c] = mu[c];
+}
+
+__global__ void __launch_bounds__(LT)
+eval_function_kernel(const __grid_constant__ slb_function fn, const double* __restrict__ points,
+                     int64_t n, double* __restrict__ out, int ncols) {
+    const int64_t i = (int64_t)blockIdx.x * LT + threadIdx.x;
+    if (i >= n) return;
+    double in[SLB_MAX_IN], o[SLB_MAX_OUT];
+    for (int c = 0; c < fn.in_dim; ++c) in[c] = points[i * fn.in_dim + c];
+    eval_fn(fn, in, o);
+    for (int c = 0; c < ncols; ++c) out[i * ncols + c] = o[c];
+}
+
+__global__ void __launch_bounds__(LT)
+index_to_state_kernel(const __grid_constant__ slb_grid g, int64_t idx_begin, int64_t n,
+                      double* __restrict__ states) {
+    const int64_t i = (int64_t)blockIdx.x * LT + threadIdx.x;
+    if (i >= n) return;
+    double x[SLB_MAX_DIM];
+    grid_index_to_state(g, idx_begin + i, x);
+    for (int c = 0; c < g.ndim; ++c) states[i * g.ndim + c] = x[c];
+}
+
+// ---- first-fail reduction ----------------------------------------------------------------
+struct ff_partial { uint64_t kv; int64_t ki; int64_t nok; int64_t pad; };
+
+SLB_DEV bool key_less(uint64_t av, int64_t ai, uint64_t bv, int64_t bi) {
+    return av < bv || (av == bv && ai < bi);
+}
+
+SLB_DEV void ff_block_reduce(uint64_t& kv, int64_t& ki, int64_t& nok) {
+    __shared__ uint64_t s_kv[32];
+    __shared__ int64_t s_ki[32];
+    __shared__ int64_t s_n[32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        const uint64_t ov = __shfl_xor_sync(0xffffffffu, kv, off);
+        const int64_t oi = __shfl_xor_sync(0xffffffffu, ki, off);
+        nok += __shfl_xor_sync(0xffffffffu, nok, off);
+        if (key_less(ov, oi, kv, ki)) { kv = ov; ki = oi; }
+    }
+    if (lane == 0) { s_kv[warp] = kv; s_ki[warp] = ki; s_n[warp] = nok; }
+    __syncthreads();
+    if (warp == 0) {
+        const int nw = (blockDim.x + 31) >> 5;
+        kv = lane < nw ? s_kv[lane] : ~0ull;
+        ki = lane < nw ? s_ki[lane] : INT64_MAX;
+        nok = lane < nw ? s_n[lane] : 0;
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            const uint64_t ov = __shfl_xor_sync(0xffffffffu, kv, off);
+            const int64_t oi = __shfl_xor_sync(0xffffffffu, ki, off);
+            nok += __shfl_xor_sync(0xffffffffu, nok, off);
+            if (key_less(ov, oi, kv, ki)) { kv = ov; ki = oi; }
+        }
+    }
+}
+
+constexpr int FF_BLOCKS = 1024;
+
+__global__ void __launch_bounds__(LT)
+first_fail_partial_kernel(const double* __restrict__ values, const uint8_t* __restrict__ negative,
+                          const uint8_t* __restrict__ initial, int64_t n, int64_t idx_begin,
+                          ff_partial* __restrict__ partial) {
+    uint64_t kv = ~0ull;
+    int64_t ki = INT64_MAX, nok = 0;
+    for (int64_t i = (int64_t)blockIdx.x * LT + threadIdx.x; i < n; i += (int64_t)gridDim.x * LT) {
+        const bool ok = negative[i] != 0 || (initial != nullptr && initial[i] != 0);
+        if (ok) {
+            ++nok;
+        } else {
+            const uint64_t v = value_key(values[i]);
+            const int64_t gi = idx_begin + i;
+            if (key_less(v, gi, kv, ki)) { kv = v; ki = gi; }
+        }
+    }
+    ff_block_reduce(kv, ki, nok);
+    if (threadIdx.x == 0) { partial[blockIdx.x].kv = kv; partial[blockIdx.x].ki = ki;
+                            partial[blockIdx.x].nok = nok; }
+}
+
+__global__ void __launch_bounds__(FF_BLOCKS)
+first_fail_final_kernel(const ff_partial* __restrict__ partial, int nparts,
+                        slb_fail_key* __restrict__ result) {
+    uint64_t kv = ~0ull;
+    int64_t ki = INT64_MAX, nok = 0;
+    if ((int)threadIdx.x < nparts) {
+        kv = partial[threadIdx.x].kv; ki = partial[threadIdx.x].ki; nok = partial[threadIdx.x].nok;
+    }
+    ff_block_reduce(kv, ki, nok);
+    if (threadIdx.x == 0) { result->key_value = kv; result->key_index = ki; result->n_ok = nok;
+                            result->_pad = 0; }
+}
+
+__global__ void __launch_bounds__(LT)
+apply_prefix_kernel(const double* __restrict__ values, const uint8_t* __restrict__ initial, int64_t n,
+                    int64_t idx_begin, const slb_fail_key* __restrict__ key,
+                    uint8_t* __restrict__ safe, slb_prefix_stats* __restrict__ stats) {
+    const uint64_t kv = key->key_value;
+    const int64_t ki = key->key_index;
+    unsigned long long n_safe = 0, n_below = 0, max_below = 0, max_all = 0;
+    for (int64_t i = (int64_t)blockIdx.x * LT + threadIdx.x; i < n; i += (int64_t)gridDim.x * LT) {
+        const uint64_t v = value_key(values[i]);
+        const bool below = key_less(v, idx_begin + i, kv, ki);
+        const bool s = below || (initial != nullptr && initial[i] != 0);
+        safe[i] = s ? 1 : 0;
+        n_safe += s;
+        n_below += below;
+        if (below && v > max_below) max_below = v;
+        if (v > max_all) max_all = v;
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        n_safe += __shfl_xor_sync(0xffffffffu, n_safe, off);
+        n_below += __shfl_xor_sync(0xffffffffu, n_below, off);
+        const unsigned long long mb = __shfl_xor_sync(0xffffffffu, max_below, off);
+        const unsigned long long ma = __shfl_xor_sync(0xffffffffu, max_all, off);
+        if (mb > max_below) max_below = mb;
+        if (ma > max_all) max_all = ma;
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(reinterpret_cast<unsigned long long*>(&stats->n_safe), n_safe);
+        atomicAdd(reinterpret_cast<unsigned long long*>(&stats->n_below), n_below);
+        atomicMax(reinterpret_cast<unsigned long long*>(&stats->max_below), max_below);
+        atomicMax(reinterpret_cast<unsigned long long*>(&stats->max_all), max_all);
+    }
+}
+
+// ---- Bellman sweep ------------------------------------------------------------------------
+// mean of the GP stack at z (mean only, reinforcement_learning.py:98-99):
+//   mean_o = (scale^2 sum_j k_j gamma_o,j + scale m_o(z)) / scale,  gamma = L^-T alpha,
+// which equals a^T alpha of functions.py:441-442 up to rounding.
+SLB_DEV void gp_mean_only(const slb_gp_stack& gp, const double* z, double* mu) {
+    const int din = gp.input_dim;
+    for (int f = 0; f < gp.num_factors; ++f) {
+        const slb_gp_factor& F = gp.factors[f];
+        double zs[SLB_MAX_IN];
+        for (int c = 0; c < din; ++c) zs[c] = z[c] / F.lengthscales[c];
+        double dot[SLB_MAX_OUT];
+        const double* gam[SLB_MAX_OUT];
+        int outs[SLB_MAX_OUT];
+        int no = 0;
+        for (int o = 0; o < gp.num_outputs; ++o)
+            if (gp.outputs[o].factor == f) { outs[no] = o; gam[no] = gp.outputs[o].gamma; dot[no] = 0.0; ++no; }
+        for (int j = 0; j < F.M; ++j) {
+            const double* xr = F.Xs + (size_t)j * din;
+            double t2 = 0.0;
+            for (int c = 0; c < din; ++c) { const double df = zs[c] - __ldg(xr + c); t2 = fma(df, df, t2); }
+            const double k = F.variance * exp(-0.5 * t2);
+            for (int q = 0; q < no; ++q) dot[q] = fma(k, __ldg(gam[q] + j), dot[q]);
+        }
+        const double s2 = f64mul(F.scale, F.scale);
+        for (int q = 0; q < no; ++q) {
+            const slb_gp_output& G = gp.outputs[outs[q]];
+            double mx = 0.0;
+            if (G.prior_mean != nullptr) {
+                mx = f64mul(z[0], G.prior_mean[0]);
+                for (int c = 1; c < din; ++c) mx = f64add(mx, f64mul(z[c], G.prior_mean[c]));
+                mx = f64mul(F.scale, mx);
+            }
+            mu[outs[q]] = f64add(f64mul(s2, dot[q]), mx) / F.scale;
+        }
+    }
+}
+
+SLB_DEV double bellman_value(const slb_bellman& cfg, const double* x, const double* u, int m) {
+    const int d = cfg.grid.ndim;
+    double z[SLB_MAX_IN], mu[SLB_MAX_OUT], r[SLB_MAX_OUT], v[SLB_MAX_OUT];
+    for (int c = 0; c < d; ++c) z[c] = x[c];
+    for (int c = 0; c < m; ++c) z[d + c] = u[c];
+    if (cfg.gp.num_outputs > 0) gp_mean_only(cfg.gp, z, mu);
+    else eval_fn(cfg.dynamics, z, mu);
+    eval_fn(cfg.reward, z, r);                               // :95
+    eval_fn(cfg.value, mu, v);                               // :101
+    return f64add(r[0], f64mul(cfg.gamma, v[0]));                // :104
+}
+
+__global__ void __launch_bounds__(LT)
+bellman_kernel(const __grid_constant__ slb_bellman cfg, int64_t idx_begin, int64_t n,
+               double* __restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * LT + threadIdx.x;
+    if (i >= n) return;
+    double x[SLB_MAX_DIM], u[SLB_MAX_OUT];
+    grid_index_to_state(cfg.grid, idx_begin + i, x);
+    int m;
+    if (cfg.fixed_action) {
+        m = cfg.policy.out_dim;
+        for (int c = 0; c < m; ++c) u[c] = cfg.action[c];
+    } else {
+        m = eval_fn(cfg.policy, x, u);
+    }
+    out[i] = bellman_value(cfg, x, u, m);
+}
+
+__global__ void __launch_bounds__(LT)
+bellman_argmax_kernel(const __grid_constant__ slb_bellman cfg, int64_t idx_begin, int64_t n,
+                      const double* __restrict__ actions, int n_actions, int m,
+                      const double* __restrict__ constraint, int32_t* __restrict__ best,
+                      double* __restrict__ best_value) {
+    const int64_t i = (int64_t)blockIdx.x * LT + threadIdx.x;
+    if (i >= n) return;
+    double x[SLB_MAX_DIM], u[SLB_MAX_ACT];
+    grid_index_to_state(cfg.grid, idx_begin + i, x);
+    int arg = 0;
+    double vmax = 0.0;
+    for (int a = 0; a < n_actions; ++a) {
+        for (int c = 0; c < m; ++c) u[c] = actions[a * m + c];
+        double v = bellman_value(cfg, x, u, m);
+        if (constraint != nullptr && constraint[(int64_t)a * n + i] < 0.0) v = -INFINITY;  // :272-275
+        if (a == 0 || v > vmax) { vmax = v; arg = a; }      // np.argmax: first maximum (:278)
+    }
+    best[i] = arg;
+    if (best_value != nullptr) best_value[i] = vmax;
+}
+
+__global__ void __launch_bounds__(LT)
+max_abs_diff_kernel(const double* __restrict__ a, const double* __restrict__ b, int64_t n,
+                    unsigned long long* __restrict__ result) {
+    double m = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * LT + threadIdx.x; i < n; i += (int64_t)gridDim.x * LT) {
+        const double dlt = fabs(a[i] - b[i]);
+        if (dlt > m || dlt != dlt) m = dlt;
+    }
+    unsigned long long bits = (unsigned long long)__double_as_longlong(m);   // m >= 0 or NaN
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        const unsigned long long o = __shfl_xor_sync(0xffffffffu, bits, off);
+        if (o > bits) bits = o;
+    }
+    if ((threadIdx.x & 31) == 0) atomicMax(result, bits);
+}
+
+inline unsigned blocks_for(int64_t n) { return (unsigned)((n + LT - 1) / LT); }
+
+}  // namespace
+
+int slb_launch_det_sweep(cudaStream_t st, const slb_sweep& cfg, const double* states, int64_t n,
+                         int64_t idx_begin, uint8_t* negative, double* values, double* decrease,
+                         double* threshold, double* mean) {
+    det_sweep_kernel<<<blocks_for(n), LT, 0, st>>>(cfg, states, n, idx_begin, negative, values,
+                                                   decrease, threshold, mean);
+    SLB_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" {
+
+int slb_abi_version(void) { return SLB_ABI_VERSION; }
+const char* slb_last_error(void) { return g_err; }
+int64_t slb_launch_count(void) { return (int64_t)g_slb_launches; }
+
+/* sizeof of every ABI struct, for bindings to verify their mirror:
+   [grid, function, gp_factor, gp_output, gp_stack, sweep, bellman, fail_key, prefix_stats] */
+int slb_struct_sizes(int64_t* out, int32_t n) {
+    const int64_t sizes[9] = {sizeof(slb_grid), sizeof(slb_function), sizeof(slb_gp_factor),
+                              sizeof(slb_gp_output), sizeof(slb_gp_stack), sizeof(slb_sweep),
+                              sizeof(slb_bellman), sizeof(slb_fail_key), sizeof(slb_prefix_stats)};
+    for (int i = 0; i < n && i < 9; ++i) out[i] = sizes[i];
+    return 9;
+}
+
+int slb_device_count(void) {
+    int n = 0;
+    const cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) {
+        slb_set_error("cudaGetDeviceCount failed: %s (libslb200 has no CPU fallback)",
+                      cudaGetErrorString(e));
+        return -1;
+    }
+    return n;
+}
+
+int64_t slb_first_fail_workspace(int64_t n) {
+    (void)n;
+    return (int64_t)FF_BLOCKS * (int64_t)sizeof(ff_partial);
+}
+
+int slb_first_fail(void* stream, const double* values_dev, const uint8_t* negative_dev,
+                   const uint8_t* initial_dev, int64_t n, int64_t idx_begin, void* workspace_dev,
+                   slb_fail_key* result_dev) {
+    SLB_CHECK(n >= 0, "slb_first_fail: negative n");
+    SLB_CHECK(workspace_dev && result_dev, "slb_first_fail: null workspace/result");
+    SLB_CHECK(n == 0 || (values_dev && negative_dev), "slb_first_fail: null input");
+    const int64_t want = (n + LT - 1) / LT;
+    const int nparts = (int)(want < 1 ? 1 : (want > FF_BLOCKS ? FF_BLOCKS : want));
+    cudaStream_t st = (cudaStream_t)stream;
+    first_fail_partial_kernel<<<nparts, LT, 0, st>>>(values_dev, negative_dev, initial_dev, n,
+                                                     idx_begin, (ff_partial*)workspace_dev);
+    SLB_LAUNCH_CHECK();
+    first_fail_final_kernel<<<1, FF_BLOCKS, 0, st>>>((const ff_partial*)workspace_dev, nparts,
+                                                     result_dev);
+    SLB_LAUNCH_CHECK();
+    return 0;
+}
+
+int slb_apply_prefix(void* stream, const double* values_dev, const uint8_t* initial_dev, int64_t n,
+                     int64_t idx_begin, const slb_fail_key* key_dev, uint8_t* safe_dev,
+                     void* workspace_dev, slb_prefix_stats* stats_dev) {
+    (void)workspace_dev;
+    SLB_CHECK(n >= 0, "slb_apply_prefix: negative n");
+    SLB_CHECK(key_dev && stats_dev, "slb_apply_prefix: null key/stats");
+    SLB_CHECK(n == 0 || (values_dev && safe_dev), "slb_apply_prefix: null buffer");
+    cudaStream_t st = (cudaStream_t)stream;
+    SLB_CUDA(cudaMemsetAsync(stats_dev, 0, sizeof(slb_prefix_stats), st));
+    if (n == 0) return 0;
+    const int64_t want = (n + LT - 1) / LT;
+    const unsigned blocks = (unsigned)(want > 2048 ? 2048 : want);
+    apply_prefix_kernel<<<blocks, LT, 0, st>>>(values_dev, initial_dev, n, idx_begin, key_dev,
+                                               safe_dev, stats_dev);
+    SLB_LAUNCH_CHECK();
+    return 0;
+}
+
+int slb_eval_function(void* stream, const slb_function* fn, const double* points_dev, int64_t n,
+                      double* out_dev) {
+    SLB_CHECK(fn != nullptr, "slb_eval_function: null function");
+    if (slb_validate_function(fn, "function", 0)) return 1;
+    SLB_CHECK(fn->kind != SLB_FN_NONE, "slb_eval_function: empty function");
+    SLB_CHECK(n >= 0, "slb_eval_function: negative n");
+    if (n == 0) return 0;
+    SLB_CHECK(points_dev && out_dev, "slb_eval_function: null buffer");
+    int ncols = (fn->flags & SLB_FLAG_NORM1) ? 1 : fn->out_dim;
+    if (fn->kind == SLB_FN_QUADRATIC) ncols = 1;
+    eval_function_kernel<<<blocks_for(n), LT, 0, (cudaStream_t)stream>>>(*fn, points_dev, n, out_dev,
+                                                                        ncols);
+    SLB_LAUNCH_CHECK();
+    return 0;
+}
+
+int slb_index_to_state(void* stream, const slb_grid* grid, int64_t idx_begin, int64_t idx_end,
+                       double* states_dev) {
+    SLB_CHECK(grid != nullptr, "slb_index_to_state: null grid");
+    if (slb_validate_grid(grid, false)) return 1;
+    SLB_CHECK(idx_begin >= 0 && idx_end >= idx_begin && idx_end <= grid->nindex,
+              "slb_index_to_state: range [%lld, %lld) outside the grid", (long long)idx_begin,
+              (long long)idx_end);
+    const int64_t n = idx_end - idx_begin;
+    if (n == 0) return 0;
+    SLB_CHECK(states_dev != nullptr, "slb_index_to_state: null output");
+    index_to_state_kernel<<<blocks_for(n), LT, 0, (cudaStream_t)stream>>>(*grid, idx_begin, n,
+                                                                         states_dev);
+    SLB_LAUNCH_CHECK();
+    return 0;
+}
+
+static int validate_bellman(const slb_bellman* cfg, int* m_out) {
+    SLB_CHECK(cfg != nullptr, "bellman: null config");
+    if (slb_validate_grid(&cfg->grid, false)) return 1;
+    const int d = cfg->grid.ndim;
+    int m;
+    if (cfg->fixed_action) {
+        m = cfg->policy.out_dim;
+        SLB_CHECK(m >= 1 && m <= SLB_MAX_ACT, "bellman: fixed action dim %d unsupported", m);
+    } else {
+        if (slb_validate_function(&cfg->policy, "policy", d)) return 1;
+        SLB_CHECK(cfg->policy.kind != SLB_FN_NONE, "bellman: a policy is required");
+        m = cfg->policy.out_dim;
+        SLB_CHECK(m >= 1 && m <= SLB_MAX_ACT, "bellman: policy output dim %d unsupported", m);
+    }
+    if (cfg->gp.num_outputs > 0) {
+        if (slb_validate_gp(&cfg->gp)) return 1;
+        SLB_CHECK(cfg->gp.num_outputs == d && cfg->gp.input_dim == d + m,
+                  "bellman: GP stack shape (%d outputs, %d inputs) does not match state %d + action %d",
+                  cfg->gp.num_outputs, cfg->gp.input_dim, d, m);
+        for (int o = 0; o < cfg->gp.num_outputs; ++o)
+            SLB_CHECK(cfg->gp.outputs[o].gamma != nullptr, "bellman: GP output %d has no gamma", o);
+    } else {
+        if (slb_validate_function(&cfg->dynamics, "dynamics", d + m)) return 1;
+        SLB_CHECK(cfg->dynamics.kind != SLB_FN_NONE, "bellman: no dynamics given");
+    }
+    if (slb_validate_function(&cfg->reward, "reward_function", d + m)) return 1;
+    SLB_CHECK(cfg->reward.kind != SLB_FN_NONE, "bellman: a reward function is required");
+    if (slb_validate_function(&cfg->value, "value_function", d)) return 1;
+    SLB_CHECK(cfg->value.kind != SLB_FN_NONE, "bellman: a value function is required");
+    *m_out = m;
+    return 0;
+}
+
+int slb_bellman_sweep(void* stream, const slb_bellman* cfg, int64_t idx_begin, int64_t idx_end,
+                      double* out_dev) {
+    int m;
+    if (validate_bellman(cfg, &m)) return 1;
+    SLB_CHECK(idx_begin >= 0 && idx_end >= idx_begin && idx_end <= cfg->grid.nindex,
+              "slb_bellman_sweep: range outside the grid");
+    const int64_t n = idx_end - idx_begin;
+    if (n == 0) return 0;
+    SLB_CHECK(out_dev != nullptr, "slb_bellman_sweep: null output");
+    bellman_kernel<<<blocks_for(n), LT, 0, (cudaStream_t)stream>>>(*cfg, idx_begin, n, out_dev);
+    SLB_LAUNCH_CHECK();
+    return 0;
+}
+
+int slb_bellman_argmax(void* stream, const slb_bellman* cfg, int64_t idx_begin, int64_t idx_end,
+                       const double* actions_dev, int32_t n_actions, const double* constraint_dev,
+                       int32_t* best_dev, double* best_value_dev) {
+    SLB_CHECK(cfg != nullptr && cfg->fixed_action, "slb_bellman_argmax: cfg.fixed_action must be set");
+    int m;
+    if (validate_bellman(cfg, &m)) return 1;
+    SLB_CHECK(n_actions >= 1 && actions_dev != nullptr, "slb_bellman_argmax: no actions");
+    SLB_CHECK(idx_begin >= 0 && idx_end >= idx_begin && idx_end <= cfg->grid.nindex,
+              "slb_bellman_argmax: range outside the grid");
+    const int64_t n = idx_end - idx_begin;
+    if (n == 0) return 0;
+    SLB_CHECK(best_dev != nullptr, "slb_bellman_argmax: null output");
+    bellman_argmax_kernel<<<blocks_for(n), LT, 0, (cudaStream_t)stream>>>(
+        *cfg, idx_begin, n, actions_dev, n_actions, m, constraint_dev, best_dev, best_value_dev);
+    SLB_LAUNCH_CHECK();
+    return 0;
+}
+
+int slb_max_abs_diff(void* stream, const double* a_dev, const double* b_dev, int64_t n,
+                     double* result_dev) {
+    SLB_CHECK(result_dev != nullptr, "slb_max_abs_diff: null result");
+    SLB_CHECK(n >= 0, "slb_max_abs_diff: negative n");
+    cudaStream_t st = (cudaStream_t)stream;
+    SLB_CUDA(cudaMemsetAsync(result_dev, 0, sizeof(double), st));
+    if (n == 0) return 0;
+    SLB_CHECK(a_dev && b_dev, "slb_max_abs_diff: null input");
+    const int64_t want = (n + LT - 1) / LT;
+    const unsigned blocks = (unsigned)(want > 1024 ? 1024 : want);
+    max_abs_diff_kernel<<<blocks, LT, 0, st>>>(a_dev, b_dev, n,
+                                               reinterpret_cast<unsigned long long*>(result_dev));
+    SLB_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,884 @@
+"""Function objects of the region-of-attraction path, as parameter containers for libslb200.
+
+API surface follows ``safe_learning/functions.py`` of the reference (class names, constructor
+arguments, attributes); cited line numbers are relative to /root/reference.  Where the
+reference's objects emit TF1 graph nodes, these objects (a) describe themselves to the CUDA
+kernels through an ``slb_function`` / ``slb_gp_stack`` descriptor and (b) evaluate eagerly on
+the GPU when called with numpy arrays, returning numpy arrays.  There is no CPU path.
+
+gpflow is replaced by the small gpflow-free containers ``RBF`` / ``GPRCached`` (same
+arithmetic as ``gpflow==0.4.0`` ``kernels.RBF`` + ``functions.py:357-458``).
+"""
+
+from __future__ import annotations
+
+import hashlib
+import itertools
+
+import numpy as np
+import scipy.signal
+import scipy.spatial
+import torch
+
+from . import _device as dev
+from . import _native as nat
+from .configuration import Configuration
+
+config = Configuration()
+
+__all__ = ["DimensionError", "GridWorld", "Function", "DeterministicFunction",
+           "UncertainFunction", "ConstantFunction", "LinearSystem", "QuadraticFunction",
+           "Saturation", "AbsFunction", "Norm1Function", "ScaledFunction", "Triangulation",
+           "RBF", "Likelihood", "GPRCached", "GPR", "GaussianProcess", "FunctionStack",
+           "InvertedPendulum", "CartPole", "concatenate_inputs"]
+
+
+class DimensionError(Exception):
+    """``functions.py:575-576``."""
+
+
+def concatenate_inputs(inputs):
+    """Column-concatenate call arguments ([x, u] layout; ``utilities.py:123-159``)."""
+    cols = [np.atleast_2d(np.asarray(a, dtype=np.float64)) for a in inputs]
+    return cols[0] if len(cols) == 1 else np.hstack(cols)
+
+
+# =============================================================================== GridWorld
+class GridWorld(object):
+    """Regular grid (``functions.py:579-817``).
+
+    The kernels never read coordinates from memory: ``descriptor()`` carries
+    offset / unit_maxes / num_points and every thread rebuilds ``ijk * unit_maxes + offset``
+    (``:731``) from its flat index.  The host-side helpers below are vectorised numpy index
+    arithmetic (not a compute path).
+    """
+
+    def __init__(self, limits, num_points):
+        self.limits = np.atleast_2d(limits).astype(np.float64)
+        npts = np.broadcast_to(num_points, len(self.limits))
+        self.num_points = npts.astype(np.int64, copy=True)
+        if np.any(self.num_points < 2):
+            raise DimensionError("There must be at least 2 points in each dimension.")
+        if len(self.limits) > nat.SLB_MAX_DIM:
+            raise DimensionError("at most %d grid dimensions are supported" % nat.SLB_MAX_DIM)
+        self.offset = self.limits[:, 0]
+        self.unit_maxes = (self.limits[:, 1] - self.offset) / (self.num_points - 1)
+        self.offset_limits = np.stack((np.zeros(len(self.limits)),
+                                       self.limits[:, 1] - self.offset), axis=1)
+        self.discrete_points = [np.linspace(lo, hi, n, dtype=np.float64)
+                                for (lo, hi), n in zip(self.limits, self.num_points)]
+        self.nrectangles = int(np.prod(self.num_points - 1))
+        self.nindex = int(np.prod(self.num_points))
+        self.ndim = len(self.limits)
+        self._all_points = None
+        self._points_dev = None
+
+    def __len__(self):
+        return self.nindex
+
+    # ---- descriptor for the kernels
+    def descriptor(self, need_points=False):
+        g = nat.SlbGrid()
+        g.ndim = self.ndim
+        g.nindex = self.nindex
+        for c in range(self.ndim):
+            g.num_points[c] = int(self.num_points[c])
+            g.offset[c] = float(self.offset[c])
+            g.unit_maxes[c] = float(self.unit_maxes[c])
+            g.upper[c] = float(self.limits[c, 1])
+        if need_points:
+            if self._points_dev is None:
+                self._points_dev = dev.to_device(np.concatenate(self.discrete_points))
+            g.discrete_points = self._points_dev.data_ptr()
+        return g
+
+    # ---- reference API
+    @property
+    def all_points(self):
+        """All grid points, C order, last dimension fastest (``:622-638``).  Host array; the
+        sweeps do not use it."""
+        if self._all_points is None:
+            mesh = np.meshgrid(*self.discrete_points, indexing="ij")
+            self._all_points = np.column_stack([m.ravel() for m in mesh])
+        return self._all_points
+
+    def sample_continuous(self, num_samples):
+        rand = np.random.uniform(0, 1, size=(num_samples, self.ndim))
+        return rand * np.diff(self.limits, axis=1).T + self.offset
+
+    def sample_discrete(self, num_samples, replace=False):
+        idx = np.random.choice(self.nindex, size=num_samples, replace=replace)
+        return self.index_to_state(idx)
+
+    def _check_dimensions(self, states):
+        if not states.shape[1] == self.ndim:
+            raise DimensionError("the input argument has the wrong dimensions.")
+
+    def _center_states(self, states, clip=True):
+        eps = np.finfo(np.float64).eps
+        states = np.atleast_2d(states).astype(np.float64) - self.offset[None, :]
+        if clip:
+            np.clip(states, self.offset_limits[:, 0] + 2 * eps,
+                    self.offset_limits[:, 1] - 2 * eps, out=states)
+        return states
+
+    def index_to_state(self, indices):
+        ijk = np.stack(np.unravel_index(np.atleast_1d(indices), self.num_points), axis=1)
+        return ijk.astype(np.float64) * self.unit_maxes + self.offset
+
+    def state_to_index(self, states):
+        states = np.atleast_2d(states)
+        self._check_dimensions(states)
+        clipped = np.clip(states, self.limits[:, 0], self.limits[:, 1])
+        ijk = np.rint((clipped - self.offset) * (1. / self.unit_maxes)).astype(np.int32)
+        return np.ravel_multi_index(ijk.T, self.num_points)
+
+    def state_to_rectangle(self, states):
+        cells = []
+        for i, (pts, n) in enumerate(zip(self.discrete_points, self.num_points)):
+            cells.append(np.clip(np.digitize(states[:, i], pts) - 1, 0, n - 2))
+        return np.ravel_multi_index(cells, self.num_points - 1)
+
+    def rectangle_to_state(self, rectangles):
+        ijk = np.stack(np.unravel_index(np.atleast_1d(rectangles), self.num_points - 1), axis=1)
+        return ijk.astype(np.float64) * self.unit_maxes + self.offset
+
+    def rectangle_corner_index(self, rectangles):
+        ijk = np.vstack(np.unravel_index(rectangles, self.num_points - 1))
+        return np.ravel_multi_index(np.atleast_2d(ijk), self.num_points)
+
+
+# =============================================================================== Function base
+class Function(object):
+    """Base class (``functions.py:31-122``): ``fun(*inputs)`` concatenates the inputs and
+    evaluates on the GPU; ``+``/``*``/``-`` with scalars build fused wrappers."""
+
+    input_dim = None
+    output_dim = None
+
+    def __init__(self, name="function"):
+        self.name = name
+        self.feed_dict = {}
+
+    # descriptor protocol --------------------------------------------------------------
+    def descriptor(self):
+        """Return an ``slb_function``; device buffers it points to are owned by ``self``."""
+        raise NotImplementedError("%s cannot be fused into the CUDA kernels"
+                                  % type(self).__name__)
+
+    @property
+    def parameters(self):
+        return []
+
+    # eager evaluation -----------------------------------------------------------------
+    def __call__(self, *inputs):
+        return self.evaluate_device(concatenate_inputs(inputs)).cpu().numpy()
+
+    def evaluate_device(self, points):
+        """points: numpy [n, in] or device tensor -> device tensor [n, out]."""
+        lib = nat.load()
+        desc = self.descriptor()
+        pts = dev.to_device(points)
+        if pts.dim() != 2 or pts.shape[1] != desc.in_dim:
+            raise DimensionError("%s expects %d input columns, got shape %s"
+                                 % (type(self).__name__, desc.in_dim, tuple(pts.shape)))
+        ncols = 1 if (desc.flags & nat.FLAG_NORM1 or desc.kind == nat.FN_QUADRATIC) \
+            else desc.out_dim
+        out = dev.empty((pts.shape[0], ncols))
+        nat.check(lib.slb_eval_function(dev.stream(), desc, pts.data_ptr(), pts.shape[0],
+                                        out.data_ptr()), "slb_eval_function")
+        return out
+
+    # algebra (``functions.py:112-122``) --------------------------------------------------
+    def __neg__(self):
+        return ScaledFunction(self, -1.0)
+
+    def __mul__(self, other):
+        if np.isscalar(other):
+            return ScaledFunction(self, float(other))
+        raise NotImplementedError("only multiplication by a scalar is fused on the GPU")
+
+    __rmul__ = __mul__
+
+    def __abs__(self):
+        return AbsFunction(self)
+
+    def __add__(self, other):
+        raise NotImplementedError("AddedFunction (functions.py:125-160) is outside the fused "
+                                  "hot path of this build")
+
+
+class DeterministicFunction(Function):
+    """``functions.py:233-238``."""
+
+
+class UncertainFunction(Function):
+    """``functions.py:202-230``."""
+
+
+class ConstantFunction(DeterministicFunction):
+    """``functions.py:241-251``."""
+
+    def __init__(self, constant, input_dim=1, name="constant_function"):
+        super().__init__(name)
+        self.constant = np.atleast_1d(np.asarray(constant, dtype=np.float64)).ravel()
+        self.input_dim, self.output_dim = input_dim, len(self.constant)
+
+    def descriptor(self):
+        d = nat.SlbFunction()
+        d.kind, d.in_dim, d.out_dim = nat.FN_CONSTANT, self.input_dim, self.output_dim
+        for i, v in enumerate(self.constant):
+            d.cparams[i] = float(v)
+        return d
+
+
+class LinearSystem(DeterministicFunction):
+    """``y = [x, u] A^T`` (``functions.py:1546-1583``)."""
+
+    def __init__(self, matrices, name="linear_system"):
+        super().__init__(name)
+        if isinstance(matrices, np.ndarray):
+            matrices = (matrices,)
+        self.matrix = np.hstack([np.atleast_2d(m).astype(np.float64) for m in matrices])
+        self.output_dim, self.input_dim = self.matrix.shape
+        self._matrix_dev = None
+
+    def descriptor(self):
+        if self._matrix_dev is None:
+            self._matrix_dev = dev.to_device(self.matrix)
+        d = nat.SlbFunction()
+        d.kind, d.in_dim, d.out_dim = nat.FN_LINEAR, self.input_dim, self.output_dim
+        d.matrix = self._matrix_dev.data_ptr()
+        return d
+
+
+class QuadraticFunction(DeterministicFunction):
+    """``sum((x P) * x)`` with P as given, not symmetrised (``functions.py:1513-1543``)."""
+
+    def __init__(self, matrix, name="quadratic"):
+        super().__init__(name)
+        self.matrix = np.atleast_2d(matrix).astype(np.float64)
+        self.ndim = self.matrix.shape[0]
+        self.input_dim, self.output_dim = self.ndim, 1
+        self._matrix_dev = None
+
+    def descriptor(self):
+        if self._matrix_dev is None:
+            self._matrix_dev = dev.to_device(self.matrix)
+        d = nat.SlbFunction()
+        d.kind, d.in_dim, d.out_dim = nat.FN_QUADRATIC, self.ndim, 1
+        d.matrix = self._matrix_dev.data_ptr()
+        return d
+
+    def gradient(self, points=None):
+        """``x (P + P^T)`` as a fusable LinearSystem (``:1541-1543``); evaluated when points
+        are given."""
+        grad = LinearSystem((self.matrix + self.matrix.T).T)
+        return grad if points is None else grad(points)
+
+
+class _PostOp(DeterministicFunction):
+    """A post-operation fused onto a wrapped function's descriptor.  The kernels apply
+    saturate -> abs -> norm1 -> scale in that order (``slb200.h``), so wrappers must be
+    nested in that order."""
+
+    _order = 0
+
+    def __init__(self, fun, name):
+        super().__init__(name)
+        if not isinstance(fun, Function):
+            raise TypeError("%s wraps a Function object, got %r" % (type(self).__name__, fun))
+        inner = getattr(fun, "_order", 0)
+        if inner >= self._order:
+            raise NotImplementedError(
+                "%s around %s: post-operations fuse only in the order "
+                "saturate -> abs -> norm1 -> scale" % (type(self).__name__, type(fun).__name__))
+        self.fun = fun
+        self.input_dim = fun.input_dim
+
+    @property
+    def parameters(self):
+        return self.fun.parameters
+
+
+class Saturation(_PostOp):
+    """``min(max(fun(x), lower), upper)`` (``functions.py:310-354``)."""
+
+    _order = 1
+
+    def __init__(self, fun, lower, upper, name="saturation"):
+        super().__init__(fun, name)
+        self.lower, self.upper = float(lower), float(upper)
+        self.output_dim = fun.output_dim
+
+    def descriptor(self):
+        d = self.fun.descriptor()
+        d.flags |= nat.FLAG_SATURATE
+        d.lower, d.upper = self.lower, self.upper
+        return d
+
+
+class AbsFunction(_PostOp):
+    """``|fun(x)|`` element-wise -- the per-dimension Lipschitz lambda
+    ``tf.abs(grad_lyapunov_function(x))`` of ``examples/adaptive_safety_verification.ipynb``
+    cell 17, as a fusable object."""
+
+    _order = 2
+
+    def __init__(self, fun, name="abs"):
+        super().__init__(fun, name)
+        self.output_dim = fun.output_dim
+
+    def descriptor(self):
+        d = self.fun.descriptor()
+        d.flags |= nat.FLAG_ABS
+        return d
+
+
+class Norm1Function(_PostOp):
+    """``tf.norm(fun(x), ord=1, axis=1, keepdims=True)`` (same notebook cell)."""
+
+    _order = 3
+
+    def __init__(self, fun, name="norm1"):
+        super().__init__(fun, name)
+        self.output_dim = 1
+
+    def descriptor(self):
+        d = self.fun.descriptor()
+        d.flags |= nat.FLAG_NORM1
+        return d
+
+
+class ScaledFunction(_PostOp):
+    """``fun * c`` / ``-fun`` (``MultipliedFunction`` with a constant, ``functions.py:163-199``)."""
+
+    _order = 4
+
+    def __init__(self, fun, factor, name="scaled"):
+        super().__init__(fun, name)
+        self.factor = float(factor)
+        self.output_dim = fun.output_dim
+
+    def __getattr__(self, item):          # e.g. (-value_function).discretization
+        if item in ("fun", "factor"):
+            raise AttributeError(item)
+        return getattr(self.fun, item)
+
+    def descriptor(self):
+        d = self.fun.descriptor()
+        d.flags |= nat.FLAG_SCALE
+        d.out_scale = self.factor
+        return d
+
+
+# =============================================================================== Triangulation
+class _Delaunay1D(object):
+    """Two-point stand-in for scipy's Delaunay in 1-D (``functions.py:935-978``)."""
+
+    def __init__(self, points):
+        self.points = points
+        self.nsimplex = 1
+        self.simplices = np.array([[0, 1]])
+
+
+class _TriangulationTables(object):
+    """Host-side tables of ``_Triangulation`` (``functions.py:1002-1101``): the unit
+    hyper-rectangle is triangulated once by Qhull; the kernels take the resulting
+    ``unit_simplices`` / ``hyperplanes`` instead of assuming a particular split."""
+
+    def __init__(self, discretization, project=False):
+        self.discretization = disc = discretization
+        self.input_dim = disc.ndim
+        self.project = project
+        if disc.ndim == 1:
+            self.triangulation = _Delaunay1D(np.array([[0.0], [disc.unit_maxes[0]]]))
+        else:
+            corners = np.array(list(itertools.product(*np.diag(disc.unit_maxes))))
+            self.triangulation = scipy.spatial.Delaunay(corners)
+        mapping = disc.state_to_index(np.atleast_2d(self.triangulation.points) + disc.offset)
+        self.unit_simplices = mapping[np.asarray(self.triangulation.simplices)].astype(np.int64)
+        self.nsimplex_unit = int(self.triangulation.nsimplex)
+        self.nsimplex = self.nsimplex_unit * disc.nrectangles
+        self.hyperplanes = np.empty((self.nsimplex_unit, disc.ndim, disc.ndim))
+        for i, simplex in enumerate(self.unit_simplices):
+            pts = disc.index_to_state(simplex)
+            self.hyperplanes[i] = np.linalg.inv(pts[1:] - pts[:1])
+        # Queries clipped in every dimension land on a unit-cell corner shared by several
+        # simplices; which one Qhull's walk returns decides the (discontinuous) extrapolation
+        # of a non-projected query, so ask Qhull once per corner pattern (functions.py:1120-1124).
+        self.corner_simplex = np.zeros(2 ** disc.ndim, dtype=np.int32)
+        if disc.ndim > 1:
+            eps = np.finfo(np.float64).eps
+            lo = disc.offset_limits[:, 0] + 2 * eps
+            hi = disc.offset_limits[:, 1] - 2 * eps
+            for pattern in range(2 ** disc.ndim):
+                bits = np.array([(pattern >> c) & 1 for c in range(disc.ndim)], dtype=bool)
+                unit = np.where(bits, hi, lo) % disc.unit_maxes
+                self.corner_simplex[pattern] = int(self.triangulation.find_simplex(unit[None, :])[0])
+
+    @property
+    def limits(self):
+        return self.discretization.limits
+
+    @property
+    def nindex(self):
+        return self.discretization.nindex
+
+
+class Triangulation(DeterministicFunction):
+    """Piecewise-linear interpolation on a GridWorld (``functions.py:1372-1510``).
+
+    The vertex values live in HBM (``_param_dev`` [nindex, out]); ``parameters`` exposes
+    them like the reference's single tf.Variable: ``tri.parameters[0]`` is the [nindex, out]
+    array, and assigning ``tri.parameters = values`` re-uploads.
+    """
+
+    def __init__(self, discretization, vertex_values, project=False, name="triangulation"):
+        super().__init__(name)
+        self.tri = _TriangulationTables(discretization, project=project)
+        self.input_dim = self.tri.input_dim
+        self._param_dev = None
+        self._hyper_dev = None
+        self._simp_dev = None
+        self._corner_dev = None
+        self.output_dim = None
+        if vertex_values is not None:
+            self.parameters = vertex_values
+
+    @property
+    def project(self):
+        return self.tri.project
+
+    @project.setter
+    def project(self, value):
+        self.tri.project = value
+
+    @property
+    def discretization(self):
+        return self.tri.discretization
+
+    @property
+    def nindex(self):
+        return self.tri.nindex
+
+    @property
+    def parameters(self):
+        if self._param_dev is None:
+            return []
+        return [self._param_dev.cpu().numpy()]
+
+    @parameters.setter
+    def parameters(self, values):
+        if isinstance(values, (list, tuple)) and len(values) == 1:
+            values = values[0]
+        if isinstance(values, torch.Tensor):
+            vals = values.to(dtype=torch.float64).reshape(self.nindex, -1)
+            self._param_dev = vals.to(dev.device()).contiguous().clone()
+        else:
+            vals = np.asarray(values, dtype=np.float64).reshape(self.nindex, -1)
+            self._param_dev = dev.to_device(vals)
+        self.output_dim = int(self._param_dev.shape[1])
+
+    def descriptor(self):
+        if self._param_dev is None:
+            raise ValueError("Triangulation has no vertex values")
+        if self.input_dim > nat.SLB_MAX_DIM:
+            raise DimensionError("Triangulation supports up to %d dims" % nat.SLB_MAX_DIM)
+        if self._hyper_dev is None:
+            self._hyper_dev = dev.to_device(self.tri.hyperplanes)
+            self._simp_dev = dev.to_device(self.tri.unit_simplices, torch.int64)
+            self._corner_dev = dev.to_device(self.tri.corner_simplex, torch.int32)
+        d = nat.SlbFunction()
+        d.kind, d.in_dim, d.out_dim = nat.FN_TRIANGULATION, self.input_dim, self.output_dim
+        d.flags = nat.FLAG_PROJECT if self.project else 0
+        d.matrix = self._param_dev.data_ptr()
+        d.hyperplanes = self._hyper_dev.data_ptr()
+        d.unit_simplices = self._simp_dev.data_ptr()
+        d.corner_simplex = self._corner_dev.data_ptr() if self.input_dim > 1 else None
+        d.nsimplex = self.tri.nsimplex_unit
+        d.grid = self.discretization.descriptor(need_points=True)
+        return d
+
+
+# =============================================================================== plants
+def _pack_norm(cp, normalization, ns, base):
+    """cparams[base:] = Tx[ns], Tu, 1/Tx[ns]; returns the flag value."""
+    if normalization is None:
+        return 0.0
+    tx, tu = (np.asarray(n, dtype=np.float64).ravel() for n in normalization)
+    inv = tx ** -1
+    for i in range(ns):
+        cp[base + i] = float(tx[i])
+    cp[base + ns] = float(tu[0])
+    for i in range(ns):
+        cp[base + ns + 1 + i] = float(inv[i])
+    return 1.0
+
+
+class InvertedPendulum(DeterministicFunction):
+    """Normalised inverted pendulum, 10 explicit-Euler sub-steps
+    (``examples/utilities.py:144-289``)."""
+
+    def __init__(self, mass, length, friction=0.0, dt=1 / 80, normalization=None,
+                 name="inverted_pendulum"):
+        super().__init__(name)
+        self.mass, self.length, self.friction, self.dt = mass, length, friction, dt
+        self.gravity = 9.81
+        self.normalization = normalization
+        if normalization is not None:
+            self.normalization = [np.array(n, dtype=np.float64) for n in normalization]
+            self.inv_norm = [n ** -1 for n in self.normalization]
+        self.input_dim, self.output_dim = 3, 2
+
+    @property
+    def inertia(self):
+        return self.mass * self.length ** 2
+
+    def linearize(self):
+        """Discretised, normalised linearisation (``examples/utilities.py:207-240``)."""
+        g, l, b, inertia = self.gravity, self.length, self.friction, self.inertia
+        A = np.array([[0, 1], [g / l, -b / inertia]], dtype=np.float64)
+        B = np.array([[0], [1 / inertia]], dtype=np.float64)
+        if self.normalization is not None:
+            Tx, Tu = map(np.diag, self.normalization)
+            Tx_inv, Tu_inv = map(np.diag, self.inv_norm)
+            A = np.linalg.multi_dot((Tx_inv, A, Tx))
+            B = np.linalg.multi_dot((Tx_inv, B, Tu))
+        sysd = scipy.signal.StateSpace(A, B, np.eye(2), np.zeros((2, 1))).to_discrete(self.dt)
+        return sysd.A, sysd.B
+
+    def descriptor(self):
+        d = nat.SlbFunction()
+        d.kind, d.in_dim, d.out_dim = nat.FN_PENDULUM, 3, 2
+        cp = d.cparams
+        cp[0] = self.gravity / self.length
+        cp[1] = self.inertia
+        cp[2] = self.friction / self.inertia
+        cp[3] = self.dt / 10
+        cp[9] = _pack_norm(cp, self.normalization, 2, 4)     # [4..5] Tx, [6] Tu, [7..8] 1/Tx
+        cp[10] = 1.0 if self.friction > 0 else 0.0
+        return d
+
+
+class CartPole(DeterministicFunction):
+    """Cart-pole (``examples/utilities.py:292-437``)."""
+
+    def __init__(self, pendulum_mass, cart_mass, length, rot_friction=0.0, dt=0.01,
+                 normalization=None, name="CartPole"):
+        super().__init__(name)
+        self.pendulum_mass, self.cart_mass, self.length = pendulum_mass, cart_mass, length
+        self.rot_friction, self.dt, self.gravity = rot_friction, dt, 9.81
+        self.state_dim, self.action_dim = 4, 1
+        self.normalization = normalization
+        if normalization is not None:
+            self.normalization = [np.array(n, dtype=np.float64) for n in normalization]
+            self.inv_norm = [n ** -1 for n in self.normalization]
+        self.input_dim, self.output_dim = 5, 4
+
+    def linearize(self):
+        m, M, L, b, g = (self.pendulum_mass, self.cart_mass, self.length, self.rot_friction,
+                         self.gravity)
+        A = np.array([[0, 0, 1, 0], [0, 0, 0, 1], [0, g * m / M, 0, -b / (M * L)],
+                      [0, g * (m + M) / (L * M), 0, -b * (m + M) / (m * M * L ** 2)]],
+                     dtype=np.float64)
+        B = np.array([0, 0, 1 / M, 1 / (M * L)]).reshape((-1, 1))
+        if self.normalization is not None:
+            Tx, Tu = map(np.diag, self.normalization)
+            Tx_inv, Tu_inv = map(np.diag, self.inv_norm)
+            A = np.linalg.multi_dot((Tx_inv, A, Tx))
+            B = np.linalg.multi_dot((Tx_inv, B, Tu))
+        Ad, Bd, _, _, _ = scipy.signal.cont2discrete((A, B, 0, 0), self.dt, method="zoh")
+        return Ad, Bd
+
+    def descriptor(self):
+        d = nat.SlbFunction()
+        d.kind, d.in_dim, d.out_dim = nat.FN_CARTPOLE, 5, 4
+        cp = d.cparams
+        cp[0], cp[1], cp[2] = self.pendulum_mass, self.cart_mass, self.length
+        cp[3], cp[4], cp[5] = self.rot_friction, self.gravity, self.dt / 10
+        cp[15] = _pack_norm(cp, self.normalization, 4, 6)    # [6..9] Tx, [10] Tu, [11..14] 1/Tx
+        return d
+
+
+# =============================================================================== Gaussian processes
+class RBF(object):
+    """Squared-exponential kernel with the arithmetic of ``gpflow==0.4.0`` ``kernels.RBF``:
+    ``variance * exp(-0.5 * sum(((x - x') / lengthscales)^2))``, ``Kdiag = variance``,
+    defaults 1 (``lengthscales`` scalar or ARD vector)."""
+
+    def __init__(self, input_dim, variance=1.0, lengthscales=1.0, ARD=False):
+        self.input_dim = int(input_dim)
+        self.variance = float(variance)
+        self.lengthscales = np.broadcast_to(np.asarray(lengthscales, dtype=np.float64),
+                                            (self.input_dim,)).copy()
+        self.ARD = ARD
+
+    def hyper_key(self):
+        return (self.input_dim, self.variance, tuple(self.lengthscales.tolist()))
+
+    def K_device(self, Xs):
+        """K(X, X) from lengthscale-divided inputs (device tensor [M, d]); same expansion as
+        gpflow's ``square_dist``."""
+        sq = (Xs * Xs).sum(dim=1)
+        dist = -2.0 * (Xs @ Xs.T) + sq[:, None] + sq[None, :]
+        return self.variance * torch.exp(-dist / 2)
+
+
+class Likelihood(object):
+    """Gaussian likelihood holder (``gp.likelihood.variance``, default 1 like gpflow)."""
+
+    def __init__(self, variance=1.0):
+        self.variance = float(variance)
+
+
+class _Factor(object):
+    """Device-resident Cholesky state of one (X, kernel, noise, scale) combination."""
+
+    __slots__ = ("key", "M", "nrb", "Xs", "L", "Wpack")
+
+
+_FACTOR_CACHE = {}
+_FACTOR_CACHE_MAX = 8
+
+
+class GPRCached(object):
+    """GP regression with the factor cached in HBM (``functions.py:357-458``).
+
+    ``update_cache`` (``:395-415``) builds ``L = chol(scale^2 (K + noise I))`` with torch's
+    cuSOLVER/cuBLAS on the device (library plumbing, between sweeps), forms ``L^-1`` and packs
+    it into the fragment order the sweep kernel streams (``slb_pack_factor``), and
+    ``alpha = L^-1 scale (Y - m(X))``.  GPs that share X, kernel, noise and scale share one
+    factor (the stacked GPs of a ``FunctionStack`` often do).
+    """
+
+    def __init__(self, x, y, kern, mean_function=None, scale=1., name="GPRCached",
+                 noise_variance=1.0):
+        self.name = name
+        self._X = np.atleast_2d(np.asarray(x, dtype=np.float64))
+        self._Y = np.atleast_2d(np.asarray(y, dtype=np.float64))
+        if self._Y.shape[1] != 1:
+            raise DimensionError("one-output GPs only; stack them with FunctionStack")
+        if not isinstance(kern, RBF):
+            raise NotImplementedError("only the RBF kernel is fused in this build (got %r)"
+                                      % type(kern).__name__)
+        if mean_function is not None and not isinstance(mean_function, LinearSystem):
+            raise NotImplementedError("prior mean must be None or a one-row LinearSystem")
+        if self._X.shape[1] > nat.SLB_MAX_IN:
+            raise DimensionError("GP input dimension above %d" % nat.SLB_MAX_IN)
+        self.kern = kern
+        self.mean_function = mean_function
+        self.likelihood = Likelihood(noise_variance)
+        self._scale = float(scale)
+        self._factor = None
+        self._alpha_dev = None
+        self._gamma_dev = None
+        self._prior_dev = None
+        self._stale = True
+
+    # data ------------------------------------------------------------------------------
+    @property
+    def X(self):
+        return self._X
+
+    @X.setter
+    def X(self, value):
+        self._X = np.atleast_2d(np.asarray(value, dtype=np.float64))
+        self._stale = True
+
+    @property
+    def Y(self):
+        return self._Y
+
+    @Y.setter
+    def Y(self, value):
+        self._Y = np.atleast_2d(np.asarray(value, dtype=np.float64))
+        self._stale = True
+
+    @property
+    def cholesky(self):
+        self._ensure()
+        return self._factor.L.cpu().numpy()
+
+    @property
+    def alpha(self):
+        self._ensure()
+        return self._alpha_dev[:self._X.shape[0]].cpu().numpy()[:, None]
+
+    # factorisation -----------------------------------------------------------------------
+    def _factor_key(self):
+        digest = hashlib.sha1(np.ascontiguousarray(self._X).tobytes()).hexdigest()
+        return (digest, self._X.shape, self.kern.hyper_key(), self.likelihood.variance,
+                self._scale)
+
+    def _ensure(self):
+        if self._stale or self._factor is None or self._factor.key != self._factor_key():
+            self.update_cache()
+
+    def update_cache(self):
+        """``functions.py:395-415`` on the device."""
+        lib = nat.load()
+        key = self._factor_key()
+        M, din = self._X.shape
+        fac = _FACTOR_CACHE.get(key)
+        if fac is None:
+            fac = _Factor()
+            fac.key, fac.M, fac.nrb = key, M, (M + 7) // 8
+            fac.Xs = dev.to_device(self._X / self.kern.lengthscales)
+            kernel = self.kern.K_device(fac.Xs)
+            kernel = kernel + torch.eye(M, dtype=torch.float64, device=kernel.device) \
+                * self.likelihood.variance
+            kernel = kernel * (self._scale ** 2)
+            fac.L = torch.linalg.cholesky(kernel)
+            linv = torch.linalg.solve_triangular(
+                fac.L, torch.eye(M, dtype=torch.float64, device=kernel.device), upper=False)
+            fac.Wpack = dev.empty((int(lib.slb_packed_len(M)),))
+            nat.check(lib.slb_pack_factor(dev.stream(), linv.contiguous().data_ptr(), M,
+                                          fac.Wpack.data_ptr()), "slb_pack_factor")
+            if len(_FACTOR_CACHE) >= _FACTOR_CACHE_MAX:
+                _FACTOR_CACHE.pop(next(iter(_FACTOR_CACHE)))
+            _FACTOR_CACHE[key] = fac
+        self._factor = fac
+        target = dev.to_device(self._Y)
+        if self.mean_function is not None:
+            target = target - self.mean_function.evaluate_device(self._X)
+            self._prior_dev = dev.to_device(self.mean_function.matrix.reshape(-1))
+        else:
+            self._prior_dev = None
+        target = self._scale * target
+        alpha = torch.linalg.solve_triangular(fac.L, target, upper=False)
+        gamma = torch.linalg.solve_triangular(fac.L.T, alpha, upper=True)
+        padded = dev.zeros((8 * fac.nrb,))
+        padded[:M] = alpha[:, 0]
+        self._alpha_dev = padded
+        self._gamma_dev = gamma[:, 0].contiguous()
+        self._stale = False
+
+    # descriptor pieces -------------------------------------------------------------------
+    def fill_factor(self, f):
+        self._ensure()
+        fac = self._factor
+        f.M, f.nrb = fac.M, fac.nrb
+        f.Xs, f.Wpack = fac.Xs.data_ptr(), fac.Wpack.data_ptr()
+        for c, ls in enumerate(self.kern.lengthscales):
+            f.lengthscales[c] = float(ls)
+        f.variance = self.kern.variance
+        f.scale = self._scale
+        f.kss = (self._scale ** 2) * self.kern.variance
+        return fac.key
+
+    def fill_output(self, o, factor_index, beta):
+        self._ensure()
+        o.factor, o.beta = factor_index, float(beta)
+        o.alpha = self._alpha_dev.data_ptr()
+        o.gamma = self._gamma_dev.data_ptr()
+        o.prior_mean = None if self._prior_dev is None else self._prior_dev.data_ptr()
+
+
+GPR = GPRCached     # the uncached gpflow.gpr.GPR of the notebooks maps onto the cached one
+
+
+def _build_stack(gps, betas):
+    """slb_gp_stack for a list of GPRCached models (factor sharing by key)."""
+    stack = nat.SlbGpStack()
+    if len(gps) > nat.SLB_MAX_OUT:
+        raise DimensionError("at most %d stacked GPs" % nat.SLB_MAX_OUT)
+    stack.num_outputs = len(gps)
+    stack.input_dim = gps[0].X.shape[1]
+    keys = []
+    for o, (gp, beta) in enumerate(zip(gps, betas)):
+        if gp.X.shape[1] != stack.input_dim:
+            raise DimensionError("stacked GPs must share the input dimension")
+        gp._ensure()
+        key = gp._factor.key
+        if key not in keys:
+            gp.fill_factor(stack.factors[len(keys)])
+            keys.append(key)
+        gp.fill_output(stack.outputs[o], keys.index(key), beta)
+    stack.num_factors = len(keys)
+    return stack
+
+
+def _gp_predict(stack, points, want_var=False):
+    lib = nat.load()
+    pts = dev.to_device(points)
+    if pts.dim() != 2 or pts.shape[1] != stack.input_dim:
+        raise DimensionError("GP expects %d input columns, got %s"
+                             % (stack.input_dim, tuple(pts.shape)))
+    n, D = pts.shape[0], stack.num_outputs
+    mean, err = dev.empty((n, D)), dev.empty((n, D))
+    nat.check(lib.slb_gp_predict(dev.stream(), stack, pts.data_ptr(), n, mean.data_ptr(),
+                                 err.data_ptr(), 1 if want_var else 0), "slb_gp_predict")
+    return mean, err
+
+
+class GaussianProcess(UncertainFunction):
+    """``(mean, beta * sqrt(var))`` of a one-output GP (``functions.py:461-546``)."""
+
+    def __init__(self, gaussian_process, beta=2., name="gaussian_process"):
+        super().__init__(name)
+        if not isinstance(gaussian_process, GPRCached):
+            raise TypeError("gaussian_process must be a safe_learning_b200 GPRCached/GPR model")
+        self.gaussian_process = gaussian_process
+        self.beta = float(beta)
+        self.n_dim = self.input_dim = gaussian_process.X.shape[1]
+        self.output_dim = gaussian_process.Y.shape[1]
+
+    @property
+    def X(self):
+        return self.gaussian_process.X
+
+    @property
+    def Y(self):
+        return self.gaussian_process.Y
+
+    def gp_stack(self):
+        return _build_stack([self.gaussian_process], [self.beta])
+
+    def __call__(self, *inputs):
+        mean, err = _gp_predict(self.gp_stack(), concatenate_inputs(inputs))
+        return mean.cpu().numpy(), err.cpu().numpy()
+
+    def predict_device(self, points, want_var=False):
+        return _gp_predict(self.gp_stack(), points, want_var)
+
+    def update_feed_dict(self):
+        """Reference hook (``functions.py:517-523``): hyper-parameters travel in the
+        descriptor here, so this only refreshes the cached factor."""
+        self.gaussian_process._ensure()
+
+    def add_data_point(self, x, y):
+        """Append observations and refresh the factor (``functions.py:525-546``)."""
+        gp = self.gaussian_process
+        gp.X = np.vstack((gp.X, np.atleast_2d(x)))
+        gp.Y = np.vstack((gp.Y, np.atleast_2d(y)))
+        gp.update_cache()
+
+
+class FunctionStack(UncertainFunction):
+    """Stack of one-output GPs, one per state dimension (``functions.py:254-307``)."""
+
+    def __init__(self, functions, name="function_stack"):
+        super().__init__(name)
+        self.functions = list(functions)
+        for f in self.functions:
+            if not isinstance(f, GaussianProcess):
+                raise TypeError("FunctionStack fuses GaussianProcess members only")
+        self.num_fun = len(self.functions)
+        self.input_dim = self.functions[0].input_dim
+        self.output_dim = sum(f.output_dim for f in self.functions)
+
+    def gp_stack(self):
+        return _build_stack([f.gaussian_process for f in self.functions],
+                            [f.beta for f in self.functions])
+
+    def __call__(self, *inputs):
+        mean, err = _gp_predict(self.gp_stack(), concatenate_inputs(inputs))
+        return mean.cpu().numpy(), err.cpu().numpy()
+
+    def predict_device(self, points, want_var=False):
+        return _gp_predict(self.gp_stack(), points, want_var)
+
+    def add_data_point(self, x, y):
+        for fun, yi in zip(self.functions, np.asarray(y).squeeze()):
+            fun.add_data_point(x, yi)

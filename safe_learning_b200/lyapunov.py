@@ -1,0 +1,413 @@
+"""Region-of-attraction estimation: the ``Lyapunov`` class of ``safe_learning/lyapunov.py:142-606``.
+
+Same constructor, attributes and methods as the reference; the work is one fused CUDA sweep
+(``slb_lyapunov_sweep``) + a sort-free prefix reduction (``slb_first_fail`` /
+``slb_apply_prefix``) instead of a Python loop of 10 000-point ``Session.run`` calls.
+With ``torch.distributed`` initialised, the grid is sharded by contiguous flat-index range
+(one process per GPU) and the ranks exchange one 32-byte key per sweep.
+"""
+
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _device as dev
+from . import _native as nat
+from .functions import (Function, FunctionStack, GaussianProcess, UncertainFunction, config,
+                        concatenate_inputs)
+
+__all__ = ["Lyapunov", "combine_fail_keys", "combine_prefix_stats"]
+
+
+class _CMax(object):
+    """Hashable stand-in for the reference's ``c_max`` placeholder: the value lives in
+    ``lyapunov.feed_dict[lyapunov.c_max]`` (``lyapunov.py:210-211, 595``)."""
+
+    def __repr__(self):
+        return "<c_max>"
+
+
+def _as_function(obj, what):
+    if isinstance(obj, Function):
+        return obj
+    raise TypeError(
+        "%s must be a safe_learning_b200 Function object (LinearSystem, QuadraticFunction, "
+        "Saturation, Triangulation, abs(fun), ...) so it can be fused into the CUDA sweep; "
+        "got %r. Arbitrary Python callables are not supported (no CPU fallback)." % (what, obj))
+
+
+def combine_fail_keys(rows):
+    """rows: int64 [world, 4] of per-rank ``slb_fail_key`` -> (winning rank, (key_value,
+    key_index, total n_ok)).  Lexicographic min on (uint64 value key, flat index)."""
+    rows = np.ascontiguousarray(rows, dtype=np.int64)
+    kv = rows[:, 0].copy().view(np.uint64)
+    best = min(range(rows.shape[0]), key=lambda r: (int(kv[r]), int(rows[r, 1])))
+    return best, (int(kv[best]), int(rows[best, 1]), int(rows[:, 2].sum()))
+
+
+def combine_prefix_stats(rows):
+    """rows: int64 [world, 4] of per-rank ``slb_prefix_stats`` -> (n_safe, n_below, max_below,
+    max_all) over all ranks."""
+    rows = np.ascontiguousarray(rows, dtype=np.int64)
+    u = rows.copy().view(np.uint64)
+    return (int(rows[:, 0].sum()), int(rows[:, 1].sum()), int(u[:, 2].max()), int(u[:, 3].max()))
+
+
+def _key_to_value(bits):
+    """Inverse of the kernels' order-preserving uint64 key."""
+    bits = int(bits)
+    raw = (bits & 0x7fffffffffffffff) if bits & 0x8000000000000000 else (~bits) & 0xffffffffffffffff
+    return float(np.array([raw], dtype=np.uint64).view(np.float64)[0])
+
+
+class Lyapunov(object):
+    """See ``lyapunov.py:142-225`` for the parameters.
+
+    ``lipschitz_lyapunov`` may be a float or a fusable Function (e.g. ``abs(LinearSystem(2P))``);
+    ``lipschitz_dynamics`` must be a float in this build.  ``adaptive=True`` is accepted but
+    refinement (``max_refinement > 1``) is not implemented (out of scope).
+    """
+
+    def __init__(self, discretization, lyapunov_function, dynamics, lipschitz_dynamics,
+                 lipschitz_lyapunov, tau, policy, initial_set=None, adaptive=False):
+        self.discretization = discretization
+        self.policy = policy
+        self.tau = tau
+        self.dynamics = dynamics
+        self.lyapunov_function = lyapunov_function
+        self._lipschitz_dynamics = lipschitz_dynamics
+        self._lipschitz_lyapunov = lipschitz_lyapunov
+        self.adaptive = adaptive
+        self.feed_dict = {}
+        self.c_max = _CMax()
+        self.feed_dict[self.c_max] = 0.
+
+        n = discretization.nindex
+        self._begin, self._end = dev.shard_range(n)
+        self._safe_host = np.zeros(n, dtype=bool)
+        self._safe_dirty = False          # device slab newer than _safe_host
+        self.initial_safe_set = initial_set
+        if initial_set is not None:
+            self._safe_host[initial_set] = True
+        self._refinement = np.zeros(n, dtype=int)
+        if initial_set is not None:
+            self._refinement[initial_set] = 1
+
+        self._values_host = None
+        self._values_dev = None           # slab [end - begin]
+        self._safe_dev = None
+        self._negative_dev = None
+        self._initial_dev = None
+        self._initial_token = None
+        self._workspace = None
+        self.last_sweep = {}
+        self.update_values()
+
+    # ------------------------------------------------------------------ attributes
+    @property
+    def safe_set(self):
+        """Boolean numpy array over the whole grid (gathers the device slabs on demand)."""
+        if self._safe_dirty:
+            slab = self._safe_dev.to(torch.bool)
+            full = self._gather(slab).cpu().numpy()
+            self._safe_host = full
+            self._safe_dirty = False
+        return self._safe_host
+
+    @safe_set.setter
+    def safe_set(self, value):
+        self._safe_host = np.asarray(value, dtype=bool).copy()
+        self._safe_dirty = False
+
+    @property
+    def values(self):
+        if self._values_host is None and self._values_dev is not None:
+            self._values_host = self._gather(self._values_dev).cpu().numpy()
+        return self._values_host
+
+    @values.setter
+    def values(self, value):
+        self._values_host = None if value is None else np.asarray(value, dtype=np.float64)
+        if value is not None:
+            self._values_dev = dev.to_device(self._values_host[self._begin:self._end])
+
+    def _gather(self, slab):
+        rank, world = dev.dist_info()
+        if world == 1:
+            return slab
+        import torch.distributed as dist
+        n = self.discretization.nindex
+        per = -(-n // world)
+        padded = torch.zeros(per, dtype=slab.dtype, device=slab.device)
+        padded[:slab.numel()] = slab
+        out = torch.empty(per * world, dtype=slab.dtype, device=slab.device)
+        if slab.dtype == torch.bool:
+            dist.all_gather_into_tensor(out.view(torch.uint8), padded.view(torch.uint8))
+        else:
+            dist.all_gather_into_tensor(out, padded)
+        return out[:n]
+
+    # ------------------------------------------------------------------ Lipschitz helpers
+    def lipschitz_dynamics(self, states):
+        """``lyapunov.py:227-244``."""
+        f = self._lipschitz_dynamics
+        return f(states) if callable(f) else f
+
+    def lipschitz_lyapunov(self, states):
+        """``lyapunov.py:246-263``."""
+        f = self._lipschitz_lyapunov
+        return f(states) if callable(f) else f
+
+    def threshold(self, states, tau=None):
+        """``-lv * (1 + lf) * tau`` (``lyapunov.py:265-288``); numpy in, numpy out."""
+        if tau is None:
+            tau = self.tau
+        lv = self.lipschitz_lyapunov(states)
+        if callable(self._lipschitz_lyapunov) and lv.shape[1] > 1:
+            lv = np.abs(lv).sum(axis=1, keepdims=True)
+        lf = self.lipschitz_dynamics(states)
+        return -lv * (1. + lf) * tau
+
+    def is_safe(self, state):
+        """``lyapunov.py:290-303``."""
+        return self.safe_set[self.discretization.state_to_index(state)]
+
+    def v_decrease_confidence(self, states, next_states):
+        """``lyapunov.py:324-354`` on explicit arrays (eager GPU evaluation of V and L_V)."""
+        if isinstance(next_states, (tuple, list)):
+            next_states, error_bounds = next_states
+            lv = self.lipschitz_lyapunov(next_states)
+            bound = np.sum(lv * error_bounds, axis=1, keepdims=True)
+        else:
+            bound = 0.
+        v_decrease = self.lyapunov_function(next_states) - self.lyapunov_function(states)
+        return v_decrease, bound
+
+    def v_decrease_bound(self, states, next_states):
+        """``lyapunov.py:356-376``."""
+        v_dot, v_dot_error = self.v_decrease_confidence(states, next_states)
+        return v_dot + v_dot_error
+
+    # ------------------------------------------------------------------ descriptor
+    def sweep_descriptor(self):
+        """The ``slb_sweep`` describing the graph of ``lyapunov.py:433-441``."""
+        cfg = nat.SlbSweep()
+        cfg.grid = self.discretization.descriptor()
+        cfg.policy = _as_function(self.policy, "policy").descriptor()
+        cfg.lyapunov = _as_function(self.lyapunov_function, "lyapunov_function").descriptor()
+        if isinstance(self.dynamics, (FunctionStack, GaussianProcess)):
+            cfg.gp = self.dynamics.gp_stack()
+        elif isinstance(self.dynamics, UncertainFunction):
+            raise TypeError("uncertain dynamics must be a GaussianProcess or FunctionStack")
+        else:
+            cfg.dynamics = _as_function(self.dynamics, "dynamics").descriptor()
+        lv = self._lipschitz_lyapunov
+        if isinstance(lv, Function):
+            cfg.lipschitz_v = lv.descriptor()
+        elif callable(lv):
+            _as_function(lv, "lipschitz_lyapunov")
+        else:
+            cfg.lv_const = float(lv)
+        lf = self._lipschitz_dynamics
+        if callable(lf):
+            raise NotImplementedError("state-dependent lipschitz_dynamics is not fused in this "
+                                      "build; pass a float")
+        cfg.lf_const = float(lf)
+        cfg.tau = float(self.tau)
+        return cfg
+
+    # ------------------------------------------------------------------ values
+    def update_values(self):
+        """``values = V(all grid points)`` (``lyapunov.py:305-322``), computed on the device
+        from flat indices in chunks (coordinates are never materialised for the full grid)."""
+        lib = nat.load()
+        fn = _as_function(self.lyapunov_function, "lyapunov_function")
+        n = self._end - self._begin
+        out = dev.empty((n,))
+        grid = self.discretization.descriptor()
+        chunk = 1 << 22
+        d = self.discretization.ndim
+        for start in range(0, n, chunk):
+            stop = min(start + chunk, n)
+            pts = dev.empty((stop - start, d))
+            nat.check(lib.slb_index_to_state(dev.stream(), grid, self._begin + start,
+                                             self._begin + stop, pts.data_ptr()),
+                      "slb_index_to_state")
+            out[start:stop] = fn.evaluate_device(pts)[:, 0]
+        self._values_dev = out
+        self._values_host = None
+
+    # ------------------------------------------------------------------ the sweep
+    def _initial_device(self):
+        """uint8 slab of the initial safe set (re-uploaded when the attribute changes)."""
+        init = self.initial_safe_set
+        if init is None:
+            return None
+        arr = np.asarray(init)
+        token = (id(init), arr.shape, arr.dtype.str)
+        if self._initial_dev is None or self._initial_token != token:
+            mask = np.zeros(self.discretization.nindex, dtype=bool)
+            mask[arr] = True
+            self._initial_dev = dev.to_device(mask[self._begin:self._end].astype(np.uint8),
+                                              torch.uint8)
+            self._initial_token = token
+        return self._initial_dev
+
+    def compute_negative(self, want_details=False):
+        """Run the fused sweep over this rank's index range.  Returns the device uint8 slab
+        ``negative`` (and, if asked, a dict of device tensors: values, decrease, threshold,
+        mean, err)."""
+        lib = nat.load()
+        cfg = self.sweep_descriptor()
+        n = self._end - self._begin
+        if self._negative_dev is None or self._negative_dev.numel() != n:
+            self._negative_dev = dev.empty((n,), torch.uint8)
+        details = {}
+        ptrs = [None] * 5
+        if want_details:
+            d = self.discretization.ndim
+            details["values"] = dev.empty((n,))
+            details["decrease"] = dev.empty((n,))
+            details["threshold"] = dev.empty((n,))
+            details["mean"] = dev.empty((n, d))
+            ptrs = [details[k].data_ptr() for k in ("values", "decrease", "threshold", "mean")]
+            if cfg.gp.num_outputs > 0:
+                details["err"] = dev.empty((n, d))
+                ptrs.append(details["err"].data_ptr())
+            else:
+                ptrs.append(None)
+        nat.check(lib.slb_lyapunov_sweep(dev.stream(), cfg, self._begin, self._end,
+                                         self._negative_dev.data_ptr(), *ptrs),
+                  "slb_lyapunov_sweep")
+        return (self._negative_dev, details) if want_details else self._negative_dev
+
+    def update_safe_set(self, can_shrink=True, max_refinement=1, safety_factor=1.,
+                        parallel_iterations=1):
+        """Compute and update the safe set (``lyapunov.py:407-606``, non-adaptive branch)."""
+        if self.adaptive and max_refinement > 1:
+            raise NotImplementedError("adaptive refinement (lyapunov.py:445-487, 540-582) is "
+                                      "outside this build's hot path")
+        lib = nat.load()
+        n_local = self._end - self._begin
+        n_total = self.discretization.nindex
+        negative = self.compute_negative()
+        initial = self._initial_device()
+        if not can_shrink:
+            return self._update_no_shrink(negative)
+
+        if self._workspace is None:
+            self._workspace = dev.empty((int(lib.slb_first_fail_workspace(n_local)) // 8 + 16,))
+            self._key_dev = dev.zeros((4,), torch.int64)
+            self._stats_dev = dev.zeros((4,), torch.int64)
+        if self._safe_dev is None or self._safe_dev.numel() != n_local:
+            self._safe_dev = dev.empty((n_local,), torch.uint8)
+        st = dev.stream()
+        nat.check(lib.slb_first_fail(st, self._values_dev.data_ptr(), negative.data_ptr(),
+                                     dev.ptr(initial), n_local, self._begin,
+                                     self._workspace.data_ptr(), self._key_dev.data_ptr()),
+                  "slb_first_fail")
+        self._allreduce_key()
+        nat.check(lib.slb_apply_prefix(st, self._values_dev.data_ptr(), dev.ptr(initial), n_local,
+                                       self._begin, self._key_dev.data_ptr(),
+                                       self._safe_dev.data_ptr(), self._workspace.data_ptr(),
+                                       self._stats_dev.data_ptr()), "slb_apply_prefix")
+        stats = self._allreduce_stats()
+        key = self._key_host
+        n_safe, n_below, max_below, max_all = stats
+        failed = key[1] != nat.INT64_MAX
+        # c_max with the reference's index arithmetic (lyapunov.py:590-595)
+        if failed:
+            position = n_below - 1
+        else:
+            batch = int(config.gp_batch_size)
+            position = ((n_total - 1) // batch) * batch - 1
+        if position < 0:
+            c_max = _key_to_value(max_all)                  # index -1: largest V on the grid
+        elif failed:
+            c_max = _key_to_value(max_below)
+        else:
+            c_max = self._kth_value(position)
+        self.feed_dict[self.c_max] = c_max
+        self.last_sweep = {"n_safe": n_safe, "first_fail_position": n_below if failed else None,
+                           "first_fail_index": key[1] if failed else None, "c_max": c_max}
+        self._safe_dirty = True
+        self._refinement = None      # materialised lazily from safe_set (0/1 in this branch)
+
+    # _refinement mirrors lyapunov.py:223-225, 531, 586, 601-606; without adaptive refinement
+    # it is 1 exactly where the state is safe.
+    @property
+    def _refinement(self):
+        if self.__dict__.get("_refinement_host") is None:
+            self.__dict__["_refinement_host"] = self.safe_set.astype(int)
+        return self.__dict__["_refinement_host"]
+
+    @_refinement.setter
+    def _refinement(self, value):
+        self.__dict__["_refinement_host"] = value
+
+    def _allreduce_key(self):
+        """Global first-fail key = lexicographic min over ranks (one 32-byte collective)."""
+        rows = dev.allgather_rows(self._key_dev)
+        best, key_host = combine_fail_keys(rows.cpu().numpy())
+        if rows.shape[0] > 1:
+            self._key_dev.copy_(rows[best])
+        self._key_host = key_host
+
+    def _allreduce_stats(self):
+        return combine_prefix_stats(dev.allgather_rows(self._stats_dev).cpu().numpy())
+
+    def _kth_value(self, position):
+        """V at sorted position `position` (only reached when no point fails)."""
+        values = self._gather(self._values_dev)
+        return float(torch.kthvalue(values, position + 1).values.item())
+
+    def _update_no_shrink(self, negative):
+        """``can_shrink=False`` (``lyapunov.py:507-510, 583-587``): previously
+        safe states seed the result and the batch size decides which trailing states keep their
+        old label, so this mode needs sorted ranks -- a stable device sort (torch), single GPU."""
+        rank, world = dev.dist_info()
+        if world > 1:
+            raise NotImplementedError("can_shrink=False needs global ranks: replicas only")
+        values = self._values_dev
+        order = torch.sort(values, stable=True).indices
+        prev = dev.to_device(self.safe_set.astype(np.uint8), torch.uint8).to(torch.bool)
+        refine_prev = dev.to_device(np.asarray(self._refinement, dtype=np.int64), torch.int64)
+        neg = negative.to(torch.bool)
+        prev_s, neg_s = prev[order], neg[order]
+        ok = prev_s | neg_s
+        n = ok.numel()
+        batch = int(config.gp_batch_size)
+        bad = torch.nonzero(~ok)
+        safe_s = prev_s.clone()
+        ref_s = refine_prev[order].clone()
+        if bad.numel() == 0:
+            safe_s = ok
+            ref_s[neg_s] = 1
+            position = ((n - 1) // batch) * batch - 1
+        else:
+            p = int(bad[0].item())
+            stop = min((p // batch + 1) * batch, n)
+            safe_s[:stop] = ok[:stop]
+            sel = neg_s.clone()
+            sel[stop:] = False
+            ref_s[sel] = 1
+            safe_s[p:stop] = False
+            ref_s[p:stop] = 0
+            position = p - 1
+        self.feed_dict[self.c_max] = float(values[order[position]].item())
+        safe = torch.zeros_like(prev)
+        safe[order] = safe_s
+        refinement = torch.zeros_like(refine_prev)
+        refinement[order] = ref_s
+        safe_host = safe.cpu().numpy()
+        ref_host = refinement.cpu().numpy().astype(int)
+        if self.initial_safe_set is not None:
+            safe_host[self.initial_safe_set] = True
+            ref_host[self.initial_safe_set] = 1
+        self._safe_host = safe_host
+        self._safe_dirty = False
+        self._safe_dev = dev.to_device(safe_host.astype(np.uint8), torch.uint8)
+        self._refinement = ref_host

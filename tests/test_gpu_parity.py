@@ -1,0 +1,428 @@
+"""GPU parity tests: the CUDA path (through the Python API -> ctypes -> C ABI) against the
+CPU oracle on the same seeded inputs.  Bar (BASELINE.json north_star): safe-set membership
+bit-exact, GP posterior and V within 1e-5 relative; the cheap element-wise pieces (grid
+coordinates, linear / quadratic / triangulation values, thresholds) are bit-exact.
+"""
+import numpy as np
+import pytest
+from numpy.testing import assert_allclose, assert_array_equal
+
+import bench_workloads as W
+import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-5   # GP posterior / V tolerance stated by north_star
+
+
+@pytest.fixture(scope="module")
+def sl():
+    import __graft_entry__
+    __graft_entry__.build()
+    import safe_learning_b200 as sl
+    return sl
+
+
+def _assert_negative_parity(gpu, cpu, details):
+    """`negative` must agree everywhere except (reported, expected none) points whose margin
+    |decrease - threshold| is below rounding noise of the GP contraction."""
+    neg_gpu = details["negative"]
+    states = cpu.discretization.all_points
+    actions = cpu.policy(states)
+    nxt = cpu.dynamics(states, actions)
+    dec = cpu.v_decrease_bound(states, nxt).ravel()
+    thr = np.broadcast_to(cpu.threshold(states), (len(states), 1)).ravel()
+    with np.errstate(invalid="ignore"):
+        neg_cpu = dec < thr
+    margin = np.abs(dec - thr)
+    scale = np.maximum(np.abs(dec), np.abs(thr))
+    mismatch = neg_gpu != neg_cpu
+    outside = mismatch & ~(margin <= 1e-9 * np.maximum(scale, 1e-300))
+    assert not outside.any(), "negative differs at %d points outside the rounding margin" \
+        % outside.sum()
+    assert mismatch.sum() == 0, "%d borderline points flipped" % mismatch.sum()
+    assert_allclose(details["decrease"], dec, rtol=RTOL, atol=1e-12)
+    assert_array_equal(details["threshold"], thr)
+
+
+def _sweep_details(lyap):
+    neg, det = lyap.compute_negative(want_details=True)
+    out = {k: v.cpu().numpy() for k, v in det.items()}
+    out["negative"] = neg.cpu().numpy().astype(bool)
+    return out
+
+
+# ------------------------------------------------------------------ reference known answers
+def test_reference_update_known_answers(sl):
+    """/root/reference/safe_learning/tests/test_lyapunov.py:48-74 through the product API."""
+    def make(eps):
+        grid = sl.GridWorld([[-1, 1]], 3)
+        return sl.Lyapunov(grid, sl.QuadraticFunction(np.array([[1.0]])),
+                           sl.LinearSystem(np.array([[1, 1.]])), 0.4, 0.3, eps,
+                           sl.LinearSystem(np.array([[-.1]])), initial_set=[1])
+    lyap = make(0.5)
+    lyap.update_safe_set()
+    assert_array_equal(lyap.safe_set, np.array([False, True, False]))
+    assert lyap.feed_dict[lyap.c_max] == 0.0
+    lyap = make(0.0)
+    lyap.update_safe_set()
+    assert_array_equal(lyap.safe_set, np.ones(3, dtype=bool))
+    assert lyap.feed_dict[lyap.c_max] == 1.0
+
+
+def test_reference_safe_set_init(sl):
+    """test_lyapunov.py:24-46."""
+    grid = sl.GridWorld([[0, 1], [0, 1]], 3)
+    dyn = sl.LinearSystem(np.array([[1, 0.01, 0, 0], [0., 1., 0, 0]]))
+    lyap = sl.Lyapunov(grid, sl.QuadraticFunction(np.eye(2)), dyn, 0.4, 0.3, 0.5,
+                       sl.LinearSystem(np.zeros((2, 2))), initial_set=[1, 3])
+    assert_array_equal(lyap.safe_set, np.array([False, True, False, True, False, False, False,
+                                                False, False]))
+
+
+def test_reference_gp_golden_vector(sl):
+    """test_functions.py:237-261 on the GPU."""
+    gp = sl.GPRCached(np.array([[1, 0], [0, 1.]]), np.array([[0], [1.]]), sl.RBF(2))
+    ufun = sl.GaussianProcess(gp)
+    ufun.add_data_point(np.array([[1.2, 2.3]]), np.array([[2.4]]))
+    a1, b1 = ufun(np.array([[0.9, 0.1], [3., 2]]))
+    assert_allclose(a1, np.array([[0.16371139], [0.22048311]]))
+    assert_allclose(b1, np.array([[1.37678679], [1.98183191]]))
+    m2, e2 = ufun(np.array([[0.9], [3.]]), np.array([[0.1], [2.]]))     # :216-235
+    assert_array_equal(a1, m2)
+    assert_array_equal(b1, e2)
+
+
+def test_reference_quadratic_and_grid(sl):
+    """test_functions.py:264-282 and :313-367."""
+    quad = sl.QuadraticFunction(np.array([[1., 0.1], [0.2, 2.]]))
+    pts = np.array([[0, 0], [0, 1], [1, 0], [1, 1]], dtype=float)
+    assert_allclose(quad(pts), np.array([[0., 2., 1., 3.3]]).T)
+    grid = sl.GridWorld([[-1.1, 1.5], [2.2, 2.4]], [7, 8])
+    idx = np.arange(grid.nindex)
+    assert_array_equal(idx, grid.state_to_index(grid.index_to_state(idx)))
+    rect = np.arange(grid.nrectangles)
+    assert_array_equal(rect, grid.state_to_rectangle(grid.rectangle_to_state(rect)
+                                                     + grid.unit_maxes / 2))
+    with pytest.raises(sl.DimensionError):
+        sl.GridWorld([[0, 1]], 1)
+
+
+# ------------------------------------------------------------------ element-wise pieces, bit-exact
+def test_index_to_state_bit_exact(sl):
+    import torch
+    from safe_learning_b200 import _device as dev, _native as nat
+    lib = nat.load()
+    for limits, num in ([[[-1.1, 1.5], [2.2, 2.4]], [7, 8]], [[[-1, 1]] * 3, [5, 9, 4]],
+                        [[[-0.3, 0.7]], [101]]):
+        g_gpu, g_cpu = sl.GridWorld(limits, num), O.GridWorld(limits, num)
+        out = dev.empty((g_gpu.nindex, g_gpu.ndim))
+        nat.check(lib.slb_index_to_state(dev.stream(), g_gpu.descriptor(), 0, g_gpu.nindex,
+                                         out.data_ptr()), "index_to_state")
+        assert_array_equal(out.cpu().numpy(), g_cpu.index_to_state(np.arange(g_cpu.nindex)))
+        assert_array_equal(out.cpu().numpy(), g_cpu.all_points)
+
+
+def test_small_functions_bit_exact(sl):
+    rng = np.random.default_rng(3)
+    x = rng.uniform(-2, 2, (257, 3))
+    A = rng.normal(size=(2, 3))
+    P = rng.normal(size=(3, 3))
+    assert_array_equal(sl.LinearSystem(A)(x), O.LinearSystem(A)(x))
+    assert_array_equal(sl.QuadraticFunction(P)(x), O.QuadraticFunction(P)(x))
+    assert_array_equal(sl.Saturation(sl.LinearSystem(A), -0.5, 0.7)(x),
+                       O.Saturation(O.LinearSystem(A), -0.5, 0.7)(x))
+    assert_array_equal(abs(sl.LinearSystem(A))(x), O.AbsFunction(O.LinearSystem(A))(x))
+    assert_array_equal(sl.Norm1Function(sl.LinearSystem(A))(x),
+                       O.Norm1Function(O.LinearSystem(A))(x))
+    assert_array_equal((-sl.QuadraticFunction(P))(x), O.ScaledFunction(O.QuadraticFunction(P), -1)(x))
+    assert_array_equal(sl.LinearSystem((A[:, :2], A[:, 2:]))(x[:, :2], x[:, 2:]),
+                       O.LinearSystem(A)(x))
+
+
+@pytest.mark.parametrize("dims,project", [(1, False), (2, False), (2, True), (3, True)])
+def test_triangulation_vs_oracle(sl, dims, project):
+    """functions.py:1103-1158, 1473-1499; reference tests test_functions.py:457-701."""
+    rng = np.random.default_rng(dims)
+    limits = [[-1.0, 1.5], [0.0, 2.0], [-0.5, 0.5]][:dims]
+    num = [5, 4, 3][:dims]
+    g_gpu, g_cpu = sl.GridWorld(limits, num), O.GridWorld(limits, num)
+    vals = rng.normal(size=(g_cpu.nindex, 2))
+    t_gpu = sl.Triangulation(g_gpu, vals, project=project)
+    t_cpu = O.Triangulation(g_cpu, vals, project=project)
+    lo, hi = np.array(limits)[:, 0], np.array(limits)[:, 1]
+    span = 0.3 * (hi - lo)
+    pts = rng.uniform(lo - span, hi + span, size=(2000, dims))
+    pts = np.vstack((pts, g_cpu.all_points))                 # vertices: shared-face lookups
+    got = t_gpu(pts)
+    # A non-projected query outside the grid in EVERY coordinate is clipped onto a unit-cell
+    # corner where several simplices meet; scipy's find_simplex walks from the previous query's
+    # simplex, so the reference's (discontinuous) extrapolation there depends on batch order.
+    # The build pins Qhull's answer for an isolated query: compare those one point at a time.
+    corner = np.all((pts < lo) | (pts > hi), axis=1) & (dims > 1) & (not project)
+    assert_allclose(got[~corner], t_cpu(pts)[~corner], rtol=1e-12, atol=1e-12)
+    for i in np.nonzero(corner)[0][:60]:
+        assert_allclose(got[i], t_cpu(pts[i:i + 1])[0], rtol=1e-12, atol=1e-12)
+    inside = rng.uniform(lo, hi, size=(500, dims))
+    assert_allclose(t_gpu(inside), t_cpu(inside), rtol=1e-13, atol=1e-13)
+
+
+def test_plants_vs_oracle(sl):
+    rng = np.random.default_rng(5)
+    norm = [(0.5, 4.4), (0.37,)]
+    sa = rng.uniform(-1, 1, (300, 3))
+    for fr in (0.0, 0.1):
+        assert_allclose(sl.InvertedPendulum(0.15, 0.5, fr, 0.01, norm)(sa),
+                        O.InvertedPendulum(0.15, 0.5, fr, 0.01, norm)(sa), rtol=1e-12)
+    sa5 = rng.uniform(-1, 1, (300, 5))
+    cn = [(1.0, 0.5, 2.0, 3.0), (20.0,)]
+    assert_allclose(sl.CartPole(0.175, 1.732, 0.28, 0.01, 0.01, cn)(sa5),
+                    O.CartPole(0.175, 1.732, 0.28, 0.01, 0.01, cn)(sa5), rtol=1e-11)
+
+
+# ------------------------------------------------------------------ GP posterior
+@pytest.mark.parametrize("M", [1, 7, 64, 255, 256, 257, 500, 513, 777])
+def test_gp_posterior_vs_oracle(sl, M):
+    """functions.py:417-458, 507-515, 278-291 at panel-boundary sizes; distinct hypers, prior
+    mean, scale != 1."""
+    par = W.make_pendulum(num_points=8, M=M, scale=1.7, seed=M)
+    _, dyn_gpu = W._build(sl, par, "product")
+    _, dyn_cpu = W._build(O, par, "oracle")
+    rng = np.random.default_rng(M + 1)
+    pts = rng.uniform(-1, 1, (333, 3))
+    m_gpu, e_gpu = dyn_gpu(pts[:, :2], pts[:, 2:])
+    m_cpu, e_cpu = dyn_cpu(pts[:, :2], pts[:, 2:])
+    assert_allclose(m_gpu, m_cpu, rtol=RTOL, atol=1e-12)
+    assert_allclose(e_gpu, e_cpu, rtol=RTOL, atol=1e-12)
+    gp_gpu = dyn_gpu.functions[1].gaussian_process
+    gp_cpu = dyn_cpu.functions[1].gaussian_process
+    assert_allclose(gp_gpu.cholesky, gp_cpu.cholesky, rtol=1e-7, atol=1e-12)
+    assert_allclose(gp_gpu.alpha, gp_cpu.alpha, rtol=1e-6, atol=1e-10)
+
+
+def test_gp_shared_factor_equals_distinct_path(sl):
+    """Outputs sharing X/kernel/noise use one Cholesky factor (D'=1); results must equal the
+    oracle, which factorises per output like the reference (functions.py:283-286)."""
+    par = W.make_pendulum(num_points=8, M=300, shared_hypers=True)
+    _, dyn_gpu = W._build(sl, par, "product")
+    _, dyn_cpu = W._build(O, par, "oracle")
+    assert dyn_gpu.gp_stack().num_factors == 1
+    pts = np.random.default_rng(0).uniform(-1, 1, (200, 3))
+    m_gpu, e_gpu = dyn_gpu(pts)
+    m_cpu, e_cpu = dyn_cpu(pts)
+    assert_allclose(m_gpu, m_cpu, rtol=RTOL, atol=1e-12)
+    assert_allclose(e_gpu, e_cpu, rtol=RTOL, atol=1e-12)
+
+
+def test_gp_negative_variance_is_nan_not_clamped(sl):
+    """functions.py:451, 514: var < 0 -> sqrt -> NaN -> unsafe.  Query AT training points of a
+    noise-free-ish GP, where cancellation can push var below zero: wherever the oracle's var is
+    NaN-producing or tiny the GPU must not clamp silently; finite stds must agree loosely."""
+    rng = np.random.default_rng(2)
+    X = rng.uniform(-1, 1, (40, 2))
+    Y = np.sin(X[:, :1])
+    gp = sl.GPRCached(X, Y, sl.RBF(2, lengthscales=2.0), noise_variance=1e-10)
+    mean, var = sl.GaussianProcess(gp).predict_device(X, want_var=True)
+    var = var.cpu().numpy()
+    assert np.all(np.abs(var) < 1e-3)
+    _, err = sl.GaussianProcess(gp)(X)
+    assert np.array_equal(np.isnan(err), var < 0)
+
+
+# ------------------------------------------------------------------ the sweep
+@pytest.mark.parametrize("shared", [False, True])
+def test_pendulum_sweep_vs_oracle(sl, shared):
+    """C2 at test size (48x48, M=150): negative / decrease / threshold / values / safe set /
+    c_max / _refinement against the oracle running the reference loop."""
+    par = W.make_pendulum(num_points=48, M=150, shared_hypers=shared, tau_scale=1 / 48.)
+    gpu, cpu = W.build_product(par), W.build_oracle(par)
+    assert_array_equal(gpu.values, cpu.values)
+    det = _sweep_details(gpu)
+    assert_array_equal(det["values"], cpu.values)
+    _assert_negative_parity(gpu, cpu, det)
+    states = cpu.discretization.all_points
+    m_cpu, e_cpu = cpu.dynamics(states, cpu.policy(states))
+    assert_allclose(det["mean"], m_cpu, rtol=RTOL, atol=1e-12)
+    assert_allclose(det["err"], e_cpu, rtol=RTOL, atol=1e-12)
+    gpu.update_safe_set()
+    cpu.update_safe_set()
+    assert cpu.safe_set.sum() > par["initial"].sum(), "test config should grow the safe set"
+    assert cpu.safe_set.sum() < cpu.safe_set.size
+    assert_array_equal(gpu.safe_set, cpu.safe_set)
+    assert gpu.feed_dict[gpu.c_max] == cpu.c_max
+    assert_array_equal(gpu._refinement, cpu._refinement)
+
+
+def test_toy_1d_sweep_vs_oracle(sl):
+    """C1: 101-point grid, M=50, V = |x| as a Triangulation on its own 3-point grid."""
+    for tau in (1.0 / 101, 0.02, 0.2):
+        par = W.make_toy_1d()
+        par["tau"] = tau
+        gpu, cpu = W.build_product(par), W.build_oracle(par)
+        assert_allclose(gpu.values, cpu.values, rtol=1e-14, atol=1e-15)
+        gpu.values = cpu.values          # identical keys -> identical prefix decisions
+        det = _sweep_details(gpu)
+        _assert_negative_parity(gpu, cpu, det)
+        gpu.update_safe_set()
+        cpu.update_safe_set()
+        assert_array_equal(gpu.safe_set, cpu.safe_set)
+        assert gpu.feed_dict[gpu.c_max] == cpu.c_max
+
+
+def test_deterministic_sweep_vs_oracle(sl):
+    """Deterministic dynamics (true pendulum plant + LinearSystem), the HBM-side variant."""
+    par = W.make_pendulum(num_points=40, M=8, tau_scale=1 / 64.)
+    gpu, cpu = W.build_product(par, deterministic=True), W.build_oracle(par, deterministic=True)
+    det = _sweep_details(gpu)
+    assert "err" not in det
+    _assert_negative_parity(gpu, cpu, det)
+    gpu.update_safe_set()
+    cpu.update_safe_set()
+    assert_array_equal(gpu.safe_set, cpu.safe_set)
+    assert gpu.feed_dict[gpu.c_max] == cpu.c_max
+
+
+def test_multi_batch_quirks_and_ragged_sizes(sl):
+    """N not a multiple of the 64-point tile, N > gp_batch_size, all-safe c_max quirk
+    (lyapunov.py:590-595)."""
+    old = (sl.config.gp_batch_size, O.config.gp_batch_size)
+    try:
+        sl.config.gp_batch_size = O.config.gp_batch_size = 100
+        for num, tau_scale in (([37, 23], 1 / 48.), ([13, 5], 0.0), ([50, 11], 1 / 16.)):
+            par = W.make_pendulum(num_points=num, M=70, tau_scale=tau_scale)
+            gpu, cpu = W.build_product(par), W.build_oracle(par)
+            gpu.update_safe_set()
+            cpu.update_safe_set()
+            assert_array_equal(gpu.safe_set, cpu.safe_set)
+            assert gpu.feed_dict[gpu.c_max] == cpu.c_max
+    finally:
+        sl.config.gp_batch_size, O.config.gp_batch_size = old
+
+
+def test_can_shrink_false_vs_oracle(sl):
+    """lyapunov.py:507-510, 583-587: previous safe set seeds, batch-dependent."""
+    old = (sl.config.gp_batch_size, O.config.gp_batch_size)
+    try:
+        sl.config.gp_batch_size = O.config.gp_batch_size = 64
+        par = W.make_pendulum(num_points=[30, 21], M=60, tau_scale=1 / 32.)
+        gpu, cpu = W.build_product(par), W.build_oracle(par)
+        rng = np.random.default_rng(9)
+        prev = rng.random(cpu.safe_set.size) < 0.3
+        gpu.safe_set = prev | par["initial"]
+        cpu.safe_set = (prev | par["initial"]).copy()
+        gpu._refinement = (prev | par["initial"]).astype(int)
+        cpu._refinement = (prev | par["initial"]).astype(int)
+        gpu.update_safe_set(can_shrink=False)
+        cpu.update_safe_set(can_shrink=False)
+        assert_array_equal(gpu.safe_set, cpu.safe_set)
+        assert gpu.feed_dict[gpu.c_max] == cpu.c_max
+        assert_array_equal(gpu._refinement, cpu._refinement)
+    finally:
+        sl.config.gp_batch_size, O.config.gp_batch_size = old
+
+
+def test_prefix_rule_random_ties(sl):
+    """slb_first_fail / slb_apply_prefix against the oracle's closed form on heavily tied V
+    (SURVEY Q1/Q2), including no-failure and first-point-fails cases."""
+    import torch
+    from safe_learning_b200 import _device as dev, _native as nat
+    lib = nat.load()
+    rng = np.random.default_rng(11)
+    for trial in range(40):
+        n = int(rng.integers(1, 5000))
+        values = rng.integers(-3, 4, n).astype(float)
+        values[rng.random(n) < 0.05] = -0.0
+        neg = rng.random(n) < (0.999 if trial % 3 else 0.5)
+        init = rng.random(n) < 0.1
+        if trial == 0:
+            neg[:] = True
+        if trial == 1:
+            neg[:] = False
+            init[:] = False
+        safe_cpu, p = O.prefix_rule(values, neg | init, init)
+        v, ng, it = dev.to_device(values), dev.to_device(neg.astype(np.uint8), torch.uint8), \
+            dev.to_device(init.astype(np.uint8), torch.uint8)
+        ws = dev.empty((int(lib.slb_first_fail_workspace(n)) // 8,))
+        key, stats = dev.zeros((4,), torch.int64), dev.zeros((4,), torch.int64)
+        safe = dev.empty((n,), torch.uint8)
+        nat.check(lib.slb_first_fail(dev.stream(), v.data_ptr(), ng.data_ptr(), it.data_ptr(), n, 0,
+                                     ws.data_ptr(), key.data_ptr()), "first_fail")
+        nat.check(lib.slb_apply_prefix(dev.stream(), v.data_ptr(), it.data_ptr(), n, 0,
+                                       key.data_ptr(), safe.data_ptr(), ws.data_ptr(),
+                                       stats.data_ptr()), "apply_prefix")
+        assert_array_equal(safe.cpu().numpy().astype(bool), safe_cpu)
+        st = stats.cpu().numpy()
+        assert st[1] == p and st[0] == safe_cpu.sum()
+        assert key.cpu().numpy()[2] == (neg | init).sum()
+
+
+# ------------------------------------------------------------------ Bellman sweep
+def _rl_objects(ns, par, kind, num=24):
+    grid = ns.GridWorld(par["limits"], num)
+    _, dynamics = W._build(ns, par, kind)
+    policy = ns.Saturation(ns.LinearSystem(-par["K"]), -1., 1.)
+    reward = ns.QuadraticFunction(-scipy_block(np.diag([1., 2.]), 1.2 * np.eye(1)))
+    value = ns.Triangulation(grid, np.zeros((grid.nindex, 1)), project=True)
+    return ns.PolicyIteration(policy, dynamics, reward, value, gamma=0.98), grid
+
+
+def scipy_block(a, b):
+    import scipy.linalg
+    return scipy.linalg.block_diag(a, b)
+
+
+def test_value_iteration_vs_oracle(sl):
+    """reinforcement_learning.py:65-114, 135-140 with GP-mean dynamics (C3 at test size)."""
+    par = W.make_pendulum(num_points=8, M=120)
+    rl_gpu, _ = _rl_objects(sl, par, "product")
+    rl_cpu, _ = _rl_objects(O, par, "oracle")
+    for sweep in range(4):
+        res = rl_gpu.value_iteration()
+        old = rl_cpu.value_function.parameters.copy()
+        new = rl_cpu.value_iteration()
+        assert_allclose(rl_gpu.value_function.parameters[0], new, rtol=1e-9, atol=1e-12)
+        assert_allclose(res, np.max(np.abs(new - old)), rtol=1e-9)
+    states = np.random.default_rng(0).uniform(-1, 1, (100, 2))
+    assert_allclose(rl_gpu.future_values(states), rl_cpu.future_values(states), rtol=1e-9,
+                    atol=1e-12)
+
+
+def test_discrete_policy_optimization_vs_oracle(sl):
+    """reinforcement_learning.py:213-279: first argmax over a discrete action set, with a
+    constraint mask."""
+    par = W.make_pendulum(num_points=8, M=60)
+    grid_g, grid_c = sl.GridWorld(par["limits"], 15), O.GridWorld(par["limits"], 15)
+    dyn_g = sl.LinearSystem((par["A_true"], par["B_true"]))
+    dyn_c = O.LinearSystem((par["A_true"], par["B_true"]))
+    rew = -scipy_block(np.diag([1., 2.]), 1.2 * np.eye(1))
+    rng = np.random.default_rng(4)
+    v0 = -rng.random((grid_c.nindex, 1))
+    rl_g = sl.PolicyIteration(sl.Triangulation(grid_g, np.zeros((grid_c.nindex, 1))), dyn_g,
+                              sl.QuadraticFunction(rew), sl.Triangulation(grid_g, v0, project=True))
+    rl_c = O.PolicyIteration(O.Triangulation(grid_c, np.zeros((grid_c.nindex, 1))), dyn_c,
+                             O.QuadraticFunction(rew), O.Triangulation(grid_c, v0, project=True))
+    actions = np.linspace(-1, 1, 21)[:, None]
+    constraint = lambda arr: np.where(np.abs(arr[:, 0]) > 0.8, -1.0, 1.0)  # noqa: E731
+    best_g = rl_g.discrete_policy_optimization(actions, constraint)
+    best_c = rl_c.discrete_policy_optimization(actions, constraint)
+    assert_array_equal(best_g.cpu().numpy(), best_c)
+    assert_array_equal(rl_g.policy.parameters[0], best_c)
+
+
+# ------------------------------------------------------------------ C-ABI error behaviour
+def test_errors_are_loud(sl):
+    from safe_learning_b200 import _native as nat
+    grid = sl.GridWorld([[-1, 1]], 3)
+    with pytest.raises(TypeError):
+        sl.Lyapunov(grid, lambda x: x, sl.LinearSystem(np.array([[1, 1.]])), 0.4, 0.3, 0.5,
+                    sl.LinearSystem(np.array([[-.1]])))
+    lyap = sl.Lyapunov(grid, sl.QuadraticFunction(np.array([[1.0]])),
+                       sl.LinearSystem(np.array([[1, 1., 1.]])), 0.4, 0.3, 0.5,
+                       sl.LinearSystem(np.array([[-.1]])))
+    with pytest.raises(nat.NativeLibraryError):
+        lyap.update_safe_set()          # dynamics expect 3 inputs, state+action give 2
+    with pytest.raises(NotImplementedError):
+        sl.Lyapunov(grid, sl.QuadraticFunction(np.array([[1.0]])),
+                    sl.LinearSystem(np.array([[1, 1.]])), 0.4, 0.3, 0.5,
+                    sl.LinearSystem(np.array([[-.1]])), adaptive=True).update_safe_set(
+                        max_refinement=4)

@@ -1,0 +1,260 @@
+"""CPU-side tests (no GPU): the C-ABI library loads and exports every symbol the header
+declares, the ctypes mirror matches the C layout, host-side logic agrees with the oracle, the
+packed-factor index arithmetic of the sweep kernel is right (numpy emulation of the kernel's
+addressing), compute calls fail loudly without a device, and the sharded (world_size 2, gloo)
+prefix reduction equals the unsharded oracle."""
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+from numpy.testing import assert_allclose, assert_array_equal
+
+import oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    import __graft_entry__
+    __graft_entry__.build()
+    from safe_learning_b200 import _native
+    return _native.load()
+
+
+def test_header_symbols_exported(lib):
+    header = open(os.path.join(ROOT, "include", "slb200.h")).read()
+    declared = set(re.findall(r"\b(slb_[a-z0-9_]+)\s*\(", header))
+    assert len(declared) >= 18
+    from safe_learning_b200 import _native
+    assert declared == set(_native.SIGNATURES), "binding and header disagree"
+    nm = subprocess.run(["nm", "-D", "--defined-only", _native.LIB_PATH], stdout=subprocess.PIPE,
+                        text=True, check=True).stdout
+    exported = set(re.findall(r"\bT (slb_[a-z0-9_]+)", nm))
+    assert declared <= exported, "missing exports: %s" % sorted(declared - exported)
+
+
+def test_struct_layout_and_version(lib):
+    from safe_learning_b200 import _native
+    assert lib.slb_abi_version() == 1
+    _native._check_layout(lib)
+    assert lib.slb_packed_len(500) == 63 * 64 * 32
+    assert lib.slb_packed_len(8) == 2 * 32
+    assert lib.slb_packed_len(0) == 0
+    assert lib.slb_first_fail_workspace(10 ** 6) >= 1024 * 32
+
+
+def test_sm100a_tensor_instructions_in_binary(lib):
+    """The GP kernel must be built for sm_100a and use the fp64 tensor pipe (DMMA)."""
+    from safe_learning_b200 import _native
+    out = subprocess.run(["cuobjdump", "-lelf", _native.LIB_PATH], stdout=subprocess.PIPE,
+                         text=True).stdout
+    assert "sm_100a" in out
+    sass = subprocess.run("cuobjdump -sass %s | grep -c DMMA" % _native.LIB_PATH, shell=True,
+                          stdout=subprocess.PIPE, text=True).stdout
+    assert int(sass.strip()) >= 80
+
+
+def test_no_cpu_fallback_without_device(lib):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    import safe_learning_b200 as sl
+    from safe_learning_b200 import _native
+    with pytest.raises(_native.NativeLibraryError):
+        sl.QuadraticFunction(np.eye(2))(np.zeros((3, 2)))
+    with pytest.raises(_native.NativeLibraryError):
+        sl.Lyapunov(sl.GridWorld([[-1, 1]], 3), sl.QuadraticFunction(np.array([[1.0]])),
+                    sl.LinearSystem(np.array([[1, 1.]])), 0.4, 0.3, 0.5,
+                    sl.LinearSystem(np.array([[-.1]])))
+    assert lib.slb_device_count() < 0 and b"no CPU fallback" in lib.slb_last_error()
+
+
+def test_product_sources_never_import_oracle():
+    pkg = os.path.join(ROOT, "safe_learning_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for name in files:
+            if name.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, name)).read()
+                assert not re.search(r"^\s*(import|from)\s+oracle\b", text, re.M), name
+
+
+def test_gridworld_host_helpers_match_oracle(lib):
+    import safe_learning_b200 as sl
+    rng = np.random.default_rng(0)
+    for limits, num in ([[[-1.1, 1.5], [2.2, 2.4]], [7, 8]], [[[-1, 1]] * 3, [5, 9, 4]],
+                        [[[0, 1]], 3]):
+        a, b = sl.GridWorld(limits, num), O.GridWorld(limits, num)
+        assert a.nindex == b.nindex and a.nrectangles == b.nrectangles and a.ndim == b.ndim
+        assert_array_equal(a.unit_maxes, b.unit_maxes)
+        assert_array_equal(a.all_points, b.all_points)
+        idx = rng.integers(0, a.nindex, 50)
+        assert_array_equal(a.index_to_state(idx), b.index_to_state(idx))
+        lo, hi = a.limits[:, 0], a.limits[:, 1]
+        pts = rng.uniform(lo - 0.2, hi + 0.2, (200, a.ndim))
+        assert_array_equal(a.state_to_index(pts), b.state_to_index(pts))
+        assert_array_equal(a.state_to_rectangle(pts), b.state_to_rectangle(pts))
+        rect = np.arange(a.nrectangles)
+        assert_array_equal(a.rectangle_to_state(rect), b.rectangle_to_state(rect))
+        assert_array_equal(a.rectangle_corner_index(rect), b.rectangle_corner_index(rect))
+        d = a.descriptor()
+        assert d.ndim == a.ndim and d.nindex == a.nindex
+        assert [d.num_points[c] for c in range(a.ndim)] == list(a.num_points)
+    with pytest.raises(sl.DimensionError):
+        sl.GridWorld([[0, 1]], 1)
+    tri_a = sl.functions._TriangulationTables(sl.GridWorld([[-1, 1], [0, 2]], [4, 5]))
+    tri_b = O.Triangulation(O.GridWorld([[-1, 1], [0, 2]], [4, 5]))
+    assert_array_equal(tri_a.unit_simplices, tri_b.unit_simplices)
+    assert_array_equal(tri_a.hyperplanes, tri_b.hyperplanes)
+
+
+def test_utilities_match_oracle():
+    from safe_learning_b200 import utilities
+    k, p = utilities.dlqr(1., 1., 1., 1.)
+    assert_allclose(k, 0.5 * (np.sqrt(5) - 1))
+    assert_allclose(p, 0.5 * (np.sqrt(5) + 1))
+    arr = np.arange(23)
+    got = [(i, [v.copy() for v in views]) for i, views in utilities.batchify((arr, arr * 2), 5)]
+    want = [(i, [v.copy() for v in views]) for i, views in O.batchify((arr, arr * 2), 5)]
+    assert [g[0] for g in got] == [w[0] for w in want]
+    for g, w in zip(got, want):
+        assert_array_equal(g[1][0], w[1][0])
+
+
+# ----------------------------------------------------------------- kernel addressing emulation
+def _pack_factor(linv):
+    """numpy twin of pack_factor_kernel (gp_sweep.cu)."""
+    M = linv.shape[0]
+    nrb = (M + 7) // 8
+    out = np.zeros(nrb * (nrb + 1) * 32)
+    for b in range(nrb):
+        for kb4 in range(2 * b + 2):
+            base = (b * (b + 1) + kb4) * 32
+            for lane in range(32):
+                row, col = 8 * b + lane // 4, 4 * kb4 + lane % 4
+                if row < M and col <= row:
+                    out[base + lane] = linv[row, col]
+    return out
+
+
+def _emulate_tile(wpack, M, K):
+    """Replays gp_tile_kernel's loop structure and fragment addressing (8 warps, panels of
+    256 rows/cols, bottom-up row-block dealing, per-q k-step limits) on the host; returns
+    a = W k [M_pad, P] accumulated exactly where the kernel accumulates it."""
+    nrb, nk4 = (M + 7) // 8, (M + 3) // 4
+    npan = (nrb + 31) // 32
+    P = K.shape[1]
+    Kpad = np.zeros((nk4 * 4, P))
+    Kpad[:M] = K
+    a = np.zeros((nrb * 8, P))
+    lanes = np.arange(32)
+    for ip in range(npan):
+        pbeg, pend = 32 * ip, min(32 * ip + 32, nrb)
+        for warp in range(8):
+            for q in range(4):
+                b = pend - 1 - warp - 8 * (3 - q)
+                if b < pbeg:
+                    continue
+                for jp in range(ip + 1):
+                    nkp = min(64, nk4 - 64 * jp)
+                    kend = min(nkp, 2 * (b - pbeg) + 2) if jp == ip else nkp
+                    for kk in range(kend):
+                        frag = wpack[(b * (b + 1) + 64 * jp) * 32 + kk * 32 + lanes]
+                        A = np.zeros((8, 4))
+                        A[lanes // 4, lanes % 4] = frag
+                        Bm = Kpad[256 * jp + 4 * kk: 256 * jp + 4 * kk + 4]
+                        a[8 * b: 8 * b + 8] += A @ Bm
+    return a
+
+
+@pytest.mark.parametrize("M", [1, 5, 8, 33, 255, 256, 257, 500, 530])
+def test_packed_factor_addressing(M):
+    rng = np.random.default_rng(M)
+    L = np.tril(rng.normal(size=(M, M))) + 3 * np.eye(M)
+    linv = np.linalg.inv(L)
+    linv = np.tril(linv)
+    K = rng.normal(size=(M, 5))
+    a = _emulate_tile(_pack_factor(linv), M, K)
+    assert_allclose(a[:M], linv @ K, rtol=1e-8, atol=1e-10)
+    assert np.all(a[M:] == 0)
+
+
+# ----------------------------------------------------------------- sharded prefix rule (gloo)
+def _numpy_first_fail(values, ok, begin):
+    """numpy twin of slb_first_fail on one shard -> the int64[4] slb_fail_key row."""
+    def key(v):
+        v = np.where(v == 0.0, 0.0, v)
+        b = v.view(np.uint64)
+        return np.where(b >> np.uint64(63) == 1, ~b, b | np.uint64(1 << 63))
+    kv = key(values.copy())
+    fail = np.nonzero(~ok)[0]
+    row = np.zeros(4, dtype=np.int64)
+    row[2] = ok.sum()
+    if len(fail) == 0:
+        row[0], row[1] = -1, np.iinfo(np.int64).max
+    else:
+        order = np.lexsort((fail + begin, kv[fail]))
+        row[0] = kv[fail][order[0]].astype(np.uint64).view(np.int64)
+        row[1] = fail[order[0]] + begin
+    return row, kv
+
+
+_WORKER = r"""
+import os, sys, numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, {root!r})
+sys.path.insert(0, os.path.join({root!r}, "tests"))
+from test_host_and_abi import _numpy_first_fail
+from safe_learning_b200 import _device as dev
+from safe_learning_b200.lyapunov import combine_fail_keys, combine_prefix_stats
+import oracle as O
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:{port}", rank=int(sys.argv[1]), world_size=2)
+rng = np.random.default_rng(123)
+for trial in range(30):
+    n = int(rng.integers(3, 400))
+    values = rng.integers(-2, 5, n).astype(float)
+    neg = rng.random(n) < 0.97
+    init = rng.random(n) < 0.1
+    begin, end = dev.shard_range(n)
+    row, kv = _numpy_first_fail(values[begin:end], (neg | init)[begin:end], begin)
+    rows = dev.allgather_rows(torch.from_numpy(row))
+    best, (kstar_v, kstar_i, n_ok) = combine_fail_keys(rows.numpy())
+    idx = np.arange(begin, end)
+    below = (kv < np.uint64(kstar_v)) | ((kv == np.uint64(kstar_v)) & (idx < kstar_i))
+    safe_local = below | init[begin:end]
+    stats = np.array([safe_local.sum(), below.sum(), 0, 0], dtype=np.int64)
+    n_safe, n_below, _, _ = combine_prefix_stats(dev.allgather_rows(torch.from_numpy(stats)).numpy())
+    safe_ref, p = O.prefix_rule(values, neg | init, init)
+    assert np.array_equal(safe_local, safe_ref[begin:end]), (trial, "safe set")
+    assert n_below == p and n_safe == safe_ref.sum() and n_ok == (neg | init).sum(), trial
+dist.barrier()
+dist.destroy_process_group()
+print("rank", sys.argv[1], "ok")
+"""
+
+
+def test_sharded_prefix_rule_world2_gloo(tmp_path, lib):
+    import socket
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER.format(root=ROOT, port=port))
+    procs = [subprocess.Popen([sys.executable, str(script), str(r)], stdout=subprocess.PIPE,
+                              stderr=subprocess.STDOUT, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=300)[0] for p in procs]
+    for r, (p, out) in enumerate(zip(procs, outs)):
+        assert p.returncode == 0, "rank %d failed:\n%s" % (r, out)
+        assert "ok" in out
+
+
+def test_shard_ranges_cover_grid():
+    from safe_learning_b200 import _device as dev
+    for n in (1, 7, 64, 65536, 16777216, 101):
+        for world in (1, 2, 3, 4, 8):
+            spans = [dev.shard_range(n, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            for (b0, e0), (b1, e1) in zip(spans, spans[1:]):
+                assert e0 == b1 and b0 <= e0
