@@ -175,6 +175,12 @@ int         slb_struct_sizes(int64_t* out, int32_t n);
 /* kernels this library has launched since load (bench.py's gpu_launches) */
 int64_t     slb_launch_count(void);
 
+/* diagnostics: when buffer_dev != NULL, every later Lyapunov sweep writes int64 cycle counts
+ * [tile][warp(8)][6] = {k-row generation, DMMA contraction, panel epilogues, whole tile} and
+ * the %globaltimer (ns) at tile start / end;
+ * pass NULL to switch it off (default) */
+int         slb_debug_phase_timing(void* buffer_dev);
+
 /* ---- GP factor packing (after GPRCached.update_cache, functions.py:395-415) ------------ */
 /* doubles needed for the packed L^-1 of an M-point GP */
 int64_t slb_packed_len(int32_t M);
@@ -209,6 +215,10 @@ int64_t slb_first_fail_workspace(int64_t n);
 int slb_first_fail(void* stream, const double* values_dev, const uint8_t* negative_dev,
                    const uint8_t* initial_dev /* may be NULL */, int64_t n, int64_t idx_begin,
                    void* workspace_dev, slb_fail_key* result_dev);
+/* multi-GPU: lexicographic min (and n_ok sum) over `world` keys all-gathered by the caller
+ * (the one collective of a sweep) -> out_dev; may alias gathered_dev[0] */
+int slb_combine_fail_keys(void* stream, const slb_fail_key* gathered_dev, int32_t world,
+                          slb_fail_key* out_dev);
 int slb_apply_prefix(void* stream, const double* values_dev, const uint8_t* initial_dev,
                      int64_t n, int64_t idx_begin, const slb_fail_key* key_dev,
                      uint8_t* safe_dev, void* workspace_dev, slb_prefix_stats* stats_dev);

@@ -98,6 +98,7 @@ SIGNATURES = {
     "slb_device_count": (C.c_int, []),
     "slb_struct_sizes": (C.c_int, [C.POINTER(C.c_int64), _i32]),
     "slb_launch_count": (C.c_int64, []),
+    "slb_debug_phase_timing": (C.c_int, [_vp]),
     "slb_packed_len": (C.c_int64, [_i32]),
     "slb_pack_factor": (C.c_int, [_vp, _dp, _i32, _dp]),
     "slb_gp_predict": (C.c_int, [_vp, C.POINTER(SlbGpStack), _dp, _i64, _dp, _dp, _i32]),
@@ -107,6 +108,7 @@ SIGNATURES = {
                                       _dp, _dp]),
     "slb_first_fail_workspace": (C.c_int64, [_i64]),
     "slb_first_fail": (C.c_int, [_vp, _dp, _dp, _dp, _i64, _i64, _vp, _vp]),
+    "slb_combine_fail_keys": (C.c_int, [_vp, _vp, _i32, _vp]),
     "slb_apply_prefix": (C.c_int, [_vp, _dp, _dp, _i64, _i64, _vp, _dp, _vp, _vp]),
     "slb_eval_function": (C.c_int, [_vp, C.POINTER(SlbFunction), _dp, _i64, _dp]),
     "slb_index_to_state": (C.c_int, [_vp, C.POINTER(SlbGrid), _i64, _i64, _dp]),

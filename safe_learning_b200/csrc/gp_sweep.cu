@@ -10,7 +10,9 @@
 //   v_decrease_bound < threshold                 lyapunov.py:436-441 -> tile epilogue
 //
 // Design (B200, fp64 pipe bound -- see DESIGN.md):
-//   * one CTA = 64 grid points x all M training points, 8 warps, 1 CTA/SM (181 KB smem).
+//   * one CTA = 64 grid points x all M training points, 8 warps, 1 CTA/SM (181 KB smem,
+//     ~245 registers).  Measured alternatives (profiles/r01_kernel_variants.md): 16 warps x
+//     (16 rows x 64 points) and 2 CTAs/SM x 32-point tiles were both 2-5% slower.
 //   * W = L^-1 (lower triangular) is pre-packed in DMMA.8x8x4 A-fragment order
 //     (slb_pack_factor); each warp streams ITS rows of W straight from L2 into registers
 //     with coalesced 256 B loads, software-pipelined two k-steps ahead -- W is used by
@@ -19,7 +21,7 @@
 //     j-panel into shared memory ([j][68] doubles: conflict-free B-fragment reads).
 //   * a 256-row i-panel of a = W k lives in registers (32 rows x 64 points per warp =
 //     64 fp64 accumulators per thread); rows are dealt to warps round-robin from the bottom
-//     of the panel so the triangular work is balanced.  sum a^2 and a.alpha are reduced in
+//     of the panel so the triangular work is balanced across warps and across SMSPs.  sum a^2 and a.alpha are reduced in
 //     the panel epilogue, so `a` is never stored.
 #include "common.cuh"
 
@@ -28,9 +30,13 @@ namespace {
 constexpr int TP = SLB_TILE_POINTS;   // points per CTA
 constexpr int PANEL = 256;            // rows per i-panel, columns per j-panel
 constexpr int KSTR = TP + 4;          // Ks row stride: (r*68 + c) mod 16 distinct for r,c in 0..3
-constexpr int NW = 8;
+constexpr int NW = 8;                 // warps per CTA
 constexpr int NT = NW * 32;
+constexpr int RQ = 4;                 // 8-row blocks per warp per 256-row panel (RQ * NW = 32)
+constexpr int NB = TP / 8;            // 8-point column blocks per warp tile
+constexpr int CTAS_PER_SM = 1;
 constexpr int NRED = 1 + SLB_MAX_OUT;
+constexpr int PREFETCH_CTAS = 148 * CTAS_PER_SM;    // one wave on a B200
 
 constexpr size_t SMEM_KS = (size_t)PANEL * KSTR * sizeof(double);
 constexpr size_t SMEM_Z = (size_t)SLB_MAX_IN * TP * sizeof(double);
@@ -53,12 +59,42 @@ struct gp_args {
     double* threshold;
     double* mean;
     double* err;
+    long long* timing;      // diagnostics: [tile][warp][6]: cycles in {generate, contract, epilogue, total}, globaltimer ns {start, end}
 };
 
 SLB_DEV double ldg_stream(const double* p) {
     double v;
     asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
     return v;
+}
+
+// exp(x) for x <= 0, <= 1 ulp (checked against glibc on 2e7 points, tools/exp_neg_check.c):
+// Cody-Waite reduction x = k ln2 + r, |r| <= ln2/2, degree-13 Taylor polynomial, 2^k by exponent
+// add.  Branch-free so four evaluations interleave in the k-row generation loop; anything
+// below exp(-700) flushes to 0 (it only ever multiplies finite L^-1 entries).
+SLB_DEV double exp_neg(double x) {
+    const double MAGIC = 6755399441055744.0;             // 1.5 * 2^52
+    const double t = fma(x, 1.4426950408889634074, MAGIC);
+    const int k = __double2loint(t);
+    const double kd = t - MAGIC;
+    double r = fma(kd, -6.93147180369123816490e-01, x);
+    r = fma(kd, -1.90821492927058770002e-10, r);
+    double p = 1.0 / 6227020800.0;
+    p = fma(p, r, 1.0 / 479001600.0);
+    p = fma(p, r, 1.0 / 39916800.0);
+    p = fma(p, r, 1.0 / 3628800.0);
+    p = fma(p, r, 1.0 / 362880.0);
+    p = fma(p, r, 1.0 / 40320.0);
+    p = fma(p, r, 1.0 / 5040.0);
+    p = fma(p, r, 1.0 / 720.0);
+    p = fma(p, r, 1.0 / 120.0);
+    p = fma(p, r, 1.0 / 24.0);
+    p = fma(p, r, 1.0 / 6.0);
+    p = fma(p, r, 0.5);
+    p = fma(p, r, 1.0);
+    p = fma(p, r, 1.0);
+    p = __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));
+    return x < -700.0 ? 0.0 : p;
 }
 
 SLB_DEV void dmma884(double& c0, double& c1, double a, double b) {
@@ -68,38 +104,40 @@ SLB_DEV void dmma884(double& c0, double& c1, double a, double b) {
 
 // k-steps [k0, k1) of the current j-panel for row blocks q >= Q0 of this warp.
 template <int Q0>
-SLB_DEV void mma_run(double (&acc)[4][8][2], const double* const (&ap)[4], int k0, int k1,
+SLB_DEV void mma_run(double (&acc)[RQ][NB][2], const double* const (&ap)[RQ], int k0, int k1,
                      const double* ks_lane) {
-    double a_cur[4], a_nxt[4];
+    // W fragments are prefetched three k-steps ahead (L2 latency under load ~1-2 k-steps).
+    double a0[RQ], a1[RQ], a2[RQ];
     const int k1m = k1 - 1;
-    const int kn = min(k0 + 1, k1m);
+    const int kn1 = min(k0 + 1, k1m), kn2 = min(k0 + 2, k1m);
 #pragma unroll
-    for (int q = Q0; q < 4; ++q) {
-        a_cur[q] = ldg_stream(ap[q] + k0 * 32);
-        a_nxt[q] = ldg_stream(ap[q] + kn * 32);
+    for (int q = Q0; q < RQ; ++q) {
+        a0[q] = ldg_stream(ap[q] + k0 * 32);
+        a1[q] = ldg_stream(ap[q] + kn1 * 32);
+        a2[q] = ldg_stream(ap[q] + kn2 * 32);
     }
 #pragma unroll 1
     for (int kk = k0; kk < k1; ++kk) {
-        const int k2 = min(kk + 2, k1m);
-        double a_pre[4];
+        const int k3 = min(kk + 3, k1m);
+        double a3[RQ];
 #pragma unroll
-        for (int q = Q0; q < 4; ++q) a_pre[q] = ldg_stream(ap[q] + k2 * 32);
+        for (int q = Q0; q < RQ; ++q) a3[q] = ldg_stream(ap[q] + k3 * 32);
         const double* kb = ks_lane + kk * (4 * KSTR);
-        double b[8];
+        double b[NB];
 #pragma unroll
-        for (int nb = 0; nb < 8; ++nb) b[nb] = kb[nb * 8];
+        for (int nb = 0; nb < NB; ++nb) b[nb] = kb[nb * 8];
 #pragma unroll
-        for (int q = Q0; q < 4; ++q) {
+        for (int q = Q0; q < RQ; ++q) {
 #pragma unroll
-            for (int nb = 0; nb < 8; ++nb) dmma884(acc[q][nb][0], acc[q][nb][1], a_cur[q], b[nb]);
+            for (int nb = 0; nb < NB; ++nb) dmma884(acc[q][nb][0], acc[q][nb][1], a0[q], b[nb]);
         }
 #pragma unroll
-        for (int q = Q0; q < 4; ++q) { a_cur[q] = a_nxt[q]; a_nxt[q] = a_pre[q]; }
+        for (int q = Q0; q < RQ; ++q) { a0[q] = a1[q]; a1[q] = a2[q]; a2[q] = a3[q]; }
     }
 }
 
-template <int DIN>
-__global__ void __launch_bounds__(NT, 1)
+template <int DIN, bool TIMING>
+__global__ void __launch_bounds__(NT, CTAS_PER_SM)
 gp_tile_kernel(const __grid_constant__ slb_sweep cfg, const gp_args a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double* Ks = reinterpret_cast<double*>(smem_raw);
@@ -111,6 +149,27 @@ gp_tile_kernel(const __grid_constant__ slb_sweep cfg, const gp_args a) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t tile0 = (int64_t)blockIdx.x * TP;
     const int D = cfg.gp.num_outputs;
+    long long t_gen = 0, t_mma = 0, t_epi = 0, t_mark = 0;
+    const long long t_start = TIMING ? clock64() : 0;
+    long long g_start = 0;
+    if (TIMING) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(g_start));
+
+    // ---- stage 0: warm L2.  Every CTA streams the whole packed L^-1 (1 MB per factor at
+    // M=500); if it is not L2-resident when the launch starts (first sweep after add_data_point,
+    // or after anything else evicted it) the first wave of 148 CTAs would pull it from HBM at
+    // streaming latency, in lockstep, and run ~2x slower (measured: +15% on the whole sweep).
+    // The first-wave CTAs therefore prefetch disjoint 128-byte lines of it into L2 while the
+    // k-row generation phase runs; the demand loads then hit.
+    if (blockIdx.x < PREFETCH_CTAS) {
+        for (int f = 0; f < cfg.gp.num_factors; ++f) {
+            const slb_gp_factor& F = cfg.gp.factors[f];
+            const char* base = reinterpret_cast<const char*>(F.Wpack);
+            const size_t nbytes = (size_t)F.nrb * (F.nrb + 1) * 32 * sizeof(double);
+            for (size_t off = ((size_t)blockIdx.x * NT + tid) * 128; off < nbytes;
+                 off += (size_t)PREFETCH_CTAS * NT * 128)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(base + off));
+        }
+    }
 
     // ---- stage 1: query points z = [x, policy(x)]  (lyapunov.py:436-437, utilities.py:143)
     if (tid < TP) {
@@ -138,8 +197,12 @@ gp_tile_kernel(const __grid_constant__ slb_sweep cfg, const gp_args a) {
     }
     __syncthreads();
 
+    // Row blocks are dealt by `wslot`; warps w and w+4 share an SMSP (and its fp64 pipe), so
+    // their slots sum to 7 and every SMSP gets the same share of the triangular panels.
+    static_assert(NW == 8, "slot permutation below assumes 8 warps (2 per SMSP)");
+    const int wslot = warp < 4 ? warp : 11 - warp;     // SMSP partners w, w+4 sum to 7
     const int p_gen = tid & (TP - 1);
-    const int jg = tid >> 6;                          // 0..3
+    const int jg = tid / TP;                          // 0..NT/TP-1
     const double* ks_lane = Ks + (lane & 3) * KSTR + (lane >> 2);
 
     for (int f = 0; f < cfg.gp.num_factors; ++f) {
@@ -161,47 +224,58 @@ gp_tile_kernel(const __grid_constant__ slb_sweep cfg, const gp_args a) {
         int resident = -1;
 
         for (int ip = 0; ip < npan; ++ip) {
-            double acc[4][8][2];
+            double acc[RQ][NB][2];
 #pragma unroll
-            for (int q = 0; q < 4; ++q)
+            for (int q = 0; q < RQ; ++q)
 #pragma unroll
-                for (int nb = 0; nb < 8; ++nb) { acc[q][nb][0] = 0.0; acc[q][nb][1] = 0.0; }
+                for (int nb = 0; nb < NB; ++nb) { acc[q][nb][0] = 0.0; acc[q][nb][1] = 0.0; }
 
             const int pbeg = 32 * ip;
             const int pend = min(pbeg + 32, nrb);
-            int bq[4];
+            int bq[RQ];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) bq[q] = pend - 1 - warp - 8 * (3 - q);
+            for (int q = 0; q < RQ; ++q) bq[q] = pend - 1 - wslot - NW * (RQ - 1 - q);
 
             for (int jp = 0; jp <= ip; ++jp) {
                 const int nkp = min(64, nk4 - 64 * jp);
                 if (jp != resident) {
                     // ---- generation phase: K[j, p] for j in this panel (functions.py:438)
+                    if (TIMING) t_mark = clock64();
                     __syncthreads();
                     const int j0 = PANEL * jp;
                     const int nj = min(PANEL, M - j0);
-                    for (int j = jg; j < nkp * 4; j += 4) {
-                        double k = 0.0;
-                        if (j < nj) {
-                            const double* xr = Xs + (size_t)(j0 + j) * DIN;
-                            double t2 = 0.0;
+                    constexpr int JS = NT / TP;       // j stride between a thread's rows
+                    for (int j = jg; j < nkp * 4; j += 4 * JS) {
+                        double t2[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const int jj = min(j + JS * u, nj - 1);
+                            const double* xr = Xs + (size_t)(j0 + jj) * DIN;
+                            double acc2 = 0.0;
 #pragma unroll
                             for (int c = 0; c < DIN; ++c) {
                                 const double df = zs[c] - __ldg(xr + c);
-                                t2 = fma(df, df, t2);
+                                acc2 = fma(df, df, acc2);
                             }
-                            k = s2 * (variance * exp(-0.5 * t2));
+                            t2[u] = acc2;
                         }
-                        Ks[j * KSTR + p_gen] = k;
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const int jj = j + JS * u;
+                            const double k = s2 * (variance * exp_neg(-0.5 * t2[u]));
+                            if (jj < nkp * 4) Ks[jj * KSTR + p_gen] = jj < nj ? k : 0.0;
+                        }
                     }
                     resident = jp;
                     __syncthreads();
+                    if (TIMING) t_gen += clock64() - t_mark;
                 }
+                if (TIMING) t_mark = clock64();
                 // ---- contraction phase: acc[rows of this warp, 64 points] += W[rows, panel] K
-                int kend[4];
-                const double* ap[4];
+                int kend[RQ];
+                const double* ap[RQ];
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
+                for (int q = 0; q < RQ; ++q) {
                     const bool valid = bq[q] >= pbeg;
                     int ke = valid ? nkp : 0;
                     if (valid && jp == ip) ke = min(nkp, 2 * (bq[q] - pbeg) + 2);
@@ -209,31 +283,34 @@ gp_tile_kernel(const __grid_constant__ slb_sweep cfg, const gp_args a) {
                     const int64_t b = valid ? bq[q] : 0;
                     ap[q] = F.Wpack + (b * (b + 1) + 64 * jp) * 32 + lane;
                 }
+                static_assert(RQ == 4, "segment dispatch below is written for RQ == 4");
                 int kprev = 0;
                 if (kend[0] > kprev) { mma_run<0>(acc, ap, kprev, kend[0], ks_lane); kprev = kend[0]; }
                 if (kend[1] > kprev) { mma_run<1>(acc, ap, kprev, kend[1], ks_lane); kprev = kend[1]; }
                 if (kend[2] > kprev) { mma_run<2>(acc, ap, kprev, kend[2], ks_lane); kprev = kend[2]; }
                 if (kend[3] > kprev) { mma_run<3>(acc, ap, kprev, kend[3], ks_lane); kprev = kend[3]; }
+                if (TIMING) t_mma += clock64() - t_mark;
             }
+            if (TIMING) t_mark = clock64();
 
             // ---- panel epilogue: sum_i a_i^2 and sum_i a_i alpha_i   (functions.py:442, 451)
             int qty = 0;
             for (int o = -1; o < D; ++o) {
-                double al[4] = {0.0, 0.0, 0.0, 0.0};
+                double al[RQ] = {};
                 if (o >= 0) {
                     if (cfg.gp.outputs[o].factor != f) continue;
                     const double* alpha = cfg.gp.outputs[o].alpha;
 #pragma unroll
-                    for (int q = 0; q < 4; ++q)
+                    for (int q = 0; q < RQ; ++q)
                         if (bq[q] >= pbeg) al[q] = __ldg(alpha + 8 * bq[q] + (lane >> 2));
                 }
 #pragma unroll
-                for (int nb = 0; nb < 8; ++nb) {
+                for (int nb = 0; nb < NB; ++nb) {
 #pragma unroll
                     for (int e = 0; e < 2; ++e) {
                         double v = 0.0;
 #pragma unroll
-                        for (int q = 0; q < 4; ++q) {
+                        for (int q = 0; q < RQ; ++q) {
                             const double x = acc[q][nb][e];
                             v = fma(x, (o < 0) ? x : al[q], v);
                         }
@@ -255,6 +332,7 @@ gp_tile_kernel(const __grid_constant__ slb_sweep cfg, const gp_args a) {
                 }
             }
             __syncthreads();
+            if (TIMING) t_epi += clock64() - t_mark;
         }
 
         // ---- factor epilogue: mean and error bound of the outputs on this factor
@@ -281,6 +359,13 @@ gp_tile_kernel(const __grid_constant__ slb_sweep cfg, const gp_args a) {
         __syncthreads();
     }
 
+    if (TIMING && lane == 0) {
+        long long* t = a.timing + ((size_t)blockIdx.x * NW + warp) * 6;
+        long long g_end;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(g_end));
+        t[0] = t_gen; t[1] = t_mma; t[2] = t_epi; t[3] = clock64() - t_start;
+        t[4] = g_start; t[5] = g_end;
+    }
     // ---- tile epilogue
     if (tid < TP && tile0 + tid < a.n) {
         const int64_t rel = tile0 + tid;
@@ -318,17 +403,17 @@ __global__ void pack_factor_kernel(const double* __restrict__ Linv, int M, int n
     W[e] = (row < M && col <= row) ? Linv[row * M + col] : 0.0;
 }
 
-template <int DIN>
+template <int DIN, bool TIMING>
 int launch_gp_tile(cudaStream_t st, const slb_sweep& cfg, const gp_args& a) {
     static bool configured = false;
     if (!configured) {
-        SLB_CUDA(cudaFuncSetAttribute(gp_tile_kernel<DIN>,
+        SLB_CUDA(cudaFuncSetAttribute(gp_tile_kernel<DIN, TIMING>,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)SMEM_TOTAL));
         configured = true;
     }
     const int64_t tiles = (a.n + TP - 1) / TP;
-    gp_tile_kernel<DIN><<<(unsigned)tiles, NT, SMEM_TOTAL, st>>>(cfg, a);
+    gp_tile_kernel<DIN, TIMING><<<(unsigned)tiles, NT, SMEM_TOTAL, st>>>(cfg, a);
     SLB_LAUNCH_CHECK();
     return 0;
 }
@@ -336,13 +421,17 @@ int launch_gp_tile(cudaStream_t st, const slb_sweep& cfg, const gp_args& a) {
 int dispatch_gp_tile(cudaStream_t st, const slb_sweep& cfg, const gp_args& a) {
     if (a.n <= 0) return 0;
     SLB_CHECK(a.n <= (int64_t)0x7fffffff * TP, "too many points for one launch");
+    if (a.timing != nullptr) {
+        SLB_CHECK(cfg.gp.input_dim == 3, "phase timing is compiled for d_in = 3 only");
+        return launch_gp_tile<3, true>(st, cfg, a);
+    }
     switch (cfg.gp.input_dim) {
-    case 1: return launch_gp_tile<1>(st, cfg, a);
-    case 2: return launch_gp_tile<2>(st, cfg, a);
-    case 3: return launch_gp_tile<3>(st, cfg, a);
-    case 4: return launch_gp_tile<4>(st, cfg, a);
-    case 5: return launch_gp_tile<5>(st, cfg, a);
-    case 6: return launch_gp_tile<6>(st, cfg, a);
+    case 1: return launch_gp_tile<1, false>(st, cfg, a);
+    case 2: return launch_gp_tile<2, false>(st, cfg, a);
+    case 3: return launch_gp_tile<3, false>(st, cfg, a);
+    case 4: return launch_gp_tile<4, false>(st, cfg, a);
+    case 5: return launch_gp_tile<5, false>(st, cfg, a);
+    case 6: return launch_gp_tile<6, false>(st, cfg, a);
     default:
         slb_set_error("GP input_dim %d not compiled (1..6)", cfg.gp.input_dim);
         return 1;
@@ -356,7 +445,14 @@ int slb_launch_det_sweep(cudaStream_t st, const slb_sweep& cfg, const double* st
                          int64_t idx_begin, uint8_t* negative, double* values, double* decrease,
                          double* threshold, double* mean);
 
+static long long* g_timing_buffer = nullptr;
+
 extern "C" {
+
+int slb_debug_phase_timing(void* buffer_dev) {
+    g_timing_buffer = static_cast<long long*>(buffer_dev);
+    return 0;
+}
 
 int64_t slb_packed_len(int32_t M) {
     if (M <= 0) return 0;
@@ -422,6 +518,7 @@ static int sweep_common(void* stream, const slb_sweep* cfg, const double* states
         a.mode = states ? MODE_SWEEP_STATES : MODE_SWEEP_GRID;
         a.negative = negative; a.values = values; a.decrease = decrease; a.threshold = threshold;
         a.mean = mean; a.err = err;
+        a.timing = g_timing_buffer;
         return dispatch_gp_tile((cudaStream_t)stream, *cfg, a);
     }
     if (slb_validate_function(&cfg->dynamics, "dynamics", d + m)) return 1;

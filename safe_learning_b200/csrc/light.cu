@@ -228,6 +228,21 @@ first_fail_final_kernel(const ff_partial* __restrict__ partial, int nparts,
                             result->_pad = 0; }
 }
 
+// Lexicographic min over the per-rank keys gathered by the caller's all-gather.
+__global__ void combine_fail_keys_kernel(const slb_fail_key* __restrict__ gathered, int world,
+                                         slb_fail_key* __restrict__ out) {
+    if (threadIdx.x != 0) return;
+    uint64_t kv = ~0ull;
+    int64_t ki = INT64_MAX, nok = 0;
+    for (int r = 0; r < world; ++r) {
+        nok += gathered[r].n_ok;
+        if (key_less(gathered[r].key_value, gathered[r].key_index, kv, ki)) {
+            kv = gathered[r].key_value; ki = gathered[r].key_index;
+        }
+    }
+    out->key_value = kv; out->key_index = ki; out->n_ok = nok; out->_pad = 0;
+}
+
 __global__ void __launch_bounds__(LT)
 apply_prefix_kernel(const double* __restrict__ values, const uint8_t* __restrict__ initial, int64_t n,
                     int64_t idx_begin, const slb_fail_key* __restrict__ key,
@@ -425,6 +440,14 @@ int slb_first_fail(void* stream, const double* values_dev, const uint8_t* negati
     SLB_LAUNCH_CHECK();
     first_fail_final_kernel<<<1, FF_BLOCKS, 0, st>>>((const ff_partial*)workspace_dev, nparts,
                                                      result_dev);
+    SLB_LAUNCH_CHECK();
+    return 0;
+}
+
+int slb_combine_fail_keys(void* stream, const slb_fail_key* gathered_dev, int32_t world,
+                          slb_fail_key* out_dev) {
+    SLB_CHECK(gathered_dev && out_dev && world >= 1, "slb_combine_fail_keys: bad arguments");
+    combine_fail_keys_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(gathered_dev, world, out_dev);
     SLB_LAUNCH_CHECK();
     return 0;
 }

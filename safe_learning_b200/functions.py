@@ -170,6 +170,12 @@ class Function(object):
     def parameters(self):
         return []
 
+    @property
+    def version(self):
+        """Changes whenever the descriptor would change (callers cache descriptors on it).
+        Plain parameter containers are immutable after construction."""
+        return 0
+
     # eager evaluation -----------------------------------------------------------------
     def __call__(self, *inputs):
         return self.evaluate_device(concatenate_inputs(inputs)).cpu().numpy()
@@ -299,6 +305,11 @@ class _PostOp(DeterministicFunction):
     @property
     def parameters(self):
         return self.fun.parameters
+
+    @property
+    def version(self):
+        return (id(self.fun), self.fun.version, getattr(self, "lower", None),
+                getattr(self, "upper", None), getattr(self, "factor", None))
 
 
 class Saturation(_PostOp):
@@ -442,6 +453,7 @@ class Triangulation(DeterministicFunction):
         self._hyper_dev = None
         self._simp_dev = None
         self._corner_dev = None
+        self._version = 0
         self.output_dim = None
         if vertex_values is not None:
             self.parameters = vertex_values
@@ -479,6 +491,14 @@ class Triangulation(DeterministicFunction):
             vals = np.asarray(values, dtype=np.float64).reshape(self.nindex, -1)
             self._param_dev = dev.to_device(vals)
         self.output_dim = int(self._param_dev.shape[1])
+        self._version += 1
+
+    @property
+    def version(self):
+        # the vertex table is swapped (new device buffer) by value_iteration, so its address
+        # is part of the descriptor identity
+        return (self._version, self.project,
+                0 if self._param_dev is None else self._param_dev.data_ptr())
 
     def descriptor(self):
         if self._param_dev is None:
@@ -675,6 +695,8 @@ class GPRCached(object):
         self._gamma_dev = None
         self._prior_dev = None
         self._stale = True
+        self._version = 0
+        self._hyper_seen = None
 
     # data ------------------------------------------------------------------------------
     @property
@@ -711,9 +733,18 @@ class GPRCached(object):
         return (digest, self._X.shape, self.kern.hyper_key(), self.likelihood.variance,
                 self._scale)
 
+    def _hyper_state(self):
+        return (self.kern.hyper_key(), self.likelihood.variance, self._scale)
+
     def _ensure(self):
-        if self._stale or self._factor is None or self._factor.key != self._factor_key():
+        """Refresh the factor if data (setters mark it stale) or hyper-parameters changed."""
+        if self._stale or self._factor is None or self._hyper_seen != self._hyper_state():
             self.update_cache()
+
+    @property
+    def version(self):
+        self._ensure()
+        return self._version
 
     def update_cache(self):
         """``functions.py:395-415`` on the device."""
@@ -753,6 +784,8 @@ class GPRCached(object):
         self._alpha_dev = padded
         self._gamma_dev = gamma[:, 0].contiguous()
         self._stale = False
+        self._hyper_seen = self._hyper_state()
+        self._version += 1
 
     # descriptor pieces -------------------------------------------------------------------
     def fill_factor(self, f):
@@ -835,6 +868,10 @@ class GaussianProcess(UncertainFunction):
     def gp_stack(self):
         return _build_stack([self.gaussian_process], [self.beta])
 
+    @property
+    def version(self):
+        return (id(self.gaussian_process), self.gaussian_process.version, self.beta)
+
     def __call__(self, *inputs):
         mean, err = _gp_predict(self.gp_stack(), concatenate_inputs(inputs))
         return mean.cpu().numpy(), err.cpu().numpy()
@@ -871,6 +908,10 @@ class FunctionStack(UncertainFunction):
     def gp_stack(self):
         return _build_stack([f.gaussian_process for f in self.functions],
                             [f.beta for f in self.functions])
+
+    @property
+    def version(self):
+        return tuple(f.version for f in self.functions)
 
     def __call__(self, *inputs):
         mean, err = _gp_predict(self.gp_stack(), concatenate_inputs(inputs))

@@ -192,8 +192,26 @@ class Lyapunov(object):
         return v_dot + v_dot_error
 
     # ------------------------------------------------------------------ descriptor
+    def _descriptor_token(self):
+        def tok(obj):
+            return (id(obj), obj.version) if isinstance(obj, Function) else obj
+        return (id(self.discretization), tok(self.policy), tok(self.dynamics),
+                tok(self.lyapunov_function), tok(self._lipschitz_lyapunov),
+                self._lipschitz_dynamics if not callable(self._lipschitz_dynamics) else id(
+                    self._lipschitz_dynamics), self.tau)
+
     def sweep_descriptor(self):
-        """The ``slb_sweep`` describing the graph of ``lyapunov.py:433-441``."""
+        """The ``slb_sweep`` describing the graph of ``lyapunov.py:433-441`` (cached until a
+        function object, the GP data / hyper-parameters or a scalar changes)."""
+        token = self._descriptor_token()
+        cached = self.__dict__.get("_cfg_cache")
+        if cached is not None and cached[0] == token:
+            return cached[1]
+        cfg = self._build_descriptor()
+        self.__dict__["_cfg_cache"] = (token, cfg)
+        return cfg
+
+    def _build_descriptor(self):
         cfg = nat.SlbSweep()
         cfg.grid = self.discretization.descriptor()
         cfg.policy = _as_function(self.policy, "policy").descriptor()
@@ -298,10 +316,12 @@ class Lyapunov(object):
         if not can_shrink:
             return self._update_no_shrink(negative)
 
+        rank, world = dev.dist_info()
         if self._workspace is None:
             self._workspace = dev.empty((int(lib.slb_first_fail_workspace(n_local)) // 8 + 16,))
-            self._key_dev = dev.zeros((4,), torch.int64)
-            self._stats_dev = dev.zeros((4,), torch.int64)
+            # [0:4] slb_fail_key, [4:8] slb_prefix_stats of this rank
+            self._ks_dev = dev.zeros((8,), torch.int64)
+            self._key_dev, self._stats_dev = self._ks_dev[0:4], self._ks_dev[4:8]
         if self._safe_dev is None or self._safe_dev.numel() != n_local:
             self._safe_dev = dev.empty((n_local,), torch.uint8)
         st = dev.stream()
@@ -309,14 +329,22 @@ class Lyapunov(object):
                                      dev.ptr(initial), n_local, self._begin,
                                      self._workspace.data_ptr(), self._key_dev.data_ptr()),
                   "slb_first_fail")
-        self._allreduce_key()
+        if world > 1:
+            # the one data-path collective of the sweep: 32 bytes per rank, reduced on device
+            gathered = dev.allgather_rows(self._key_dev)
+            nat.check(lib.slb_combine_fail_keys(st, gathered.data_ptr(), world,
+                                                self._key_dev.data_ptr()), "slb_combine_fail_keys")
         nat.check(lib.slb_apply_prefix(st, self._values_dev.data_ptr(), dev.ptr(initial), n_local,
                                        self._begin, self._key_dev.data_ptr(),
                                        self._safe_dev.data_ptr(), self._workspace.data_ptr(),
                                        self._stats_dev.data_ptr()), "slb_apply_prefix")
-        stats = self._allreduce_stats()
-        key = self._key_host
-        n_safe, n_below, max_below, max_all = stats
+        # single host read-back per sweep: key + statistics (64 bytes per rank)
+        if world > 1:
+            host = dev.allgather_rows(self._ks_dev).cpu().numpy()
+        else:
+            host = self._ks_dev.cpu().numpy()[None, :]
+        key = (int(host[0, 0:1].view(np.uint64)[0]), int(host[0, 1]), int(host[0, 2]))
+        n_safe, n_below, max_below, max_all = combine_prefix_stats(host[:, 4:8])
         failed = key[1] != nat.INT64_MAX
         # c_max with the reference's index arithmetic (lyapunov.py:590-595)
         if failed:
@@ -347,17 +375,6 @@ class Lyapunov(object):
     @_refinement.setter
     def _refinement(self, value):
         self.__dict__["_refinement_host"] = value
-
-    def _allreduce_key(self):
-        """Global first-fail key = lexicographic min over ranks (one 32-byte collective)."""
-        rows = dev.allgather_rows(self._key_dev)
-        best, key_host = combine_fail_keys(rows.cpu().numpy())
-        if rows.shape[0] > 1:
-            self._key_dev.copy_(rows[best])
-        self._key_host = key_host
-
-    def _allreduce_stats(self):
-        return combine_prefix_stats(dev.allgather_rows(self._stats_dev).cpu().numpy())
 
     def _kth_value(self, position):
         """V at sorted position `position` (only reached when no point fails)."""

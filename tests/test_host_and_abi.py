@@ -141,8 +141,8 @@ def _pack_factor(linv):
 
 
 def _emulate_tile(wpack, M, K):
-    """Replays gp_tile_kernel's loop structure and fragment addressing (8 warps, panels of
-    256 rows/cols, bottom-up row-block dealing, per-q k-step limits) on the host; returns
+    """Replays gp_tile_kernel's loop structure and fragment addressing (8 warps x 4 row blocks,
+    panels of 256 rows/cols, bottom-up row-block dealing, per-q k-step limits) on the host; returns
     a = W k [M_pad, P] accumulated exactly where the kernel accumulates it."""
     nrb, nk4 = (M + 7) // 8, (M + 3) // 4
     npan = (nrb + 31) // 32
@@ -153,9 +153,9 @@ def _emulate_tile(wpack, M, K):
     lanes = np.arange(32)
     for ip in range(npan):
         pbeg, pend = 32 * ip, min(32 * ip + 32, nrb)
-        for warp in range(8):
+        for wslot in range(8):
             for q in range(4):
-                b = pend - 1 - warp - 8 * (3 - q)
+                b = pend - 1 - wslot - 8 * (3 - q)
                 if b < pbeg:
                     continue
                 for jp in range(ip + 1):
