@@ -106,22 +106,23 @@ SLB_DEV void dmma884(double& c0, double& c1, double a, double b) {
 template <int Q0>
 SLB_DEV void mma_run(double (&acc)[RQ][NB][2], const double* const (&ap)[RQ], int k0, int k1,
                      const double* ks_lane) {
-    // W fragments are prefetched three k-steps ahead (L2 latency under load ~1-2 k-steps).
-    double a0[RQ], a1[RQ], a2[RQ];
+    // W fragments are prefetched PF k-steps ahead in a register ring (L2 latency under load
+    // is 1-2 k-steps; it grows when L2 was just swept by another kernel).
+    constexpr int PF = 3;
+    double ar[PF][RQ];
     const int k1m = k1 - 1;
-    const int kn1 = min(k0 + 1, k1m), kn2 = min(k0 + 2, k1m);
 #pragma unroll
-    for (int q = Q0; q < RQ; ++q) {
-        a0[q] = ldg_stream(ap[q] + k0 * 32);
-        a1[q] = ldg_stream(ap[q] + kn1 * 32);
-        a2[q] = ldg_stream(ap[q] + kn2 * 32);
+    for (int d = 0; d < PF; ++d) {
+        const int kd = min(k0 + d, k1m);
+#pragma unroll
+        for (int q = Q0; q < RQ; ++q) ar[d][q] = ldg_stream(ap[q] + kd * 32);
     }
 #pragma unroll 1
     for (int kk = k0; kk < k1; ++kk) {
-        const int k3 = min(kk + 3, k1m);
-        double a3[RQ];
+        const int kp = min(kk + PF, k1m);
+        double an[RQ];
 #pragma unroll
-        for (int q = Q0; q < RQ; ++q) a3[q] = ldg_stream(ap[q] + k3 * 32);
+        for (int q = Q0; q < RQ; ++q) an[q] = ldg_stream(ap[q] + kp * 32);
         const double* kb = ks_lane + kk * (4 * KSTR);
         double b[NB];
 #pragma unroll
@@ -129,10 +130,14 @@ SLB_DEV void mma_run(double (&acc)[RQ][NB][2], const double* const (&ap)[RQ], in
 #pragma unroll
         for (int q = Q0; q < RQ; ++q) {
 #pragma unroll
-            for (int nb = 0; nb < NB; ++nb) dmma884(acc[q][nb][0], acc[q][nb][1], a0[q], b[nb]);
+            for (int nb = 0; nb < NB; ++nb) dmma884(acc[q][nb][0], acc[q][nb][1], ar[0][q], b[nb]);
         }
 #pragma unroll
-        for (int q = Q0; q < RQ; ++q) { a0[q] = a1[q]; a1[q] = a2[q]; a2[q] = a3[q]; }
+        for (int q = Q0; q < RQ; ++q) {
+#pragma unroll
+            for (int d = 0; d + 1 < PF; ++d) ar[d][q] = ar[d + 1][q];
+            ar[PF - 1][q] = an[q];
+        }
     }
 }
 

@@ -45,7 +45,9 @@ if "--phases" in sys.argv:
         print(label, "| kernel span ms %.3f" % ((t[:, :, 5].max() - t[:, :, 4].min()) * 1e-6),
               "| SM MHz by tile start order: first 148 %.0f, middle %.0f, last 148 %.0f"
               % (mhz[order[:148]].mean(), mhz[order[400:600]].mean(), mhz[order[-148:]].mean()),
-              "| cycles/tile %.0f" % cyc.mean())
+              "| cycles/tile %.0f" % cyc.mean(),
+              "| by start decile", [int(cyc[order[i * len(order) // 10:(i + 1) * len(order) // 10]].mean() / 1000)
+                                    for i in range(10)])
     print("per-tile cycles, mean over tiles, per warp: [gen, mma, epi, total]")
     print(np.round(t.mean(axis=0)[:, :4]).astype(int))
 
