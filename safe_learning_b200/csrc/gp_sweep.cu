@@ -68,35 +68,6 @@ SLB_DEV double ldg_stream(const double* p) {
     return v;
 }
 
-// exp(x) for x <= 0, <= 1 ulp (checked against glibc on 2e7 points, tools/exp_neg_check.c):
-// Cody-Waite reduction x = k ln2 + r, |r| <= ln2/2, degree-13 Taylor polynomial, 2^k by exponent
-// add.  Branch-free so four evaluations interleave in the k-row generation loop; anything
-// below exp(-700) flushes to 0 (it only ever multiplies finite L^-1 entries).
-SLB_DEV double exp_neg(double x) {
-    const double MAGIC = 6755399441055744.0;             // 1.5 * 2^52
-    const double t = fma(x, 1.4426950408889634074, MAGIC);
-    const int k = __double2loint(t);
-    const double kd = t - MAGIC;
-    double r = fma(kd, -6.93147180369123816490e-01, x);
-    r = fma(kd, -1.90821492927058770002e-10, r);
-    double p = 1.0 / 6227020800.0;
-    p = fma(p, r, 1.0 / 479001600.0);
-    p = fma(p, r, 1.0 / 39916800.0);
-    p = fma(p, r, 1.0 / 3628800.0);
-    p = fma(p, r, 1.0 / 362880.0);
-    p = fma(p, r, 1.0 / 40320.0);
-    p = fma(p, r, 1.0 / 5040.0);
-    p = fma(p, r, 1.0 / 720.0);
-    p = fma(p, r, 1.0 / 120.0);
-    p = fma(p, r, 1.0 / 24.0);
-    p = fma(p, r, 1.0 / 6.0);
-    p = fma(p, r, 0.5);
-    p = fma(p, r, 1.0);
-    p = fma(p, r, 1.0);
-    p = __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));
-    return x < -700.0 ? 0.0 : p;
-}
-
 SLB_DEV void dmma884(double& c0, double& c1, double a, double b) {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
                  : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
@@ -222,10 +193,11 @@ gp_tile_kernel(const __grid_constant__ slb_sweep cfg, const gp_args a) {
         double zs[DIN];
 #pragma unroll
         for (int c = 0; c < DIN; ++c) zs[c] = zraw[c * TP + p_gen] / F.lengthscales[c];
-        if (tid < TP) {
-#pragma unroll
-            for (int r = 0; r < NRED; ++r) tot[r * TP + tid] = 0.0;
-        }
+        // red[warp][col][qty] holds THIS warp's running partial sums over its row blocks of all
+        // panels of the factor; only the owning warp touches it, so the panel epilogues need no
+        // barrier and warps that finish a triangular panel early move straight on.
+        for (int i = lane; i < TP * NRED; i += 32) red[warp * TP * NRED + i] = 0.0;
+        __syncwarp();
         int resident = -1;
 
         for (int ip = 0; ip < npan; ++ip) {
@@ -322,23 +294,26 @@ gp_tile_kernel(const __grid_constant__ slb_sweep cfg, const gp_args a) {
                         v += __shfl_xor_sync(0xffffffffu, v, 4);
                         v += __shfl_xor_sync(0xffffffffu, v, 8);
                         v += __shfl_xor_sync(0xffffffffu, v, 16);
-                        if (lane < 4) red[(warp * TP + nb * 8 + 2 * lane + e) * NRED + qty] = v;
+                        if (lane < 4) red[(warp * TP + nb * 8 + 2 * lane + e) * NRED + qty] += v;
                     }
                 }
                 ++qty;
             }
-            __syncthreads();
-            if (tid < TP) {
-                for (int r = 0; r < qty; ++r) {
-                    double s = 0.0;
-#pragma unroll
-                    for (int w = 0; w < NW; ++w) s += red[(w * TP + tid) * NRED + r];
-                    tot[r * TP + tid] += s;
-                }
-            }
-            __syncthreads();
+            __syncwarp();
             if (TIMING) t_epi += clock64() - t_mark;
         }
+
+        // ---- cross-warp reduction in a fixed order (deterministic)
+        __syncthreads();
+        if (tid < TP) {
+            for (int r = 0; r < NRED; ++r) {
+                double s = 0.0;
+#pragma unroll
+                for (int w = 0; w < NW; ++w) s += red[(w * TP + tid) * NRED + r];
+                tot[r * TP + tid] = s;
+            }
+        }
+        __syncthreads();
 
         // ---- factor epilogue: mean and error bound of the outputs on this factor
         if (tid < TP) {

@@ -278,55 +278,94 @@ apply_prefix_kernel(const double* __restrict__ values, const uint8_t* __restrict
 }
 
 // ---- Bellman sweep ------------------------------------------------------------------------
+// One factor with NO outputs on it: NO is a compile-time constant so the running dot products
+// stay in registers (a runtime-bounded loop over outputs would push them to local memory).
+template <int DIN, int NO>
+SLB_DEV void gp_mean_factor(const slb_gp_stack& gp, const slb_gp_factor& F, const int* outs,
+                            const double* z, double* mu) {
+    double zs[DIN];
+#pragma unroll
+    for (int c = 0; c < DIN; ++c) zs[c] = z[c] / F.lengthscales[c];
+    double dot[NO];
+    const double* gam[NO];
+#pragma unroll
+    for (int q = 0; q < NO; ++q) { dot[q] = 0.0; gam[q] = gp.outputs[outs[q]].gamma; }
+    const double* __restrict__ Xs = F.Xs;
+    const int M = F.M;
+    // 4 independent exp chains per thread (the loop is bound by the fp64 pipe through exp)
+    for (int j0 = 0; j0 < M; j0 += 4) {
+        double t2[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int j = min(j0 + u, M - 1);
+            const double* xr = Xs + (size_t)j * DIN;
+            double acc = 0.0;
+#pragma unroll
+            for (int c = 0; c < DIN; ++c) { const double df = zs[c] - __ldg(xr + c); acc = fma(df, df, acc); }
+            t2[u] = acc;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            double k = F.variance * exp_neg(-0.5 * t2[u]);
+            if (j0 + u >= M) k = 0.0;
+            const int j = min(j0 + u, M - 1);
+#pragma unroll
+            for (int q = 0; q < NO; ++q) dot[q] = fma(k, __ldg(gam[q] + j), dot[q]);
+        }
+    }
+    const double s2 = f64mul(F.scale, F.scale);
+#pragma unroll
+    for (int q = 0; q < NO; ++q) {
+        const slb_gp_output& G = gp.outputs[outs[q]];
+        double mx = 0.0;
+        if (G.prior_mean != nullptr) {
+            mx = f64mul(z[0], G.prior_mean[0]);
+#pragma unroll
+            for (int c = 1; c < DIN; ++c) mx = f64add(mx, f64mul(z[c], G.prior_mean[c]));
+            mx = f64mul(F.scale, mx);
+        }
+        mu[outs[q]] = f64add(f64mul(s2, dot[q]), mx) / F.scale;
+    }
+}
+
 // mean of the GP stack at z (mean only, reinforcement_learning.py:98-99):
 //   mean_o = (scale^2 sum_j k_j gamma_o,j + scale m_o(z)) / scale,  gamma = L^-T alpha,
 // which equals a^T alpha of functions.py:441-442 up to rounding.
+template <int DIN>
 SLB_DEV void gp_mean_only(const slb_gp_stack& gp, const double* z, double* mu) {
-    const int din = gp.input_dim;
     for (int f = 0; f < gp.num_factors; ++f) {
         const slb_gp_factor& F = gp.factors[f];
-        double zs[SLB_MAX_IN];
-        for (int c = 0; c < din; ++c) zs[c] = z[c] / F.lengthscales[c];
-        double dot[SLB_MAX_OUT];
-        const double* gam[SLB_MAX_OUT];
         int outs[SLB_MAX_OUT];
         int no = 0;
         for (int o = 0; o < gp.num_outputs; ++o)
-            if (gp.outputs[o].factor == f) { outs[no] = o; gam[no] = gp.outputs[o].gamma; dot[no] = 0.0; ++no; }
-        for (int j = 0; j < F.M; ++j) {
-            const double* xr = F.Xs + (size_t)j * din;
-            double t2 = 0.0;
-            for (int c = 0; c < din; ++c) { const double df = zs[c] - __ldg(xr + c); t2 = fma(df, df, t2); }
-            const double k = F.variance * exp(-0.5 * t2);
-            for (int q = 0; q < no; ++q) dot[q] = fma(k, __ldg(gam[q] + j), dot[q]);
-        }
-        const double s2 = f64mul(F.scale, F.scale);
-        for (int q = 0; q < no; ++q) {
-            const slb_gp_output& G = gp.outputs[outs[q]];
-            double mx = 0.0;
-            if (G.prior_mean != nullptr) {
-                mx = f64mul(z[0], G.prior_mean[0]);
-                for (int c = 1; c < din; ++c) mx = f64add(mx, f64mul(z[c], G.prior_mean[c]));
-                mx = f64mul(F.scale, mx);
-            }
-            mu[outs[q]] = f64add(f64mul(s2, dot[q]), mx) / F.scale;
+            if (gp.outputs[o].factor == f) outs[no++] = o;
+        switch (no) {
+        case 1: gp_mean_factor<DIN, 1>(gp, F, outs, z, mu); break;
+        case 2: gp_mean_factor<DIN, 2>(gp, F, outs, z, mu); break;
+        case 3: gp_mean_factor<DIN, 3>(gp, F, outs, z, mu); break;
+        case 4: gp_mean_factor<DIN, 4>(gp, F, outs, z, mu); break;
+        case 5: gp_mean_factor<DIN, 5>(gp, F, outs, z, mu); break;
+        case 6: gp_mean_factor<DIN, 6>(gp, F, outs, z, mu); break;
+        default: break;
         }
     }
 }
 
+template <int DIN>
 SLB_DEV double bellman_value(const slb_bellman& cfg, const double* x, const double* u, int m) {
     const int d = cfg.grid.ndim;
     double z[SLB_MAX_IN], mu[SLB_MAX_OUT], r[SLB_MAX_OUT], v[SLB_MAX_OUT];
     for (int c = 0; c < d; ++c) z[c] = x[c];
     for (int c = 0; c < m; ++c) z[d + c] = u[c];
-    if (cfg.gp.num_outputs > 0) gp_mean_only(cfg.gp, z, mu);
+    if (cfg.gp.num_outputs > 0) gp_mean_only<DIN>(cfg.gp, z, mu);
     else eval_fn(cfg.dynamics, z, mu);
     eval_fn(cfg.reward, z, r);                               // :95
     eval_fn(cfg.value, mu, v);                               // :101
     return f64add(r[0], f64mul(cfg.gamma, v[0]));                // :104
 }
 
-__global__ void __launch_bounds__(LT)
+template <int DIN>
+__global__ void __launch_bounds__(LT, 2)
 bellman_kernel(const __grid_constant__ slb_bellman cfg, int64_t idx_begin, int64_t n,
                double* __restrict__ out) {
     const int64_t i = (int64_t)blockIdx.x * LT + threadIdx.x;
@@ -340,10 +379,11 @@ bellman_kernel(const __grid_constant__ slb_bellman cfg, int64_t idx_begin, int64
     } else {
         m = eval_fn(cfg.policy, x, u);
     }
-    out[i] = bellman_value(cfg, x, u, m);
+    out[i] = bellman_value<DIN>(cfg, x, u, m);
 }
 
-__global__ void __launch_bounds__(LT)
+template <int DIN>
+__global__ void __launch_bounds__(LT, 2)
 bellman_argmax_kernel(const __grid_constant__ slb_bellman cfg, int64_t idx_begin, int64_t n,
                       const double* __restrict__ actions, int n_actions, int m,
                       const double* __restrict__ constraint, int32_t* __restrict__ best,
@@ -356,7 +396,7 @@ bellman_argmax_kernel(const __grid_constant__ slb_bellman cfg, int64_t idx_begin
     double vmax = 0.0;
     for (int a = 0; a < n_actions; ++a) {
         for (int c = 0; c < m; ++c) u[c] = actions[a * m + c];
-        double v = bellman_value(cfg, x, u, m);
+        double v = bellman_value<DIN>(cfg, x, u, m);
         if (constraint != nullptr && constraint[(int64_t)a * n + i] < 0.0) v = -INFINITY;  // :272-275
         if (a == 0 || v > vmax) { vmax = v; arg = a; }      // np.argmax: first maximum (:278)
     }
@@ -544,7 +584,17 @@ int slb_bellman_sweep(void* stream, const slb_bellman* cfg, int64_t idx_begin, i
     const int64_t n = idx_end - idx_begin;
     if (n == 0) return 0;
     SLB_CHECK(out_dev != nullptr, "slb_bellman_sweep: null output");
-    bellman_kernel<<<blocks_for(n), LT, 0, (cudaStream_t)stream>>>(*cfg, idx_begin, n, out_dev);
+    const int din = cfg->grid.ndim + m;
+#define SLB_BELLMAN_CASE(D) \
+    case D: bellman_kernel<D><<<blocks_for(n), LT, 0, (cudaStream_t)stream>>>(*cfg, idx_begin, n, out_dev); break;
+    switch (din) {
+        SLB_BELLMAN_CASE(1) SLB_BELLMAN_CASE(2) SLB_BELLMAN_CASE(3) SLB_BELLMAN_CASE(4)
+        SLB_BELLMAN_CASE(5) SLB_BELLMAN_CASE(6)
+    default:
+        slb_set_error("bellman: state+action dimension %d not compiled (1..6)", din);
+        return 1;
+    }
+#undef SLB_BELLMAN_CASE
     SLB_LAUNCH_CHECK();
     return 0;
 }
@@ -561,8 +611,18 @@ int slb_bellman_argmax(void* stream, const slb_bellman* cfg, int64_t idx_begin, 
     const int64_t n = idx_end - idx_begin;
     if (n == 0) return 0;
     SLB_CHECK(best_dev != nullptr, "slb_bellman_argmax: null output");
-    bellman_argmax_kernel<<<blocks_for(n), LT, 0, (cudaStream_t)stream>>>(
-        *cfg, idx_begin, n, actions_dev, n_actions, m, constraint_dev, best_dev, best_value_dev);
+    const int din = cfg->grid.ndim + m;
+#define SLB_ARGMAX_CASE(D)                                                               \
+    case D: bellman_argmax_kernel<D><<<blocks_for(n), LT, 0, (cudaStream_t)stream>>>(  \
+        *cfg, idx_begin, n, actions_dev, n_actions, m, constraint_dev, best_dev, best_value_dev); break;
+    switch (din) {
+        SLB_ARGMAX_CASE(1) SLB_ARGMAX_CASE(2) SLB_ARGMAX_CASE(3) SLB_ARGMAX_CASE(4)
+        SLB_ARGMAX_CASE(5) SLB_ARGMAX_CASE(6)
+    default:
+        slb_set_error("bellman: state+action dimension %d not compiled (1..6)", din);
+        return 1;
+    }
+#undef SLB_ARGMAX_CASE
     SLB_LAUNCH_CHECK();
     return 0;
 }

@@ -1,0 +1,118 @@
+"""Secondary measurements (not the bench.py headline): one JSON line each.
+
+  bellman   C3: PolicyIteration.value_iteration on a 512x512 grid, GP-mean dynamics M=500
+  det       deterministic-dynamics Lyapunov sweep (true pendulum plant) on large grids: the
+            HBM-side variant of the path
+  c5        resolution x M sweep of the GP Lyapunov sweep kernel (C5), single GPU
+  shared    C2 with shared hyper-parameters (one Cholesky factor for both outputs)
+
+    python tools/bench_extra.py [bellman] [det] [c5] [shared]
+"""
+import json
+import os
+import sys
+
+import numpy as np
+import scipy.linalg
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+import bench_workloads as W  # noqa: E402
+import safe_learning_b200 as sl  # noqa: E402
+from bench import algorithmic_flops_per_point  # noqa: E402
+
+PEAK_TF, HBM_GBS = 37.1, 6483.3
+try:
+    PEAK_TF = json.load(open(os.path.join(ROOT, "profiles", "r01_fp64_peaks.json")))["dmma_tflops_w8_acc8"]
+    HBM_GBS = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+except Exception:
+    pass
+
+
+def timed(fn, steps=10, warmup=3):
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    ev = []
+    for _ in range(steps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        ev.append((e0, e1))
+    torch.cuda.synchronize()
+    return float(np.median([a.elapsed_time(b) for a, b in ev]))
+
+
+def bellman():
+    par = W.make_pendulum(num_points=8, M=500)
+    grid = sl.GridWorld(par["limits"], 512)
+    _, dyn = W._build(sl, par, "product")
+    policy = sl.Saturation(sl.LinearSystem(-par["K"]), -1., 1.)
+    reward = sl.QuadraticFunction(-scipy.linalg.block_diag(np.diag([1., 2.]), 1.2 * np.eye(1)))
+    value = sl.Triangulation(grid, np.zeros((grid.nindex, 1)), project=True)
+    rl = sl.PolicyIteration(policy, dyn, reward, value, gamma=0.98)
+    ms = timed(rl.value_iteration, steps=10)
+    n = grid.nindex
+    exps = 2 * 500
+    print(json.dumps({"bench": "bellman_value_iteration", "grid": "512x512", "M": 500,
+                      "ms_per_sweep": ms, "state_updates_per_s": n / (ms * 1e-3),
+                      "exp_per_s": n * exps / (ms * 1e-3),
+                      "note": "mean-only GP dynamics (2 x 500 fp64 exp per state), Triangulation V "
+                              "gather, Jacobi; includes max|dV| reduction and table swap"}))
+
+
+def det():
+    for num in (1024, 4096):
+        par = W.make_pendulum(num_points=num, M=8)
+        lyap = W.build_product(par, deterministic=True)
+        ms = timed(lyap.compute_negative, steps=10)
+        n = lyap.discretization.nindex
+        ms_full = timed(lyap.update_safe_set, steps=5)
+        print(json.dumps({"bench": "deterministic_sweep", "grid": "%dx%d" % (num, num),
+                          "kernel_ms": ms, "points_per_s": n / (ms * 1e-3),
+                          "hbm_algorithmic_gbs": n * 17 / (ms * 1e-3) * 1e-9,
+                          "hbm_frac_of_measured": n * 17 / (ms * 1e-3) * 1e-9 / HBM_GBS,
+                          "update_safe_set_ms": ms_full,
+                          "update_safe_set_points_per_s": n / (ms_full * 1e-3),
+                          "note": "pendulum plant: 10 Euler sub-steps with fp64 sin per point -> "
+                                  "fp64-CUDA-core bound, not HBM bound; 17 algorithmic B/pt"}))
+
+
+def c5():
+    for num, M in ((128, 100), (256, 100), (256, 200), (256, 500), (512, 500), (1024, 500),
+                   (256, 1000), (256, 2000), (128, 5000)):
+        par = W.make_pendulum(num_points=num, M=M)
+        lyap = W.build_product(par)
+        ms = timed(lyap.compute_negative, steps=5, warmup=2)
+        n = lyap.discretization.nindex
+        fl = algorithmic_flops_per_point(M, 3, 2, 2)
+        print(json.dumps({"bench": "c5_gp_sweep", "grid": "%dx%d" % (num, num), "M": M,
+                          "kernel_ms": ms, "points_per_s": n / (ms * 1e-3),
+                          "tflops": fl * n / (ms * 1e-3) * 1e-12,
+                          "frac_of_fp64_peak": fl * n / (ms * 1e-3) * 1e-12 / PEAK_TF}))
+        del lyap
+        torch.cuda.empty_cache()
+
+
+def shared():
+    par = W.make_pendulum(num_points=256, M=500, shared_hypers=True)
+    lyap = W.build_product(par)
+    ms = timed(lyap.compute_negative, steps=10)
+    ms_full = timed(lyap.update_safe_set, steps=10)
+    n = lyap.discretization.nindex
+    fl = algorithmic_flops_per_point(500, 3, 1, 2)
+    print(json.dumps({"bench": "c2_shared_factor", "grid": "256x256", "M": 500, "factors": 1,
+                      "kernel_ms": ms, "points_per_s_kernel": n / (ms * 1e-3),
+                      "update_safe_set_ms": ms_full, "points_per_s": n / (ms_full * 1e-3),
+                      "tflops": fl * n / (ms * 1e-3) * 1e-12,
+                      "frac_of_fp64_peak": fl * n / (ms * 1e-3) * 1e-12 / PEAK_TF}))
+
+
+if __name__ == "__main__":
+    which = sys.argv[1:] or ["bellman", "det", "c5", "shared"]
+    for name in which:
+        globals()[name]()
