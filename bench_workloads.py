@@ -122,6 +122,72 @@ def make_toy_1d(num_points=101, M=50, seed=0):
                 L_dyn=0.25, L_v=1.0)
 
 
+def _cartpole_step(sa, m, M, L, b, dt, state_norm, action_norm):
+    g = 9.81
+    s = sa[:, :4] * np.asarray(state_norm)
+    u = sa[:, 4:5] * np.asarray(action_norm)
+    h = dt / 10
+    for _ in range(10):
+        th, v, om = s[:, 1:2], s[:, 2:3], s[:, 3:4]
+        det = L * (M + m * np.square(np.sin(th)))
+        v_dot = (u - m * L * np.square(om) * np.sin(th) - b * om * np.cos(th)
+                 + 0.5 * m * g * L * np.sin(2 * th)) * L / det
+        om_dot = (u * np.cos(th) - 0.5 * m * L * np.square(om) * np.sin(2 * th)
+                  - b * (m + M) * om / (m * L) + (m + M) * g * np.sin(th)) / det
+        s = s + h * np.concatenate((v, om, v_dot, om_dot), axis=1)
+    return s / np.asarray(state_norm)
+
+
+def make_cartpole(num_points=16, M=200, seed=4, tau_scale=1.0):
+    """Config C4: 4-D cart-pole (reinforcement_learning_cartpole.ipynb cell 7 constants), four
+    stacked RBF GPs on [x, u], V = LyapunovNetwork(4, [64, 64, 64], tanh) with fixed-seed
+    weights, saturated LQR policy, scalar Lipschitz constants."""
+    m, Mc, L, b, dt = 0.175, 1.732, 0.28, 0.01, 0.01
+    g = 9.81
+    x_max, theta_max, v_max, omega_max = 0.5, np.deg2rad(20), 2.0, np.sqrt(g / L)
+    u_max = (m + Mc) * (x_max * 10)
+    state_norm, action_norm = (x_max, theta_max, v_max, omega_max), (u_max,)
+    A = np.array([[0, 0, 1, 0], [0, 0, 0, 1], [0, g * m / Mc, 0, -b / (Mc * L)],
+                  [0, g * (m + Mc) / (L * Mc), 0, -b * (m + Mc) / (m * Mc * L ** 2)]])
+    B = np.array([0, 0, 1 / Mc, 1 / (Mc * L)]).reshape((-1, 1))
+    Tx, Tu = np.diag(state_norm), np.diag(action_norm)
+    A = np.linalg.multi_dot((np.linalg.inv(Tx), A, Tx))
+    B = np.linalg.multi_dot((np.linalg.inv(Tx), B, Tu))
+    Ad, Bd, _, _, _ = scipy.signal.cont2discrete((A, B, 0, 0), dt, method="zoh")
+    K, P = _dlqr(Ad, Bd, np.diag([0.1, 0.1, 0.1, 0.1]), 0.1 * np.eye(1))
+    rng = np.random.default_rng(seed)
+    X = rng.uniform(-1, 1, size=(M, 5))
+    Y = _cartpole_step(X, m, Mc, L, b, dt, state_norm, action_norm)
+    Y = Y + 1e-3 * rng.standard_normal(Y.shape)
+    prior_rows = np.hstack((Ad, Bd))
+    resid = Y - X.dot(prior_rows.T)
+    variances = [float(max(v, 1e-6)) for v in resid.var(axis=0)]
+    lengthscales = [[1.5, 1.2, 1.5, 1.3, 2.0], [1.4, 1.0, 1.5, 1.2, 1.8],
+                    [1.5, 1.1, 1.4, 1.3, 1.9], [1.3, 1.0, 1.5, 1.1, 1.7]]
+    limits = np.array([[-1., 1.]] * 4)
+    num = np.broadcast_to(num_points, 4).astype(int)
+    unit = (limits[:, 1] - limits[:, 0]) / (num - 1)
+    axes = [np.arange(n) * u + lo for n, u, lo in zip(num, unit, limits[:, 0])]
+    mesh = np.meshgrid(*axes, indexing="ij")
+    pts = np.column_stack([mm.ravel() for mm in mesh])
+    initial = np.linalg.norm(pts, ord=2, axis=1) <= 0.3
+    wrng = np.random.default_rng(123)
+    weights, din = [], 4
+    for width in (64, 64, 64):
+        hid = int(np.ceil((din + 1) / 2))
+        lim0, lim1 = np.sqrt(6.0 / (hid + din)), np.sqrt(6.0 / (max(width - din, 1) + din))
+        w0 = wrng.uniform(-lim0, lim0, (hid, din))
+        w1 = wrng.uniform(-lim1, lim1, (width - din, din)) if width > din else None
+        weights.append((w0, w1))
+        din = width
+    return dict(name="cartpole%d^4_M%d" % (num[0], M), limits=limits, num_points=num,
+                tau=float(np.sum(unit) / 2) * tau_scale, X=X, Y=Y, variances=variances,
+                lengthscales=lengthscales, noise_variance=1e-6, beta=2.0, scale=1.0,
+                prior_rows=prior_rows, K=K, P=P, initial=initial, nn_weights=weights,
+                L_dyn=float(np.linalg.norm(Ad, 1) + np.linalg.norm(Bd, 1) * np.linalg.norm(K, 1)),
+                L_v=1.0)
+
+
 # --------------------------------------------------------------------------- builders
 def _build(ns, par, kind):
     """ns: module namespace providing GridWorld, RBF, GPRCached, ... (product or oracle)."""
@@ -166,10 +232,23 @@ def _toy_objects(ns, par, kind):
                        initial_set=par["initial"])
 
 
+def _cartpole_objects(ns, par, kind):
+    grid, dynamics = _build(ns, par, kind)
+    policy = ns.Saturation(ns.LinearSystem(-par["K"]), -1., 1.)
+    if kind == "oracle":
+        lyap_fun = ns.LyapunovNetwork(4, [64, 64, 64], [np.tanh] * 3, par["nn_weights"])
+    else:
+        lyap_fun = ns.LyapunovNetwork(4, [64, 64, 64], ["tanh"] * 3, weights=par["nn_weights"])
+    return ns.Lyapunov(grid, lyap_fun, dynamics, par["L_dyn"], par["L_v"], par["tau"], policy,
+                       initial_set=par["initial"])
+
+
 def build_product(par, deterministic=False):
     import safe_learning_b200 as ns
     if par["name"].startswith("toy1d"):
         return _toy_objects(ns, par, "product")
+    if par["name"].startswith("cartpole"):
+        return _cartpole_objects(ns, par, "product")
     return _pendulum_objects(ns, par, "product", deterministic)
 
 
@@ -177,4 +256,6 @@ def build_oracle(par, deterministic=False):
     import oracle as ns
     if par["name"].startswith("toy1d"):
         return _toy_objects(ns, par, "oracle")
+    if par["name"].startswith("cartpole"):
+        return _cartpole_objects(ns, par, "oracle")
     return _pendulum_objects(ns, par, "oracle", deterministic)

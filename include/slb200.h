@@ -74,7 +74,9 @@ typedef struct slb_function {
     double  out_scale;
     double  lower, upper;       /* saturation bounds                                   */
     double  cparams[24];        /* CONSTANT: value; PENDULUM/CARTPOLE: plant constants
-                                   (see safe_learning_b200/functions.py); NN: layer dims */
+                                   (see safe_learning_b200/functions.py); LYAPUNOV_NN: [0] layers,
+                                   [1+i] width of layer i (<= 64), [9+i] activation (0 tanh,
+                                   1 relu, 2 identity) */
     const double*  matrix;      /* LINEAR [out,in]; QUADRATIC [in,in]; TRIANGULATION
                                    vertex values [nindex,out]; LYAPUNOV_NN packed kernels */
     const double*  hyperplanes; /* TRIANGULATION [nsimplex, d, d]  (functions.py:1090-1101) */

@@ -28,6 +28,7 @@ __all__ = [
     "RBF", "LinearMean", "GPRCached", "GaussianProcess", "FunctionStack", "Triangulation",
     "InvertedPendulum", "CartPole", "LyapunovNetwork", "Lyapunov", "PolicyIteration",
     "batchify", "dlqr", "hstack_inputs", "stable_value_order", "prefix_rule",
+    "perturb_actions", "get_safe_sample", "unique_rows",
 ]
 
 
@@ -865,3 +866,54 @@ class PolicyIteration(object):
         best = action_space[np.argmax(values, axis=1)]
         self.policy.parameters = best
         return best
+
+
+# --------------------------------------------------------------------------- safe sampling
+def unique_rows(array):
+    """``utilities.py:496-516``."""
+    array = np.ascontiguousarray(array)
+    dtype = np.dtype((np.void, array.dtype.itemsize * array.shape[1]))
+    _, idx = np.unique(array.view(dtype=dtype), return_index=True)
+    return array[idx]
+
+
+def perturb_actions(states, actions, perturbations, limits=None):
+    """``lyapunov.py:609-651``."""
+    num_states, state_dim = states.shape
+    states_new = np.repeat(states, len(perturbations), axis=0)
+    actions_new = (np.repeat(actions, len(perturbations), axis=0)
+                   + np.tile(perturbations, (num_states, 1)))
+    state_actions = np.column_stack((states_new, actions_new))
+    if limits is not None:
+        limits = np.asarray(limits)
+        acts = state_actions[:, state_dim:]
+        np.clip(acts, limits[:, 0], limits[:, 1], out=acts)
+        state_actions = unique_rows(state_actions)
+    return state_actions
+
+
+def get_safe_sample(lyapunov, perturbations, limits=None, positive=False, safe_states=None):
+    """``lyapunov.py:657-797`` with the random sub-sampling factored out (pass ``safe_states``
+    to evaluate a fixed candidate set).  Returns (state_action [1, n+m], bound)."""
+    disc = lyapunov.discretization
+    if safe_states is None:
+        safe_states = disc.index_to_state(np.where(lyapunov.safe_set)[0])
+    safe_actions = lyapunov.policy(safe_states)
+    state_actions = perturb_actions(safe_states, safe_actions, perturbations, limits)
+    mean, std = lyapunov.dynamics(state_actions)
+    bound = np.sum(std, axis=1, keepdims=True)
+    lv = lyapunov.lipschitz_lyapunov(mean)
+    error = np.sum(lv * std, axis=1, keepdims=True)
+    future = lyapunov.lyapunov_function(mean) + error
+    maps_inside = (future < lyapunov.c_max)[:, 0]
+    if not positive:
+        maps_inside &= lyapunov.safe_set[disc.state_to_index(mean)]
+    bound_safe = bound[maps_inside]
+    if len(bound_safe) == 0:
+        state_actions = perturb_actions(safe_states, safe_actions, np.array([[0.]]), limits)
+        _, std = lyapunov.dynamics(state_actions)
+        bound = np.sum(std, axis=1, keepdims=True)
+        max_id = int(np.argmax(bound))
+        return state_actions[[max_id]], bound[max_id].squeeze()
+    max_id = int(np.argmax(bound_safe))
+    return state_actions[maps_inside, :][[max_id]], bound_safe[max_id].squeeze()

@@ -234,6 +234,35 @@ SLB_DEV void eval_cartpole(const slb_function& f, const double* in, double* out)
     for (int c = 0; c < 4; ++c) out[c] = s[c];
 }
 
+// ---- LyapunovNetwork (examples/utilities.py:85-104): net <- act(net . kernel_i^T), V = |net|^2.
+// cparams: [0] number of layers, [1 + i] output width of layer i, [9 + i] activation of layer i
+// (0 tanh, 1 relu, 2 identity); `matrix` holds the layer kernels [out_i, in_i] back to back
+// (kernel_i = [W^T W + eps I; W_extra], built on the host).  Widths up to SLB_NN_MAX_WIDTH.
+#define SLB_NN_MAX_WIDTH 64
+SLB_DEV void eval_lyapunov_nn(const slb_function& f, const double* in, double* out) {
+    double h[SLB_NN_MAX_WIDTH], g[SLB_NN_MAX_WIDTH];
+    int width = f.in_dim;
+    for (int k = 0; k < width; ++k) h[k] = in[k];
+    const double* K = f.matrix;
+    const int layers = (int)f.cparams[0];
+    for (int l = 0; l < layers; ++l) {
+        const int od = (int)f.cparams[1 + l];
+        const int act = (int)f.cparams[9 + l];
+        for (int o = 0; o < od; ++o) {
+            const double* row = K + (size_t)o * width;
+            double acc = f64mul(h[0], row[0]);
+            for (int k = 1; k < width; ++k) acc = f64add(acc, f64mul(h[k], row[k]));
+            g[o] = act == 0 ? tanh(acc) : (act == 1 ? fmax(acc, 0.0) : acc);
+        }
+        K += (size_t)od * width;
+        width = od;
+        for (int k = 0; k < width; ++k) h[k] = g[k];
+    }
+    double v = f64mul(h[0], h[0]);
+    for (int k = 1; k < width; ++k) v = f64add(v, f64mul(h[k], h[k]));
+    out[0] = v;
+}
+
 // Evaluate a fused function object. `in` has f.in_dim entries, `out` receives the result
 // columns; returns the number of columns (1 after NORM1).
 SLB_DEV int eval_fn(const slb_function& f, const double* in, double* out) {
@@ -271,6 +300,9 @@ SLB_DEV int eval_fn(const slb_function& f, const double* in, double* out) {
         break;
     case SLB_FN_CARTPOLE:
         eval_cartpole(f, in, out); od = 4;
+        break;
+    case SLB_FN_LYAPUNOV_NN:
+        eval_lyapunov_nn(f, in, out); od = 1;
         break;
     default:
         for (int o = 0; o < od; ++o) out[o] = __longlong_as_double(0x7ff8000000000000ll);

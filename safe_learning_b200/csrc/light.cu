@@ -71,6 +71,17 @@ int slb_validate_function(const slb_function* f, const char* what, int expect_in
     case SLB_FN_CARTPOLE:
         SLB_CHECK(f->in_dim == 5 && f->out_dim == 4, "%s: cart-pole must map 5 -> 4", what);
         break;
+    case SLB_FN_LYAPUNOV_NN: {
+        SLB_CHECK(f->matrix != nullptr, "%s: LyapunovNetwork without kernels", what);
+        const int layers = (int)f->cparams[0];
+        SLB_CHECK(layers >= 1 && layers <= 8, "%s: LyapunovNetwork with %d layers (1..8)", what, layers);
+        SLB_CHECK(f->in_dim >= 1 && f->in_dim <= SLB_MAX_IN && f->out_dim == 1,
+                  "%s: LyapunovNetwork maps <=%d inputs to 1 output", what, SLB_MAX_IN);
+        for (int l = 0; l < layers; ++l)
+            SLB_CHECK(f->cparams[1 + l] >= 1 && f->cparams[1 + l] <= 64,
+                      "%s: LyapunovNetwork layer %d width %g outside 1..64", what, l, f->cparams[1 + l]);
+        break;
+    }
     default:
         slb_set_error("%s: function kind %d is not implemented in this build", what, f->kind);
         return 1;
@@ -519,7 +530,7 @@ int slb_eval_function(void* stream, const slb_function* fn, const double* points
     if (n == 0) return 0;
     SLB_CHECK(points_dev && out_dev, "slb_eval_function: null buffer");
     int ncols = (fn->flags & SLB_FLAG_NORM1) ? 1 : fn->out_dim;
-    if (fn->kind == SLB_FN_QUADRATIC) ncols = 1;
+    if (fn->kind == SLB_FN_QUADRATIC || fn->kind == SLB_FN_LYAPUNOV_NN) ncols = 1;
     eval_function_kernel<<<blocks_for(n), LT, 0, (cudaStream_t)stream>>>(*fn, points_dev, n, out_dev,
                                                                         ncols);
     SLB_LAUNCH_CHECK();

@@ -30,7 +30,7 @@ __all__ = ["DimensionError", "GridWorld", "Function", "DeterministicFunction",
            "UncertainFunction", "ConstantFunction", "LinearSystem", "QuadraticFunction",
            "Saturation", "AbsFunction", "Norm1Function", "ScaledFunction", "Triangulation",
            "RBF", "Likelihood", "GPRCached", "GPR", "GaussianProcess", "FunctionStack",
-           "InvertedPendulum", "CartPole", "concatenate_inputs"]
+           "InvertedPendulum", "CartPole", "LyapunovNetwork", "concatenate_inputs"]
 
 
 class DimensionError(Exception):
@@ -618,6 +618,77 @@ class CartPole(DeterministicFunction):
         cp[0], cp[1], cp[2] = self.pendulum_mass, self.cart_mass, self.length
         cp[3], cp[4], cp[5] = self.rot_friction, self.gravity, self.dt / 10
         cp[15] = _pack_norm(cp, self.normalization, 4, 6)    # [6..9] Tx, [10] Tu, [11..14] 1/Tx
+        return d
+
+
+class LyapunovNetwork(DeterministicFunction):
+    """Positive-definite network ``V(x) = |phi(x)|^2`` (``examples/utilities.py:48-104``),
+    inference only: layer i applies ``act(net . [W_i^T W_i + eps I; W_i'']^T)``.
+
+    ``weights[i] = (W_posdef, W_extra or None)`` with the reference's shapes
+    (``[ceil((in+1)/2), in]`` and ``[out - in, in]``); when omitted they are drawn Xavier-uniform
+    from ``seed`` (the reference uses ``tf.contrib.layers.xavier_initializer``).  ``activations``
+    are 'tanh' | 'relu' | 'linear' (or ``numpy.tanh``).
+    """
+
+    _ACT = {"tanh": 0, "relu": 1, "linear": 2, "identity": 2}
+
+    def __init__(self, input_dim, layer_dims, activations, eps=1e-6, initializer=None,
+                 name="lyapunov_network", weights=None, seed=0):
+        super().__init__(name)
+        self.input_dim, self.output_dim = int(input_dim), 1
+        self.num_layers = len(layer_dims)
+        self.output_dims = [int(v) for v in layer_dims]
+        self.eps = eps
+        if self.output_dims[0] < self.input_dim:
+            raise ValueError("The first layer dimension must be at least the input dimension!")
+        if np.any(np.diff(self.output_dims) < 0):
+            raise ValueError("Each layer must maintain or increase the dimension of its input!")
+        if max(self.output_dims) > 64 or self.num_layers > 8:
+            raise DimensionError("LyapunovNetwork: at most 8 layers of width <= 64 are fused")
+        self.activations = []
+        for act in activations:
+            key = act if isinstance(act, str) else getattr(act, "__name__", "")
+            if key not in self._ACT:
+                raise NotImplementedError("activation %r is not fused (tanh/relu/linear)" % (act,))
+            self.activations.append(key)
+        self.hidden_dims = [int(np.ceil(((self.input_dim if i == 0 else self.output_dims[i - 1])
+                                         + 1) / 2)) for i in range(self.num_layers)]
+        if weights is None:
+            rng = np.random.default_rng(seed)
+            weights = []
+            for i in range(self.num_layers):
+                din = self.input_dim if i == 0 else self.output_dims[i - 1]
+                def xavier(rows, cols):
+                    lim = np.sqrt(6.0 / (rows + cols))
+                    return rng.uniform(-lim, lim, size=(rows, cols))
+                extra = self.output_dims[i] - din
+                weights.append((xavier(self.hidden_dims[i], din),
+                                xavier(extra, din) if extra > 0 else None))
+        self.weights = weights
+        self._kernel_dev = None
+
+    def kernels(self):
+        """Layer kernels ``[W^T W + eps I; W_extra]`` ([out_i, in_i])."""
+        out = []
+        for i, (w0, w1) in enumerate(self.weights):
+            din = self.input_dim if i == 0 else self.output_dims[i - 1]
+            k = w0.T.dot(w0) + self.eps * np.eye(din)
+            if w1 is not None:
+                k = np.concatenate([k, w1], axis=0)
+            out.append(k)
+        return out
+
+    def descriptor(self):
+        if self._kernel_dev is None:
+            self._kernel_dev = dev.to_device(np.concatenate([k.ravel() for k in self.kernels()]))
+        d = nat.SlbFunction()
+        d.kind, d.in_dim, d.out_dim = nat.FN_LYAPUNOV_NN, self.input_dim, 1
+        d.cparams[0] = self.num_layers
+        for i, (od, act) in enumerate(zip(self.output_dims, self.activations)):
+            d.cparams[1 + i] = od
+            d.cparams[9 + i] = self._ACT[act]
+        d.matrix = self._kernel_dev.data_ptr()
         return d
 
 

@@ -19,7 +19,83 @@ from . import _native as nat
 from .functions import (Function, FunctionStack, GaussianProcess, UncertainFunction, config,
                         concatenate_inputs)
 
-__all__ = ["Lyapunov", "combine_fail_keys", "combine_prefix_stats"]
+__all__ = ["Lyapunov", "get_safe_sample", "perturb_actions", "combine_fail_keys",
+           "combine_prefix_stats"]
+
+
+def _unique_rows(array):
+    """Unique rows in byte order (``utilities.py:496-516``)."""
+    array = np.ascontiguousarray(array)
+    dtype = np.dtype((np.void, array.dtype.itemsize * array.shape[1]))
+    _, idx = np.unique(array.view(dtype=dtype), return_index=True)
+    return array[idx]
+
+
+def perturb_actions(states, actions, perturbations, limits=None):
+    """State-action pairs from perturbed baseline actions (``lyapunov.py:609-651``)."""
+    num_states, state_dim = states.shape
+    states_new = np.repeat(states, len(perturbations), axis=0)
+    actions_new = (np.repeat(actions, len(perturbations), axis=0)
+                   + np.tile(perturbations, (num_states, 1)))
+    state_actions = np.column_stack((states_new, actions_new))
+    if limits is not None:
+        limits = np.asarray(limits)
+        acts = state_actions[:, state_dim:]
+        np.clip(acts, limits[:, 0], limits[:, 1], out=acts)
+        state_actions = _unique_rows(state_actions)
+    return state_actions
+
+
+def get_safe_sample(lyapunov, perturbations=None, limits=None, positive=False, num_samples=None,
+                    actions=None):
+    """Most uncertain safe state-action pair near the current policy (``lyapunov.py:657-797``).
+
+    The candidate evaluation -- GP mean / beta*sigma at every (safe state, perturbed action),
+    ``V(mean) + sum(L_V(mean) * sigma) < c_max`` and, unless ``positive``, membership of the mean
+    in the safe set -- runs on the GPU (``slb_gp_predict`` + fused function evaluations); the
+    candidate list itself (<= num_samples x perturbations rows) is assembled on the host like
+    the reference does.
+    """
+    import warnings
+    disc = lyapunov.discretization
+    safe_idx = np.where(lyapunov.safe_set)[0]
+    safe_states = disc.index_to_state(safe_idx)
+    if num_samples is not None and len(safe_states) > num_samples:
+        idx = np.random.choice(len(safe_states), num_samples, replace=True)
+        safe_states = safe_states[idx]
+    safe_actions = None
+    if perturbations is None:
+        arrays = [arr.ravel() for arr in np.meshgrid(safe_states, actions, indexing="ij")]
+        state_actions = np.column_stack(arrays)
+    else:
+        safe_actions = lyapunov.policy(safe_states)
+        state_actions = perturb_actions(safe_states, safe_actions, perturbations, limits)
+
+    c_max = lyapunov.feed_dict[lyapunov.c_max]
+
+    def evaluate(sa):
+        mean, std = lyapunov.dynamics.predict_device(sa)
+        bound = std.sum(dim=1, keepdim=True)
+        lv = lyapunov._lipschitz_lyapunov
+        lv = lv.evaluate_device(mean) if isinstance(lv, Function) else float(lv)
+        error = (lv * std).sum(dim=1, keepdim=True)
+        future = lyapunov.lyapunov_function.evaluate_device(mean) + error
+        return (future < c_max)[:, 0].cpu().numpy(), mean.cpu().numpy(), bound.cpu().numpy()
+
+    maps_inside, mean, bound = evaluate(state_actions)
+    if not positive:
+        maps_inside &= lyapunov.safe_set[disc.state_to_index(mean)]
+    bound_safe = bound[maps_inside]
+    if len(bound_safe) == 0:
+        warnings.warn("No safe state-action pairs found! Using backup policy ...", RuntimeWarning)
+        if safe_actions is None:
+            safe_actions = lyapunov.policy(safe_states)
+        state_actions = perturb_actions(safe_states, safe_actions, np.array([[0.]]), limits)
+        _, _, bound = evaluate(state_actions)
+        max_id = int(np.argmax(bound))
+        return state_actions[[max_id]], bound[max_id].squeeze()
+    max_id = int(np.argmax(bound_safe))
+    return state_actions[maps_inside, :][[max_id]], bound_safe[max_id].squeeze()
 
 
 class _CMax(object):

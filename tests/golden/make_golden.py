@@ -117,6 +117,14 @@ def gen_lyapunov(out):
             res["safe_set"] = lyap.safe_set.copy()
             res["c_max"] = np.array(lyap.feed_dict[lyap.c_max])
             res["refinement"] = lyap._refinement.copy()
+            if name == "pendulum":       # lyapunov.py:657-797 on the fresh safe set
+                pert = np.array([[-0.2], [-0.05], [0.0], [0.05], [0.2]])
+                lim = np.array([[-1., 1.]])
+                res["gss_perturbations"], res["gss_limits"] = pert, lim
+                for positive in (True, False):
+                    sa, bound = sl.get_safe_sample(lyap, pert, lim, positive=positive)
+                    res["gss_state_action_%d" % positive] = sa
+                    res["gss_bound_%d" % positive] = np.array(bound)
             # second phase: add a data point (Cholesky update path) then can_shrink=False
             xnew = np.array([[0.3, -0.2, 0.1]])[:, :par["X"].shape[1]]
             ynew = np.array([[0.05, -0.02]])[:, :par["Y"].shape[1]]

@@ -141,6 +141,13 @@ def test_lyapunov_fixture(kind, case):
         assert c_max == float(fix["c_max"])
         assert_array_equal(lyap._refinement, fix["refinement"])
 
+        if "gss_perturbations" in fix.files:       # get_safe_sample (lyapunov.py:657-797)
+            for positive in (True, False):
+                sa, bound = ns.get_safe_sample(lyap, fix["gss_perturbations"], fix["gss_limits"],
+                                               positive=positive)
+                assert_array_equal(sa, fix["gss_state_action_%d" % positive])
+                assert_allclose(bound, fix["gss_bound_%d" % positive], rtol=RTOL)
+
         stack = lyap.dynamics
         if par["Y"].shape[1] == 1:
             stack.functions[0].add_data_point(fix["xnew"], fix["ynew"])

@@ -282,6 +282,47 @@ def test_deterministic_sweep_vs_oracle(sl):
     assert gpu.feed_dict[gpu.c_max] == cpu.c_max
 
 
+def test_cartpole_4d_lyapunov_network_vs_oracle(sl):
+    """C4 at test size: 4-D grid (7^4), four GPs on 5-D inputs (4 Cholesky factors), V = fixed-weight
+    LyapunovNetwork(4, [64, 64, 64], tanh) (examples/utilities.py:48-104)."""
+    par = W.make_cartpole(num_points=7, M=150, tau_scale=0.01)
+    gpu, cpu = W.build_product(par), W.build_oracle(par)
+    pts = np.random.default_rng(1).uniform(-1, 1, (300, 4))
+    assert_allclose(gpu.lyapunov_function(pts), cpu.lyapunov_function(pts), rtol=1e-12, atol=1e-14)
+    assert_allclose(gpu.values, cpu.values, rtol=1e-12, atol=1e-14)
+    gpu.values = cpu.values                      # identical sort keys (tanh differs by an ulp)
+    det = _sweep_details(gpu)
+    _assert_negative_parity(gpu, cpu, det)
+    states = cpu.discretization.all_points
+    m_cpu, e_cpu = cpu.dynamics(states, cpu.policy(states))
+    assert_allclose(det["mean"], m_cpu, rtol=RTOL, atol=1e-12)
+    assert_allclose(det["err"], e_cpu, rtol=RTOL, atol=1e-12)
+    gpu.update_safe_set()
+    cpu.update_safe_set()
+    assert_array_equal(gpu.safe_set, cpu.safe_set)
+    assert gpu.feed_dict[gpu.c_max] == cpu.c_max
+
+
+def test_get_safe_sample_vs_oracle(sl):
+    """lyapunov.py:609-651, 657-797: most uncertain safe state-action pair."""
+    par = W.make_pendulum(num_points=40, M=60, tau_scale=1 / 100.)
+    gpu, cpu = W.build_product(par), W.build_oracle(par)
+    gpu.update_safe_set()
+    cpu.update_safe_set()
+    assert_array_equal(gpu.safe_set, cpu.safe_set)
+    assert cpu.safe_set.sum() > 30
+    perturbations = np.array([[-0.2], [-0.05], [0.0], [0.05], [0.2]])
+    limits = np.array([[-1., 1.]])
+    for positive in (True, False):
+        sa_g, b_g = sl.get_safe_sample(gpu, perturbations, limits, positive=positive)
+        sa_c, b_c = O.get_safe_sample(cpu, perturbations, limits, positive=positive)
+        assert_array_equal(sa_g, sa_c)
+        assert_allclose(b_g, b_c, rtol=RTOL)
+    states = cpu.discretization.index_to_state(np.where(cpu.safe_set)[0])
+    assert_array_equal(sl.perturb_actions(states, cpu.policy(states), perturbations, limits),
+                       O.perturb_actions(states, cpu.policy(states), perturbations, limits))
+
+
 def test_multi_batch_quirks_and_ragged_sizes(sl):
     """N not a multiple of the 64-point tile, N > gp_batch_size, all-safe c_max quirk
     (lyapunov.py:590-595)."""

@@ -71,3 +71,8 @@ if "--flush" in sys.argv:
     print("small 8MB fill  ", timed(lambda: small.fill_(1)))
     rd = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     print("flush by read   ", timed(lambda: rd.sum()))
+    print("flush, 1 untimed sweep, then timed", timed(lambda: (flush.fill_(1), lyap.compute_negative())))
+    print("flush 64MB      ", timed(lambda: flush[:64 << 20].fill_(1)))
+    print("flush 128MB     ", timed(lambda: flush[:128 << 20].fill_(1)))
+    warm = torch.zeros(1 << 20, dtype=torch.float64, device="cuda")
+    print("fill + 8MB elementwise compute", timed(lambda: (flush.fill_(1), warm.mul_(1.0001).add_(1.0))))
