@@ -95,8 +95,9 @@ typedef struct slb_gp_factor {
     int32_t M;                  /* training points                                      */
     int32_t nrb;                /* ceil(M / 8) row blocks of the packed factor          */
     const double* Xs;           /* device [M, d_in]: X / lengthscales (gpflow RBF)      */
-    const double* Wpack;        /* device: L^-1 in DMMA fragment order (slb_pack_factor);
-                                   L = chol(scale^2 (K + noise I))  functions.py:399-408 */
+    const double* Wpack;        /* device: L^-1 in DMMA fragment order, k-steps paired
+                                   (slb_pack_factor); L = chol(scale^2 (K + noise I))
+                                   functions.py:399-408 */
     double lengthscales[SLB_MAX_IN];
     double variance;            /* RBF variance (Kdiag)                                 */
     double scale;               /* GPRCached _scale                functions.py:392     */

@@ -87,7 +87,9 @@ class SlbPrefixStats(C.Structure):
 _STRUCTS = (SlbGrid, SlbFunction, SlbGpFactor, SlbGpOutput, SlbGpStack, SlbSweep, SlbBellman,
             SlbFailKey, SlbPrefixStats)
 
-LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libslb200.so")
+# SLB200_LIB lets a diagnostic run load an alternative build (A/B timing of kernel variants)
+LIB_PATH = os.environ.get("SLB200_LIB") or os.path.join(
+    os.path.dirname(os.path.abspath(__file__)), "libslb200.so")
 
 _vp, _i64, _i32, _dp = C.c_void_p, C.c_int64, C.c_int32, C.c_void_p
 

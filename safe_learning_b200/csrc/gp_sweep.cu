@@ -13,9 +13,9 @@
 //   * one CTA = 64 grid points x all M training points, 8 warps, 1 CTA/SM (181 KB smem,
 //     ~245 registers).  Measured alternatives (profiles/r01_kernel_variants.md): 16 warps x
 //     (16 rows x 64 points) and 2 CTAs/SM x 32-point tiles were both 2-5% slower.
-//   * W = L^-1 (lower triangular) is pre-packed in DMMA.8x8x4 A-fragment order
-//     (slb_pack_factor); each warp streams ITS rows of W straight from L2 into registers
-//     with coalesced 256 B loads, software-pipelined two k-steps ahead -- W is used by
+//   * W = L^-1 (lower triangular) is pre-packed in DMMA.8x8x4 A-fragment order, two k-steps
+//     per 128-bit element (slb_pack_factor); each warp streams ITS rows of W straight from L2
+//     into registers with coalesced 512 B loads, prefetched two pairs ahead -- W is used by
 //     exactly one warp per CTA, so it never needs shared memory.
 //   * the k-row tile K[j, p] = s^2 exp(-|z_p - X_j|^2/2) is generated once per 256-row
 //     j-panel into shared memory ([j][68] doubles: conflict-free B-fragment reads).
@@ -29,7 +29,12 @@ namespace {
 
 constexpr int TP = SLB_TILE_POINTS;   // points per CTA
 constexpr int PANEL = 256;            // rows per i-panel, columns per j-panel
-constexpr int KSTR = TP + 4;          // Ks row stride: (r*68 + c) mod 16 distinct for r,c in 0..3
+// K-row tile layout in shared memory: k-steps are handled in PAIRS (8 rows of K).  Row j of a
+// panel lives at pair m = j / 8, half h = (j / 4) % 2, fragment row r = j % 4; element (j, p) is
+// Ks[((m * 4 + r) * KSTR + p) * 2 + h], so one 128-bit load gives a lane its B fragments of both
+// k-steps of a pair.  KSTR = 66: (r * 66 + c) mod 8 is distinct for r in 0..3, c in 0..1, i.e. the
+// eight lanes of a quarter-warp hit eight different 16-byte bank groups (conflict-free LDS.128).
+constexpr int KSTR = TP + 2;
 constexpr int NW = 8;                 // warps per CTA
 constexpr int NT = NW * 32;
 constexpr int RQ = 4;                 // 8-row blocks per warp per 256-row panel (RQ * NW = 32)
@@ -38,7 +43,7 @@ constexpr int CTAS_PER_SM = 1;
 constexpr int NRED = 1 + SLB_MAX_OUT;
 constexpr int PREFETCH_CTAS = 148 * CTAS_PER_SM;    // one wave on a B200
 
-constexpr size_t SMEM_KS = (size_t)PANEL * KSTR * sizeof(double);
+constexpr size_t SMEM_KS = (size_t)(PANEL / 8) * 4 * KSTR * 2 * sizeof(double);
 constexpr size_t SMEM_Z = (size_t)SLB_MAX_IN * TP * sizeof(double);
 constexpr size_t SMEM_RED = (size_t)NW * TP * NRED * sizeof(double);
 constexpr size_t SMEM_TOT = (size_t)NRED * TP * sizeof(double);
@@ -68,46 +73,71 @@ SLB_DEV double ldg_stream(const double* p) {
     return v;
 }
 
+SLB_DEV double2 ldg_stream2(const double2* p) {
+    double2 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];"
+                 : "=d"(v.x), "=d"(v.y) : "l"(p));
+    return v;
+}
+
 SLB_DEV void dmma884(double& c0, double& c1, double a, double b) {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
                  : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
 // k-steps [k0, k1) of the current j-panel for row blocks q >= Q0 of this warp.
+// Pairs [m0, m1) of k-steps of the current j-panel for row blocks q >= Q0 of this warp.
+// Per pair and row block ONE 128-bit global load brings the A fragments of both k-steps
+// (the packed factor stores them adjacent), per column block ONE 128-bit shared load brings both
+// B fragments.  The A prefetch ring (RING pairs ahead) is unrolled with static registers: no
+// rotation moves.  Measured in isolation (tools/dmma_mix.cu, "wide"): 94% of the DMMA peak with
+// 4 active row blocks and ~90% with 1-3, against 90% / <=85% for one 64-bit load per fragment.
 template <int Q0>
-SLB_DEV void mma_run(double (&acc)[RQ][NB][2], const double* const (&ap)[RQ], int k0, int k1,
-                     const double* ks_lane) {
-    // W fragments are prefetched PF k-steps ahead in a register ring (L2 latency under load
-    // is 1-2 k-steps; it grows when L2 was just swept by another kernel).
-    constexpr int PF = 3;
-    double ar[PF][RQ];
-    const int k1m = k1 - 1;
+SLB_DEV void mma_run(double (&acc)[RQ][NB][2], const double2* const (&ap)[RQ], int m0, int m1,
+                     const double2* ks_lane) {
+#ifndef SLB_RING
+#define SLB_RING 3
+#endif
+#ifndef SLB_BGROUP
+#define SLB_BGROUP 4
+#endif
+    constexpr int RING = SLB_RING;
+    constexpr int BG = SLB_BGROUP;       // column blocks whose B fragments are loaded together
+    double2 ar[RING][RQ];
+    const int m1m = m1 - 1;
 #pragma unroll
-    for (int d = 0; d < PF; ++d) {
-        const int kd = min(k0 + d, k1m);
+    for (int d = 0; d < RING; ++d) {
+        const int md = min(m0 + d, m1m);
 #pragma unroll
-        for (int q = Q0; q < RQ; ++q) ar[d][q] = ldg_stream(ap[q] + kd * 32);
+        for (int q = Q0; q < RQ; ++q) ar[d][q] = ldg_stream2(ap[q] + md * 32);
     }
+    int m = m0;
 #pragma unroll 1
-    for (int kk = k0; kk < k1; ++kk) {
-        const int kp = min(kk + PF, k1m);
-        double an[RQ];
+    while (true) {
 #pragma unroll
-        for (int q = Q0; q < RQ; ++q) an[q] = ldg_stream(ap[q] + kp * 32);
-        const double* kb = ks_lane + kk * (4 * KSTR);
-        double b[NB];
+        for (int d = 0; d < RING; ++d) {
+            if (m >= m1) return;
+            const double2* kb = ks_lane + m * (4 * KSTR);
 #pragma unroll
-        for (int nb = 0; nb < NB; ++nb) b[nb] = kb[nb * 8];
+            for (int half = 0; half < NB; half += BG) {
+                double2 b[BG];
 #pragma unroll
-        for (int q = Q0; q < RQ; ++q) {
+                for (int nb = 0; nb < BG; ++nb) b[nb] = kb[(half + nb) * 8];
 #pragma unroll
-            for (int nb = 0; nb < NB; ++nb) dmma884(acc[q][nb][0], acc[q][nb][1], ar[0][q], b[nb]);
-        }
+                for (int q = Q0; q < RQ; ++q)
 #pragma unroll
-        for (int q = Q0; q < RQ; ++q) {
+                    for (int nb = 0; nb < BG; ++nb)
+                        dmma884(acc[q][half + nb][0], acc[q][half + nb][1], ar[d][q].x, b[nb].x);
 #pragma unroll
-            for (int d = 0; d + 1 < PF; ++d) ar[d][q] = ar[d + 1][q];
-            ar[PF - 1][q] = an[q];
+                for (int q = Q0; q < RQ; ++q)
+#pragma unroll
+                    for (int nb = 0; nb < BG; ++nb)
+                        dmma884(acc[q][half + nb][0], acc[q][half + nb][1], ar[d][q].y, b[nb].y);
+            }
+            const int mp = min(m + RING, m1m);
+#pragma unroll
+            for (int q = Q0; q < RQ; ++q) ar[d][q] = ldg_stream2(ap[q] + mp * 32);
+            ++m;
         }
     }
 }
@@ -117,7 +147,7 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM)
 gp_tile_kernel(const __grid_constant__ slb_sweep cfg, const gp_args a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double* Ks = reinterpret_cast<double*>(smem_raw);
-    double* zraw = Ks + PANEL * KSTR;                 // [SLB_MAX_IN][TP]
+    double* zraw = Ks + (PANEL / 8) * 4 * KSTR * 2;   // [SLB_MAX_IN][TP]
     double* red = zraw + SLB_MAX_IN * TP;             // [NW][TP][NRED]
     double* tot = red + NW * TP * NRED;               // [NRED][TP]
     double* post = tot + NRED * TP;                   // mean [MAX_OUT][TP], err [MAX_OUT][TP]
@@ -179,7 +209,7 @@ gp_tile_kernel(const __grid_constant__ slb_sweep cfg, const gp_args a) {
     const int wslot = warp < 4 ? warp : 11 - warp;     // SMSP partners w, w+4 sum to 7
     const int p_gen = tid & (TP - 1);
     const int jg = tid / TP;                          // 0..NT/TP-1
-    const double* ks_lane = Ks + (lane & 3) * KSTR + (lane >> 2);
+    const double2* ks_lane = reinterpret_cast<const double2*>(Ks) + (lane & 3) * KSTR + (lane >> 2);
 
     for (int f = 0; f < cfg.gp.num_factors; ++f) {
         const slb_gp_factor& F = cfg.gp.factors[f];
@@ -221,12 +251,16 @@ gp_tile_kernel(const __grid_constant__ slb_sweep cfg, const gp_args a) {
                     __syncthreads();
                     const int j0 = PANEL * jp;
                     const int nj = min(PANEL, M - j0);
-                    constexpr int JS = NT / TP;       // j stride between a thread's rows
-                    for (int j = jg; j < nkp * 4; j += 4 * JS) {
+                    // thread (p_gen, jg): fragment row r = jg of every pair m, both halves (rows
+                    // 8m + jg and 8m + 4 + jg); two pairs per iteration = 4 interleaved exps
+                    static_assert(NT / TP == 4, "generation assumes 4 thread groups per point");
+                    const int npairs = (nkp + 1) >> 1;
+                    double2* ks2 = reinterpret_cast<double2*>(Ks);
+                    for (int mm = 0; mm < npairs; mm += 2) {
                         double t2[4];
 #pragma unroll
                         for (int u = 0; u < 4; ++u) {
-                            const int jj = min(j + JS * u, nj - 1);
+                            const int jj = min(8 * (mm + (u >> 1)) + 4 * (u & 1) + jg, nj - 1);
                             const double* xr = Xs + (size_t)(j0 + jj) * DIN;
                             double acc2 = 0.0;
 #pragma unroll
@@ -236,12 +270,16 @@ gp_tile_kernel(const __grid_constant__ slb_sweep cfg, const gp_args a) {
                             }
                             t2[u] = acc2;
                         }
+                        double kv[4];
 #pragma unroll
                         for (int u = 0; u < 4; ++u) {
-                            const int jj = j + JS * u;
+                            const int jj = 8 * (mm + (u >> 1)) + 4 * (u & 1) + jg;
                             const double k = s2 * (variance * exp_neg(-0.5 * t2[u]));
-                            if (jj < nkp * 4) Ks[jj * KSTR + p_gen] = jj < nj ? k : 0.0;
+                            kv[u] = jj < nj ? k : 0.0;          // zero rows pad the last pair
                         }
+                        ks2[(mm * 4 + jg) * KSTR + p_gen] = make_double2(kv[0], kv[1]);
+                        if (mm + 1 < npairs)
+                            ks2[((mm + 1) * 4 + jg) * KSTR + p_gen] = make_double2(kv[2], kv[3]);
                     }
                     resident = jp;
                     __syncthreads();
@@ -249,23 +287,27 @@ gp_tile_kernel(const __grid_constant__ slb_sweep cfg, const gp_args a) {
                 }
                 if (TIMING) t_mark = clock64();
                 // ---- contraction phase: acc[rows of this warp, 64 points] += W[rows, panel] K
-                int kend[RQ];
-                const double* ap[RQ];
+                // active pairs of k-steps per row block: block b needs columns j <= 8b + 7, i.e.
+                // pairs <= b; in the diagonal j-panel that is (b - pbeg) + 1 pairs
+                const int npairs_mma = (nkp + 1) >> 1;
+                int mend[RQ];
+                const double2* ap[RQ];
 #pragma unroll
                 for (int q = 0; q < RQ; ++q) {
                     const bool valid = bq[q] >= pbeg;
-                    int ke = valid ? nkp : 0;
-                    if (valid && jp == ip) ke = min(nkp, 2 * (bq[q] - pbeg) + 2);
-                    kend[q] = ke;
+                    int me = valid ? npairs_mma : 0;
+                    if (valid && jp == ip) me = min(npairs_mma, bq[q] - pbeg + 1);
+                    mend[q] = me;
                     const int64_t b = valid ? bq[q] : 0;
-                    ap[q] = F.Wpack + (b * (b + 1) + 64 * jp) * 32 + lane;
+                    ap[q] = reinterpret_cast<const double2*>(F.Wpack) +
+                            (b * (b + 1) / 2 + 32 * jp) * 32 + lane;
                 }
                 static_assert(RQ == 4, "segment dispatch below is written for RQ == 4");
-                int kprev = 0;
-                if (kend[0] > kprev) { mma_run<0>(acc, ap, kprev, kend[0], ks_lane); kprev = kend[0]; }
-                if (kend[1] > kprev) { mma_run<1>(acc, ap, kprev, kend[1], ks_lane); kprev = kend[1]; }
-                if (kend[2] > kprev) { mma_run<2>(acc, ap, kprev, kend[2], ks_lane); kprev = kend[2]; }
-                if (kend[3] > kprev) { mma_run<3>(acc, ap, kprev, kend[3], ks_lane); kprev = kend[3]; }
+                int mprev = 0;
+                if (mend[0] > mprev) { mma_run<0>(acc, ap, mprev, mend[0], ks_lane); mprev = mend[0]; }
+                if (mend[1] > mprev) { mma_run<1>(acc, ap, mprev, mend[1], ks_lane); mprev = mend[1]; }
+                if (mend[2] > mprev) { mma_run<2>(acc, ap, mprev, mend[2], ks_lane); mprev = mend[2]; }
+                if (mend[3] > mprev) { mma_run<3>(acc, ap, mprev, mend[3], ks_lane); mprev = mend[3]; }
                 if (TIMING) t_mma += clock64() - t_mark;
             }
             if (TIMING) t_mark = clock64();
@@ -368,18 +410,21 @@ gp_tile_kernel(const __grid_constant__ slb_sweep cfg, const gp_args a) {
     }
 }
 
+// Packed factor: for 8-row block b and k-step PAIR kp <= b, 32 lanes x 2 doubles: lane T holds
+// L^-1[8b + T/4, 8kp + T%4] and L^-1[8b + T/4, 8kp + 4 + T%4]; pair offset b(b+1)/2 + kp.
 __global__ void pack_factor_kernel(const double* __restrict__ Linv, int M, int nrb,
                                    double* __restrict__ W, int64_t total) {
     const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= total) return;
-    const int64_t blk = e >> 5;
-    const int lane = (int)(e & 31);
-    int64_t b = (int64_t)((sqrt(4.0 * (double)blk + 1.0) - 1.0) * 0.5);
-    while (b * (b + 1) > blk) --b;
-    while ((b + 1) * (b + 2) <= blk) ++b;
-    const int64_t kb4 = blk - b * (b + 1);
+    const int64_t pair = e >> 6;
+    const int lane = (int)((e >> 1) & 31);
+    const int half = (int)(e & 1);
+    int64_t b = (int64_t)((sqrt(8.0 * (double)pair + 1.0) - 1.0) * 0.5);
+    while (b * (b + 1) / 2 > pair) --b;
+    while ((b + 1) * (b + 2) / 2 <= pair) ++b;
+    const int64_t kp = pair - b * (b + 1) / 2;
     const int64_t row = 8 * b + (lane >> 2);
-    const int64_t col = 4 * kb4 + (lane & 3);
+    const int64_t col = 8 * kp + 4 * half + (lane & 3);
     W[e] = (row < M && col <= row) ? Linv[row * M + col] : 0.0;
 }
 

@@ -126,28 +126,29 @@ def test_utilities_match_oracle():
 
 # ----------------------------------------------------------------- kernel addressing emulation
 def _pack_factor(linv):
-    """numpy twin of pack_factor_kernel (gp_sweep.cu)."""
+    """numpy twin of pack_factor_kernel (gp_sweep.cu): k-steps paired, 2 doubles per lane."""
     M = linv.shape[0]
     nrb = (M + 7) // 8
     out = np.zeros(nrb * (nrb + 1) * 32)
     for b in range(nrb):
-        for kb4 in range(2 * b + 2):
-            base = (b * (b + 1) + kb4) * 32
+        for kp in range(b + 1):
+            base = (b * (b + 1) // 2 + kp) * 64
             for lane in range(32):
-                row, col = 8 * b + lane // 4, 4 * kb4 + lane % 4
-                if row < M and col <= row:
-                    out[base + lane] = linv[row, col]
+                for half in range(2):
+                    row, col = 8 * b + lane // 4, 8 * kp + 4 * half + lane % 4
+                    if row < M and col <= row:
+                        out[base + 2 * lane + half] = linv[row, col]
     return out
 
 
 def _emulate_tile(wpack, M, K):
     """Replays gp_tile_kernel's loop structure and fragment addressing (8 warps x 4 row blocks,
-    panels of 256 rows/cols, bottom-up row-block dealing, per-q k-step limits) on the host; returns
-    a = W k [M_pad, P] accumulated exactly where the kernel accumulates it."""
+    panels of 256 rows/cols, bottom-up row-block dealing, per-block limits in PAIRS of k-steps)
+    on the host; returns a = W k [M_pad, P] accumulated exactly where the kernel accumulates."""
     nrb, nk4 = (M + 7) // 8, (M + 3) // 4
     npan = (nrb + 31) // 32
     P = K.shape[1]
-    Kpad = np.zeros((nk4 * 4, P))
+    Kpad = np.zeros((npan * 256 + 8, P))
     Kpad[:M] = K
     a = np.zeros((nrb * 8, P))
     lanes = np.arange(32)
@@ -160,13 +161,15 @@ def _emulate_tile(wpack, M, K):
                     continue
                 for jp in range(ip + 1):
                     nkp = min(64, nk4 - 64 * jp)
-                    kend = min(nkp, 2 * (b - pbeg) + 2) if jp == ip else nkp
-                    for kk in range(kend):
-                        frag = wpack[(b * (b + 1) + 64 * jp) * 32 + kk * 32 + lanes]
-                        A = np.zeros((8, 4))
-                        A[lanes // 4, lanes % 4] = frag
-                        Bm = Kpad[256 * jp + 4 * kk: 256 * jp + 4 * kk + 4]
-                        a[8 * b: 8 * b + 8] += A @ Bm
+                    npairs = (nkp + 1) // 2
+                    mend = min(npairs, b - pbeg + 1) if jp == ip else npairs
+                    for m in range(mend):
+                        frag = wpack[(b * (b + 1) // 2 + 32 * jp + m) * 64:][:64].reshape(32, 2)
+                        for half in range(2):
+                            A = np.zeros((8, 4))
+                            A[lanes // 4, lanes % 4] = frag[:, half]
+                            r0 = 256 * jp + 8 * m + 4 * half
+                            a[8 * b: 8 * b + 8] += A @ Kpad[r0:r0 + 4]
     return a
 
 
