@@ -177,6 +177,9 @@ int         slb_device_count(void);
 int         slb_struct_sizes(int64_t* out, int32_t n);
 /* kernels this library has launched since load (bench.py's gpu_launches) */
 int64_t     slb_launch_count(void);
+/* a caller that replays a CUDA graph captured around `kernels` launches of this library reports
+   each replay here so that slb_launch_count stays truthful */
+void        slb_note_graph_replay(int64_t kernels);
 
 /* diagnostics: when buffer_dev != NULL, every later Lyapunov sweep writes int64 cycle counts
  * [tile][warp(8)][6] = {k-row generation, DMMA contraction, panel epilogues, whole tile} and

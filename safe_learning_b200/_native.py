@@ -100,6 +100,7 @@ SIGNATURES = {
     "slb_device_count": (C.c_int, []),
     "slb_struct_sizes": (C.c_int, [C.POINTER(C.c_int64), _i32]),
     "slb_launch_count": (C.c_int64, []),
+    "slb_note_graph_replay": (None, [_i64]),
     "slb_debug_phase_timing": (C.c_int, [_vp]),
     "slb_packed_len": (C.c_int64, [_i32]),
     "slb_pack_factor": (C.c_int, [_vp, _dp, _i32, _dp]),

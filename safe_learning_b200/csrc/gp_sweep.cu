@@ -323,22 +323,48 @@ gp_tile_kernel(const __grid_constant__ slb_sweep cfg, const gp_args a) {
                     for (int q = 0; q < RQ; ++q)
                         if (bq[q] >= pbeg) al[q] = __ldg(alpha + 8 * bq[q] + (lane >> 2));
                 }
+                // per-thread sums over this warp's row blocks: 16 values, column 8nb + 2(T%4) + e
+                static_assert(NB == 8, "butterfly below reduces 16 values over the 8 row lanes");
+                double v[16];
 #pragma unroll
                 for (int nb = 0; nb < NB; ++nb) {
 #pragma unroll
                     for (int e = 0; e < 2; ++e) {
-                        double v = 0.0;
+                        double t = 0.0;
 #pragma unroll
                         for (int q = 0; q < RQ; ++q) {
                             const double x = acc[q][nb][e];
-                            v = fma(x, (o < 0) ? x : al[q], v);
+                            t = fma(x, (o < 0) ? x : al[q], t);
                         }
-                        v += __shfl_xor_sync(0xffffffffu, v, 4);
-                        v += __shfl_xor_sync(0xffffffffu, v, 8);
-                        v += __shfl_xor_sync(0xffffffffu, v, 16);
-                        if (lane < 4) red[(warp * TP + nb * 8 + 2 * lane + e) * NRED + qty] += v;
+                        v[nb * 2 + e] = t;
                     }
                 }
+                // reduce-scatter over the 8 lanes that share T%4 (lane bits 4,3,2): 8+4+2
+                // shuffles instead of 3 per value; every lane ends with two finished columns
+                const bool g2 = (lane & 16) != 0, g1 = (lane & 8) != 0, g0 = (lane & 4) != 0;
+                double w8[8], w4[4], w2[2];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const double send = g2 ? v[i] : v[i + 8];
+                    const double keep = g2 ? v[i + 8] : v[i];
+                    w8[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+                }
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const double send = g1 ? w8[i] : w8[i + 4];
+                    const double keep = g1 ? w8[i + 4] : w8[i];
+                    w4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+                }
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    const double send = g0 ? w4[i] : w4[i + 2];
+                    const double keep = g0 ? w4[i + 2] : w4[i];
+                    w2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+                }
+                // value index 2g + e  <->  nb = g = lane / 4, column 8g + 2(T%4) + e
+                double* slot = red + (warp * TP + 8 * (lane >> 2) + 2 * (lane & 3)) * NRED + qty;
+                slot[0] += w2[0];
+                slot[NRED] += w2[1];
                 ++qty;
             }
             __syncwarp();

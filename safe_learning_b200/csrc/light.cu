@@ -450,6 +450,7 @@ extern "C" {
 int slb_abi_version(void) { return SLB_ABI_VERSION; }
 const char* slb_last_error(void) { return g_err; }
 int64_t slb_launch_count(void) { return (int64_t)g_slb_launches; }
+void slb_note_graph_replay(int64_t kernels) { g_slb_launches += kernels; }
 
 /* sizeof of every ABI struct, for bindings to verify their mirror:
    [grid, function, gp_factor, gp_output, gp_stack, sweep, bellman, fail_key, prefix_stats] */
