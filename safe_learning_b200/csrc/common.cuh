@@ -93,6 +93,52 @@ SLB_DEV double exp_neg(double x) {
     return x < -700.0 ? 0.0 : p;
 }
 
+// Table-driven exp(x) for x <= 0 (<= 1 ulp against glibc on 2e7 points, tools/exp_neg_check.c):
+// x = (64 k + j) ln2/64 + r, |r| <= ln2/128;  exp(x) = 2^k * T[j] * (1 + r + ... + r^5/120).
+// 10 fp64 operations instead of 17; T (64 correctly rounded doubles) is read from a shared-memory
+// copy because the index differs per lane (constant memory would serialise).
+__constant__ double c_exp2_tab[64] = {
+    1.0, 1.0108892860517005, 1.0218971486541166, 1.0330248790212284,
+    1.0442737824274138, 1.0556451783605572, 1.0671404006768237, 1.0787607977571199,
+    1.0905077326652577, 1.102382583307841, 1.1143867425958924, 1.1265216186082418,
+    1.1387886347566916, 1.1511892299529827, 1.1637248587775775, 1.1763969916502812,
+    1.189207115002721, 1.202156731452703, 1.215247359980469, 1.22848053610687,
+    1.241857812073484, 1.255380757024691, 1.2690509571917332, 1.2828700160787783,
+    1.2968395546510096, 1.3109612115247644, 1.3252366431597413, 1.339667524053303,
+    1.3542555469368927, 1.3690024229745905, 1.383909881963832, 1.3989796725383112,
+    1.4142135623730951, 1.42961333839197, 1.4451808069770467, 1.460917794180647,
+    1.4768261459394993, 1.4929077282912648, 1.5091644275934228, 1.5255981507445384,
+    1.5422108254079407, 1.559004400237837, 1.5759808451078865, 1.593142151342267,
+    1.6104903319492543, 1.6280274218573478, 1.645755478153965, 1.6636765803267364,
+    1.681792830507429, 1.7001063537185235, 1.718619298122478, 1.7373338352737062,
+    1.7562521603732995, 1.7753764925265212, 1.7947090750031072, 1.8142521755003989,
+    1.8340080864093424, 1.8539791250833855, 1.8741676341103, 1.8945759815869656,
+    1.9152065613971474, 1.9360617934922943, 1.9571441241754002, 1.978456026387951
+};
+
+SLB_DEV void load_exp_table(double* tab_smem) {
+    for (int i = threadIdx.x; i < 64; i += blockDim.x) tab_smem[i] = c_exp2_tab[i];
+}
+
+SLB_DEV double exp_neg_tab(double x, const double* __restrict__ tab) {
+    const double MAGIC = 6755399441055744.0;             // 1.5 * 2^52
+    const double t = fma(x, 92.33248261689366, MAGIC);                  // 64 / ln2
+    const int n = __double2loint(t);
+    const double nd = t - MAGIC;
+    double r = fma(nd, -0.01083042469326756, x);                          // ln2/64, high part (32 bits)
+    r = fma(nd, -2.9815858269852933e-12, r);                                 // ln2/64, low part
+    double p = 1.0 / 120.0;
+    p = fma(p, r, 1.0 / 24.0);
+    p = fma(p, r, 1.0 / 6.0);
+    p = fma(p, r, 0.5);
+    p = fma(p, r, 1.0);
+    p = p * r;                                           // e^r - 1
+    const double T = tab[n & 63];
+    const double v = fma(T, p, T);
+    const double s = __hiloint2double(__double2hiint(v) + ((n >> 6) << 20), __double2loint(v));
+    return x < -700.0 ? 0.0 : s;
+}
+
 // GridWorld.index_to_state (functions.py:714-731): ijk * unit_maxes + offset, two roundings.
 SLB_DEV void grid_index_to_state(const slb_grid& g, int64_t idx, double* x) {
 #pragma unroll

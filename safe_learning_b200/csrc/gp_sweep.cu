@@ -48,7 +48,8 @@ constexpr size_t SMEM_Z = (size_t)SLB_MAX_IN * TP * sizeof(double);
 constexpr size_t SMEM_RED = (size_t)NW * TP * NRED * sizeof(double);
 constexpr size_t SMEM_TOT = (size_t)NRED * TP * sizeof(double);
 constexpr size_t SMEM_POST = (size_t)2 * SLB_MAX_OUT * TP * sizeof(double);
-constexpr size_t SMEM_TOTAL = SMEM_KS + SMEM_Z + SMEM_RED + SMEM_TOT + SMEM_POST;
+constexpr size_t SMEM_EXPTAB = 64 * sizeof(double);
+constexpr size_t SMEM_TOTAL = SMEM_KS + SMEM_Z + SMEM_RED + SMEM_TOT + SMEM_POST + SMEM_EXPTAB;
 
 enum { MODE_SWEEP_GRID = 0, MODE_SWEEP_STATES = 1, MODE_PREDICT = 2 };
 
@@ -151,6 +152,7 @@ gp_tile_kernel(const __grid_constant__ slb_sweep cfg, const gp_args a) {
     double* red = zraw + SLB_MAX_IN * TP;             // [NW][TP][NRED]
     double* tot = red + NW * TP * NRED;               // [NRED][TP]
     double* post = tot + NRED * TP;                   // mean [MAX_OUT][TP], err [MAX_OUT][TP]
+    double* exptab = post + 2 * SLB_MAX_OUT * TP;     // 2^(j/64), j = 0..63
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t tile0 = (int64_t)blockIdx.x * TP;
@@ -176,6 +178,8 @@ gp_tile_kernel(const __grid_constant__ slb_sweep cfg, const gp_args a) {
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(base + off));
         }
     }
+
+    load_exp_table(exptab);
 
     // ---- stage 1: query points z = [x, policy(x)]  (lyapunov.py:436-437, utilities.py:143)
     if (tid < TP) {
@@ -252,14 +256,15 @@ gp_tile_kernel(const __grid_constant__ slb_sweep cfg, const gp_args a) {
                     const int j0 = PANEL * jp;
                     const int nj = min(PANEL, M - j0);
                     // thread (p_gen, jg): fragment row r = jg of every pair m, both halves (rows
-                    // 8m + jg and 8m + 4 + jg); two pairs per iteration = 4 interleaved exps
+                    // 8m + jg and 8m + 4 + jg); GP pairs per iteration = 2 GP interleaved exps
                     static_assert(NT / TP == 4, "generation assumes 4 thread groups per point");
                     const int npairs = (nkp + 1) >> 1;
                     double2* ks2 = reinterpret_cast<double2*>(Ks);
-                    for (int mm = 0; mm < npairs; mm += 2) {
-                        double t2[4];
+                    constexpr int GP = 2;            // pairs per iteration = 2 GP interleaved exps
+                    for (int mm = 0; mm < npairs; mm += GP) {
+                        double t2[2 * GP];
 #pragma unroll
-                        for (int u = 0; u < 4; ++u) {
+                        for (int u = 0; u < 2 * GP; ++u) {
                             const int jj = min(8 * (mm + (u >> 1)) + 4 * (u & 1) + jg, nj - 1);
                             const double* xr = Xs + (size_t)(j0 + jj) * DIN;
                             double acc2 = 0.0;
@@ -270,16 +275,18 @@ gp_tile_kernel(const __grid_constant__ slb_sweep cfg, const gp_args a) {
                             }
                             t2[u] = acc2;
                         }
-                        double kv[4];
+                        double kv[2 * GP];
 #pragma unroll
-                        for (int u = 0; u < 4; ++u) {
+                        for (int u = 0; u < 2 * GP; ++u) {
                             const int jj = 8 * (mm + (u >> 1)) + 4 * (u & 1) + jg;
-                            const double k = s2 * (variance * exp_neg(-0.5 * t2[u]));
+                            const double k = s2 * (variance * exp_neg_tab(-0.5 * t2[u], exptab));
                             kv[u] = jj < nj ? k : 0.0;          // zero rows pad the last pair
                         }
-                        ks2[(mm * 4 + jg) * KSTR + p_gen] = make_double2(kv[0], kv[1]);
-                        if (mm + 1 < npairs)
-                            ks2[((mm + 1) * 4 + jg) * KSTR + p_gen] = make_double2(kv[2], kv[3]);
+#pragma unroll
+                        for (int g = 0; g < GP; ++g)
+                            if (mm + g < npairs)
+                                ks2[((mm + g) * 4 + jg) * KSTR + p_gen] =
+                                    make_double2(kv[2 * g], kv[2 * g + 1]);
                     }
                     resident = jp;
                     __syncthreads();

@@ -293,7 +293,7 @@ apply_prefix_kernel(const double* __restrict__ values, const uint8_t* __restrict
 // stay in registers (a runtime-bounded loop over outputs would push them to local memory).
 template <int DIN, int NO>
 SLB_DEV void gp_mean_factor(const slb_gp_stack& gp, const slb_gp_factor& F, const int* outs,
-                            const double* z, double* mu) {
+                            const double* z, double* mu, const double* exptab) {
     double zs[DIN];
 #pragma unroll
     for (int c = 0; c < DIN; ++c) zs[c] = z[c] / F.lengthscales[c];
@@ -317,7 +317,7 @@ SLB_DEV void gp_mean_factor(const slb_gp_stack& gp, const slb_gp_factor& F, cons
         }
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-            double k = F.variance * exp_neg(-0.5 * t2[u]);
+            double k = F.variance * exp_neg_tab(-0.5 * t2[u], exptab);
             if (j0 + u >= M) k = 0.0;
             const int j = min(j0 + u, M - 1);
 #pragma unroll
@@ -343,7 +343,8 @@ SLB_DEV void gp_mean_factor(const slb_gp_stack& gp, const slb_gp_factor& F, cons
 //   mean_o = (scale^2 sum_j k_j gamma_o,j + scale m_o(z)) / scale,  gamma = L^-T alpha,
 // which equals a^T alpha of functions.py:441-442 up to rounding.
 template <int DIN>
-SLB_DEV void gp_mean_only(const slb_gp_stack& gp, const double* z, double* mu) {
+SLB_DEV void gp_mean_only(const slb_gp_stack& gp, const double* z, double* mu,
+                          const double* exptab) {
     for (int f = 0; f < gp.num_factors; ++f) {
         const slb_gp_factor& F = gp.factors[f];
         int outs[SLB_MAX_OUT];
@@ -351,24 +352,25 @@ SLB_DEV void gp_mean_only(const slb_gp_stack& gp, const double* z, double* mu) {
         for (int o = 0; o < gp.num_outputs; ++o)
             if (gp.outputs[o].factor == f) outs[no++] = o;
         switch (no) {
-        case 1: gp_mean_factor<DIN, 1>(gp, F, outs, z, mu); break;
-        case 2: gp_mean_factor<DIN, 2>(gp, F, outs, z, mu); break;
-        case 3: gp_mean_factor<DIN, 3>(gp, F, outs, z, mu); break;
-        case 4: gp_mean_factor<DIN, 4>(gp, F, outs, z, mu); break;
-        case 5: gp_mean_factor<DIN, 5>(gp, F, outs, z, mu); break;
-        case 6: gp_mean_factor<DIN, 6>(gp, F, outs, z, mu); break;
+        case 1: gp_mean_factor<DIN, 1>(gp, F, outs, z, mu, exptab); break;
+        case 2: gp_mean_factor<DIN, 2>(gp, F, outs, z, mu, exptab); break;
+        case 3: gp_mean_factor<DIN, 3>(gp, F, outs, z, mu, exptab); break;
+        case 4: gp_mean_factor<DIN, 4>(gp, F, outs, z, mu, exptab); break;
+        case 5: gp_mean_factor<DIN, 5>(gp, F, outs, z, mu, exptab); break;
+        case 6: gp_mean_factor<DIN, 6>(gp, F, outs, z, mu, exptab); break;
         default: break;
         }
     }
 }
 
 template <int DIN>
-SLB_DEV double bellman_value(const slb_bellman& cfg, const double* x, const double* u, int m) {
+SLB_DEV double bellman_value(const slb_bellman& cfg, const double* x, const double* u, int m,
+                             const double* exptab) {
     const int d = cfg.grid.ndim;
     double z[SLB_MAX_IN], mu[SLB_MAX_OUT], r[SLB_MAX_OUT], v[SLB_MAX_OUT];
     for (int c = 0; c < d; ++c) z[c] = x[c];
     for (int c = 0; c < m; ++c) z[d + c] = u[c];
-    if (cfg.gp.num_outputs > 0) gp_mean_only<DIN>(cfg.gp, z, mu);
+    if (cfg.gp.num_outputs > 0) gp_mean_only<DIN>(cfg.gp, z, mu, exptab);
     else eval_fn(cfg.dynamics, z, mu);
     eval_fn(cfg.reward, z, r);                               // :95
     eval_fn(cfg.value, mu, v);                               // :101
@@ -379,6 +381,9 @@ template <int DIN>
 __global__ void __launch_bounds__(LT, 2)
 bellman_kernel(const __grid_constant__ slb_bellman cfg, int64_t idx_begin, int64_t n,
                double* __restrict__ out) {
+    __shared__ double exptab[64];
+    load_exp_table(exptab);
+    __syncthreads();
     const int64_t i = (int64_t)blockIdx.x * LT + threadIdx.x;
     if (i >= n) return;
     double x[SLB_MAX_DIM], u[SLB_MAX_OUT];
@@ -390,7 +395,7 @@ bellman_kernel(const __grid_constant__ slb_bellman cfg, int64_t idx_begin, int64
     } else {
         m = eval_fn(cfg.policy, x, u);
     }
-    out[i] = bellman_value<DIN>(cfg, x, u, m);
+    out[i] = bellman_value<DIN>(cfg, x, u, m, exptab);
 }
 
 template <int DIN>
@@ -399,6 +404,9 @@ bellman_argmax_kernel(const __grid_constant__ slb_bellman cfg, int64_t idx_begin
                       const double* __restrict__ actions, int n_actions, int m,
                       const double* __restrict__ constraint, int32_t* __restrict__ best,
                       double* __restrict__ best_value) {
+    __shared__ double exptab[64];
+    load_exp_table(exptab);
+    __syncthreads();
     const int64_t i = (int64_t)blockIdx.x * LT + threadIdx.x;
     if (i >= n) return;
     double x[SLB_MAX_DIM], u[SLB_MAX_ACT];
@@ -407,7 +415,7 @@ bellman_argmax_kernel(const __grid_constant__ slb_bellman cfg, int64_t idx_begin
     double vmax = 0.0;
     for (int a = 0; a < n_actions; ++a) {
         for (int c = 0; c < m; ++c) u[c] = actions[a * m + c];
-        double v = bellman_value<DIN>(cfg, x, u, m);
+        double v = bellman_value<DIN>(cfg, x, u, m, exptab);
         if (constraint != nullptr && constraint[(int64_t)a * n + i] < 0.0) v = -INFINITY;  // :272-275
         if (a == 0 || v > vmax) { vmax = v; arg = a; }      // np.argmax: first maximum (:278)
     }
