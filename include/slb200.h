@@ -182,8 +182,8 @@ int64_t     slb_launch_count(void);
 void        slb_note_graph_replay(int64_t kernels);
 
 /* diagnostics: when buffer_dev != NULL, every later Lyapunov sweep writes int64 cycle counts
- * [tile][warp(8)][6] = {k-row generation, DMMA contraction, panel epilogues, whole tile} and
- * the %globaltimer (ns) at tile start / end;
+ * [tile][warp(8)][8] = {k-row generation, DMMA contraction, panel epilogues, whole tile}, the
+ * %globaltimer (ns) at tile start / end, cycles spent waiting at block barriers, 0;
  * pass NULL to switch it off (default) */
 int         slb_debug_phase_timing(void* buffer_dev);
 

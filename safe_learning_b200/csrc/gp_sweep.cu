@@ -65,7 +65,7 @@ struct gp_args {
     double* threshold;
     double* mean;
     double* err;
-    long long* timing;      // diagnostics: [tile][warp][6]: cycles in {generate, contract, epilogue, total}, globaltimer ns {start, end}
+    long long* timing;      // diagnostics: [tile][warp][8]: cycles in {generate, contract, epilogue, total}, globaltimer ns {start, end}, cycles waiting at barriers, 0
 };
 
 SLB_DEV double ldg_stream(const double* p) {
@@ -157,7 +157,7 @@ gp_tile_kernel(const __grid_constant__ slb_sweep cfg, const gp_args a) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t tile0 = (int64_t)blockIdx.x * TP;
     const int D = cfg.gp.num_outputs;
-    long long t_gen = 0, t_mma = 0, t_epi = 0, t_mark = 0;
+    long long t_gen = 0, t_mma = 0, t_epi = 0, t_mark = 0, t_sync = 0, t_s0 = 0;
     const long long t_start = TIMING ? clock64() : 0;
     long long g_start = 0;
     if (TIMING) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(g_start));
@@ -251,8 +251,9 @@ gp_tile_kernel(const __grid_constant__ slb_sweep cfg, const gp_args a) {
                 const int nkp = min(64, nk4 - 64 * jp);
                 if (jp != resident) {
                     // ---- generation phase: K[j, p] for j in this panel (functions.py:438)
-                    if (TIMING) t_mark = clock64();
+                    if (TIMING) t_s0 = clock64();
                     __syncthreads();
+                    if (TIMING) { t_mark = clock64(); t_sync += t_mark - t_s0; }
                     const int j0 = PANEL * jp;
                     const int nj = min(PANEL, M - j0);
                     // thread (p_gen, jg): fragment row r = jg of every pair m, both halves (rows
@@ -289,8 +290,9 @@ gp_tile_kernel(const __grid_constant__ slb_sweep cfg, const gp_args a) {
                                     make_double2(kv[2 * g], kv[2 * g + 1]);
                     }
                     resident = jp;
+                    if (TIMING) { t_s0 = clock64(); t_gen += t_s0 - t_mark; }
                     __syncthreads();
-                    if (TIMING) t_gen += clock64() - t_mark;
+                    if (TIMING) t_sync += clock64() - t_s0;
                 }
                 if (TIMING) t_mark = clock64();
                 // ---- contraction phase: acc[rows of this warp, 64 points] += W[rows, panel] K
@@ -379,7 +381,9 @@ gp_tile_kernel(const __grid_constant__ slb_sweep cfg, const gp_args a) {
         }
 
         // ---- cross-warp reduction in a fixed order (deterministic)
+        if (TIMING) t_s0 = clock64();
         __syncthreads();
+        if (TIMING) t_sync += clock64() - t_s0;
         if (tid < TP) {
             for (int r = 0; r < NRED; ++r) {
                 double s = 0.0;
@@ -415,11 +419,11 @@ gp_tile_kernel(const __grid_constant__ slb_sweep cfg, const gp_args a) {
     }
 
     if (TIMING && lane == 0) {
-        long long* t = a.timing + ((size_t)blockIdx.x * NW + warp) * 6;
+        long long* t = a.timing + ((size_t)blockIdx.x * NW + warp) * 8;
         long long g_end;
         asm volatile("mov.u64 %0, %globaltimer;" : "=l"(g_end));
         t[0] = t_gen; t[1] = t_mma; t[2] = t_epi; t[3] = clock64() - t_start;
-        t[4] = g_start; t[5] = g_end;
+        t[4] = g_start; t[5] = g_end; t[6] = t_sync; t[7] = 0;
     }
     // ---- tile epilogue
     if (tid < TP && tile0 + tid < a.n) {

@@ -27,7 +27,7 @@ if "--phases" in sys.argv:
     from safe_learning_b200 import _native as nat, _device as dev
     lib = nat.load()
     ntiles = (lyap._end - lyap._begin + 63) // 64
-    buf = torch.zeros((ntiles, 8, 6), dtype=torch.int64, device="cuda")
+    buf = torch.zeros((ntiles, 8, 8), dtype=torch.int64, device="cuda")
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     for label, pre in (("back-to-back", lambda: lyap.compute_negative()),
                        ("after 256MB fill", lambda: flush.fill_(1)),
@@ -48,8 +48,8 @@ if "--phases" in sys.argv:
               "| cycles/tile %.0f" % cyc.mean(),
               "| by start decile", [int(cyc[order[i * len(order) // 10:(i + 1) * len(order) // 10]].mean() / 1000)
                                     for i in range(10)])
-    print("per-tile cycles, mean over tiles, per warp: [gen, mma, epi, total]")
-    print(np.round(t.mean(axis=0)[:, :4]).astype(int))
+    print("per-tile cycles, mean over tiles, per warp: [gen, mma, epi, total, barrier-wait]")
+    print(np.round(t.mean(axis=0)[:, [0, 1, 2, 3, 6]]).astype(int))
 
 if "--flush" in sys.argv:
     import time
