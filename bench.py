@@ -235,16 +235,15 @@ def run_ours(args, rank, world, local_rank):
 
     # ---- device-resident arm: whole update_safe_set per step
     # The clock sampler (nvidia-smi, 100 ms period) runs from here to the end of the e2e arm; the
-    # warm-up is stretched to >= 1 s of sweeps so that samples under load exist even though the
-    # timed region itself lasts only K x ~1.6 ms.
+    # warm-up is stretched by 600 sweeps (~1 s) so that samples under load exist even though the
+    # timed region itself lasts only K x ~1.5 ms.
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    t_warm = time.perf_counter()
-    n_warm = 0
-    while n_warm < max(args.warmup, 3) or time.perf_counter() - t_warm < 1.0:
+    # a FIXED count (identical on every rank -- each sweep contains a collective): W + 600 sweeps
+    n_warm = max(args.warmup, 3) + 600
+    for _ in range(n_warm):
         lyap.update_safe_set()
-        n_warm += 1
     barrier()
     launches0 = nat.launch_count()
     ms_total, _ = timed(lyap.update_safe_set, args.steps)

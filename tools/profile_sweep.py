@@ -74,5 +74,8 @@ if "--flush" in sys.argv:
     print("flush, 1 untimed sweep, then timed", timed(lambda: (flush.fill_(1), lyap.compute_negative())))
     print("flush 64MB      ", timed(lambda: flush[:64 << 20].fill_(1)))
     print("flush 128MB     ", timed(lambda: flush[:128 << 20].fill_(1)))
+    A64 = torch.randn(2048, 2048, dtype=torch.float64, device="cuda")
+    print("fill + fp64 matmul 2048^3 (cuBLAS DMMA)", timed(lambda: (flush.fill_(1), torch.matmul(A64, A64))))
+    print("fp64 matmul only (no fill)", timed(lambda: torch.matmul(A64, A64)))
     warm = torch.zeros(1 << 20, dtype=torch.float64, device="cuda")
     print("fill + 8MB elementwise compute", timed(lambda: (flush.fill_(1), warm.mul_(1.0001).add_(1.0))))
