@@ -310,8 +310,11 @@ SLB_DEV void eval_lyapunov_nn(const slb_function& f, const double* in, double* o
 }
 
 // Evaluate a fused function object. `in` has f.in_dim entries, `out` receives the result
-// columns; returns the number of columns (1 after NORM1).
-SLB_DEV int eval_fn(const slb_function& f, const double* in, double* out) {
+// columns; returns the number of columns (1 after NORM1).  Deliberately NOT inlined: the sweep
+// kernels call it five times per point (policy, V twice, L_V twice); one shared copy keeps the
+// kernel text small (27 k -> ~8 k instructions) so the cold prologue / epilogue code of every
+// tile does not stream hundreds of KB through the instruction caches.
+static __device__ __noinline__ int eval_fn(const slb_function& f, const double* in, double* out) {
     int od = f.out_dim;
     switch (f.kind) {
     case SLB_FN_CONSTANT:
