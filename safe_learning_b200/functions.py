@@ -726,11 +726,17 @@ class Likelihood(object):
 class _Factor(object):
     """Device-resident Cholesky state of one (X, kernel, noise, scale) combination."""
 
-    __slots__ = ("key", "M", "nrb", "Xs", "L", "Wpack")
+    __slots__ = ("key", "M", "nrb", "Xs", "L", "Linv", "Wpack", "appends")
 
 
 _FACTOR_CACHE = {}
 _FACTOR_CACHE_MAX = 8
+
+
+def _remember_factor(fac):
+    if len(_FACTOR_CACHE) >= _FACTOR_CACHE_MAX:
+        _FACTOR_CACHE.pop(next(iter(_FACTOR_CACHE)))
+    _FACTOR_CACHE[fac.key] = fac
 
 
 class GPRCached(object):
@@ -832,14 +838,83 @@ class GPRCached(object):
                 * self.likelihood.variance
             kernel = kernel * (self._scale ** 2)
             fac.L = torch.linalg.cholesky(kernel)
-            linv = torch.linalg.solve_triangular(
-                fac.L, torch.eye(M, dtype=torch.float64, device=kernel.device), upper=False)
-            fac.Wpack = dev.empty((int(lib.slb_packed_len(M)),))
-            nat.check(lib.slb_pack_factor(dev.stream(), linv.contiguous().data_ptr(), M,
-                                          fac.Wpack.data_ptr()), "slb_pack_factor")
-            if len(_FACTOR_CACHE) >= _FACTOR_CACHE_MAX:
-                _FACTOR_CACHE.pop(next(iter(_FACTOR_CACHE)))
-            _FACTOR_CACHE[key] = fac
+            fac.Linv = torch.linalg.solve_triangular(
+                fac.L, torch.eye(M, dtype=torch.float64, device=kernel.device),
+                upper=False).contiguous()
+            fac.appends = 0
+            self._pack(fac)
+            _remember_factor(fac)
+        self._finish_cache(fac)
+
+    @staticmethod
+    def _pack(fac):
+        lib = nat.load()
+        fac.Wpack = dev.empty((int(lib.slb_packed_len(fac.M)),))
+        nat.check(lib.slb_pack_factor(dev.stream(), fac.Linv.data_ptr(), fac.M,
+                                      fac.Wpack.data_ptr()), "slb_pack_factor")
+
+    def _append_rows(self, x_new):
+        """Rank-one growth of the cached factor for each appended observation (SURVEY.md 8f
+        item 2) -- O(M^2) on the device instead of the O(M^3) refactorisation of
+        ``functions.py:395-415``:  L' = [[L, 0], [l^T, lam]],  l = L^-1 k,  lam = sqrt(k** - l.l),
+        L'^-1 = [[L^-1, 0], [-(l^T L^-1) / lam, 1 / lam]].  Returns the new factor, or None when
+        a full refit is due (every 256 appends, or if the pivot is not safely positive)."""
+        old = self._factor
+        if old is None or self._hyper_seen != self._hyper_state():
+            return None
+        key = self._factor_key()
+        cached = _FACTOR_CACHE.get(key)
+        if cached is not None:
+            return cached
+        x_new = np.atleast_2d(np.asarray(x_new, dtype=np.float64))
+        if old.appends + len(x_new) > 256 or old.M + len(x_new) != self._X.shape[0]:
+            return None
+        s2 = self._scale ** 2
+        Xs, L, Linv = old.Xs, old.L, old.Linv
+        for row in x_new:
+            xs = dev.to_device((row / self.kern.lengthscales)[None, :])
+            M = Xs.shape[0]
+            # same expansion as RBF.K_device (gpflow square_dist)
+            dist = -2.0 * (Xs @ xs.T)[:, 0] + (Xs * Xs).sum(dim=1) + (xs * xs).sum()
+            k = s2 * (self.kern.variance * torch.exp(-dist / 2))
+            kss = s2 * (self.kern.variance + self.likelihood.variance)
+            l = Linv @ k
+            lam2 = kss - torch.dot(l, l)
+            if not bool(lam2 > 1e-12 * kss):
+                return None
+            lam = torch.sqrt(lam2)
+            L_new = torch.zeros((M + 1, M + 1), dtype=torch.float64, device=L.device)
+            L_new[:M, :M] = L
+            L_new[M, :M] = l
+            L_new[M, M] = lam
+            Linv_new = torch.zeros_like(L_new)
+            Linv_new[:M, :M] = Linv
+            Linv_new[M, :M] = -(l @ Linv) / lam
+            Linv_new[M, M] = 1.0 / lam
+            Xs, L, Linv = torch.cat((Xs, xs), dim=0), L_new, Linv_new
+        fac = _Factor()
+        fac.key, fac.M, fac.nrb = key, Xs.shape[0], (Xs.shape[0] + 7) // 8
+        fac.Xs, fac.L, fac.Linv = Xs.contiguous(), L, Linv.contiguous()
+        fac.appends = old.appends + len(x_new)
+        self._pack(fac)
+        _remember_factor(fac)
+        return fac
+
+    def append_data(self, x, y):
+        """Append observations; grows the cached factor incrementally when possible."""
+        self._X = np.vstack((self._X, np.atleast_2d(x)))
+        self._Y = np.vstack((self._Y, np.atleast_2d(y)))
+        was_fresh = not self._stale
+        self._stale = True
+        fac = self._append_rows(x) if was_fresh else None
+        if fac is None:
+            self.update_cache()
+        else:
+            self._finish_cache(fac)
+
+    def _finish_cache(self, fac):
+        """alpha / gamma / prior mean for this GP's targets on factor `fac` (functions.py:405-409)."""
+        M = fac.M
         self._factor = fac
         target = dev.to_device(self._Y)
         if self.mean_function is not None:
@@ -848,8 +923,8 @@ class GPRCached(object):
         else:
             self._prior_dev = None
         target = self._scale * target
-        alpha = torch.linalg.solve_triangular(fac.L, target, upper=False)
-        gamma = torch.linalg.solve_triangular(fac.L.T, alpha, upper=True)
+        alpha = fac.Linv @ target
+        gamma = fac.Linv.T @ alpha
         padded = dev.zeros((8 * fac.nrb,))
         padded[:M] = alpha[:, 0]
         self._alpha_dev = padded
@@ -957,10 +1032,7 @@ class GaussianProcess(UncertainFunction):
 
     def add_data_point(self, x, y):
         """Append observations and refresh the factor (``functions.py:525-546``)."""
-        gp = self.gaussian_process
-        gp.X = np.vstack((gp.X, np.atleast_2d(x)))
-        gp.Y = np.vstack((gp.Y, np.atleast_2d(y)))
-        gp.update_cache()
+        self.gaussian_process.append_data(x, y)
 
 
 class FunctionStack(UncertainFunction):

@@ -214,6 +214,43 @@ def test_gp_shared_factor_equals_distinct_path(sl):
     assert_allclose(e_gpu, e_cpu, rtol=RTOL, atol=1e-12)
 
 
+def test_incremental_factor_growth_equals_refit(sl):
+    """add_data_point grows the cached factor by rank-one appends (O(M^2)); the result must equal
+    a fresh factorisation (functions.py:395-415, 525-546) and the oracle's predictions."""
+    import time
+    import torch
+    par = W.make_pendulum(num_points=8, M=200, seed=3)
+    _, dyn_gpu = W._build(sl, par, "product")
+    _, dyn_cpu = W._build(O, par, "oracle")
+    dyn_gpu(np.zeros((1, 3)))                                  # build the initial factors
+    rng = np.random.default_rng(0)
+    for i in range(5):
+        x = rng.uniform(-1, 1, (1, 3))
+        y = rng.normal(scale=0.01, size=(1, 2))
+        dyn_gpu.add_data_point(x, y)
+        dyn_cpu.add_data_point(x, y)
+    gp = dyn_gpu.functions[1].gaussian_process
+    assert gp._factor.appends == 5 and gp._factor.M == 205
+    fresh = sl.GPRCached(gp.X, gp.Y, gp.kern, mean_function=gp.mean_function,
+                         noise_variance=gp.likelihood.variance, scale=gp._scale)
+    import safe_learning_b200.functions as F
+    F._FACTOR_CACHE.clear()
+    fresh.update_cache()
+    assert fresh._factor.appends == 0
+    assert_allclose(gp.cholesky, fresh.cholesky, rtol=1e-9, atol=1e-13)
+    assert_allclose(gp.alpha, fresh.alpha, rtol=1e-7, atol=1e-11)
+    pts = rng.uniform(-1, 1, (100, 3))
+    m_gpu, e_gpu = dyn_gpu(pts)
+    m_cpu, e_cpu = dyn_cpu(pts)
+    assert_allclose(m_gpu, m_cpu, rtol=RTOL, atol=1e-12)
+    assert_allclose(e_gpu, e_cpu, rtol=RTOL, atol=1e-12)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    dyn_gpu.add_data_point(rng.uniform(-1, 1, (1, 3)), rng.normal(scale=0.01, size=(1, 2)))
+    torch.cuda.synchronize()
+    print("incremental add_data_point (2 GPs, M=205): %.3f ms" % (1e3 * (time.perf_counter() - t0)))
+
+
 def test_gp_negative_variance_is_nan_not_clamped(sl):
     """functions.py:451, 514: var < 0 -> sqrt -> NaN -> unsafe.  Query AT training points of a
     noise-free-ish GP, where cancellation can push var below zero: wherever the oracle's var is
