@@ -57,7 +57,8 @@ enum slb_fn_kind {
     SLB_FN_TRIANGULATION = 4,  /* Triangulation               functions.py:1103-1158,1442-1499 */
     SLB_FN_PENDULUM = 5,       /* InvertedPendulum            examples/utilities.py:144-289 */
     SLB_FN_CARTPOLE = 6,       /* CartPole                    examples/utilities.py:292-437 */
-    SLB_FN_LYAPUNOV_NN = 7     /* LyapunovNetwork             examples/utilities.py:48-104  */
+    SLB_FN_LYAPUNOV_NN = 7,    /* LyapunovNetwork             examples/utilities.py:48-104  */
+    SLB_FN_MLP = 8             /* NeuralNetwork (inference)   functions.py:1702-1729        */
 };
 /* post-ops, applied in this order: saturate -> abs -> norm1 -> out_scale */
 #define SLB_FLAG_SATURATE 1u   /* Saturation  functions.py:349-354                     */
@@ -74,9 +75,10 @@ typedef struct slb_function {
     double  out_scale;
     double  lower, upper;       /* saturation bounds                                   */
     double  cparams[24];        /* CONSTANT: value; PENDULUM/CARTPOLE: plant constants
-                                   (see safe_learning_b200/functions.py); LYAPUNOV_NN: [0] layers,
-                                   [1+i] width of layer i (<= 64), [9+i] activation (0 tanh,
-                                   1 relu, 2 identity) */
+                                   (see safe_learning_b200/functions.py); LYAPUNOV_NN / MLP:
+                                   [0] layers, [1+i] width of layer i (<= 64), [9+i] activation
+                                   (0 tanh, 1 relu, 2 identity); MLP: [17] output_scale, [18] 1 if
+                                   hidden layers carry a bias (matrix = [W_i (out x in), b_i] ...) */
     const double*  matrix;      /* LINEAR [out,in]; QUADRATIC [in,in]; TRIANGULATION
                                    vertex values [nindex,out]; LYAPUNOV_NN packed kernels */
     const double*  hyperplanes; /* TRIANGULATION [nsimplex, d, d]  (functions.py:1090-1101) */

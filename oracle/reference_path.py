@@ -26,7 +26,8 @@ __all__ = [
     "config", "DimensionError", "GridWorld", "LinearSystem", "QuadraticFunction",
     "Saturation", "ConstantFunction", "ScaledFunction", "AbsFunction", "Norm1Function",
     "RBF", "LinearMean", "GPRCached", "GaussianProcess", "FunctionStack", "Triangulation",
-    "InvertedPendulum", "CartPole", "LyapunovNetwork", "Lyapunov", "PolicyIteration",
+    "InvertedPendulum", "CartPole", "LyapunovNetwork", "NeuralNetwork", "Lyapunov",
+    "PolicyIteration",
     "batchify", "dlqr", "hstack_inputs", "stable_value_order", "prefix_rule",
     "perturb_actions", "get_safe_sample", "unique_rows",
 ]
@@ -664,6 +665,27 @@ class LyapunovNetwork(object):
         for c in range(1, sq.shape[1]):
             acc = acc + sq[:, c]
         return acc[:, None]
+
+
+class NeuralNetwork(object):
+    """``functions.py:1665-1729`` forward pass with explicit parameters: ``tf.layers.dense`` with
+    bias in the hidden layers only, bias-free output layer, ``output_scale``."""
+
+    def __init__(self, layers, nonlinearities, weights, biases, output_scale=1., use_bias=True):
+        self.layers, self.nonlinearities = list(layers), list(nonlinearities)
+        self.weights, self.biases = weights, biases
+        self.output_scale, self.use_bias = output_scale, use_bias
+        self.input_dim, self.output_dim = layers[0], layers[-1]
+
+    def __call__(self, *inputs):
+        net = hstack_inputs(inputs)
+        for i, (w, act) in enumerate(zip(self.weights, self.nonlinearities)):
+            net = _seq_dot(net, np.asarray(w).T)
+            if self.use_bias and i + 1 < len(self.weights):
+                net = net + self.biases[i]
+            if act is not None:
+                net = act(net)
+        return net * self.output_scale
 
 
 # --------------------------------------------------------------------------- Lyapunov

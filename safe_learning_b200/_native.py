@@ -18,7 +18,7 @@ SLB_MAX_ACT = 2
 SLB_TILE_POINTS = 64
 
 FN_NONE, FN_CONSTANT, FN_LINEAR, FN_QUADRATIC, FN_TRIANGULATION, FN_PENDULUM, FN_CARTPOLE, \
-    FN_LYAPUNOV_NN = range(8)
+    FN_LYAPUNOV_NN, FN_MLP = range(9)
 FLAG_SATURATE, FLAG_ABS, FLAG_NORM1, FLAG_PROJECT, FLAG_SCALE = 1, 2, 4, 8, 16
 
 UINT64_MAX = (1 << 64) - 1

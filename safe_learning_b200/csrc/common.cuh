@@ -309,6 +309,36 @@ SLB_DEV void eval_lyapunov_nn(const slb_function& f, const double* in, double* o
     out[0] = v;
 }
 
+// ---- NeuralNetwork inference (functions.py:1702-1729): dense layers, bias in the hidden layers
+// only, output layer without bias, result scaled by output_scale.  matrix = per layer the weight
+// [out_i, in_i] (already transposed to row-per-output) followed, for hidden layers with bias, by
+// the bias [out_i].
+SLB_DEV void eval_mlp(const slb_function& f, const double* in, double* out) {
+    double h[SLB_NN_MAX_WIDTH], g[SLB_NN_MAX_WIDTH];
+    int width = f.in_dim;
+    for (int k = 0; k < width; ++k) h[k] = in[k];
+    const double* P = f.matrix;
+    const int layers = (int)f.cparams[0];
+    const bool use_bias = f.cparams[18] != 0.0;
+    for (int l = 0; l < layers; ++l) {
+        const int od = (int)f.cparams[1 + l];
+        const int act = (int)f.cparams[9 + l];
+        const bool bias = use_bias && (l + 1 < layers);
+        const double* b = P + (size_t)od * width;
+        for (int o = 0; o < od; ++o) {
+            const double* row = P + (size_t)o * width;
+            double acc = f64mul(h[0], row[0]);
+            for (int k = 1; k < width; ++k) acc = f64add(acc, f64mul(h[k], row[k]));
+            if (bias) acc = f64add(acc, b[o]);
+            g[o] = act == 0 ? tanh(acc) : (act == 1 ? fmax(acc, 0.0) : acc);
+        }
+        P += (size_t)od * width + (bias ? od : 0);
+        width = od;
+        for (int k = 0; k < width; ++k) h[k] = g[k];
+    }
+    for (int k = 0; k < width; ++k) out[k] = f64mul(h[k], f.cparams[17]);
+}
+
 // Evaluate a fused function object. `in` has f.in_dim entries, `out` receives the result
 // columns; returns the number of columns (1 after NORM1).  Deliberately NOT inlined: the sweep
 // kernels call it five times per point (policy, V twice, L_V twice); one shared copy keeps the
@@ -352,6 +382,9 @@ static __device__ __noinline__ int eval_fn(const slb_function& f, const double* 
         break;
     case SLB_FN_LYAPUNOV_NN:
         eval_lyapunov_nn(f, in, out); od = 1;
+        break;
+    case SLB_FN_MLP:
+        eval_mlp(f, in, out);
         break;
     default:
         for (int o = 0; o < od; ++o) out[o] = __longlong_as_double(0x7ff8000000000000ll);

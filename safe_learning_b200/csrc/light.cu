@@ -82,6 +82,19 @@ int slb_validate_function(const slb_function* f, const char* what, int expect_in
                       "%s: LyapunovNetwork layer %d width %g outside 1..64", what, l, f->cparams[1 + l]);
         break;
     }
+    case SLB_FN_MLP: {
+        SLB_CHECK(f->matrix != nullptr, "%s: NeuralNetwork without parameters", what);
+        const int layers = (int)f->cparams[0];
+        SLB_CHECK(layers >= 1 && layers <= 8, "%s: NeuralNetwork with %d layers (1..8)", what, layers);
+        SLB_CHECK(f->in_dim >= 1 && f->in_dim <= SLB_MAX_IN, "%s: NeuralNetwork input dim %d", what,
+                  f->in_dim);
+        for (int l = 0; l < layers; ++l)
+            SLB_CHECK(f->cparams[1 + l] >= 1 && f->cparams[1 + l] <= 64,
+                      "%s: NeuralNetwork layer %d width %g outside 1..64", what, l, f->cparams[1 + l]);
+        SLB_CHECK((int)f->cparams[layers] == f->out_dim && f->out_dim <= SLB_MAX_OUT,
+                  "%s: NeuralNetwork output width must equal out_dim (<= %d)", what, SLB_MAX_OUT);
+        break;
+    }
     default:
         slb_set_error("%s: function kind %d is not implemented in this build", what, f->kind);
         return 1;

@@ -30,7 +30,8 @@ __all__ = ["DimensionError", "GridWorld", "Function", "DeterministicFunction",
            "UncertainFunction", "ConstantFunction", "LinearSystem", "QuadraticFunction",
            "Saturation", "AbsFunction", "Norm1Function", "ScaledFunction", "Triangulation",
            "RBF", "Likelihood", "GPRCached", "GPR", "GaussianProcess", "FunctionStack",
-           "InvertedPendulum", "CartPole", "LyapunovNetwork", "concatenate_inputs"]
+           "InvertedPendulum", "CartPole", "LyapunovNetwork", "NeuralNetwork",
+           "concatenate_inputs"]
 
 
 class DimensionError(Exception):
@@ -689,6 +690,65 @@ class LyapunovNetwork(DeterministicFunction):
             d.cparams[1 + i] = od
             d.cparams[9 + i] = self._ACT[act]
         d.matrix = self._kernel_dev.data_ptr()
+        return d
+
+
+class NeuralNetwork(DeterministicFunction):
+    """Dense MLP, inference only (``functions.py:1665-1729``): bias in the hidden layers only,
+    no bias in the output layer, output multiplied by ``output_scale``.  ``layers`` =
+    [in, h1, ..., out]; ``nonlinearities`` one per layer after the input ('tanh' | 'relu' | None).
+    ``weights[i]`` has the TF layout ``[in_i, out_i]``, ``biases[i]`` ``[out_i]`` (hidden layers);
+    both are drawn Xavier-uniform / zero from ``seed`` when omitted.  Training (the reference
+    optimises these with TF optimisers) is outside this build.
+    """
+
+    def __init__(self, layers, nonlinearities, output_scale=1., use_bias=True,
+                 name="neural_network", weights=None, biases=None, seed=0):
+        super().__init__(name)
+        self.layers = [int(v) for v in layers]
+        self.nonlinearities = []
+        for act in nonlinearities:
+            key = "linear" if act is None else (act if isinstance(act, str)
+                                                else getattr(act, "__name__", ""))
+            if key not in LyapunovNetwork._ACT:
+                raise NotImplementedError("nonlinearity %r is not fused (tanh/relu/None)" % (act,))
+            self.nonlinearities.append(key)
+        if len(self.nonlinearities) != len(self.layers) - 1:
+            raise ValueError("one nonlinearity per layer after the input is required")
+        self.output_scale = float(output_scale)
+        self.use_bias = bool(use_bias)
+        self.input_dim, self.output_dim = self.layers[0], self.layers[-1]
+        if max(self.layers[1:]) > 64 or len(self.layers) - 1 > 8 or self.output_dim > nat.SLB_MAX_OUT:
+            raise DimensionError("NeuralNetwork: at most 8 layers of width <= 64 are fused")
+        rng = np.random.default_rng(seed)
+        if weights is None:
+            weights = []
+            for din, dout in zip(self.layers[:-1], self.layers[1:]):
+                lim = np.sqrt(6.0 / (din + dout))
+                weights.append(rng.uniform(-lim, lim, size=(din, dout)))
+        if biases is None:
+            biases = [np.zeros(d) for d in self.layers[1:-1]]
+        self.weights = [np.asarray(w, dtype=np.float64) for w in weights]
+        self.biases = [np.asarray(b, dtype=np.float64) for b in biases]
+        self._param_dev = None
+
+    def descriptor(self):
+        if self._param_dev is None:
+            parts = []
+            for i, w in enumerate(self.weights):
+                parts.append(w.T.ravel())                       # [out, in] rows
+                if self.use_bias and i + 1 < len(self.weights):
+                    parts.append(self.biases[i].ravel())
+            self._param_dev = dev.to_device(np.concatenate(parts))
+        d = nat.SlbFunction()
+        d.kind, d.in_dim, d.out_dim = nat.FN_MLP, self.input_dim, self.output_dim
+        d.cparams[0] = len(self.weights)
+        for i, (od, act) in enumerate(zip(self.layers[1:], self.nonlinearities)):
+            d.cparams[1 + i] = od
+            d.cparams[9 + i] = LyapunovNetwork._ACT[act]
+        d.cparams[17] = self.output_scale
+        d.cparams[18] = 1.0 if self.use_bias else 0.0
+        d.matrix = self._param_dev.data_ptr()
         return d
 
 

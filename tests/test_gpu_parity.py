@@ -167,6 +167,53 @@ def test_triangulation_vs_oracle(sl, dims, project):
     assert_allclose(t_gpu(inside), t_cpu(inside), rtol=1e-13, atol=1e-13)
 
 
+def test_neural_network_policy_vs_oracle(sl):
+    """functions.py:1702-1729 inference (the 2-32-32-1 policy of inverted_pendulum.ipynb cell 9)
+    and its use as the policy of a Lyapunov sweep."""
+    rng = np.random.default_rng(8)
+    net_g = sl.NeuralNetwork([2, 32, 32, 1], ["relu", "relu", "tanh"], output_scale=0.8, seed=4)
+    net_g.biases = [rng.normal(scale=0.1, size=32), rng.normal(scale=0.1, size=32)]
+    net_c = O.NeuralNetwork([2, 32, 32, 1], [lambda v: np.maximum(v, 0.0)] * 2 + [np.tanh],
+                            net_g.weights, net_g.biases, output_scale=0.8)
+    x = rng.uniform(-1, 1, (500, 2))
+    assert_allclose(net_g(x), net_c(x), rtol=1e-13, atol=1e-15)
+    par = W.make_pendulum(num_points=24, M=50, tau_scale=1 / 64.)
+    gpu, cpu = W.build_product(par), W.build_oracle(par)
+    gpu.policy, cpu.policy = net_g, net_c
+    det = _sweep_details(gpu)
+    _assert_negative_parity(gpu, cpu, det)
+    gpu.update_safe_set()
+    cpu.update_safe_set()
+    assert_array_equal(gpu.safe_set, cpu.safe_set)
+
+
+def test_learning_loop_vs_oracle(sl):
+    """The loop of adaptive_safety_verification.ipynb cells 23-25: update_safe_set ->
+    get_safe_sample -> measure the true plant -> add_data_point -> update_safe_set ..."""
+    par = W.make_pendulum(num_points=32, M=20, tau_scale=1 / 64., seed=11)
+    gpu, cpu = W.build_product(par), W.build_oracle(par)
+    pl = par["plant"]
+    true_dyn = O.InvertedPendulum(normalization=[pl["state_norm"], pl["action_norm"]], **pl["true"])
+    perturbations = np.array([[0.0]])
+    limits = np.array([[-1., 1.]])
+    gpu.update_safe_set()
+    cpu.update_safe_set()
+    for it in range(6):
+        assert_array_equal(gpu.safe_set, cpu.safe_set)
+        assert gpu.feed_dict[gpu.c_max] == cpu.c_max
+        sa_g, b_g = sl.get_safe_sample(gpu, perturbations, limits, positive=True)
+        sa_c, b_c = O.get_safe_sample(cpu, perturbations, limits, positive=True)
+        assert_array_equal(sa_g, sa_c)
+        assert_allclose(b_g, b_c, rtol=RTOL)
+        measurement = true_dyn(sa_c)
+        gpu.dynamics.add_data_point(sa_g, measurement)
+        cpu.dynamics.add_data_point(sa_c, measurement)
+        gpu.update_safe_set(can_shrink=bool(it % 2))
+        cpu.update_safe_set(can_shrink=bool(it % 2))
+    assert_array_equal(gpu.safe_set, cpu.safe_set)
+    assert gpu.dynamics.functions[0].gaussian_process._factor.appends == 6
+
+
 def test_plants_vs_oracle(sl):
     rng = np.random.default_rng(5)
     norm = [(0.5, 4.4), (0.37,)]
