@@ -5,6 +5,8 @@
             HBM-side variant of the path
   c5        resolution x M sweep of the GP Lyapunov sweep kernel (C5), single GPU
   shared    C2 with shared hyper-parameters (one Cholesky factor for both outputs)
+  det_linear  deterministic LinearSystem dynamics on 4096^2 / 8192^2 (closest to the HBM roofline)
+  c4        cart-pole 32^4 grid, M=2000, four factors, LyapunovNetwork V (C4 at 1-GPU size)
 
     python tools/bench_extra.py [bellman] [det] [c5] [shared]
 """
@@ -82,6 +84,41 @@ def det():
                                   "fp64-CUDA-core bound, not HBM bound; 17 algorithmic B/pt"}))
 
 
+def det_linear():
+    """Cheapest deterministic variant: LinearSystem dynamics, quadratic V, |2Px| Lipschitz term --
+    ~10^2 fp64 operations per point against 17 algorithmic HBM bytes."""
+    for num in (4096, 8192):
+        par = W.make_pendulum(num_points=num, M=8)
+        grid = sl.GridWorld(par["limits"], par["num_points"])
+        policy = sl.Saturation(sl.LinearSystem(-par["K"]), -1., 1.)
+        dyn = sl.LinearSystem((par["A_true"], par["B_true"]))
+        lyap = sl.Lyapunov(grid, sl.QuadraticFunction(par["P"]), dyn, par["L_dyn"],
+                           abs(sl.LinearSystem((2 * par["P"],))), par["tau"], policy)
+        ms = timed(lyap.compute_negative, steps=10)
+        n = grid.nindex
+        print(json.dumps({"bench": "deterministic_linear_sweep", "grid": "%dx%d" % (num, num),
+                          "kernel_ms": ms, "points_per_s": n / (ms * 1e-3),
+                          "hbm_algorithmic_gbs": n * 17 / (ms * 1e-3) * 1e-9,
+                          "hbm_frac_of_measured": n * 17 / (ms * 1e-3) * 1e-9 / HBM_GBS,
+                          "note": "writes 1 B flag per point (V not written); coordinates generated"}))
+        del lyap
+        torch.cuda.empty_cache()
+
+
+def c4():
+    """C4 at single-GPU size: 4-D cart-pole grid 32^4, four RBF GPs on 5-D inputs (M=2000, four
+    Cholesky factors), V = LyapunovNetwork(4, [64, 64, 64], tanh)."""
+    par = W.make_cartpole(num_points=32, M=2000)
+    lyap = W.build_product(par)
+    ms = timed(lyap.update_safe_set, steps=2, warmup=1)
+    n = lyap.discretization.nindex
+    fl = algorithmic_flops_per_point(2000, 5, 4, 4)
+    print(json.dumps({"bench": "c4_cartpole_update_safe_set", "grid": "32^4", "M": 2000,
+                      "factors": 4, "ms_per_sweep": ms, "points_per_s": n / (ms * 1e-3),
+                      "tflops": fl * n / (ms * 1e-3) * 1e-12,
+                      "frac_of_fp64_peak": fl * n / (ms * 1e-3) * 1e-12 / PEAK_TF}))
+
+
 def c5():
     for num, M in ((128, 100), (256, 100), (256, 200), (256, 500), (512, 500), (1024, 500),
                    (256, 1000), (256, 2000), (128, 5000)):
@@ -113,6 +150,6 @@ def shared():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["bellman", "det", "c5", "shared"]
+    which = sys.argv[1:] or ["bellman", "det", "det_linear", "c5", "shared", "c4"]
     for name in which:
         globals()[name]()
