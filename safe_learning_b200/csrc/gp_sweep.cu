@@ -35,9 +35,13 @@ constexpr int PANEL = 256;            // rows per i-panel, columns per j-panel
 // k-steps of a pair.  KSTR = 66: (r * 66 + c) mod 8 is distinct for r in 0..3, c in 0..1, i.e. the
 // eight lanes of a quarter-warp hit eight different 16-byte bank groups (conflict-free LDS.128).
 constexpr int KSTR = TP + 2;
-constexpr int NW = 8;                 // warps per CTA
+#ifndef SLB_NW
+#define SLB_NW 8
+#endif
+constexpr int NW = SLB_NW;            // warps per CTA (8 or 16)
 constexpr int NT = NW * 32;
-constexpr int RQ = 4;                 // 8-row blocks per warp per 256-row panel (RQ * NW = 32)
+constexpr int RQ = 32 / NW;           // 8-row blocks per warp per 256-row panel (RQ * NW = 32)
+static_assert(NW == 8 || NW == 16, "NW must be 8 or 16");
 constexpr int NB = TP / 8;            // 8-point column blocks per warp tile
 constexpr int CTAS_PER_SM = 1;
 constexpr int NRED = 1 + SLB_MAX_OUT;
@@ -209,8 +213,11 @@ gp_tile_kernel(const __grid_constant__ slb_sweep cfg, const gp_args a) {
 
     // Row blocks are dealt by `wslot`; warps w and w+4 share an SMSP (and its fp64 pipe), so
     // their slots sum to 7 and every SMSP gets the same share of the triangular panels.
-    static_assert(NW == 8, "slot permutation below assumes 8 warps (2 per SMSP)");
-    const int wslot = warp < 4 ? warp : 11 - warp;     // SMSP partners w, w+4 sum to 7
+    // SMSP partners (warps with equal warp % 4) get slots with equal sums: {g, 7-g} for 8 warps,
+    // {g, 7-g, 8+g, 15-g} for 16
+    const int wg_ = warp & 3, wr_ = warp >> 2;
+    const int wslot = NW == 8 ? (wr_ == 0 ? wg_ : 7 - wg_)
+                              : (wr_ == 0 ? wg_ : wr_ == 1 ? 7 - wg_ : wr_ == 2 ? 8 + wg_ : 15 - wg_);
     const int p_gen = tid & (TP - 1);
     const int jg = tid / TP;                          // 0..NT/TP-1
     const double2* ks_lane = reinterpret_cast<const double2*>(Ks) + (lane & 3) * KSTR + (lane >> 2);
@@ -256,17 +263,20 @@ gp_tile_kernel(const __grid_constant__ slb_sweep cfg, const gp_args a) {
                     if (TIMING) { t_mark = clock64(); t_sync += t_mark - t_s0; }
                     const int j0 = PANEL * jp;
                     const int nj = min(PANEL, M - j0);
-                    // thread (p_gen, jg): fragment row r = jg of every pair m, both halves (rows
-                    // 8m + jg and 8m + 4 + jg); GP pairs per iteration = 2 GP interleaved exps
-                    static_assert(NT / TP == 4, "generation assumes 4 thread groups per point");
+                    // thread (p_gen, jg): fragment row r = jg % 4 of the pairs m = jg / 4 (mod PS),
+                    // both halves (rows 8m + r and 8m + 4 + r); GP pairs per iteration = 2 GP
+                    // interleaved exps
+                    constexpr int PS = NT / TP / 4;      // pair stride between a thread's pairs
+                    static_assert(NT / TP == 4 * PS, "generation needs a multiple of 4 groups");
+                    const int gr = jg & 3, gpo = jg >> 2;
                     const int npairs = (nkp + 1) >> 1;
                     double2* ks2 = reinterpret_cast<double2*>(Ks);
                     constexpr int GP = 2;            // pairs per iteration = 2 GP interleaved exps
-                    for (int mm = 0; mm < npairs; mm += GP) {
+                    for (int mm = gpo; mm < npairs; mm += GP * PS) {
                         double t2[2 * GP];
 #pragma unroll
                         for (int u = 0; u < 2 * GP; ++u) {
-                            const int jj = min(8 * (mm + (u >> 1)) + 4 * (u & 1) + jg, nj - 1);
+                            const int jj = min(8 * (mm + PS * (u >> 1)) + 4 * (u & 1) + gr, nj - 1);
                             const double* xr = Xs + (size_t)(j0 + jj) * DIN;
                             double acc2 = 0.0;
 #pragma unroll
@@ -279,14 +289,14 @@ gp_tile_kernel(const __grid_constant__ slb_sweep cfg, const gp_args a) {
                         double kv[2 * GP];
 #pragma unroll
                         for (int u = 0; u < 2 * GP; ++u) {
-                            const int jj = 8 * (mm + (u >> 1)) + 4 * (u & 1) + jg;
+                            const int jj = 8 * (mm + PS * (u >> 1)) + 4 * (u & 1) + gr;
                             const double k = s2 * (variance * exp_neg_tab(-0.5 * t2[u], exptab));
                             kv[u] = jj < nj ? k : 0.0;          // zero rows pad the last pair
                         }
 #pragma unroll
                         for (int g = 0; g < GP; ++g)
-                            if (mm + g < npairs)
-                                ks2[((mm + g) * 4 + jg) * KSTR + p_gen] =
+                            if (mm + PS * g < npairs)
+                                ks2[((mm + PS * g) * 4 + gr) * KSTR + p_gen] =
                                     make_double2(kv[2 * g], kv[2 * g + 1]);
                     }
                     resident = jp;
@@ -311,12 +321,13 @@ gp_tile_kernel(const __grid_constant__ slb_sweep cfg, const gp_args a) {
                     ap[q] = reinterpret_cast<const double2*>(F.Wpack) +
                             (b * (b + 1) / 2 + 32 * jp) * 32 + lane;
                 }
-                static_assert(RQ == 4, "segment dispatch below is written for RQ == 4");
                 int mprev = 0;
                 if (mend[0] > mprev) { mma_run<0>(acc, ap, mprev, mend[0], ks_lane); mprev = mend[0]; }
                 if (mend[1] > mprev) { mma_run<1>(acc, ap, mprev, mend[1], ks_lane); mprev = mend[1]; }
-                if (mend[2] > mprev) { mma_run<2>(acc, ap, mprev, mend[2], ks_lane); mprev = mend[2]; }
-                if (mend[3] > mprev) { mma_run<3>(acc, ap, mprev, mend[3], ks_lane); mprev = mend[3]; }
+                if constexpr (RQ == 4) {
+                    if (mend[2] > mprev) { mma_run<2>(acc, ap, mprev, mend[2], ks_lane); mprev = mend[2]; }
+                    if (mend[3] > mprev) { mma_run<3>(acc, ap, mprev, mend[3], ks_lane); mprev = mend[3]; }
+                }
                 if (TIMING) t_mma += clock64() - t_mark;
             }
             if (TIMING) t_mark = clock64();
