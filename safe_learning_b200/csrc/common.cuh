@@ -340,11 +340,17 @@ SLB_DEV void eval_mlp(const slb_function& f, const double* in, double* out) {
 }
 
 // Evaluate a fused function object. `in` has f.in_dim entries, `out` receives the result
-// columns; returns the number of columns (1 after NORM1).  Deliberately NOT inlined: the sweep
-// kernels call it five times per point (policy, V twice, L_V twice); one shared copy keeps the
-// kernel text small (27 k -> ~8 k instructions) so the cold prologue / epilogue code of every
-// tile does not stream hundreds of KB through the instruction caches.
-static __device__ __noinline__ int eval_fn(const slb_function& f, const double* in, double* out) {
+// columns; returns the number of columns (1 after NORM1).  In gp_sweep.cu (SLB_EVAL_NOINLINE) it
+// is deliberately NOT inlined: the tile kernel calls it five times per point (policy, V twice,
+// L_V twice) in cold prologue / epilogue code, and one shared copy keeps the kernel text small
+// (27 k -> ~10 k instructions: -1.3% back-to-back, -3.3% after an L2 flush).  The thread-per-point
+// kernels of light.cu inline it (the call overhead costs them ~20%).
+#ifdef SLB_EVAL_NOINLINE
+#define SLB_EVAL_ATTR static __device__ __noinline__
+#else
+#define SLB_EVAL_ATTR static __device__ __forceinline__
+#endif
+SLB_EVAL_ATTR int eval_fn(const slb_function& f, const double* in, double* out) {
     int od = f.out_dim;
     switch (f.kind) {
     case SLB_FN_CONSTANT:

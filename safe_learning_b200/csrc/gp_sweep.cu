@@ -23,6 +23,7 @@
 //     64 fp64 accumulators per thread); rows are dealt to warps round-robin from the bottom
 //     of the panel so the triangular work is balanced across warps and across SMSPs.  sum a^2 and a.alpha are reduced in
 //     the panel epilogue, so `a` is never stored.
+#define SLB_EVAL_NOINLINE 1
 #include "common.cuh"
 
 namespace {
