@@ -9,20 +9,24 @@
 //   FunctionStack concat                         functions.py:278-291
 //   v_decrease_bound < threshold                 lyapunov.py:436-441 -> tile epilogue
 //
-// Design (B200, fp64 pipe bound -- see DESIGN.md):
-//   * one CTA = 64 grid points x all M training points, 8 warps, 1 CTA/SM (181 KB smem,
-//     ~245 registers).  Measured alternatives (profiles/r01_kernel_variants.md): 16 warps x
-//     (16 rows x 64 points) and 2 CTAs/SM x 32-point tiles were both 2-5% slower.
+// Design (B200, fp64 pipe bound -- see DESIGN.md section 3.1):
+//   * one CTA = 64 grid points x all M training points, 8 warps, 1 CTA/SM (~178 KB shared
+//     memory, 232 registers, no spills).  Measured alternatives (profiles/r01_kernel_variants.md):
+//     16 warps x (16 rows x 64 points) is +1% with spills, 2 CTAs/SM x 32-point tiles is slower.
 //   * W = L^-1 (lower triangular) is pre-packed in DMMA.8x8x4 A-fragment order, two k-steps
 //     per 128-bit element (slb_pack_factor); each warp streams ITS rows of W straight from L2
-//     into registers with coalesced 512 B loads, prefetched two pairs ahead -- W is used by
-//     exactly one warp per CTA, so it never needs shared memory.
-//   * the k-row tile K[j, p] = s^2 exp(-|z_p - X_j|^2/2) is generated once per 256-row
-//     j-panel into shared memory ([j][68] doubles: conflict-free B-fragment reads).
-//   * a 256-row i-panel of a = W k lives in registers (32 rows x 64 points per warp =
-//     64 fp64 accumulators per thread); rows are dealt to warps round-robin from the bottom
-//     of the panel so the triangular work is balanced across warps and across SMSPs.  sum a^2 and a.alpha are reduced in
-//     the panel epilogue, so `a` is never stored.
+//     into registers with coalesced 512 B loads through a static three-deep register ring --
+//     W is used by exactly one warp per CTA, so it never needs shared memory.
+//   * the k-row tile K[j, p] = s^2 v exp(-|z_p - X_j|^2 / 2) is generated once per 256-row
+//     j-panel into shared memory in a pair-interleaved layout (conflict-free 128-bit
+//     B-fragment reads), with a branch-free table-driven exp, four evaluations in flight.
+//   * a 256-row i-panel of a = W k lives in registers (32 rows x 64 points per warp = 64 fp64
+//     accumulators per thread); row blocks are dealt to warps round-robin from the bottom of the
+//     panel so the triangular work is balanced across warps and across SMSPs.  sum a^2 and
+//     a.alpha are reduced by a butterfly reduce-scatter in the panel epilogue into per-warp
+//     running sums (no block barrier per panel); `a` is never stored.
+//   * first-wave CTAs prefetch the packed factor into L2 (cold-L2 launches otherwise stream it
+//     from HBM in lockstep); eval_fn is not inlined here to keep the cold code small.
 #define SLB_EVAL_NOINLINE 1
 #include "common.cuh"
 

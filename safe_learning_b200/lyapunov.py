@@ -9,15 +9,14 @@ With ``torch.distributed`` initialised, the grid is sharded by contiguous flat-i
 
 from __future__ import annotations
 
-import ctypes
+import os
 
 import numpy as np
 import torch
 
 from . import _device as dev
 from . import _native as nat
-from .functions import (Function, FunctionStack, GaussianProcess, UncertainFunction, config,
-                        concatenate_inputs)
+from .functions import Function, FunctionStack, GaussianProcess, UncertainFunction, config
 
 __all__ = ["Lyapunov", "get_safe_sample", "perturb_actions", "combine_fail_keys",
            "combine_prefix_stats"]
@@ -98,8 +97,9 @@ def get_safe_sample(lyapunov, perturbations=None, limits=None, positive=False, n
     return state_actions[maps_inside, :][[max_id]], bound_safe[max_id].squeeze()
 
 
-import os as _os
-_USE_GRAPHS = _os.environ.get("SLB200_GRAPHS", "0") == "1"   # measured: no gain, launches are already hidden behind the 1.5 ms sweep kernel
+# CUDA-graph replay of the five launches of a sweep (opt-in): measured to give no gain, the
+# launches are already hidden behind the ~1.4 ms sweep kernel.
+_USE_GRAPHS = os.environ.get("SLB200_GRAPHS", "0") == "1"
 
 
 class _CMax(object):

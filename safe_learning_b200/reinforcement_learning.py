@@ -15,7 +15,7 @@ import torch
 from . import _device as dev
 from . import _native as nat
 from .functions import (Function, FunctionStack, GaussianProcess, ScaledFunction, Triangulation,
-                        UncertainFunction, concatenate_inputs)
+                        UncertainFunction)
 
 __all__ = ["PolicyIteration", "OptimizationError"]
 

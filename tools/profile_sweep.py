@@ -24,7 +24,7 @@ print("kernel ms", e0.elapsed_time(e1) / 5, "safe", int(lyap.safe_set.sum()))
 if "--phases" in sys.argv:
     import time
     import numpy as np
-    from safe_learning_b200 import _native as nat, _device as dev
+    from safe_learning_b200 import _native as nat
     lib = nat.load()
     ntiles = (lyap._end - lyap._begin + 63) // 64
     buf = torch.zeros((ntiles, 8, 8), dtype=torch.int64, device="cuda")
