@@ -304,9 +304,11 @@ apply_prefix_kernel(const double* __restrict__ values, const uint8_t* __restrict
 // ---- Bellman sweep ------------------------------------------------------------------------
 // One factor with NO outputs on it: NO is a compile-time constant so the running dot products
 // stay in registers (a runtime-bounded loop over outputs would push them to local memory).
+constexpr int BCHUNK = 256;    // training rows staged per pass in the Bellman kernels
+
 template <int DIN, int NO>
 SLB_DEV void gp_mean_factor(const slb_gp_stack& gp, const slb_gp_factor& F, const int* outs,
-                            const double* z, double* mu, const double* exptab) {
+                            const double* z, double* mu, const double* exptab, double* stage) {
     double zs[DIN];
 #pragma unroll
     for (int c = 0; c < DIN; ++c) zs[c] = z[c] / F.lengthscales[c];
@@ -316,25 +318,39 @@ SLB_DEV void gp_mean_factor(const slb_gp_stack& gp, const slb_gp_factor& F, cons
     for (int q = 0; q < NO; ++q) { dot[q] = 0.0; gam[q] = gp.outputs[outs[q]].gamma; }
     const double* __restrict__ Xs = F.Xs;
     const int M = F.M;
-    // 4 independent exp chains per thread (the loop is bound by the fp64 pipe through exp)
-    for (int j0 = 0; j0 < M; j0 += 4) {
-        double t2[4];
+    // The training inputs and gamma are staged chunk-wise in shared memory (one coalesced pass
+    // per block): every thread needs every row once, and read from global the first toucher
+    // of a row pays an L2 round trip inside the exp dependency chain.  All threads of the
+    // block take part (callers must not exit early).
+    double* xch = stage;                       // [BCHUNK][DIN]
+    double* gch = stage + BCHUNK * DIN;        // [NO][BCHUNK]
+    for (int c0 = 0; c0 < M; c0 += BCHUNK) {
+        const int nc = min(BCHUNK, M - c0);
+        __syncthreads();
+        for (int i = threadIdx.x; i < nc * DIN; i += blockDim.x) xch[i] = Xs[(size_t)c0 * DIN + i];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int j = min(j0 + u, M - 1);
-            const double* xr = Xs + (size_t)j * DIN;
-            double acc = 0.0;
+        for (int q = 0; q < NO; ++q)
+            for (int i = threadIdx.x; i < nc; i += blockDim.x) gch[q * BCHUNK + i] = gam[q][c0 + i];
+        __syncthreads();
+        // 4 independent exp chains per thread (the loop is bound by the fp64 pipe through exp)
+        for (int j0 = 0; j0 < nc; j0 += 4) {
+            double t2[4];
 #pragma unroll
-            for (int c = 0; c < DIN; ++c) { const double df = zs[c] - __ldg(xr + c); acc = fma(df, df, acc); }
-            t2[u] = acc;
-        }
+            for (int u = 0; u < 4; ++u) {
+                const double* xr = xch + min(j0 + u, nc - 1) * DIN;
+                double acc = 0.0;
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            double k = F.variance * exp_neg_tab(-0.5 * t2[u], exptab);
-            if (j0 + u >= M) k = 0.0;
-            const int j = min(j0 + u, M - 1);
+                for (int c = 0; c < DIN; ++c) { const double df = zs[c] - xr[c]; acc = fma(df, df, acc); }
+                t2[u] = acc;
+            }
 #pragma unroll
-            for (int q = 0; q < NO; ++q) dot[q] = fma(k, __ldg(gam[q] + j), dot[q]);
+            for (int u = 0; u < 4; ++u) {
+                double k = F.variance * exp_neg_tab(-0.5 * t2[u], exptab);
+                if (j0 + u >= nc) k = 0.0;
+                const int j = min(j0 + u, nc - 1);
+#pragma unroll
+                for (int q = 0; q < NO; ++q) dot[q] = fma(k, gch[q * BCHUNK + j], dot[q]);
+            }
         }
     }
     const double s2 = f64mul(F.scale, F.scale);
@@ -357,7 +373,7 @@ SLB_DEV void gp_mean_factor(const slb_gp_stack& gp, const slb_gp_factor& F, cons
 // which equals a^T alpha of functions.py:441-442 up to rounding.
 template <int DIN>
 SLB_DEV void gp_mean_only(const slb_gp_stack& gp, const double* z, double* mu,
-                          const double* exptab) {
+                          const double* exptab, double* stage) {
     for (int f = 0; f < gp.num_factors; ++f) {
         const slb_gp_factor& F = gp.factors[f];
         int outs[SLB_MAX_OUT];
@@ -365,12 +381,12 @@ SLB_DEV void gp_mean_only(const slb_gp_stack& gp, const double* z, double* mu,
         for (int o = 0; o < gp.num_outputs; ++o)
             if (gp.outputs[o].factor == f) outs[no++] = o;
         switch (no) {
-        case 1: gp_mean_factor<DIN, 1>(gp, F, outs, z, mu, exptab); break;
-        case 2: gp_mean_factor<DIN, 2>(gp, F, outs, z, mu, exptab); break;
-        case 3: gp_mean_factor<DIN, 3>(gp, F, outs, z, mu, exptab); break;
-        case 4: gp_mean_factor<DIN, 4>(gp, F, outs, z, mu, exptab); break;
-        case 5: gp_mean_factor<DIN, 5>(gp, F, outs, z, mu, exptab); break;
-        case 6: gp_mean_factor<DIN, 6>(gp, F, outs, z, mu, exptab); break;
+        case 1: gp_mean_factor<DIN, 1>(gp, F, outs, z, mu, exptab, stage); break;
+        case 2: gp_mean_factor<DIN, 2>(gp, F, outs, z, mu, exptab, stage); break;
+        case 3: gp_mean_factor<DIN, 3>(gp, F, outs, z, mu, exptab, stage); break;
+        case 4: gp_mean_factor<DIN, 4>(gp, F, outs, z, mu, exptab, stage); break;
+        case 5: gp_mean_factor<DIN, 5>(gp, F, outs, z, mu, exptab, stage); break;
+        case 6: gp_mean_factor<DIN, 6>(gp, F, outs, z, mu, exptab, stage); break;
         default: break;
         }
     }
@@ -378,12 +394,12 @@ SLB_DEV void gp_mean_only(const slb_gp_stack& gp, const double* z, double* mu,
 
 template <int DIN>
 SLB_DEV double bellman_value(const slb_bellman& cfg, const double* x, const double* u, int m,
-                             const double* exptab) {
+                             const double* exptab, double* stage) {
     const int d = cfg.grid.ndim;
     double z[SLB_MAX_IN], mu[SLB_MAX_OUT], r[SLB_MAX_OUT], v[SLB_MAX_OUT];
     for (int c = 0; c < d; ++c) z[c] = x[c];
     for (int c = 0; c < m; ++c) z[d + c] = u[c];
-    if (cfg.gp.num_outputs > 0) gp_mean_only<DIN>(cfg.gp, z, mu, exptab);
+    if (cfg.gp.num_outputs > 0) gp_mean_only<DIN>(cfg.gp, z, mu, exptab, stage);
     else eval_fn(cfg.dynamics, z, mu);
     eval_fn(cfg.reward, z, r);                               // :95
     eval_fn(cfg.value, mu, v);                               // :101
@@ -395,10 +411,12 @@ __global__ void __launch_bounds__(LT, 2)
 bellman_kernel(const __grid_constant__ slb_bellman cfg, int64_t idx_begin, int64_t n,
                double* __restrict__ out) {
     __shared__ double exptab[64];
+    __shared__ double stage[BCHUNK * (DIN + SLB_MAX_OUT)];
     load_exp_table(exptab);
     __syncthreads();
-    const int64_t i = (int64_t)blockIdx.x * LT + threadIdx.x;
-    if (i >= n) return;
+    const int64_t i0 = (int64_t)blockIdx.x * LT + threadIdx.x;
+    const bool valid = i0 < n;
+    const int64_t i = valid ? i0 : n - 1;       // every thread stays for the block barriers
     double x[SLB_MAX_DIM], u[SLB_MAX_OUT];
     grid_index_to_state(cfg.grid, idx_begin + i, x);
     int m;
@@ -408,7 +426,8 @@ bellman_kernel(const __grid_constant__ slb_bellman cfg, int64_t idx_begin, int64
     } else {
         m = eval_fn(cfg.policy, x, u);
     }
-    out[i] = bellman_value<DIN>(cfg, x, u, m, exptab);
+    const double v = bellman_value<DIN>(cfg, x, u, m, exptab, stage);
+    if (valid) out[i] = v;
 }
 
 template <int DIN>
@@ -418,22 +437,26 @@ bellman_argmax_kernel(const __grid_constant__ slb_bellman cfg, int64_t idx_begin
                       const double* __restrict__ constraint, int32_t* __restrict__ best,
                       double* __restrict__ best_value) {
     __shared__ double exptab[64];
+    __shared__ double stage[BCHUNK * (DIN + SLB_MAX_OUT)];
     load_exp_table(exptab);
     __syncthreads();
-    const int64_t i = (int64_t)blockIdx.x * LT + threadIdx.x;
-    if (i >= n) return;
+    const int64_t i0 = (int64_t)blockIdx.x * LT + threadIdx.x;
+    const bool valid = i0 < n;
+    const int64_t i = valid ? i0 : n - 1;       // every thread stays for the block barriers
     double x[SLB_MAX_DIM], u[SLB_MAX_ACT];
     grid_index_to_state(cfg.grid, idx_begin + i, x);
     int arg = 0;
     double vmax = 0.0;
     for (int a = 0; a < n_actions; ++a) {
         for (int c = 0; c < m; ++c) u[c] = actions[a * m + c];
-        double v = bellman_value<DIN>(cfg, x, u, m, exptab);
+        double v = bellman_value<DIN>(cfg, x, u, m, exptab, stage);
         if (constraint != nullptr && constraint[(int64_t)a * n + i] < 0.0) v = -INFINITY;  // :272-275
         if (a == 0 || v > vmax) { vmax = v; arg = a; }      // np.argmax: first maximum (:278)
     }
-    best[i] = arg;
-    if (best_value != nullptr) best_value[i] = vmax;
+    if (valid) {
+        best[i] = arg;
+        if (best_value != nullptr) best_value[i] = vmax;
+    }
 }
 
 __global__ void __launch_bounds__(LT)
