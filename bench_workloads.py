@@ -189,13 +189,55 @@ def make_cartpole(num_points=16, M=200, seed=4, tau_scale=1.0):
 
 
 # --------------------------------------------------------------------------- builders
+def build_kernel(ns, spec):
+    """Kernel from a portable nested-list spec (JSON string or list):
+    ["add", k1, k2, ...] | ["prod", k1, k2, ...] | [kind, input_dim, {constructor kwargs}] with kind in
+    rbf / matern12 / matern32 / matern52 / linear / constant / white.  `ns` provides classes with
+    gpflow 0.4.0's constructor signatures (the oracle, the product, or the fixture shim's
+    ``gpflow.kernels``)."""
+    import json
+    if isinstance(spec, (str, bytes, np.str_)):
+        spec = json.loads(str(spec))
+    head = spec[0]
+    if head in ("add", "prod"):
+        parts = [build_kernel(ns, sub) for sub in spec[1:]]
+        out = parts[0]
+        for k in parts[1:]:
+            out = out + k if head == "add" else out * k
+        return out
+    cls = {"rbf": "RBF", "matern12": "Matern12", "matern32": "Matern32", "matern52": "Matern52",
+           "linear": "Linear", "constant": "Constant", "white": "White"}[head]
+    kwargs = dict(spec[2]) if len(spec) > 2 else {}
+    for key in ("variance", "lengthscales"):
+        if isinstance(kwargs.get(key), list):
+            kwargs[key] = np.asarray(kwargs[key], dtype=np.float64)
+    return getattr(ns, cls)(int(spec[1]), **kwargs)
+
+
+def notebook_pendulum_kernels(variances):
+    """Kernel specs of examples/inverted_pendulum.ipynb cell 6 / adaptive_safety_verification.ipynb
+    cell 9: Linear(3, ARD) + Matern32(1, active_dims=[0]) * Linear(1), one per output row of
+    `variances` ((m_true - m)^2 clipped)."""
+    import json
+    specs = []
+    for row in np.asarray(variances, dtype=np.float64):
+        specs.append(json.dumps(
+            ["add", ["linear", 3, {"variance": row.tolist(), "ARD": True}],
+             ["prod", ["matern32", 1, {"lengthscales": 1.0, "active_dims": [0]}],
+              ["linear", 1, {"variance": float(row[1])}]]]))
+    return specs
+
+
 def _build(ns, par, kind):
     """ns: module namespace providing GridWorld, RBF, GPRCached, ... (product or oracle)."""
     grid = ns.GridWorld(par["limits"], par["num_points"])
     gps = []
     for j in range(par["Y"].shape[1]):
         din = par["X"].shape[1]
-        kern = ns.RBF(din, variance=par["variances"][j], lengthscales=par["lengthscales"][j])
+        if par.get("kernel_specs") is not None:
+            kern = build_kernel(ns, par["kernel_specs"][j])
+        else:
+            kern = ns.RBF(din, variance=par["variances"][j], lengthscales=par["lengthscales"][j])
         if par["prior_rows"] is None:
             mean = None
         elif kind == "oracle":

@@ -92,11 +92,47 @@ typedef struct slb_function {
     slb_grid grid;              /* TRIANGULATION discretization                        */
 } slb_function;
 
+/* ---- covariance functions ------------------------------------------------------------------
+ * The reference hands any gpflow kernel to GPRCached (functions.py:370-393) and only ever calls
+ * kern.K(X), kern.K(X, Xnew) and kern.Kdiag(Xnew) on it (functions.py:399, 438, 450).  Its
+ * experiments use sums of products of gpflow==0.4.0 primitives with `active_dims`
+ * (examples/inverted_pendulum.ipynb cell 6, adaptive_safety_verification.ipynb cell 9,
+ * 1d_region_of_attraction_estimate.ipynb cell 5):
+ *     k(x, x') = sum over terms t of  prod over primitives p with p.term == t of  k_p(x, x')
+ * gpflow 0.4.0 kernels.py arithmetic of the primitives (r^2 = sum_c ((x_c - x'_c) w_c)^2 with
+ * w_c = 1 / lengthscale_c on active dimensions and 0 elsewhere; r = sqrt(r^2 + 1e-12)):          */
+enum slb_kernel_kind {
+    SLB_K_RBF = 0,        /* variance exp(-r^2 / 2)                                          */
+    SLB_K_MATERN12 = 1,   /* variance exp(-r)                                                */
+    SLB_K_MATERN32 = 2,   /* variance (1 + sqrt3 r) exp(-sqrt3 r)                            */
+    SLB_K_MATERN52 = 3,   /* variance (1 + sqrt5 r + 5/3 r^2) exp(-sqrt5 r)                  */
+    SLB_K_LINEAR = 4,     /* sum_c w_c x_c x'_c, w_c = variance_c on active dims (ARD or not) */
+    SLB_K_CONSTANT = 5,   /* variance (gpflow Constant / Bias)                               */
+    SLB_K_WHITE = 6       /* variance on the diagonal (Kdiag, K(X)); 0 against new points    */
+};
+#define SLB_MAX_KPRIM 6
+
+typedef struct slb_kernel_prim {
+    int32_t kind;               /* slb_kernel_kind                                      */
+    int32_t term;               /* product term; primitives are listed in term order    */
+    double  variance;           /* stationary / constant / white primitives             */
+    double  w[SLB_MAX_IN];      /* per input column, see above; 0 = inactive dimension  */
+} slb_kernel_prim;
+
+typedef struct slb_kernel {
+    int32_t num_prims;          /* 0 => the factor is the plain full-dimensional RBF described
+                                   by slb_gp_factor.lengthscales / variance / kss (fast path)  */
+    int32_t _pad;
+    slb_kernel_prim prims[SLB_MAX_KPRIM];
+} slb_kernel;
+
 /* ---- GP stack: FunctionStack of GaussianProcess(GPRCached) (functions.py:254-546) ---- */
 typedef struct slb_gp_factor {
-    int32_t M;                  /* training points                                      */
+    int32_t M;                  /* training points; 0 => prior only (empty data set of the
+                                   notebooks before the first add_data_point)           */
     int32_t nrb;                /* ceil(M / 8) row blocks of the packed factor          */
-    const double* Xs;           /* device [M, d_in]: X / lengthscales (gpflow RBF)      */
+    const double* Xs;           /* device [M, d_in]: X / lengthscales when kernel.num_prims == 0
+                                   (gpflow RBF), the raw X otherwise                    */
     const double* Wpack;        /* device: L^-1 in DMMA fragment order, k-steps paired
                                    (slb_pack_factor); L = chol(scale^2 (K + noise I))
                                    functions.py:399-408 */
@@ -104,6 +140,7 @@ typedef struct slb_gp_factor {
     double variance;            /* RBF variance (Kdiag)                                 */
     double scale;               /* GPRCached _scale                functions.py:392     */
     double kss;                 /* (scale**2) * variance           functions.py:450     */
+    slb_kernel kernel;          /* general covariance expression (num_prims > 0)        */
 } slb_gp_factor;
 
 typedef struct slb_gp_output {

@@ -25,7 +25,8 @@ import scipy.spatial
 __all__ = [
     "config", "DimensionError", "GridWorld", "LinearSystem", "QuadraticFunction",
     "Saturation", "ConstantFunction", "ScaledFunction", "AbsFunction", "Norm1Function",
-    "RBF", "LinearMean", "GPRCached", "GaussianProcess", "FunctionStack", "Triangulation",
+    "RBF", "Matern12", "Matern32", "Matern52", "Linear", "Constant", "Bias", "White", "Add", "Prod",
+    "LinearMean", "GPRCached", "GaussianProcess", "FunctionStack", "Triangulation",
     "InvertedPendulum", "CartPole", "LyapunovNetwork", "NeuralNetwork", "Lyapunov",
     "PolicyIteration",
     "batchify", "dlqr", "hstack_inputs", "stable_value_order", "prefix_rule",
@@ -278,22 +279,79 @@ def _row_norm1(values):
 
 
 # --------------------------------------------------------------------------- GP (gpflow 0.4.0 restated)
-class RBF(object):
-    """``gpflow==0.4.0`` ``kernels.RBF`` (third party, pinned ``requirements.txt:3``).
+class Kernel(object):
+    """``gpflow==0.4.0`` ``kernels.Kern`` algebra (third party, pinned ``requirements.txt:3``; not under
+    /root/reference, restated from its published arithmetic): every primitive works on the columns
+    ``active_dims`` (default: the first ``input_dim``), ``k1 + k2`` / ``k1 * k2`` add / multiply the
+    covariance matrices (``Add`` / ``Prod``).  Used by the reference's experiments
+    (``examples/inverted_pendulum.ipynb`` cell 6, ``1d_region_of_attraction_estimate.ipynb`` cell 5)."""
 
-    ``K = variance * exp(-square_dist/2)`` with ``square_dist`` computed by the
-    ``|x|^2 + |x'|^2 - 2 x.x'`` expansion on lengthscale-divided inputs;
-    ``Kdiag = variance``.  Defaults variance = lengthscales = 1.  Pinned by the
-    golden vector ``tests/test_functions.py:237-261``.
-    """
-
-    def __init__(self, input_dim, variance=1.0, lengthscales=1.0):
+    def __init__(self, input_dim, active_dims=None):
         self.input_dim = int(input_dim)
+        if active_dims is None:
+            active_dims = range(self.input_dim)
+        elif isinstance(active_dims, slice):
+            active_dims = range(*active_dims.indices(1 << 30))[:self.input_dim]
+        self.active_dims = [int(a) for a in active_dims]
+
+    def _slice(self, X, X2):
+        X = X[:, self.active_dims]
+        return X, (None if X2 is None else X2[:, self.active_dims])
+
+    def __add__(self, other):
+        return Add([self, other])
+
+    def __mul__(self, other):
+        return Prod([self, other])
+
+
+class Add(Kernel):
+    def __init__(self, kern_list):
+        self.kern_list = list(kern_list)
+
+    def K(self, X, X2=None):
+        out = self.kern_list[0].K(X, X2)
+        for k in self.kern_list[1:]:
+            out = out + k.K(X, X2)
+        return out
+
+    def Kdiag(self, X):
+        out = self.kern_list[0].Kdiag(X)
+        for k in self.kern_list[1:]:
+            out = out + k.Kdiag(X)
+        return out
+
+
+class Prod(Kernel):
+    def __init__(self, kern_list):
+        self.kern_list = list(kern_list)
+
+    def K(self, X, X2=None):
+        out = self.kern_list[0].K(X, X2)
+        for k in self.kern_list[1:]:
+            out = out * k.K(X, X2)
+        return out
+
+    def Kdiag(self, X):
+        out = self.kern_list[0].Kdiag(X)
+        for k in self.kern_list[1:]:
+            out = out * k.Kdiag(X)
+        return out
+
+
+class Stationary(Kernel):
+    """gpflow 0.4.0 ``Stationary``: ``square_dist`` by the ``|x|^2 + |x'|^2 - 2 x.x'`` expansion on
+    lengthscale-divided inputs, ``euclid_dist = sqrt(square_dist + 1e-12)``, ``Kdiag = variance``."""
+
+    def __init__(self, input_dim, variance=1.0, lengthscales=None, active_dims=None, ARD=False):
+        Kernel.__init__(self, input_dim, active_dims)
         self.variance = float(variance)
-        self.lengthscales = np.broadcast_to(np.asarray(lengthscales, dtype=np.float64),
+        ls = 1.0 if lengthscales is None else lengthscales
+        self.lengthscales = np.broadcast_to(np.asarray(ls, dtype=np.float64),
                                             (self.input_dim,)).copy()
 
     def square_dist(self, X, X2=None):
+        X, X2 = self._slice(X, X2)
         X = X / self.lengthscales
         Xs = np.sum(np.square(X), axis=1)
         if X2 is None:
@@ -302,8 +360,79 @@ class RBF(object):
         X2s = np.sum(np.square(X2), axis=1)
         return -2 * X.dot(X2.T) + Xs[:, None] + X2s[None, :]
 
+    def euclid_dist(self, X, X2=None):
+        return np.sqrt(self.square_dist(X, X2) + 1e-12)
+
+    def Kdiag(self, X):
+        return np.full(X.shape[0], self.variance, dtype=np.float64)
+
+
+class RBF(Stationary):
+    """``gpflow==0.4.0`` ``kernels.RBF``: ``K = variance * exp(-square_dist/2)``.  Defaults
+    variance = lengthscales = 1.  Pinned by the golden vector ``tests/test_functions.py:237-261``."""
+
     def K(self, X, X2=None):
         return self.variance * np.exp(-self.square_dist(X, X2) / 2)
+
+
+class Matern12(Stationary):
+    def K(self, X, X2=None):
+        return self.variance * np.exp(-self.euclid_dist(X, X2))
+
+
+class Matern32(Stationary):
+    def K(self, X, X2=None):
+        r = self.euclid_dist(X, X2)
+        return self.variance * (1. + np.sqrt(3.) * r) * np.exp(-np.sqrt(3.) * r)
+
+
+class Matern52(Stationary):
+    def K(self, X, X2=None):
+        r = self.euclid_dist(X, X2)
+        return self.variance * (1. + np.sqrt(5.) * r + 5. / 3. * np.square(r)) * np.exp(-np.sqrt(5.) * r)
+
+
+class Linear(Kernel):
+    """gpflow 0.4.0 ``kernels.Linear``: ``K = (X * variance) X2^T``, ``Kdiag = sum(X^2 * variance)``."""
+
+    def __init__(self, input_dim, variance=1.0, active_dims=None, ARD=False):
+        Kernel.__init__(self, input_dim, active_dims)
+        self.variance = np.broadcast_to(np.asarray(variance, dtype=np.float64),
+                                        (self.input_dim,)).copy()
+
+    def K(self, X, X2=None):
+        X, X2 = self._slice(X, X2)
+        return (X * self.variance).dot((X if X2 is None else X2).T)
+
+    def Kdiag(self, X):
+        X, _ = self._slice(X, None)
+        return np.sum(np.square(X) * self.variance, axis=1)
+
+
+class Constant(Kernel):
+    def __init__(self, input_dim, variance=1.0, active_dims=None):
+        Kernel.__init__(self, input_dim, active_dims)
+        self.variance = float(variance)
+
+    def K(self, X, X2=None):
+        return np.full((X.shape[0], (X if X2 is None else X2).shape[0]), self.variance)
+
+    def Kdiag(self, X):
+        return np.full(X.shape[0], self.variance, dtype=np.float64)
+
+
+Bias = Constant
+
+
+class White(Kernel):
+    def __init__(self, input_dim, variance=1.0, active_dims=None):
+        Kernel.__init__(self, input_dim, active_dims)
+        self.variance = float(variance)
+
+    def K(self, X, X2=None):
+        if X2 is None:
+            return self.variance * np.eye(X.shape[0])
+        return np.zeros((X.shape[0], X2.shape[0]))
 
     def Kdiag(self, X):
         return np.full(X.shape[0], self.variance, dtype=np.float64)
@@ -344,6 +473,9 @@ class GPRCached(object):
         return self.mean_function(X)
 
     def update_cache(self):
+        if self.X.shape[0] == 0:        # empty data set: prior only (zero-size TF ops upstream)
+            self.cholesky, self.alpha = np.zeros((0, 0)), np.zeros((0, 1))
+            return
         kernel = self.kern.K(self.X) + np.eye(self.X.shape[0]) * self.noise_variance
         kernel = kernel * (self._scale ** 2)
         target = self._scale * (self.Y - self._mean(self.X))
@@ -352,9 +484,12 @@ class GPRCached(object):
 
     def build_predict(self, Xnew):
         Xnew = np.atleast_2d(np.asarray(Xnew, dtype=np.float64))
-        Kx = (self._scale ** 2) * self.kern.K(self.X, Xnew)
         mx = self._scale * self._mean(Xnew)
-        a = scipy.linalg.solve_triangular(self.cholesky, Kx, lower=True)
+        if self.X.shape[0] == 0:
+            a = np.zeros((0, Xnew.shape[0]))
+        else:
+            Kx = (self._scale ** 2) * self.kern.K(self.X, Xnew)
+            a = scipy.linalg.solve_triangular(self.cholesky, Kx, lower=True)
         fmean = a.T.dot(self.alpha) + mx
         Knew = (self._scale ** 2) * self.kern.Kdiag(Xnew)
         fvar = Knew - np.sum(np.square(a), axis=0)

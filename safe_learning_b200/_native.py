@@ -20,6 +20,8 @@ SLB_TILE_POINTS = 64
 FN_NONE, FN_CONSTANT, FN_LINEAR, FN_QUADRATIC, FN_TRIANGULATION, FN_PENDULUM, FN_CARTPOLE, \
     FN_LYAPUNOV_NN, FN_MLP = range(9)
 FLAG_SATURATE, FLAG_ABS, FLAG_NORM1, FLAG_PROJECT, FLAG_SCALE = 1, 2, 4, 8, 16
+K_RBF, K_MATERN12, K_MATERN32, K_MATERN52, K_LINEAR, K_CONSTANT, K_WHITE = range(7)
+SLB_MAX_KPRIM = 6
 
 UINT64_MAX = (1 << 64) - 1
 INT64_MAX = (1 << 63) - 1
@@ -44,10 +46,20 @@ class SlbFunction(C.Structure):
                 ("corner_simplex", C.c_void_p), ("nsimplex", C.c_int32), ("_pad", C.c_int32), ("grid", SlbGrid)]
 
 
+class SlbKernelPrim(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("term", C.c_int32), ("variance", C.c_double),
+                ("w", C.c_double * SLB_MAX_IN)]
+
+
+class SlbKernel(C.Structure):
+    _fields_ = [("num_prims", C.c_int32), ("_pad", C.c_int32),
+                ("prims", SlbKernelPrim * SLB_MAX_KPRIM)]
+
+
 class SlbGpFactor(C.Structure):
     _fields_ = [("M", C.c_int32), ("nrb", C.c_int32), ("Xs", C.c_void_p), ("Wpack", C.c_void_p),
                 ("lengthscales", C.c_double * SLB_MAX_IN), ("variance", C.c_double),
-                ("scale", C.c_double), ("kss", C.c_double)]
+                ("scale", C.c_double), ("kss", C.c_double), ("kernel", SlbKernel)]
 
 
 class SlbGpOutput(C.Structure):

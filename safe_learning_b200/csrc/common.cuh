@@ -139,6 +139,71 @@ SLB_DEV double exp_neg_tab(double x, const double* __restrict__ tab) {
     return x < -700.0 ? 0.0 : s;
 }
 
+// ---- covariance expressions (slb_kernel): sum over terms of products of gpflow primitives ------
+// cross form k(z, x) against a training row (kern.K(X, Xnew), functions.py:438)
+template <int DIN>
+SLB_DEV double kernel_expr_cross(const slb_kernel& K, const double* z, const double* x,
+                                 const double* exptab) {
+    double total = 0.0, term = 1.0;
+    int cur = 0;
+    for (int i = 0; i < K.num_prims; ++i) {
+        const slb_kernel_prim& P = K.prims[i];
+        if (P.term != cur) { total += term; term = 1.0; cur = P.term; }
+        double v;
+        if (P.kind == SLB_K_LINEAR) {
+            v = 0.0;
+#pragma unroll
+            for (int c = 0; c < DIN; ++c) v = fma(P.w[c] * z[c], x[c], v);
+        } else if (P.kind == SLB_K_CONSTANT) {
+            v = P.variance;
+        } else if (P.kind == SLB_K_WHITE) {
+            v = 0.0;
+        } else {
+            double r2 = 0.0;
+#pragma unroll
+            for (int c = 0; c < DIN; ++c) {
+                const double df = (z[c] - x[c]) * P.w[c];
+                r2 = fma(df, df, r2);
+            }
+            if (P.kind == SLB_K_RBF) {
+                v = P.variance * exp_neg_tab(-0.5 * r2, exptab);
+            } else {
+                const double r = sqrt(r2 + 1e-12);
+                if (P.kind == SLB_K_MATERN12) {
+                    v = P.variance * exp_neg_tab(-r, exptab);
+                } else if (P.kind == SLB_K_MATERN32) {
+                    const double sr = 1.7320508075688772 * r;
+                    v = P.variance * (1.0 + sr) * exp_neg_tab(-sr, exptab);
+                } else {
+                    const double sr = 2.23606797749979 * r;
+                    v = P.variance * (1.0 + sr + (5.0 / 3.0) * (r * r)) * exp_neg_tab(-sr, exptab);
+                }
+            }
+        }
+        term *= v;
+    }
+    return K.num_prims > 0 ? total + term : 0.0;
+}
+
+// diagonal form k(z, z) (kern.Kdiag(Xnew), functions.py:450)
+template <int DIN>
+SLB_DEV double kernel_expr_diag(const slb_kernel& K, const double* z) {
+    double total = 0.0, term = 1.0;
+    int cur = 0;
+    for (int i = 0; i < K.num_prims; ++i) {
+        const slb_kernel_prim& P = K.prims[i];
+        if (P.term != cur) { total += term; term = 1.0; cur = P.term; }
+        double v = P.variance;
+        if (P.kind == SLB_K_LINEAR) {
+            v = 0.0;
+#pragma unroll
+            for (int c = 0; c < DIN; ++c) v = fma(P.w[c] * z[c], z[c], v);
+        }
+        term *= v;
+    }
+    return K.num_prims > 0 ? total + term : 0.0;
+}
+
 // GridWorld.index_to_state (functions.py:714-731): ijk * unit_maxes + offset, two roundings.
 SLB_DEV void grid_index_to_state(const slb_grid& g, int64_t idx, double* x) {
 #pragma unroll

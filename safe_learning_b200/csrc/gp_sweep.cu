@@ -154,7 +154,9 @@ SLB_DEV void mma_run(double (&acc)[RQ][NB][2], const double2* const (&ap)[RQ], i
     }
 }
 
-template <int DIN, bool TIMING>
+// KEXPR: at least one factor carries a covariance expression (slb_kernel) instead of the plain
+// RBF; the RBF-only instantiation keeps the lean generation loop.
+template <int DIN, bool TIMING, bool KEXPR>
 __global__ void __launch_bounds__(NT, CTAS_PER_SM)
 gp_tile_kernel(const __grid_constant__ slb_sweep cfg, const gp_args a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -239,9 +241,11 @@ gp_tile_kernel(const __grid_constant__ slb_sweep cfg, const gp_args a) {
         const double variance = F.variance;
         const double* __restrict__ Xs = F.Xs;
 
+        const bool general = KEXPR && F.kernel.num_prims > 0;
         double zs[DIN];
 #pragma unroll
-        for (int c = 0; c < DIN; ++c) zs[c] = zraw[c * TP + p_gen] / F.lengthscales[c];
+        for (int c = 0; c < DIN; ++c)
+            zs[c] = general ? zraw[c * TP + p_gen] : zraw[c * TP + p_gen] / F.lengthscales[c];
         // red[warp][col][qty] holds THIS warp's running partial sums over its row blocks of all
         // panels of the factor; only the owning warp touches it, so the panel epilogues need no
         // barrier and warps that finish a triangular panel early move straight on.
@@ -286,6 +290,20 @@ gp_tile_kernel(const __grid_constant__ slb_sweep cfg, const gp_args a) {
                     const int npairs = (nkp + 1) >> 1;
                     double2* ks2 = reinterpret_cast<double2*>(Ks);
                     constexpr int GP = 2;            // pairs per iteration = 2 GP interleaved exps
+                    if (general) {
+                        // covariance expression on the raw inputs (one pair per iteration)
+                        for (int mm = gpo; mm < npairs; mm += PS) {
+                            double kv[2];
+#pragma unroll
+                            for (int u = 0; u < 2; ++u) {
+                                const int jj = 8 * mm + 4 * u + gr;
+                                const double k = s2 * kernel_expr_cross<DIN>(
+                                    F.kernel, zs, Xp + min(jj, nj - 1) * DIN, exptab);
+                                kv[u] = jj < nj ? k : 0.0;
+                            }
+                            ks2[(mm * 4 + gr) * KSTR + p_gen] = make_double2(kv[0], kv[1]);
+                        }
+                    } else
                     for (int mm = gpo; mm < npairs; mm += GP * PS) {
                         double t2[2 * GP];
 #pragma unroll
@@ -433,7 +451,14 @@ gp_tile_kernel(const __grid_constant__ slb_sweep cfg, const gp_args a) {
                     mx = f64mul(F.scale, mx);
                 }
                 const double fmean = f64add(tot[qty * TP + tid], mx) / F.scale;   // :442, :455
-                const double fvar = f64sub(F.kss, tot[tid]) / s2;                  // :450-451, :456
+                double kss = F.kss;
+                if (general) {
+                    double zt[DIN];
+#pragma unroll
+                    for (int c = 0; c < DIN; ++c) zt[c] = zraw[c * TP + tid];
+                    kss = s2 * kernel_expr_diag<DIN>(F.kernel, zt);
+                }
+                const double fvar = f64sub(kss, tot[tid]) / s2;                    // :450-451, :456
                 post[o * TP + tid] = fmean;
                 post[(SLB_MAX_OUT + o) * TP + tid] =
                     a.want_var ? fvar : f64mul(G.beta, sqrt(fvar));               // :514
@@ -490,17 +515,17 @@ __global__ void pack_factor_kernel(const double* __restrict__ Linv, int M, int n
     W[e] = (row < M && col <= row) ? Linv[row * M + col] : 0.0;
 }
 
-template <int DIN, bool TIMING>
+template <int DIN, bool TIMING, bool KEXPR>
 int launch_gp_tile(cudaStream_t st, const slb_sweep& cfg, const gp_args& a) {
     static bool configured = false;
     if (!configured) {
-        SLB_CUDA(cudaFuncSetAttribute(gp_tile_kernel<DIN, TIMING>,
+        SLB_CUDA(cudaFuncSetAttribute(gp_tile_kernel<DIN, TIMING, KEXPR>,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)SMEM_TOTAL));
         configured = true;
     }
     const int64_t tiles = (a.n + TP - 1) / TP;
-    gp_tile_kernel<DIN, TIMING><<<(unsigned)tiles, NT, SMEM_TOTAL, st>>>(cfg, a);
+    gp_tile_kernel<DIN, TIMING, KEXPR><<<(unsigned)tiles, NT, SMEM_TOTAL, st>>>(cfg, a);
     SLB_LAUNCH_CHECK();
     return 0;
 }
@@ -510,15 +535,22 @@ int dispatch_gp_tile(cudaStream_t st, const slb_sweep& cfg, const gp_args& a) {
     SLB_CHECK(a.n <= (int64_t)0x7fffffff * TP, "too many points for one launch");
     if (a.timing != nullptr) {
         SLB_CHECK(cfg.gp.input_dim == 3, "phase timing is compiled for d_in = 3 only");
-        return launch_gp_tile<3, true>(st, cfg, a);
+        return launch_gp_tile<3, true, false>(st, cfg, a);
     }
+    bool kexpr = false;
+    for (int f = 0; f < cfg.gp.num_factors; ++f) kexpr |= cfg.gp.factors[f].kernel.num_prims > 0;
+#define SLB_TILE_CASE(d)                                                         \
+    case d:                                                                      \
+        return kexpr ? launch_gp_tile<d, false, true>(st, cfg, a)                \
+                     : launch_gp_tile<d, false, false>(st, cfg, a);
     switch (cfg.gp.input_dim) {
-    case 1: return launch_gp_tile<1, false>(st, cfg, a);
-    case 2: return launch_gp_tile<2, false>(st, cfg, a);
-    case 3: return launch_gp_tile<3, false>(st, cfg, a);
-    case 4: return launch_gp_tile<4, false>(st, cfg, a);
-    case 5: return launch_gp_tile<5, false>(st, cfg, a);
-    case 6: return launch_gp_tile<6, false>(st, cfg, a);
+        SLB_TILE_CASE(1)
+        SLB_TILE_CASE(2)
+        SLB_TILE_CASE(3)
+        SLB_TILE_CASE(4)
+        SLB_TILE_CASE(5)
+        SLB_TILE_CASE(6)
+#undef SLB_TILE_CASE
     default:
         slb_set_error("GP input_dim %d not compiled (1..6)", cfg.gp.input_dim);
         return 1;

@@ -114,12 +114,30 @@ int slb_validate_gp(const slb_gp_stack* gp) {
               gp->input_dim);
     for (int f = 0; f < gp->num_factors; ++f) {
         const slb_gp_factor& F = gp->factors[f];
-        SLB_CHECK(F.M >= 1 && F.nrb == (F.M + 7) / 8, "GP factor %d: bad M/nrb (%d/%d)", f, F.M,
+        SLB_CHECK(F.M >= 0 && F.nrb == (F.M + 7) / 8, "GP factor %d: bad M/nrb (%d/%d)", f, F.M,
                   F.nrb);
-        SLB_CHECK(F.Xs != nullptr && F.Wpack != nullptr, "GP factor %d: null table", f);
+        SLB_CHECK(F.M == 0 || (F.Xs != nullptr && F.Wpack != nullptr), "GP factor %d: null table", f);
         SLB_CHECK(F.scale > 0.0, "GP factor %d: scale must be positive", f);
-        for (int c = 0; c < gp->input_dim; ++c)
-            SLB_CHECK(F.lengthscales[c] > 0.0, "GP factor %d: lengthscale[%d] must be positive", f, c);
+        const slb_kernel& K = F.kernel;
+        SLB_CHECK(K.num_prims >= 0 && K.num_prims <= SLB_MAX_KPRIM,
+                  "GP factor %d: %d kernel primitives outside 0..%d", f, K.num_prims, SLB_MAX_KPRIM);
+        if (K.num_prims == 0) {
+            for (int c = 0; c < gp->input_dim; ++c)
+                SLB_CHECK(F.lengthscales[c] > 0.0, "GP factor %d: lengthscale[%d] must be positive",
+                          f, c);
+        }
+        for (int i = 0; i < K.num_prims; ++i) {
+            const slb_kernel_prim& P = K.prims[i];
+            SLB_CHECK(P.kind >= SLB_K_RBF && P.kind <= SLB_K_WHITE,
+                      "GP factor %d: kernel primitive %d has unknown kind %d", f, i, P.kind);
+            const int prev = i == 0 ? 0 : K.prims[i - 1].term;
+            SLB_CHECK(P.term == prev || P.term == prev + 1,
+                      "GP factor %d: kernel primitives must be listed in term order", f);
+            SLB_CHECK(i > 0 || P.term == 0, "GP factor %d: kernel terms start at 0", f);
+            for (int c = 0; c < gp->input_dim; ++c)
+                SLB_CHECK(P.w[c] >= 0.0, "GP factor %d: kernel primitive %d has a negative weight",
+                          f, i);
+        }
     }
     for (int o = 0; o < gp->num_outputs; ++o) {
         const slb_gp_output& G = gp->outputs[o];
@@ -309,9 +327,10 @@ constexpr int BCHUNK = 256;    // training rows staged per pass in the Bellman k
 template <int DIN, int NO>
 SLB_DEV void gp_mean_factor(const slb_gp_stack& gp, const slb_gp_factor& F, const int* outs,
                             const double* z, double* mu, const double* exptab, double* stage) {
+    const bool general = F.kernel.num_prims > 0;     // covariance expression on the raw inputs
     double zs[DIN];
 #pragma unroll
-    for (int c = 0; c < DIN; ++c) zs[c] = z[c] / F.lengthscales[c];
+    for (int c = 0; c < DIN; ++c) zs[c] = general ? z[c] : z[c] / F.lengthscales[c];
     double dot[NO];
     const double* gam[NO];
 #pragma unroll
@@ -345,9 +364,10 @@ SLB_DEV void gp_mean_factor(const slb_gp_stack& gp, const slb_gp_factor& F, cons
             }
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-                double k = F.variance * exp_neg_tab(-0.5 * t2[u], exptab);
-                if (j0 + u >= nc) k = 0.0;
                 const int j = min(j0 + u, nc - 1);
+                double k = general ? kernel_expr_cross<DIN>(F.kernel, zs, xch + j * DIN, exptab)
+                                   : F.variance * exp_neg_tab(-0.5 * t2[u], exptab);
+                if (j0 + u >= nc) k = 0.0;
 #pragma unroll
                 for (int q = 0; q < NO; ++q) dot[q] = fma(k, gch[q * BCHUNK + j], dot[q]);
             }

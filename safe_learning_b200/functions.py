@@ -29,7 +29,8 @@ config = Configuration()
 __all__ = ["DimensionError", "GridWorld", "Function", "DeterministicFunction",
            "UncertainFunction", "ConstantFunction", "LinearSystem", "QuadraticFunction",
            "Saturation", "AbsFunction", "Norm1Function", "ScaledFunction", "Triangulation",
-           "RBF", "Likelihood", "GPRCached", "GPR", "GaussianProcess", "FunctionStack",
+           "Kernel", "RBF", "Matern12", "Matern32", "Matern52", "Linear", "Constant", "Bias",
+           "White", "Sum", "Add", "Product", "Prod", "kernels", "Likelihood", "GPRCached", "GPR", "GaussianProcess", "FunctionStack",
            "InvertedPendulum", "CartPole", "LyapunovNetwork", "NeuralNetwork",
            "concatenate_inputs"]
 
@@ -753,27 +754,280 @@ class NeuralNetwork(DeterministicFunction):
 
 
 # =============================================================================== Gaussian processes
-class RBF(object):
-    """Squared-exponential kernel with the arithmetic of ``gpflow==0.4.0`` ``kernels.RBF``:
-    ``variance * exp(-0.5 * sum(((x - x') / lengthscales)^2))``, ``Kdiag = variance``,
-    defaults 1 (``lengthscales`` scalar or ARD vector)."""
+class Kernel(object):
+    """Covariance function with the algebra of ``gpflow==0.4.0`` ``kernels`` (third-party code the
+    reference hands to ``GPRCached``, ``functions.py:370-393``): primitives carry ``input_dim`` and
+    ``active_dims`` (default: the first ``input_dim`` columns), ``+`` and ``*`` build sums and
+    products.  The device evaluates the sum-of-products normal form (``slb_kernel``)."""
 
-    def __init__(self, input_dim, variance=1.0, lengthscales=1.0, ARD=False):
+    def __add__(self, other):
+        return Sum([self, other])
+
+    def __mul__(self, other):
+        return Product([self, other])
+
+    def terms(self):
+        """Normal form: list of product terms, each a list of primitives."""
+        raise NotImplementedError
+
+    def hyper_key(self):
+        return tuple(tuple(p.hyper_key() for p in term) for term in self.terms())
+
+    def is_plain_rbf(self, din):
+        return False
+
+    def K_device(self, X, X2=None):
+        """K(X, X2) on raw inputs (device tensors), gpflow arithmetic."""
+        total = None
+        for term in self.terms():
+            prod = None
+            for p in term:
+                k = p._K(X, X2)
+                prod = k if prod is None else prod * k
+            total = prod if total is None else total + prod
+        return total
+
+    def Kdiag_device(self, X):
+        total = None
+        for term in self.terms():
+            prod = None
+            for p in term:
+                k = p._Kdiag(X)
+                prod = k if prod is None else prod * k
+            total = prod if total is None else total + prod
+        return total
+
+    def fill(self, kstruct, din):
+        """Write the normal form into an ``slb_kernel``."""
+        terms = self.terms()
+        count = sum(len(t) for t in terms)
+        if count > nat.SLB_MAX_KPRIM:
+            raise NotImplementedError("kernel expands to %d primitives; the device descriptor "
+                                      "holds %d" % (count, nat.SLB_MAX_KPRIM))
+        i = 0
+        for t, term in enumerate(terms):
+            for p in term:
+                if max(p.active_dims) >= din:
+                    raise DimensionError("kernel active_dims %r outside the %d GP input columns"
+                                         % (p.active_dims, din))
+                prim = kstruct.prims[i]
+                prim.kind, prim.term, prim.variance = p.KIND, t, p._scalar_variance()
+                weights = p._weights()
+                for c in range(nat.SLB_MAX_IN):
+                    prim.w[c] = 0.0
+                for c, w in zip(p.active_dims, weights):
+                    prim.w[c] = float(w)
+                i += 1
+        kstruct.num_prims = count
+
+
+class Sum(Kernel):
+    def __init__(self, kern_list):
+        self.kern_list = list(kern_list)
+
+    def terms(self):
+        return [term for k in self.kern_list for term in k.terms()]
+
+
+Add = Sum
+
+
+class Product(Kernel):
+    def __init__(self, kern_list):
+        self.kern_list = list(kern_list)
+
+    def terms(self):
+        out = [[]]
+        for k in self.kern_list:
+            out = [a + b for a in out for b in k.terms()]
+        return out
+
+
+Prod = Product
+
+
+class _Primitive(Kernel):
+    KIND = None
+
+    def __init__(self, input_dim, active_dims=None):
         self.input_dim = int(input_dim)
+        if active_dims is None:
+            active_dims = range(self.input_dim)
+        elif isinstance(active_dims, slice):
+            active_dims = range(*active_dims.indices(1 << 30))[:self.input_dim]
+        self.active_dims = [int(a) for a in active_dims]
+        if len(self.active_dims) != self.input_dim:
+            raise DimensionError("active_dims %r does not select input_dim = %d columns"
+                                 % (self.active_dims, self.input_dim))
+
+    def terms(self):
+        return [[self]]
+
+    def _slice(self, X):
+        return X[:, self.active_dims]
+
+    def _scalar_variance(self):
+        return float(self.variance)
+
+    def _weights(self):
+        return np.zeros(self.input_dim)
+
+    def hyper_key(self):
+        return (self.KIND, tuple(self.active_dims), self._scalar_variance(),
+                tuple(np.asarray(self._weights(), dtype=np.float64).tolist()))
+
+
+class _Stationary(_Primitive):
+    def __init__(self, input_dim, variance=1.0, lengthscales=None, active_dims=None, ARD=False):
+        _Primitive.__init__(self, input_dim, active_dims)
         self.variance = float(variance)
-        self.lengthscales = np.broadcast_to(np.asarray(lengthscales, dtype=np.float64),
+        ls = 1.0 if lengthscales is None else lengthscales
+        self.lengthscales = np.broadcast_to(np.asarray(ls, dtype=np.float64),
                                             (self.input_dim,)).copy()
         self.ARD = ARD
 
-    def hyper_key(self):
-        return (self.input_dim, self.variance, tuple(self.lengthscales.tolist()))
+    def _weights(self):
+        return 1.0 / self.lengthscales
 
-    def K_device(self, Xs):
-        """K(X, X) from lengthscale-divided inputs (device tensor [M, d]); same expansion as
-        gpflow's ``square_dist``."""
+    def hyper_key(self):
+        return (self.KIND, tuple(self.active_dims), self.variance,
+                tuple(self.lengthscales.tolist()))
+
+    def _square_dist(self, X, X2):
+        """gpflow ``Stationary.square_dist``: the |x|^2 + |x'|^2 - 2 x.x' expansion."""
+        ls = torch.as_tensor(self.lengthscales, dtype=torch.float64, device=X.device)
+        X = self._slice(X) / ls
+        sq = (X * X).sum(dim=1)
+        if X2 is None:
+            return -2.0 * (X @ X.T) + sq[:, None] + sq[None, :]
+        X2 = self._slice(X2) / ls
+        sq2 = (X2 * X2).sum(dim=1)
+        return -2.0 * (X @ X2.T) + sq[:, None] + sq2[None, :]
+
+    def _euclid_dist(self, X, X2):
+        return torch.sqrt(self._square_dist(X, X2) + 1e-12)
+
+    def _Kdiag(self, X):
+        return torch.full((X.shape[0],), self.variance, dtype=torch.float64, device=X.device)
+
+
+class RBF(_Stationary):
+    """Squared-exponential kernel with the arithmetic of ``gpflow==0.4.0`` ``kernels.RBF``:
+    ``variance * exp(-0.5 * sum(((x - x') / lengthscales)^2))``, ``Kdiag = variance``,
+    defaults 1 (``lengthscales`` scalar or ARD vector)."""
+    KIND = nat.K_RBF
+
+    def is_plain_rbf(self, din):
+        return self.active_dims == list(range(din))
+
+    def _K(self, X, X2=None):
+        return self.variance * torch.exp(-self._square_dist(X, X2) / 2)
+
+    def K_scaled(self, Xs):
+        """K(X, X) from lengthscale-divided inputs (device tensor [M, d])."""
         sq = (Xs * Xs).sum(dim=1)
         dist = -2.0 * (Xs @ Xs.T) + sq[:, None] + sq[None, :]
         return self.variance * torch.exp(-dist / 2)
+
+
+class Matern12(_Stationary):
+    """``variance * exp(-r)``, ``r = sqrt(square_dist + 1e-12)`` (gpflow 0.4.0)."""
+    KIND = nat.K_MATERN12
+
+    def _K(self, X, X2=None):
+        return self.variance * torch.exp(-self._euclid_dist(X, X2))
+
+
+class Matern32(_Stationary):
+    """``variance * (1 + sqrt(3) r) * exp(-sqrt(3) r)`` (gpflow 0.4.0)."""
+    KIND = nat.K_MATERN32
+
+    def _K(self, X, X2=None):
+        r = self._euclid_dist(X, X2)
+        return self.variance * (1. + np.sqrt(3.) * r) * torch.exp(-np.sqrt(3.) * r)
+
+
+class Matern52(_Stationary):
+    """``variance * (1 + sqrt(5) r + 5/3 r^2) * exp(-sqrt(5) r)`` (gpflow 0.4.0)."""
+    KIND = nat.K_MATERN52
+
+    def _K(self, X, X2=None):
+        r = self._euclid_dist(X, X2)
+        return self.variance * (1. + np.sqrt(5.) * r + 5. / 3. * r * r) * torch.exp(-np.sqrt(5.) * r)
+
+
+class Linear(_Primitive):
+    """gpflow 0.4.0 ``kernels.Linear``: ``K = (X * variance) X'^T`` on the active columns,
+    ``variance`` a scalar or (``ARD=True``) one value per column."""
+    KIND = nat.K_LINEAR
+
+    def __init__(self, input_dim, variance=1.0, active_dims=None, ARD=False):
+        _Primitive.__init__(self, input_dim, active_dims)
+        self.ARD = ARD
+        self.variance = np.broadcast_to(np.asarray(variance, dtype=np.float64),
+                                        (self.input_dim,)).copy()
+
+    def _scalar_variance(self):
+        return 1.0
+
+    def _weights(self):
+        return self.variance
+
+    def _K(self, X, X2=None):
+        var = torch.as_tensor(self.variance, dtype=torch.float64, device=X.device)
+        X = self._slice(X)
+        X2 = X if X2 is None else self._slice(X2)
+        return (X * var) @ X2.T
+
+    def _Kdiag(self, X):
+        var = torch.as_tensor(self.variance, dtype=torch.float64, device=X.device)
+        X = self._slice(X)
+        return (X * X * var).sum(dim=1)
+
+
+class Constant(_Primitive):
+    """gpflow 0.4.0 ``kernels.Constant`` / ``Bias``: ``K = variance`` everywhere."""
+    KIND = nat.K_CONSTANT
+
+    def __init__(self, input_dim, variance=1.0, active_dims=None):
+        _Primitive.__init__(self, input_dim, active_dims)
+        self.variance = float(variance)
+
+    def _K(self, X, X2=None):
+        n2 = X.shape[0] if X2 is None else X2.shape[0]
+        return torch.full((X.shape[0], n2), self.variance, dtype=torch.float64, device=X.device)
+
+    def _Kdiag(self, X):
+        return torch.full((X.shape[0],), self.variance, dtype=torch.float64, device=X.device)
+
+
+Bias = Constant
+
+
+class White(_Primitive):
+    """gpflow 0.4.0 ``kernels.White``: ``variance * I`` for ``K(X)``, zeros against new points."""
+    KIND = nat.K_WHITE
+
+    def __init__(self, input_dim, variance=1.0, active_dims=None):
+        _Primitive.__init__(self, input_dim, active_dims)
+        self.variance = float(variance)
+
+    def _K(self, X, X2=None):
+        if X2 is None:
+            return self.variance * torch.eye(X.shape[0], dtype=torch.float64, device=X.device)
+        return torch.zeros((X.shape[0], X2.shape[0]), dtype=torch.float64, device=X.device)
+
+    def _Kdiag(self, X):
+        return torch.full((X.shape[0],), self.variance, dtype=torch.float64, device=X.device)
+
+
+class _KernelNamespace(object):
+    """``gpflow.kernels``-style access: ``safe_learning_b200.kernels.Matern32(...)``."""
+    RBF, Matern12, Matern32, Matern52 = RBF, Matern12, Matern32, Matern52
+    Linear, Constant, Bias, White, Add, Prod = Linear, Constant, Bias, White, Add, Prod
+
+
+kernels = _KernelNamespace()
 
 
 class Likelihood(object):
@@ -786,7 +1040,7 @@ class Likelihood(object):
 class _Factor(object):
     """Device-resident Cholesky state of one (X, kernel, noise, scale) combination."""
 
-    __slots__ = ("key", "M", "nrb", "Xs", "L", "Linv", "Wpack", "appends")
+    __slots__ = ("key", "M", "nrb", "Xs", "L", "Linv", "Wpack", "appends", "plain")
 
 
 _FACTOR_CACHE = {}
@@ -816,9 +1070,10 @@ class GPRCached(object):
         self._Y = np.atleast_2d(np.asarray(y, dtype=np.float64))
         if self._Y.shape[1] != 1:
             raise DimensionError("one-output GPs only; stack them with FunctionStack")
-        if not isinstance(kern, RBF):
-            raise NotImplementedError("only the RBF kernel is fused in this build (got %r)"
-                                      % type(kern).__name__)
+        if not isinstance(kern, Kernel):
+            raise TypeError("kern must be built from safe_learning_b200 kernels (RBF, Matern12/32/52, "
+                            "Linear, Constant, White and their sums / products), got %r"
+                            % type(kern).__name__)
         if mean_function is not None and not isinstance(mean_function, LinearSystem):
             raise NotImplementedError("prior mean must be None or a one-row LinearSystem")
         if self._X.shape[1] > nat.SLB_MAX_IN:
@@ -892,17 +1147,28 @@ class GPRCached(object):
         if fac is None:
             fac = _Factor()
             fac.key, fac.M, fac.nrb = key, M, (M + 7) // 8
-            fac.Xs = dev.to_device(self._X / self.kern.lengthscales)
-            kernel = self.kern.K_device(fac.Xs)
-            kernel = kernel + torch.eye(M, dtype=torch.float64, device=kernel.device) \
-                * self.likelihood.variance
-            kernel = kernel * (self._scale ** 2)
-            fac.L = torch.linalg.cholesky(kernel)
-            fac.Linv = torch.linalg.solve_triangular(
-                fac.L, torch.eye(M, dtype=torch.float64, device=kernel.device),
-                upper=False).contiguous()
+            fac.plain = self.kern.is_plain_rbf(din)
             fac.appends = 0
-            self._pack(fac)
+            if M == 0:
+                # empty data set (the notebooks start from np.empty((0, d))): prior only
+                fac.Xs = dev.zeros((0, din))
+                fac.L = fac.Linv = dev.zeros((0, 0))
+                fac.Wpack = dev.zeros((1,))
+            else:
+                if fac.plain:
+                    fac.Xs = dev.to_device(self._X / self.kern.lengthscales)
+                    kernel = self.kern.K_scaled(fac.Xs)
+                else:
+                    fac.Xs = dev.to_device(self._X)
+                    kernel = self.kern.K_device(fac.Xs)
+                kernel = kernel + torch.eye(M, dtype=torch.float64, device=kernel.device) \
+                    * self.likelihood.variance
+                kernel = kernel * (self._scale ** 2)
+                fac.L = torch.linalg.cholesky(kernel)
+                fac.Linv = torch.linalg.solve_triangular(
+                    fac.L, torch.eye(M, dtype=torch.float64, device=kernel.device),
+                    upper=False).contiguous()
+                self._pack(fac)
             _remember_factor(fac)
         self._finish_cache(fac)
 
@@ -931,13 +1197,20 @@ class GPRCached(object):
             return None
         s2 = self._scale ** 2
         Xs, L, Linv = old.Xs, old.L, old.Linv
+        if old.M == 0:
+            return None
         for row in x_new:
-            xs = dev.to_device((row / self.kern.lengthscales)[None, :])
             M = Xs.shape[0]
-            # same expansion as RBF.K_device (gpflow square_dist)
-            dist = -2.0 * (Xs @ xs.T)[:, 0] + (Xs * Xs).sum(dim=1) + (xs * xs).sum()
-            k = s2 * (self.kern.variance * torch.exp(-dist / 2))
-            kss = s2 * (self.kern.variance + self.likelihood.variance)
+            if old.plain:
+                xs = dev.to_device((row / self.kern.lengthscales)[None, :])
+                # same expansion as RBF.K_scaled (gpflow square_dist)
+                dist = -2.0 * (Xs @ xs.T)[:, 0] + (Xs * Xs).sum(dim=1) + (xs * xs).sum()
+                k = s2 * (self.kern.variance * torch.exp(-dist / 2))
+                kss = s2 * (self.kern.variance + self.likelihood.variance)
+            else:
+                xs = dev.to_device(row[None, :])
+                k = s2 * self.kern.K_device(Xs, xs)[:, 0]
+                kss = s2 * (self.kern.Kdiag_device(xs)[0] + self.likelihood.variance)
             l = Linv @ k
             lam2 = kss - torch.dot(l, l)
             if not bool(lam2 > 1e-12 * kss):
@@ -955,7 +1228,7 @@ class GPRCached(object):
         fac = _Factor()
         fac.key, fac.M, fac.nrb = key, Xs.shape[0], (Xs.shape[0] + 7) // 8
         fac.Xs, fac.L, fac.Linv = Xs.contiguous(), L, Linv.contiguous()
-        fac.appends = old.appends + len(x_new)
+        fac.appends, fac.plain = old.appends + len(x_new), old.plain
         self._pack(fac)
         _remember_factor(fac)
         return fac
@@ -978,17 +1251,18 @@ class GPRCached(object):
         self._factor = fac
         target = dev.to_device(self._Y)
         if self.mean_function is not None:
-            target = target - self.mean_function.evaluate_device(self._X)
+            if M:
+                target = target - self.mean_function.evaluate_device(self._X)
             self._prior_dev = dev.to_device(self.mean_function.matrix.reshape(-1))
         else:
             self._prior_dev = None
         target = self._scale * target
         alpha = fac.Linv @ target
         gamma = fac.Linv.T @ alpha
-        padded = dev.zeros((8 * fac.nrb,))
+        padded = dev.zeros((max(8 * fac.nrb, 8),))
         padded[:M] = alpha[:, 0]
         self._alpha_dev = padded
-        self._gamma_dev = gamma[:, 0].contiguous()
+        self._gamma_dev = gamma[:, 0].contiguous() if M else dev.zeros((1,))
         self._stale = False
         self._hyper_seen = self._hyper_state()
         self._version += 1
@@ -999,11 +1273,15 @@ class GPRCached(object):
         fac = self._factor
         f.M, f.nrb = fac.M, fac.nrb
         f.Xs, f.Wpack = fac.Xs.data_ptr(), fac.Wpack.data_ptr()
-        for c, ls in enumerate(self.kern.lengthscales):
-            f.lengthscales[c] = float(ls)
-        f.variance = self.kern.variance
         f.scale = self._scale
-        f.kss = (self._scale ** 2) * self.kern.variance
+        if fac.plain:
+            for c, ls in enumerate(self.kern.lengthscales):
+                f.lengthscales[c] = float(ls)
+            f.variance = self.kern.variance
+            f.kss = (self._scale ** 2) * self.kern.variance
+            f.kernel.num_prims = 0
+        else:
+            self.kern.fill(f.kernel, self._X.shape[1])
         return fac.key
 
     def fill_output(self, o, factor_index, beta):

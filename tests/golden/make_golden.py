@@ -1,7 +1,7 @@
 """Generate golden fixtures by executing the UNMODIFIED reference (/root/reference) on the
 numpy-backed TF1 / gpflow API shims in ``tf1_shim/`` (build container only).
 
-    python tests/golden/make_golden.py          # rewrites tests/golden/*.npz
+    python tests/golden/make_golden.py [grid|gp|gp_kernels|lyapunov|policy ...]   # rewrites tests/golden/*.npz
 
 Each fixture stores the raw inputs and the reference's outputs; tests/test_golden_fixtures.py
 rebuilds the numpy oracle (CPU tests) and the CUDA product (GPU tests) from the same inputs
@@ -13,6 +13,7 @@ value_iteration, discrete_policy_optimization), utilities (batchify, dlqr, conca
 What is restated in the shim (third-party, not under /root/reference): tf ops -> numpy,
 gpflow 0.4.0 RBF kernel arithmetic.
 """
+import json
 import os
 import sys
 
@@ -36,8 +37,11 @@ def ref_gp_stack(par):
     gps = []
     for j in range(par["Y"].shape[1]):
         din = par["X"].shape[1]
-        kern = gpflow.kernels.RBF(din, variance=par["variances"][j],
-                                  lengthscales=np.asarray(par["lengthscales"][j]), ARD=True)
+        if par.get("kernel_specs") is not None:
+            kern = W.build_kernel(gpflow.kernels, par["kernel_specs"][j])
+        else:
+            kern = gpflow.kernels.RBF(din, variance=par["variances"][j],
+                                      lengthscales=np.asarray(par["lengthscales"][j]), ARD=True)
         mean = gpflow.mean_functions.Zero() if par["prior_rows"] is None else \
             sl.LinearSystem((par["prior_rows"][j][None, :],), name="prior_%d" % j)
         gp = sl.GPRCached(par["X"], par["Y"][:, [j]], kern, mean, par["scale"])
@@ -95,7 +99,7 @@ def sweep_outputs(lyap, feed=None):
                 mean=mean.eval(fd), err=err.eval(fd))
 
 
-def gen_lyapunov(out):
+def gen_lyapunov(out, only=None):
     cases = {}
     # C2-like pendulum, multi-batch (batch 64), growing safe set
     par = W.make_pendulum(num_points=[26, 21], M=90, tau_scale=1 / 150.)
@@ -105,7 +109,21 @@ def gen_lyapunov(out):
     par = W.make_toy_1d(num_points=101, M=25)
     par["tau"] = 0.02
     cases["toy1d"] = (par, ref_toy_lyapunov, 40)
+    # the kernels of the reference's own experiments (inverted_pendulum.ipynb cell 6): linear ARD +
+    # Matern32 x linear, one expression per output, linear prior mean
+    par = W.make_pendulum(num_points=[24, 19], M=90, tau_scale=1 / 150., with_prior_mean=True, seed=3)
+    par["kernel_specs"] = W.notebook_pendulum_kernels([[2e-3, 6e-3, 1.5e-3], [2.5e-2, 8e-3, 1.2e-2]])
+    cases["pendulum_nbkernel"] = (par, ref_pendulum_lyapunov, 64)
+    # 1d_region_of_attraction_estimate.ipynb cell 5: Matern32 x Linear on the state column
+    par = W.make_toy_1d(num_points=91, M=20)
+    par["tau"] = 0.02
+    par["kernel_specs"] = [json.dumps(
+        ["prod", ["matern32", 1, {"lengthscales": 1.0, "variance": 0.16, "active_dims": [0]}],
+         ["linear", 1, {"active_dims": [0]}]])]
+    cases["toy1d_nbkernel"] = (par, ref_toy_lyapunov, 40)
     for name, (par, builder, batch) in cases.items():
+        if only and name not in only:
+            continue
         with tf.Session():
             sl.config.gp_batch_size = batch
             lyap = builder(par)
@@ -168,6 +186,50 @@ def gen_gp(out):
             res[tag + "_alpha0"] = gp0.alpha.value.copy()
     np.savez_compressed(os.path.join(out, "gp_predict.npz"), **res)
     print("gp fixtures:", sorted(k for k in res if k.endswith("_mean")))
+
+
+def gen_gp_kernels(out):
+    """GP posterior through the reference's GPRCached / GaussianProcess / FunctionStack for the
+    covariance expressions of SURVEY.md 8(f) item 3 (every primitive, active_dims, sums of
+    products, shared and distinct factors, empty data set)."""
+    rng = np.random.default_rng(7)
+    nb = W.notebook_pendulum_kernels([[0.02, 0.06, 0.015], [0.25, 0.08, 0.12]])
+    mix = json.dumps(
+        ["add",
+         ["prod", ["rbf", 2, {"variance": 0.7, "lengthscales": [0.8, 1.3], "active_dims": [0, 2],
+                              "ARD": True}],
+          ["matern52", 1, {"variance": 1.4, "lengthscales": 0.6, "active_dims": [1]}]],
+         ["matern12", 3, {"variance": 0.3, "lengthscales": 1.7}],
+         ["prod", ["constant", 3, {"variance": 0.05}], ["linear", 1, {"variance": 0.9, "active_dims": [2]}]],
+         ["white", 3, {"variance": 0.01}]])
+    m32 = json.dumps(["matern32", 3, {"variance": 0.9, "lengthscales": [0.5, 1.1, 0.9], "ARD": True}])
+    rbf_sub = json.dumps(["rbf", 2, {"variance": 1.2, "lengthscales": [0.7, 0.4], "active_dims": [1, 0],
+                                     "ARD": True}])
+    cases = {"notebook": (nb, 45, True, 1.0), "mix": ([mix, mix], 33, False, 2.0),
+             "matern32": ([m32, rbf_sub], 70, True, 1.0), "empty": (nb, 0, True, 1.0)}
+    res = {}
+    with tf.Session():
+        for tag, (specs, M, with_mean, scale) in cases.items():
+            par = W.make_pendulum(num_points=8, M=max(M, 1), scale=scale, with_prior_mean=with_mean,
+                                  seed=11)
+            if M == 0:
+                par["X"], par["Y"] = par["X"][:0], par["Y"][:0]
+            par["kernel_specs"] = specs
+            stack = ref_gp_stack(par)
+            pts = rng.uniform(-1.2, 1.2, (70, 3))
+            pts[:min(M, 5)] = par["X"][:min(M, 5)]           # a few queries on training inputs
+            mean, err = stack(pts)
+            res.update({tag + "_" + k: v for k, v in flat_par(par).items()})
+            res[tag + "_points"] = pts
+            res[tag + "_mean"] = mean.eval(stack.feed_dict)
+            res[tag + "_err"] = err.eval(stack.feed_dict)
+            gp0 = stack.functions[0].gaussian_process
+            _, v0 = gp0.build_predict(pts)
+            res[tag + "_var0"] = v0.eval()
+            if M:
+                res[tag + "_cholesky0"] = gp0.cholesky.value.copy()
+    np.savez_compressed(os.path.join(out, "gp_kernels.npz"), **res)
+    print("gp kernel fixtures:", sorted(k for k in res if k.endswith("_mean")))
 
 
 def gen_grid_triangulation(out):
@@ -239,7 +301,11 @@ def gen_policy_iteration(out):
 
 
 if __name__ == "__main__":
-    gen_grid_triangulation(HERE)
-    gen_gp(HERE)
-    gen_lyapunov(HERE)
-    gen_policy_iteration(HERE)
+    generators = {"grid": gen_grid_triangulation, "gp": gen_gp, "gp_kernels": gen_gp_kernels,
+                  "lyapunov": gen_lyapunov, "policy": gen_policy_iteration}
+    for name in (sys.argv[1:] or list(generators)):     # "lyapunov:case1,case2" limits the cases
+        name, _, only = name.partition(":")
+        if only:
+            generators[name](HERE, only.split(","))
+        else:
+            generators[name](HERE)

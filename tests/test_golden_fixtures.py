@@ -30,6 +30,7 @@ def par_from(fix, prefix="par_"):
     par["variances"] = [float(v) for v in par["variances"]]
     par["lengthscales"] = [list(map(float, ls)) for ls in par["lengthscales"]]
     par.setdefault("prior_rows", None)
+    par["kernel_specs"] = [str(k) for k in par["kernel_specs"]] if "kernel_specs" in par else None
     par["num_points"] = par["num_points"].astype(int)
     par["name"] = "toy1d" if par["X"].shape[1] == 2 else "pendulum"
     return par
@@ -102,9 +103,36 @@ def test_gp_predict_fixture(kind):
         assert_allclose(var, fix[tag + "_var0"], rtol=RTOL, atol=1e-14)
 
 
+@pytest.mark.parametrize("kind", KINDS)
+@pytest.mark.parametrize("tag", ["notebook", "mix", "matern32", "empty"])
+def test_gp_kernel_expression_fixture(kind, tag):
+    """Covariance expressions: Linear(ARD) + Matern32 x Linear of the
+    reference's notebooks, every primitive with active_dims in one sum of products, a plain
+    Matern32 next to an RBF on permuted columns, and the empty data set the notebooks start from."""
+    ns, _, which = backend(kind)
+    fix = load("gp_kernels.npz")
+    par = par_from(fix, tag + "_par_")
+    _, stack = W._build(ns, par, which)
+    pts = fix[tag + "_points"]
+    mean, err = stack(pts)
+    # queries on training inputs have variance ~ noise: compare those on an absolute scale
+    assert_allclose(mean, fix[tag + "_mean"], rtol=RTOL, atol=1e-9)
+    assert_allclose(err, fix[tag + "_err"], rtol=RTOL, atol=1e-6)
+    gp0 = stack.functions[0].gaussian_process
+    if kind == "oracle":
+        _, var = gp0.build_predict(pts)
+    else:
+        _, var = stack.functions[0].predict_device(pts, want_var=True)
+        var = var.cpu().numpy()
+    assert_allclose(var, fix[tag + "_var0"], rtol=RTOL, atol=1e-10)
+    if par["X"].shape[0]:
+        assert_allclose(gp0.cholesky, fix[tag + "_cholesky0"], rtol=1e-7, atol=1e-12)
+
+
 # ------------------------------------------------------------------ Lyapunov sweeps
 @pytest.mark.parametrize("kind", KINDS)
-@pytest.mark.parametrize("case", ["pendulum", "pendulum_allsafe", "toy1d"])
+@pytest.mark.parametrize("case", ["pendulum", "pendulum_allsafe", "toy1d", "pendulum_nbkernel",
+                                  "toy1d_nbkernel"])
 def test_lyapunov_fixture(kind, case):
     ns, build, _ = backend(kind)
     fix = load("lyapunov_%s.npz" % case)

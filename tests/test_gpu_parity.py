@@ -247,6 +247,61 @@ def test_gp_posterior_vs_oracle(sl, M):
     assert_allclose(gp_gpu.alpha, gp_cpu.alpha, rtol=1e-6, atol=1e-10)
 
 
+@pytest.mark.parametrize("M", [5, 257, 600])
+def test_gp_kernel_expressions_vs_oracle(sl, M):
+    """Sums of products of gpflow primitives with active_dims (the kernels of
+    examples/inverted_pendulum.ipynb cell 6) through the sweep kernel's generation phase, across
+    panel boundaries; one output keeps the plain RBF fast path in the same launch."""
+    par = W.make_pendulum(num_points=8, M=M, scale=1.3, seed=M, with_prior_mean=True)
+    nb = W.notebook_pendulum_kernels([[2e-3, 6e-3, 1.5e-3], [2.5e-2, 8e-3, 1.2e-2]])
+    plain = '["rbf", 3, {"variance": 0.8, "lengthscales": [0.9, 1.4, 0.7], "ARD": true}]'
+    m52 = ('["add", ["matern52", 2, {"variance": 0.5, "lengthscales": [0.8, 1.1], "active_dims": [0, 2], '
+           '"ARD": true}], ["prod", ["matern12", 1, {"lengthscales": 2.0, "active_dims": [1]}], '
+           '["constant", 3, {"variance": 0.3}]], ["white", 3, {"variance": 0.02}]]')
+    for specs in ([nb[0], nb[1]], [m52, plain]):
+        par["kernel_specs"] = specs
+        _, dyn_gpu = W._build(sl, par, "product")
+        _, dyn_cpu = W._build(O, par, "oracle")
+        pts = np.random.default_rng(M + 1).uniform(-1, 1, (333, 3))
+        m_gpu, e_gpu = dyn_gpu(pts)
+        m_cpu, e_cpu = dyn_cpu(pts)
+        assert_allclose(m_gpu, m_cpu, rtol=RTOL, atol=1e-10)
+        assert_allclose(e_gpu, e_cpu, rtol=RTOL, atol=1e-7)
+        gp_gpu, gp_cpu = (d.functions[0].gaussian_process for d in (dyn_gpu, dyn_cpu))
+        assert_allclose(gp_gpu.cholesky, gp_cpu.cholesky, rtol=1e-7, atol=1e-12)
+    # the mean-only Bellman path evaluates the same expressions (reinforcement_learning.py:98-99)
+    par["kernel_specs"] = [nb[0], m52]
+    rl_gpu, _ = _rl_objects(sl, par, "product")
+    rl_cpu, _ = _rl_objects(O, par, "oracle")
+    states = np.random.default_rng(3).uniform(-1, 1, (150, 2))
+    assert_allclose(rl_gpu.future_values(states), rl_cpu.future_values(states), rtol=1e-8,
+                    atol=1e-10)
+
+
+def test_gp_empty_data_is_the_prior(sl):
+    """The notebooks start from np.empty((0, d)) data (inverted_pendulum.ipynb cell 6): the
+    posterior is the prior mean and kern.Kdiag, and the first add_data_point refits."""
+    par = W.make_pendulum(num_points=[15, 13], M=1, with_prior_mean=True, tau_scale=1 / 150.)
+    par["X"], par["Y"] = par["X"][:0], par["Y"][:0]
+    for specs in (None, W.notebook_pendulum_kernels([[2e-3, 6e-3, 1.5e-3], [2.5e-2, 8e-3, 1.2e-2]])):
+        par["kernel_specs"] = specs
+        gpu, cpu = W.build_product(par), W.build_oracle(par)
+        pts = np.random.default_rng(1).uniform(-1, 1, (70, 3))
+        for a, b in zip(gpu.dynamics(pts), cpu.dynamics(pts)):
+            assert_allclose(a, b, rtol=1e-12, atol=1e-15)
+        gpu.update_safe_set()
+        cpu.update_safe_set()
+        assert_array_equal(gpu.safe_set, cpu.safe_set)
+        x, y = np.array([[0.1, -0.2, 0.05]]), np.array([[0.02, -0.01]])
+        gpu.dynamics.add_data_point(x, y)
+        cpu.dynamics.add_data_point(x, y)
+        for a, b in zip(gpu.dynamics(pts), cpu.dynamics(pts)):
+            assert_allclose(a, b, rtol=RTOL, atol=1e-10)
+        gpu.update_safe_set()
+        cpu.update_safe_set()
+        assert_array_equal(gpu.safe_set, cpu.safe_set)
+
+
 def test_gp_shared_factor_equals_distinct_path(sl):
     """Outputs sharing X/kernel/noise use one Cholesky factor (D'=1); results must equal the
     oracle, which factorises per output like the reference (functions.py:283-286)."""
