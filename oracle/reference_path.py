@@ -845,10 +845,13 @@ def prefix_rule(values, ok, initial=None):
 
 
 class Lyapunov(object):
-    """``lyapunov.py:142-606`` (non-adaptive branch)."""
+    """``lyapunov.py:142-606``.  The adaptive branch (``:445-487, 540-582``) is restated with two
+    refined checks, see ``refined_negative``; its parity is UNPINNED: the reference has no test for
+    it and its graph tests the wrong tensor (dead code at ``:469-476``)."""
 
     def __init__(self, discretization, lyapunov_function, dynamics, lipschitz_dynamics,
-                 lipschitz_lyapunov, tau, policy, initial_set=None):
+                 lipschitz_lyapunov, tau, policy, initial_set=None, adaptive=False):
+        self.adaptive = adaptive
         self.discretization = discretization
         self.policy = policy
         self.safe_set = np.zeros(discretization.nindex, dtype=bool)
@@ -933,9 +936,69 @@ class Lyapunov(object):
             out[i:i + len(idx)] = self.negative(self.discretization.index_to_state(idx))
         return out
 
-    def update_safe_set(self, can_shrink=True):
+    def decrease_and_threshold(self, states, tau=None):
+        actions = self.policy(states)
+        next_states = self.dynamics(states, actions)
+        decrease = self.v_decrease_bound(states, next_states)
+        threshold = np.broadcast_to(self.threshold(states, tau), decrease.shape)
+        return decrease, threshold
+
+    def required_refinement(self, states, safety_factor=1.):
+        """``lyapunov.py:445-455``: ``n_req = ceil(max(safety_factor * threshold / decrease, 0))``,
+        NaN -> 0."""
+        decrease, threshold = self.decrease_and_threshold(states)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            ratio = safety_factor * threshold / decrease
+        ratio = np.where(np.isnan(ratio), 0.0, ratio)
+        return np.ceil(np.maximum(ratio, 0)).ravel()
+
+    def refinement_mesh(self, center, n):
+        """``lyapunov.py:459-472``: the ``n^d`` points ``center + 0.5 (1 - 1/n) unit_maxes
+        linspace(-1, 1, n)`` (``indexing='ij'``; ``linspace(-1, 1, 1) = [-1]`` times 0 for n = 1)."""
+        lengths = self.discretization.unit_maxes.reshape((-1, 1))
+        spacing = np.linspace(-1., 1., n).reshape(1, -1)
+        border = 0.5 * (1 - 1 / n) * lengths * np.tile(spacing, [len(lengths), 1])
+        mesh = np.meshgrid(*border, indexing="ij")
+        points = np.stack([col.reshape(-1) for col in mesh], axis=1)
+        return points + np.asarray(center).reshape(1, -1)
+
+    def refined_negative(self, states, refinement, mode="mesh", known_safe=None):
+        """The per-state refined check of ``lyapunov.py:457-481``.
+
+        ``mode="reference"``: as written -- ``refined_safety_check`` builds the mesh (``:461-472``)
+        but compares the OUTER ``decrease`` tensor (all fed states) with ``threshold(center,
+        tau / n)`` and reduces over everything (``:474-478``), so one failing state in the fed
+        slice fails every state.
+        ``mode="mesh"``: the evident intent -- the decrease condition is evaluated on the mesh
+        points of the cell with ``tau / n``: ``all_p v_decrease_bound(p) < threshold(p, tau / n)``,
+        and "cells that correspond to known safe states" (``:548-551``: ``negative`` or in the
+        initial safe set, ``known_safe``) are not re-checked -- as written they are re-checked
+        with n = 1, which fails every initial state whose own decrease is not negative and ends
+        the prefix there.
+        """
+        out = np.zeros(len(states), dtype=bool)
+        if mode == "reference":
+            decrease, _ = self.decrease_and_threshold(states)
+        for i, (center, n) in enumerate(zip(states, refinement)):
+            n = int(n)
+            if mode != "reference" and known_safe is not None and known_safe[i]:
+                out[i] = True
+                continue
+            with np.errstate(invalid="ignore"):
+                if mode == "reference":
+                    thr = self.threshold(center.reshape(1, -1), self.tau / n)
+                    out[i] = bool(np.all(np.less(decrease, thr)))
+                else:
+                    dec, thr = self.decrease_and_threshold(self.refinement_mesh(center, n),
+                                                           self.tau / n)
+                    out[i] = bool(np.all(np.less(dec, thr)))
+        return out
+
+    def update_safe_set(self, can_shrink=True, max_refinement=1, safety_factor=1.,
+                        refinement_mode="mesh"):
         """The host loop of ``lyapunov.py:497-606`` as written (batches, early break,
-        ``c_max`` index quirks), non-adaptive."""
+        ``c_max`` index quirks), including the adaptive branch ``:540-582``."""
+        safety_factor = np.maximum(safety_factor, 1.)
         if can_shrink:
             safe_set = np.zeros_like(self.safe_set, dtype=bool)
             refinement = np.zeros_like(self._refinement, dtype=int)
@@ -958,12 +1021,36 @@ class Lyapunov(object):
             safe_batch |= negative
             refine_batch[negative] = 1
             bound = int(np.argmin(safe_batch))
+            refine_bound = 0
             if bound > 0 or not safe_batch[0]:
-                safe_batch[bound:] = False
-                refine_batch[bound:] = 0
-                break
+                if self.adaptive and max_refinement > 1:                       # :540-577
+                    refine_batch[bound:] = self.required_refinement(states[bound:], safety_factor)
+                    initial = np.zeros(self.discretization.nindex, dtype=bool)
+                    if self.initial_safe_set is not None:
+                        initial[self.initial_safe_set] = True
+                    idx_safe = np.logical_or(negative, initial[indices])
+                    refine_batch[idx_safe] = 1
+                    to_check = np.logical_and(refine_batch >= 1,
+                                              refine_batch <= max_refinement)[bound:]
+                    stop = len(to_check) if np.all(to_check) else int(np.argmin(to_check))
+                    if stop > 0:
+                        refined_safe = self.refined_negative(states[bound:bound + stop],
+                                                             refine_batch[bound:bound + stop],
+                                                             refinement_mode,
+                                                             idx_safe[bound:bound + stop])
+                        refine_bound = len(refined_safe) if np.all(refined_safe) \
+                            else int(np.argmin(refined_safe))
+                        safe_batch[bound:bound + refine_bound] = True
+                    if stop < len(to_check) or refine_bound < stop:
+                        safe_batch[bound + refine_bound:] = False
+                        refine_batch[bound + refine_bound:] = 0
+                        break
+                else:
+                    safe_batch[bound:] = False
+                    refine_batch[bound:] = 0
+                    break
 
-        max_index = i + bound - 1
+        max_index = i + bound + refine_bound - 1
         self.c_max = self.values[value_order[max_index]]
 
         safe_nodes = value_order[safe_set]

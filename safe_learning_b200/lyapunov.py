@@ -147,8 +147,9 @@ class Lyapunov(object):
     """See ``lyapunov.py:142-225`` for the parameters.
 
     ``lipschitz_lyapunov`` may be a float or a fusable Function (e.g. ``abs(LinearSystem(2P))``);
-    ``lipschitz_dynamics`` must be a float in this build.  ``adaptive=True`` is accepted but
-    refinement (``max_refinement > 1``) is not implemented (out of scope).
+    ``lipschitz_dynamics`` must be a float in this build.  With ``adaptive=True``,
+    ``update_safe_set(max_refinement=R)`` re-checks failing cells on a locally refined mesh
+    (``lyapunov.py:445-487, 540-582``, see ``_adaptive_ok``).
     """
 
     def __init__(self, discretization, lyapunov_function, dynamics, lipschitz_dynamics,
@@ -382,12 +383,88 @@ class Lyapunov(object):
                   "slb_lyapunov_sweep")
         return (self._negative_dev, details) if want_details else self._negative_dev
 
+    def negative_at_points(self, points, tau=None):
+        """The decision of ``lyapunov.py:436-441`` on an explicit device point list ``[n, d]``
+        (``slb_lyapunov_points``), optionally with another discretisation constant."""
+        lib = nat.load()
+        cfg = self.sweep_descriptor()
+        if tau is not None and float(tau) != float(self.tau):
+            cfg = nat.SlbSweep.from_buffer_copy(cfg)
+            cfg.tau = float(tau)
+        points = points.contiguous()
+        n = points.shape[0]
+        neg = dev.empty((n,), torch.uint8)
+        if n:
+            nat.check(lib.slb_lyapunov_points(dev.stream(), cfg, points.data_ptr(), n,
+                                              neg.data_ptr(), None, None, None, None, None),
+                      "slb_lyapunov_points")
+        return neg
+
+    def _refinement_offsets(self, n):
+        """Mesh of ``lyapunov.py:459-472`` relative to the cell centre: ``0.5 (1 - 1/n) unit_maxes
+        linspace(-1, 1, n)`` per dimension, ``indexing='ij'`` -> ``[n^d, d]``."""
+        lengths = self.discretization.unit_maxes.reshape((-1, 1))
+        spacing = np.linspace(-1., 1., n).reshape(1, -1)
+        border = 0.5 * (1 - 1 / n) * lengths * np.tile(spacing, [len(lengths), 1])
+        mesh = np.meshgrid(*border, indexing="ij")
+        return np.stack([col.reshape(-1) for col in mesh], axis=1)
+
+    def _adaptive_ok(self, max_refinement, safety_factor, initial):
+        """Adaptive discretisation (``lyapunov.py:445-487, 540-582``) in closed form.
+
+        ``n_req = ceil(max(safety_factor * threshold / decrease, 0))`` (NaN -> 0, ``:447-455``).  A
+        point counts as verified if ``negative``, or if ``2 <= n_req <= max_refinement`` and the
+        decrease condition holds with ``tau / n_req`` on all ``n_req^d`` mesh points of its cell
+        (``:459-472``).  The reference's graph builds that mesh but compares the outer
+        ``decrease`` tensor (``:474-478``, dead code); this implements the evident intent, the
+        same as ``oracle.Lyapunov.update_safe_set(refinement_mode="mesh")``.  The V-sorted prefix
+        rule then runs on the verified flags; refined candidates are only evaluated up to the
+        first point that cannot be verified at all.  Returns (flags uint8, n_req int64) slabs.
+        """
+        neg, det = self.compute_negative(want_details=True)
+        negb = neg.to(torch.bool)
+        ratio = float(safety_factor) * det["threshold"] / det["decrease"]
+        ratio = torch.where(torch.isnan(ratio), torch.zeros_like(ratio), ratio)
+        n_req = torch.ceil(torch.clamp(ratio, min=0.0))
+        known = negb if initial is None else negb | initial.to(torch.bool)
+        cand = ~known & (n_req >= 2) & (n_req <= max_refinement)
+        hopeless = ~known & ~cand
+        values = self._values_dev
+        if bool(hopeless.any()):
+            cand &= values <= values[hopeless].min()
+        ok = negb.clone()
+        grid = self.discretization
+        d = grid.ndim
+        num = torch.as_tensor(np.asarray(grid.num_points, dtype=np.int64), device=values.device)
+        unit = dev.to_device(np.asarray(grid.unit_maxes, dtype=np.float64))
+        offset = dev.to_device(np.asarray(grid.offset, dtype=np.float64))
+        for n in range(2, int(max_refinement) + 1):
+            idx = torch.nonzero(cand & (n_req == n))[:, 0]
+            if idx.numel() == 0:
+                continue
+            offsets = dev.to_device(self._refinement_offsets(n))          # [n^d, d]
+            chunk = max(1, (1 << 21) // offsets.shape[0])
+            for c0 in range(0, idx.numel(), chunk):
+                part = idx[c0:c0 + chunk]
+                flat = part + self._begin
+                ijk = torch.empty((part.numel(), d), dtype=torch.int64, device=values.device)
+                for c in range(d - 1, -1, -1):
+                    ijk[:, c] = flat % num[c]
+                    flat = flat // num[c]
+                centers = ijk.to(torch.float64) * unit + offset            # functions.py:714-731
+                points = (offsets[None, :, :] + centers[:, None, :]).reshape(-1, d)
+                fine = self.negative_at_points(points, self.tau / n)
+                ok[part] = fine.view(part.numel(), -1).to(torch.bool).all(dim=1)
+        return ok.to(torch.uint8), n_req.to(torch.int64), negb
+
     def update_safe_set(self, can_shrink=True, max_refinement=1, safety_factor=1.,
                         parallel_iterations=1):
-        """Compute and update the safe set (``lyapunov.py:407-606``, non-adaptive branch)."""
-        if self.adaptive and max_refinement > 1:
-            raise NotImplementedError("adaptive refinement (lyapunov.py:445-487, 540-582) is "
-                                      "outside this build's hot path")
+        """Compute and update the safe set (``lyapunov.py:407-606``)."""
+        adaptive = bool(self.adaptive and max_refinement > 1)
+        if adaptive and not can_shrink:
+            raise NotImplementedError("adaptive refinement with can_shrink=False is not "
+                                      "implemented")
+        safety_factor = max(float(safety_factor), 1.)
         lib = nat.load()
         n_local = self._end - self._begin
         n_total = self.discretization.nindex
@@ -404,9 +481,14 @@ class Lyapunov(object):
         if self._safe_dev is None or self._safe_dev.numel() != n_local:
             self._safe_dev = dev.empty((n_local,), torch.uint8)
 
+        self.__dict__["_adaptive_state"] = None
+        if adaptive:
+            flags, n_req, negb = self._adaptive_ok(max_refinement, safety_factor, initial)
+            self.__dict__["_adaptive_state"] = (n_req, negb)
+
         def enqueue():
             st = dev.stream()
-            neg = self.compute_negative()
+            neg = flags if adaptive else self.compute_negative()
             nat.check(lib.slb_first_fail(st, self._values_dev.data_ptr(), neg.data_ptr(),
                                          dev.ptr(initial), n_local, self._begin,
                                          self._workspace.data_ptr(), self._key_dev.data_ptr()),
@@ -425,7 +507,7 @@ class Lyapunov(object):
         # Single GPU: the five launches of a sweep are captured once into a CUDA graph and replayed
         # while nothing they depend on (function objects, GP state, buffers) has changed.
         token = None
-        if world == 1 and _USE_GRAPHS:
+        if world == 1 and _USE_GRAPHS and not adaptive:
             token = (self._descriptor_token(), self._values_dev.data_ptr(),
                      0 if initial is None else initial.data_ptr(), n_local)
         cached = self.__dict__.get("_sweep_graph")
@@ -457,6 +539,15 @@ class Lyapunov(object):
         else:
             batch = int(config.gp_batch_size)
             position = ((n_total - 1) // batch) * batch - 1
+            if adaptive:
+                # lyapunov.py:586-590 with refine_bound: if the last batch holds a cell that only
+                # the refinement verified, the index is that of the largest V (rare path: needs ranks)
+                values = self._gather(self._values_dev)
+                known = negb if initial is None else negb | initial.to(torch.bool)
+                known = self._gather(known.to(torch.uint8)).to(torch.bool)
+                order = torch.sort(values, stable=True).indices
+                if bool((~known[order[position + 1:]]).any()):
+                    position = n_total - 1
         if position < 0:
             c_max = _key_to_value(max_all)                  # index -1: largest V on the grid
         elif failed:
@@ -474,7 +565,16 @@ class Lyapunov(object):
     @property
     def _refinement(self):
         if self.__dict__.get("_refinement_host") is None:
-            self.__dict__["_refinement_host"] = self.safe_set.astype(int)
+            safe = self.safe_set
+            refinement = safe.astype(int)
+            state = self.__dict__.get("_adaptive_state")
+            if state is not None:     # N(x) = n_req where the refined mesh verified the cell
+                n_req = self._gather(state[0]).cpu().numpy()
+                negative = self._gather(state[1].to(torch.uint8)).cpu().numpy().astype(bool)
+                refinement = np.where(safe & ~negative, n_req, refinement)
+                if self.initial_safe_set is not None:
+                    refinement[self.initial_safe_set] = 1
+            self.__dict__["_refinement_host"] = refinement
         return self.__dict__["_refinement_host"]
 
     @_refinement.setter

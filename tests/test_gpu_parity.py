@@ -479,6 +479,51 @@ def test_multi_batch_quirks_and_ragged_sizes(sl):
         sl.config.gp_batch_size, O.config.gp_batch_size = old
 
 
+@pytest.mark.parametrize("tau_scale,max_refinement,safety_factor",
+                         [(1 / 60., 4, 2.0), (1 / 30., 8, 2.0), (1 / 30., 4, 2.0), (1 / 60., 12, 4.0)])
+def test_adaptive_refinement_vs_oracle(sl, tau_scale, max_refinement, safety_factor):
+    """Adaptive discretisation (lyapunov.py:445-487, 540-582) with the decrease evaluated on the
+    refined mesh: the closed form on the GPU against the oracle's batch loop (several batches)."""
+    par = W.make_pendulum(num_points=[26, 21], M=90, tau_scale=tau_scale)
+    old = (sl.config.gp_batch_size, O.config.gp_batch_size)
+    try:
+        sl.config.gp_batch_size = O.config.gp_batch_size = 64
+        lyaps = []
+        for ns, kind in ((sl, "product"), (O, "oracle")):
+            grid, dyn = W._build(ns, par, kind)
+            policy = ns.Saturation(ns.LinearSystem(-par["K"]), -1., 1.)
+            lyaps.append(ns.Lyapunov(grid, ns.QuadraticFunction(par["P"]), dyn, par["L_dyn"],
+                                     ns.AbsFunction(ns.LinearSystem((2 * par["P"],))), par["tau"],
+                                     policy, initial_set=par["initial"], adaptive=True))
+        gpu, cpu = lyaps
+        gpu.update_safe_set(max_refinement=max_refinement, safety_factor=safety_factor)
+        cpu.update_safe_set(max_refinement=max_refinement, safety_factor=safety_factor,
+                            refinement_mode="mesh")
+        assert_array_equal(gpu.safe_set, cpu.safe_set)
+        assert_array_equal(gpu._refinement, cpu._refinement)
+        assert gpu.feed_dict[gpu.c_max] == cpu.c_max
+        # max_refinement = 1 is the plain sweep
+        gpu.update_safe_set(max_refinement=1)
+        cpu.update_safe_set(max_refinement=1)
+        assert_array_equal(gpu.safe_set, cpu.safe_set)
+        assert_array_equal(gpu._refinement, cpu._refinement)
+    finally:
+        sl.config.gp_batch_size, O.config.gp_batch_size = old
+
+
+def test_future_values_lyapunov_penalty_vs_oracle(sl):
+    """reinforcement_learning.py:107-112: values - lambda (v_decrease_bound - threshold)."""
+    par = W.make_pendulum(num_points=[15, 13], M=60)
+    rl_gpu, _ = _rl_objects(sl, par, "product")
+    rl_cpu, _ = _rl_objects(O, par, "oracle")
+    gpu, cpu = W.build_product(par), W.build_oracle(par)
+    states = np.random.default_rng(5).uniform(-1, 1, (120, 2))
+    for lam in (1.0, 3.5):
+        assert_allclose(rl_gpu.future_values(states, lyapunov=gpu, lagrange_multiplier=lam),
+                        rl_cpu.future_values(states, lyapunov=cpu, lagrange_multiplier=lam),
+                        rtol=1e-8, atol=1e-10)
+
+
 def test_can_shrink_false_vs_oracle(sl):
     """lyapunov.py:507-510, 583-587: previous safe set seeds, batch-dependent."""
     old = (sl.config.gp_batch_size, O.config.gp_batch_size)
@@ -605,4 +650,9 @@ def test_errors_are_loud(sl):
         sl.Lyapunov(grid, sl.QuadraticFunction(np.array([[1.0]])),
                     sl.LinearSystem(np.array([[1, 1.]])), 0.4, 0.3, 0.5,
                     sl.LinearSystem(np.array([[-.1]])), adaptive=True).update_safe_set(
-                        max_refinement=4)
+                        can_shrink=False, max_refinement=4)
+    with pytest.raises(TypeError):
+        sl.GPRCached(np.zeros((2, 2)), np.zeros((2, 1)), kern="rbf")
+    with pytest.raises(NotImplementedError):      # expands to 8 primitives, the descriptor holds 6
+        k = sl.RBF(2) + sl.Matern32(2)
+        sl.GaussianProcess(sl.GPRCached(np.zeros((2, 2)), np.zeros((2, 1)), (k * k) * k))(np.zeros((1, 2)))

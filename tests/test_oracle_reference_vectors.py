@@ -165,3 +165,50 @@ def test_prefix_rule_matches_batch_loop():
             assert_equal(lyap.safe_set, safe)
     finally:
         O.config.gp_batch_size = old
+
+
+def test_adaptive_closed_form_matches_batch_loop():
+    """The adaptive branch (lyapunov.py:540-582) of the oracle's batch loop, with the refined check
+    evaluated on the mesh and known-safe cells skipped, equals the closed form the CUDA path uses:
+    ok = negative | initial | (2 <= n_req <= R and refined check) followed by the prefix rule, with
+    N(x) = 1 / n_req / 0.  Random labels, refinement demands, ties and batch sizes."""
+    rng = np.random.default_rng(11)
+    old = O.config.gp_batch_size
+    try:
+        for _ in range(300):
+            n = int(rng.integers(2, 40))
+            R = int(rng.integers(2, 6))
+            grid = O.GridWorld([[-1, 1]], n)
+            values = rng.integers(0, 6, n).astype(float)
+            neg = rng.random(n) < 0.6
+            init = rng.random(n) < 0.15
+            n_req = np.where(neg, 1, rng.integers(0, 8, n))
+            fine = rng.random(n) < 0.7                      # outcome of the refined mesh check
+            lyap = O.Lyapunov(grid, lambda x: np.zeros((len(x), 1)), None, 0., 0., 0.,
+                              None, initial_set=init, adaptive=True)
+            lyap.values = values
+            index = grid.state_to_index
+            lyap.negative = lambda states: neg[index(states)]
+            lyap.required_refinement = lambda states, sf=1.: n_req[index(states)].astype(float)
+            lyap.refined_negative = lambda states, refinement, mode="mesh", known_safe=None: \
+                np.where(known_safe, True, fine[index(states)] & (refinement >= 2))   # n = 1: plain check
+            O.config.gp_batch_size = int(rng.integers(1, 24))
+            lyap.update_safe_set(max_refinement=R)
+            ok = neg | init | ((n_req >= 2) & (n_req <= R) & fine)
+            safe, p = O.prefix_rule(values, ok, init)
+            assert_equal(lyap.safe_set, safe)
+            expect = np.where(safe, np.where(neg | init, 1, n_req), 0)
+            assert_equal(lyap._refinement, expect)
+            # c_max index arithmetic (lyapunov.py:586-590): when nothing fails it depends on
+            # whether the LAST batch holds a cell that only the refinement verified
+            order = O.stable_value_order(values)
+            if p < n:
+                position = p - 1
+            else:
+                batch = O.config.gp_batch_size
+                start = ((n - 1) // batch) * batch
+                rescued = ~(neg | init)[order[start:]]
+                position = n - 1 if rescued.any() else start - 1
+            assert lyap.c_max == values[order[position]]
+    finally:
+        O.config.gp_batch_size = old
