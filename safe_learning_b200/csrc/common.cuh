@@ -185,6 +185,77 @@ SLB_DEV double kernel_expr_cross(const slb_kernel& K, const double* z, const dou
     return K.num_prims > 0 ? total + term : 0.0;
 }
 
+// U training rows at once: the primitive loop is outermost so its parameters are fetched once per
+// batch and the U exp / sqrt chains of a primitive are independent (the one-row form above runs
+// one dependent chain per primitive; measured 6x the RBF generation cost against ~2x here).
+template <int DIN, int U>
+SLB_DEV void kernel_expr_cross_n(const slb_kernel& K, const double* z, const double* const (&x)[U],
+                                 const double* exptab, double (&out)[U]) {
+    double total[U], term[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) { total[u] = 0.0; term[u] = 1.0; }
+    int cur = 0;
+    for (int i = 0; i < K.num_prims; ++i) {
+        const slb_kernel_prim& P = K.prims[i];
+        const int kind = P.kind;
+        const double var = P.variance;
+        if (P.term != cur) {
+#pragma unroll
+            for (int u = 0; u < U; ++u) { total[u] += term[u]; term[u] = 1.0; }
+            cur = P.term;
+        }
+        double w[DIN];
+#pragma unroll
+        for (int c = 0; c < DIN; ++c) w[c] = P.w[c];
+        double v[U];
+        if (kind == SLB_K_LINEAR) {
+#pragma unroll
+            for (int c = 0; c < DIN; ++c) w[c] *= z[c];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                double a = 0.0;
+#pragma unroll
+                for (int c = 0; c < DIN; ++c) a = fma(w[c], x[u][c], a);
+                v[u] = a;
+            }
+        } else if (kind == SLB_K_CONSTANT || kind == SLB_K_WHITE) {
+#pragma unroll
+            for (int u = 0; u < U; ++u) v[u] = kind == SLB_K_CONSTANT ? var : 0.0;
+        } else {
+            double r2[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                double a = 0.0;
+#pragma unroll
+                for (int c = 0; c < DIN; ++c) {
+                    const double df = (z[c] - x[u][c]) * w[c];
+                    a = fma(df, df, a);
+                }
+                r2[u] = a;
+            }
+            if (kind == SLB_K_RBF) {
+#pragma unroll
+                for (int u = 0; u < U; ++u) v[u] = var * exp_neg_tab(-0.5 * r2[u], exptab);
+            } else {
+                // s = c r with c = 1, sqrt(3), sqrt(5); polynomial 1, 1 + s, 1 + s + s^2 / 3
+                const double cs = kind == SLB_K_MATERN12 ? 1.0
+                                : kind == SLB_K_MATERN32 ? 1.7320508075688772 : 2.23606797749979;
+                const double c1 = kind == SLB_K_MATERN12 ? 0.0 : 1.0;
+                const double c2 = kind == SLB_K_MATERN52 ? 1.0 / 3.0 : 0.0;
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const double sr = cs * sqrt(r2[u] + 1e-12);
+                    v[u] = var * fma(fma(c2, sr, c1), sr, 1.0) * exp_neg_tab(-sr, exptab);
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) term[u] *= v[u];
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) out[u] = K.num_prims > 0 ? total[u] + term[u] : 0.0;
+}
+
 // diagonal form k(z, z) (kern.Kdiag(Xnew), functions.py:450)
 template <int DIN>
 SLB_DEV double kernel_expr_diag(const slb_kernel& K, const double* z) {

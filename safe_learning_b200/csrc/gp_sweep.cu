@@ -59,8 +59,9 @@ constexpr size_t SMEM_TOT = (size_t)NRED * TP * sizeof(double);
 constexpr size_t SMEM_POST = (size_t)2 * SLB_MAX_OUT * TP * sizeof(double);
 constexpr size_t SMEM_EXPTAB = 64 * sizeof(double);
 constexpr size_t SMEM_XP = (size_t)PANEL * SLB_MAX_IN * sizeof(double);
+constexpr size_t SMEM_KEXPR = (sizeof(slb_kernel) + 15) / 16 * 16;
 constexpr size_t SMEM_TOTAL =
-    SMEM_KS + SMEM_Z + SMEM_RED + SMEM_TOT + SMEM_POST + SMEM_EXPTAB + SMEM_XP;
+    SMEM_KS + SMEM_Z + SMEM_RED + SMEM_TOT + SMEM_POST + SMEM_EXPTAB + SMEM_XP + SMEM_KEXPR;
 
 enum { MODE_SWEEP_GRID = 0, MODE_SWEEP_STATES = 1, MODE_PREDICT = 2 };
 
@@ -167,6 +168,9 @@ gp_tile_kernel(const __grid_constant__ slb_sweep cfg, const gp_args a) {
     double* post = tot + NRED * TP;                   // mean [MAX_OUT][TP], err [MAX_OUT][TP]
     double* exptab = post + 2 * SLB_MAX_OUT * TP;     // 2^(j/64), j = 0..63
     double* Xp = exptab + 64;                         // scaled training inputs of the j-panel
+    // covariance expression of the current factor (KEXPR): shared memory serves the primitive
+    // loop's dynamically indexed reads as broadcasts, the kernel-parameter bank does not
+    slb_kernel* kexpr = reinterpret_cast<slb_kernel*>(Xp + PANEL * SLB_MAX_IN);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t tile0 = (int64_t)blockIdx.x * TP;
@@ -242,6 +246,13 @@ gp_tile_kernel(const __grid_constant__ slb_sweep cfg, const gp_args a) {
         const double* __restrict__ Xs = F.Xs;
 
         const bool general = KEXPR && F.kernel.num_prims > 0;
+        if (general) {
+            __syncthreads();                          // previous factor's readers are done
+            const int* src = reinterpret_cast<const int*>(&F.kernel);
+            for (int i = tid; i < (int)(sizeof(slb_kernel) / sizeof(int)); i += NT)
+                reinterpret_cast<int*>(kexpr)[i] = src[i];
+            __syncthreads();
+        }
         double zs[DIN];
 #pragma unroll
         for (int c = 0; c < DIN; ++c)
@@ -291,17 +302,26 @@ gp_tile_kernel(const __grid_constant__ slb_sweep cfg, const gp_args a) {
                     double2* ks2 = reinterpret_cast<double2*>(Ks);
                     constexpr int GP = 2;            // pairs per iteration = 2 GP interleaved exps
                     if (general) {
-                        // covariance expression on the raw inputs (one pair per iteration)
-                        for (int mm = gpo; mm < npairs; mm += PS) {
-                            double kv[2];
+                        // covariance expression on the raw inputs, GP pairs = 2 GP rows per batch
+                        for (int mm = gpo; mm < npairs; mm += GP * PS) {
+                            const double* xr[2 * GP];
 #pragma unroll
-                            for (int u = 0; u < 2; ++u) {
-                                const int jj = 8 * mm + 4 * u + gr;
-                                const double k = s2 * kernel_expr_cross<DIN>(
-                                    F.kernel, zs, Xp + min(jj, nj - 1) * DIN, exptab);
-                                kv[u] = jj < nj ? k : 0.0;
+                            for (int u = 0; u < 2 * GP; ++u) {
+                                const int jj = 8 * (mm + PS * (u >> 1)) + 4 * (u & 1) + gr;
+                                xr[u] = Xp + min(jj, nj - 1) * DIN;
                             }
-                            ks2[(mm * 4 + gr) * KSTR + p_gen] = make_double2(kv[0], kv[1]);
+                            double kv[2 * GP];
+                            kernel_expr_cross_n<DIN, 2 * GP>(*kexpr, zs, xr, exptab, kv);
+#pragma unroll
+                            for (int u = 0; u < 2 * GP; ++u) {
+                                const int jj = 8 * (mm + PS * (u >> 1)) + 4 * (u & 1) + gr;
+                                kv[u] = jj < nj ? s2 * kv[u] : 0.0;   // zero rows pad the last pair
+                            }
+#pragma unroll
+                            for (int g = 0; g < GP; ++g)
+                                if (mm + PS * g < npairs)
+                                    ks2[((mm + PS * g) * 4 + gr) * KSTR + p_gen] =
+                                        make_double2(kv[2 * g], kv[2 * g + 1]);
                         }
                     } else
                     for (int mm = gpo; mm < npairs; mm += GP * PS) {
@@ -456,7 +476,7 @@ gp_tile_kernel(const __grid_constant__ slb_sweep cfg, const gp_args a) {
                     double zt[DIN];
 #pragma unroll
                     for (int c = 0; c < DIN; ++c) zt[c] = zraw[c * TP + tid];
-                    kss = s2 * kernel_expr_diag<DIN>(F.kernel, zt);
+                    kss = s2 * kernel_expr_diag<DIN>(*kexpr, zt);
                 }
                 const double fvar = f64sub(kss, tot[tid]) / s2;                    // :450-451, :456
                 post[o * TP + tid] = fmean;

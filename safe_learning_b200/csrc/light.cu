@@ -353,21 +353,29 @@ SLB_DEV void gp_mean_factor(const slb_gp_stack& gp, const slb_gp_factor& F, cons
         __syncthreads();
         // 4 independent exp chains per thread (the loop is bound by the fp64 pipe through exp)
         for (int j0 = 0; j0 < nc; j0 += 4) {
-            double t2[4];
+            double kv[4];
+            if (general) {
+                const double* xr[4];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const double* xr = xch + min(j0 + u, nc - 1) * DIN;
-                double acc = 0.0;
+                for (int u = 0; u < 4; ++u) xr[u] = xch + min(j0 + u, nc - 1) * DIN;
+                kernel_expr_cross_n<DIN, 4>(F.kernel, zs, xr, exptab, kv);
+            } else {
+                double t2[4];
 #pragma unroll
-                for (int c = 0; c < DIN; ++c) { const double df = zs[c] - xr[c]; acc = fma(df, df, acc); }
-                t2[u] = acc;
+                for (int u = 0; u < 4; ++u) {
+                    const double* xr = xch + min(j0 + u, nc - 1) * DIN;
+                    double acc = 0.0;
+#pragma unroll
+                    for (int c = 0; c < DIN; ++c) { const double df = zs[c] - xr[c]; acc = fma(df, df, acc); }
+                    t2[u] = acc;
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) kv[u] = F.variance * exp_neg_tab(-0.5 * t2[u], exptab);
             }
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 const int j = min(j0 + u, nc - 1);
-                double k = general ? kernel_expr_cross<DIN>(F.kernel, zs, xch + j * DIN, exptab)
-                                   : F.variance * exp_neg_tab(-0.5 * t2[u], exptab);
-                if (j0 + u >= nc) k = 0.0;
+                const double k = j0 + u >= nc ? 0.0 : kv[u];
 #pragma unroll
                 for (int q = 0; q < NO; ++q) dot[q] = fma(k, gch[q * BCHUNK + j], dot[q]);
             }

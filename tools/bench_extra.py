@@ -7,6 +7,7 @@
   shared    C2 with shared hyper-parameters (one Cholesky factor for both outputs)
   det_linear  deterministic LinearSystem dynamics on 4096^2 / 8192^2 (closest to the HBM roofline)
   c4        cart-pole 32^4 grid, M=2000, four factors, LyapunovNetwork V (C4 at 1-GPU size)
+  nb        the reference's 2001x1501 pendulum experiment with its own covariance expressions
 
     python tools/bench_extra.py [bellman] [det] [c5] [shared]
 """
@@ -135,6 +136,28 @@ def c5():
         torch.cuda.empty_cache()
 
 
+def nb():
+    """The reference's own pendulum experiment (examples/inverted_pendulum.ipynb cells 4-6): 2001 x
+    1501 grid, per-output kernel Linear(3, ARD) + Matern32(1, active_dims=[0]) * Linear(1), linear
+    prior mean, two factors; M as it grows during the learning loop."""
+    for M in (50, 200, 500):
+        par = W.make_pendulum(num_points=[2001, 1501], M=M, with_prior_mean=True)
+        par["kernel_specs"] = W.notebook_pendulum_kernels([[2e-3, 6e-3, 1.5e-3], [2.5e-2, 8e-3, 1.2e-2]])
+        lyap = W.build_product(par)
+        ms = timed(lyap.compute_negative, steps=3, warmup=1)
+        ms_full = timed(lyap.update_safe_set, steps=3, warmup=1)
+        n = lyap.discretization.nindex
+        fl = algorithmic_flops_per_point(M, 3, 2, 2)
+        print(json.dumps({"bench": "notebook_pendulum_kernels", "grid": "2001x1501", "M": M,
+                          "kernel": "Linear(3,ARD) + Matern32(1,[0]) * Linear(1)",
+                          "kernel_ms": ms, "update_safe_set_ms": ms_full,
+                          "points_per_s": n / (ms_full * 1e-3),
+                          "tflops_rbf_equivalent": fl * n / (ms * 1e-3) * 1e-12,
+                          "frac_of_fp64_peak_rbf_equivalent": fl * n / (ms * 1e-3) * 1e-12 / PEAK_TF}))
+        del lyap
+        torch.cuda.empty_cache()
+
+
 def shared():
     par = W.make_pendulum(num_points=256, M=500, shared_hypers=True)
     lyap = W.build_product(par)
@@ -150,6 +173,6 @@ def shared():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["bellman", "det", "det_linear", "c5", "shared", "c4"]
+    which = sys.argv[1:] or ["bellman", "det", "det_linear", "c5", "shared", "c4", "nb"]
     for name in which:
         globals()[name]()
