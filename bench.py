@@ -98,10 +98,11 @@ def cpu_reference_rate(par, seconds_budget, steps=1, warmup=0):
     (early exit disabled).  Returns (points/s, cores, sample description, per-step seconds)."""
     import bench_workloads as W
     import oracle as O
+    # every host thread this process may use -- not the BLAS pools' current size, which torchrun
+    # pins to 1 through OMP_NUM_THREADS (threadpool_limits below can raise it again)
     try:
-        from threadpoolctl import threadpool_info
-        threads = max([p.get("num_threads", 1) for p in threadpool_info()] or [1])
-    except Exception:  # pragma: no cover
+        threads = len(os.sched_getaffinity(0))
+    except AttributeError:  # pragma: no cover
         threads = os.cpu_count() or 1
     lyap = W.build_oracle(par)
     grid = lyap.discretization
