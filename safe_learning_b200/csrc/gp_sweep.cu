@@ -80,12 +80,6 @@ struct gp_args {
     long long* timing;      // diagnostics: [tile][warp][8]: cycles in {generate, contract, epilogue, total}, globaltimer ns {start, end}, cycles waiting at barriers, 0
 };
 
-SLB_DEV double ldg_stream(const double* p) {
-    double v;
-    asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
-    return v;
-}
-
 SLB_DEV double2 ldg_stream2(const double2* p) {
     double2 v;
     asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];"
@@ -98,7 +92,6 @@ SLB_DEV void dmma884(double& c0, double& c1, double a, double b) {
                  : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
-// k-steps [k0, k1) of the current j-panel for row blocks q >= Q0 of this warp.
 // Pairs [m0, m1) of k-steps of the current j-panel for row blocks q >= Q0 of this warp.
 // Per pair and row block ONE 128-bit global load brings the A fragments of both k-steps
 // (the packed factor stores them adjacent), per column block ONE 128-bit shared load brings both
