@@ -33,6 +33,36 @@ for num, tau_scale in (([37, 23], 1 / 48.), ([48, 48], 1 / 48.), ([9, 7], 0.0)):
     assert gpu.feed_dict[gpu.c_max] == cpu.c_max, (rank, num, gpu.feed_dict[gpu.c_max], cpu.c_max)
     assert gpu.last_sweep["n_safe"] == int(cpu.safe_set.sum())
 
+# --- covariance expressions (the notebook kernels) on sharded slabs
+par = W.make_pendulum(num_points=[24, 19], M=90, tau_scale=1 / 150., with_prior_mean=True, seed=3)
+par["kernel_specs"] = W.notebook_pendulum_kernels([[2e-3, 6e-3, 1.5e-3], [2.5e-2, 8e-3, 1.2e-2]])
+gpu, cpu = W.build_product(par), W.build_oracle(par)
+gpu.update_safe_set()
+cpu.update_safe_set()
+assert np.array_equal(gpu.safe_set, cpu.safe_set) and 50 < cpu.safe_set.sum() < cpu.safe_set.size
+assert gpu.feed_dict[gpu.c_max] == cpu.c_max
+
+# --- adaptive refinement on sharded slabs (several batches)
+par = W.make_pendulum(num_points=[26, 21], M=90, tau_scale=1 / 30.)
+old_batch = (sl.config.gp_batch_size, O.config.gp_batch_size)
+sl.config.gp_batch_size = O.config.gp_batch_size = 64
+pair = []
+for ns, kind in ((sl, "product"), (O, "oracle")):
+    grid, dyn = W._build(ns, par, kind)
+    policy = ns.Saturation(ns.LinearSystem(-par["K"]), -1., 1.)
+    pair.append(ns.Lyapunov(grid, ns.QuadraticFunction(par["P"]), dyn, par["L_dyn"],
+                            ns.AbsFunction(ns.LinearSystem((2 * par["P"],))), par["tau"], policy,
+                            initial_set=par["initial"], adaptive=True))
+gpu, cpu = pair
+for kwargs in (dict(), dict(max_refinement=8, safety_factor=2.0)):
+    gpu.update_safe_set(**kwargs)
+    cpu.update_safe_set(**kwargs)
+    assert np.array_equal(gpu.safe_set, cpu.safe_set), (rank, kwargs)
+    assert np.array_equal(gpu._refinement, cpu._refinement), (rank, kwargs)
+    assert gpu.feed_dict[gpu.c_max] == cpu.c_max, (rank, kwargs)
+assert cpu._refinement.max() > 1
+sl.config.gp_batch_size, O.config.gp_batch_size = old_batch
+
 # --- Bellman sweep: slabs all-gathered into the full vertex table every sweep
 import scipy.linalg  # noqa: E402
 par = W.make_pendulum(num_points=8, M=80)
