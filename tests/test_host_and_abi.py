@@ -261,3 +261,44 @@ def test_shard_ranges_cover_grid():
             assert spans[0][0] == 0 and spans[-1][1] == n
             for (b0, e0), (b1, e1) in zip(spans, spans[1:]):
                 assert e0 == b1 and b0 <= e0
+
+
+def test_kernel_algebra_normal_form_and_descriptor():
+    """Host side of the covariance expressions: sums of products expand to the normal form the
+    device evaluates, the descriptor carries active_dims as zero weights, and the torch
+    evaluation used for the Cholesky refit equals the oracle's gpflow restatement."""
+    import torch
+    import oracle as O
+    import bench_workloads as W
+    import safe_learning_b200 as sl
+    from safe_learning_b200 import _native as nat
+
+    spec = ('["prod", ["add", ["rbf", 2, {"variance": 0.7, "lengthscales": [0.8, 1.3], "active_dims": [0, 2], '
+            '"ARD": true}], ["linear", 3, {"variance": [0.1, 0.2, 0.3], "ARD": true}]], '
+            '["add", ["matern32", 1, {"lengthscales": 0.6, "active_dims": [1]}], ["white", 3, {"variance": 0.01}]]]')
+    k_prod, k_orc = W.build_kernel(sl, spec), W.build_kernel(O, spec)
+    terms = k_prod.terms()
+    assert [[type(p).__name__ for p in t] for t in terms] == [
+        ["RBF", "Matern32"], ["RBF", "White"], ["Linear", "Matern32"], ["Linear", "White"]]
+    X = np.random.default_rng(0).normal(size=(7, 3))
+    X2 = np.random.default_rng(1).normal(size=(4, 3))
+    Xt, X2t = torch.as_tensor(X), torch.as_tensor(X2)
+    assert np.allclose(k_prod.K_device(Xt).numpy(), k_orc.K(X), rtol=1e-13, atol=1e-15)
+    assert np.allclose(k_prod.K_device(Xt, X2t).numpy(), k_orc.K(X, X2), rtol=1e-13, atol=1e-15)
+    assert np.allclose(k_prod.Kdiag_device(Xt).numpy(), k_orc.Kdiag(X), rtol=1e-13, atol=1e-15)
+
+    desc = nat.SlbKernel()
+    with pytest.raises(NotImplementedError):           # 8 primitives > SLB_MAX_KPRIM
+        k_prod.fill(desc, 3)
+    nb = W.build_kernel(sl, W.notebook_pendulum_kernels([[0.1, 0.2, 0.3]])[0])
+    nb.fill(desc, 3)
+    assert desc.num_prims == 3
+    prims = [desc.prims[i] for i in range(3)]
+    assert [(p.kind, p.term) for p in prims] == [(nat.K_LINEAR, 0), (nat.K_MATERN32, 1), (nat.K_LINEAR, 1)]
+    assert list(prims[0].w)[:3] == [0.1, 0.2, 0.3]
+    assert list(prims[1].w)[:3] == [1.0, 0.0, 0.0] and prims[1].variance == 1.0
+    assert list(prims[2].w)[:3] == [0.2, 0.0, 0.0]
+    with pytest.raises(sl.DimensionError):
+        sl.Matern32(1, active_dims=[4]).fill(desc, 3)
+    assert sl.RBF(3, lengthscales=[1., 2., 3.]).is_plain_rbf(3)
+    assert not sl.RBF(2, active_dims=[0, 2]).is_plain_rbf(3)
