@@ -6,8 +6,9 @@ reference's objects emit TF1 graph nodes, these objects (a) describe themselves 
 kernels through an ``slb_function`` / ``slb_gp_stack`` descriptor and (b) evaluate eagerly on
 the GPU when called with numpy arrays, returning numpy arrays.  There is no CPU path.
 
-gpflow is replaced by the small gpflow-free containers ``RBF`` / ``GPRCached`` (same
-arithmetic as ``gpflow==0.4.0`` ``kernels.RBF`` + ``functions.py:357-458``).
+gpflow is replaced by small gpflow-free containers: the ``kernels`` (RBF, Matern12/32/52, Linear,
+Constant, White, sums and products, ``active_dims``; arithmetic of ``gpflow==0.4.0``
+``kernels``) and ``GPRCached`` (``functions.py:357-458``).
 """
 
 from __future__ import annotations
@@ -30,7 +31,8 @@ __all__ = ["DimensionError", "GridWorld", "Function", "DeterministicFunction",
            "UncertainFunction", "ConstantFunction", "LinearSystem", "QuadraticFunction",
            "Saturation", "AbsFunction", "Norm1Function", "ScaledFunction", "Triangulation",
            "Kernel", "RBF", "Matern12", "Matern32", "Matern52", "Linear", "Constant", "Bias",
-           "White", "Sum", "Add", "Product", "Prod", "kernels", "Likelihood", "GPRCached", "GPR", "GaussianProcess", "FunctionStack",
+           "White", "Sum", "Add", "Product", "Prod", "kernels", "Likelihood", "GPRCached", "GPR",
+           "GaussianProcess", "FunctionStack",
            "InvertedPendulum", "CartPole", "LyapunovNetwork", "NeuralNetwork",
            "concatenate_inputs"]
 
