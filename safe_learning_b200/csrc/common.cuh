@@ -552,33 +552,14 @@ SLB_EVAL_ATTR int eval_fn(const slb_function& f, const double* in, double* out) 
 //   dynamics are deterministic.  Returns negative = decrease < threshold (false on NaN).
 struct slb_decision { double vx, decrease, threshold; bool negative; };
 
-SLB_DEV slb_decision lyapunov_decide(const slb_sweep& cfg, const double* x, const double* mu,
-                                     const double* err) {
-    const int d = cfg.grid.ndim;
-    double tmp[SLB_MAX_OUT];
-    slb_decision r;
-    double vx[1], vm[1];
+// The decision of lyapunov.py:436-441 in three independent pieces (the tile kernel evaluates the
+// x-only piece while the GP runs, and the two mean-dependent pieces on different warps):
+// (1) V(x) and threshold(x) = -|L_V(x)|_1 (1 + L_f) tau                      :284-288
+SLB_DEV void lyapunov_state_terms(const slb_sweep& cfg, const double* x, double* vx_out,
+                                  double* threshold_out) {
+    double tmp[SLB_MAX_OUT], vx[1];
     eval_fn(cfg.lyapunov, x, vx);
-    eval_fn(cfg.lyapunov, mu, vm);
-    r.vx = vx[0];
-    const double v_dec = f64sub(vm[0], vx[0]);                 // :351-352
-    double bound = 0.0;
-    if (err != nullptr) {                                    // :344-347, lv at the MEAN
-        if (cfg.lipschitz_v.kind != SLB_FN_NONE) {
-            const int nl = eval_fn(cfg.lipschitz_v, mu, tmp);
-            if (nl == 1) {
-                bound = f64mul(tmp[0], err[0]);
-                for (int j = 1; j < d; ++j) bound = f64add(bound, f64mul(tmp[0], err[j]));
-            } else {
-                bound = f64mul(tmp[0], err[0]);
-                for (int j = 1; j < d; ++j) bound = f64add(bound, f64mul(tmp[j], err[j]));
-            }
-        } else {
-            bound = f64mul(cfg.lv_const, err[0]);
-            for (int j = 1; j < d; ++j) bound = f64add(bound, f64mul(cfg.lv_const, err[j]));
-        }
-    }
-    r.decrease = f64add(v_dec, bound);                         // :376
+    *vx_out = vx[0];
     double lvx;
     if (cfg.lipschitz_v.kind != SLB_FN_NONE) {               // :284-286 (1-norm of a vector lv)
         const int nl = eval_fn(cfg.lipschitz_v, x, tmp);
@@ -590,7 +571,45 @@ SLB_DEV slb_decision lyapunov_decide(const slb_sweep& cfg, const double* x, cons
     } else {
         lvx = cfg.lv_const;
     }
-    r.threshold = f64mul(f64mul(-lvx, f64add(1.0, cfg.lf_const)), cfg.tau);   // :288
+    *threshold_out = f64mul(f64mul(-lvx, f64add(1.0, cfg.lf_const)), cfg.tau);   // :288
+}
+
+// (2) sum_j L_V(mu)_j err_j, L_V evaluated at the predicted MEAN                :344-347
+SLB_DEV double lyapunov_error_bound(const slb_sweep& cfg, const double* mu, const double* err) {
+    const int d = cfg.grid.ndim;
+    double tmp[SLB_MAX_OUT];
+    double bound;
+    if (cfg.lipschitz_v.kind != SLB_FN_NONE) {
+        const int nl = eval_fn(cfg.lipschitz_v, mu, tmp);
+        if (nl == 1) {
+            bound = f64mul(tmp[0], err[0]);
+            for (int j = 1; j < d; ++j) bound = f64add(bound, f64mul(tmp[0], err[j]));
+        } else {
+            bound = f64mul(tmp[0], err[0]);
+            for (int j = 1; j < d; ++j) bound = f64add(bound, f64mul(tmp[j], err[j]));
+        }
+    } else {
+        bound = f64mul(cfg.lv_const, err[0]);
+        for (int j = 1; j < d; ++j) bound = f64add(bound, f64mul(cfg.lv_const, err[j]));
+    }
+    return bound;
+}
+
+// (3) V(mu); then decrease = (V(mu) - V(x)) + bound  and  negative = decrease < threshold
+SLB_DEV slb_decision lyapunov_combine(double vx, double threshold, double vm, double bound) {
+    slb_decision r;
+    r.vx = vx;
+    r.threshold = threshold;
+    r.decrease = f64add(f64sub(vm, vx), bound);                // :351-352, :376
     r.negative = r.decrease < r.threshold;                   // :441 strict, NaN -> false
     return r;
+}
+
+SLB_DEV slb_decision lyapunov_decide(const slb_sweep& cfg, const double* x, const double* mu,
+                                     const double* err) {
+    double vx, threshold, vm[1];
+    lyapunov_state_terms(cfg, x, &vx, &threshold);
+    eval_fn(cfg.lyapunov, mu, vm);
+    const double bound = err != nullptr ? lyapunov_error_bound(cfg, mu, err) : 0.0;
+    return lyapunov_combine(vx, threshold, vm[0], bound);
 }

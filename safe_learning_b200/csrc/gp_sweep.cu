@@ -60,8 +60,9 @@ constexpr size_t SMEM_POST = (size_t)2 * SLB_MAX_OUT * TP * sizeof(double);
 constexpr size_t SMEM_EXPTAB = 64 * sizeof(double);
 constexpr size_t SMEM_XP = (size_t)PANEL * SLB_MAX_IN * sizeof(double);
 constexpr size_t SMEM_KEXPR = (sizeof(slb_kernel) + 15) / 16 * 16;
-constexpr size_t SMEM_TOTAL =
-    SMEM_KS + SMEM_Z + SMEM_RED + SMEM_TOT + SMEM_POST + SMEM_EXPTAB + SMEM_XP + SMEM_KEXPR;
+constexpr size_t SMEM_PRE = (size_t)4 * TP * sizeof(double);
+constexpr size_t SMEM_TOTAL = SMEM_KS + SMEM_Z + SMEM_RED + SMEM_TOT + SMEM_POST + SMEM_EXPTAB +
+                              SMEM_XP + SMEM_KEXPR + SMEM_PRE;
 
 enum { MODE_SWEEP_GRID = 0, MODE_SWEEP_STATES = 1, MODE_PREDICT = 2 };
 
@@ -164,6 +165,8 @@ gp_tile_kernel(const __grid_constant__ slb_sweep cfg, const gp_args a) {
     // covariance expression of the current factor (KEXPR): shared memory serves the primitive
     // loop's dynamically indexed reads as broadcasts, the kernel-parameter bank does not
     slb_kernel* kexpr = reinterpret_cast<slb_kernel*>(Xp + PANEL * SLB_MAX_IN);
+    // decision terms per point: V(x), threshold(x) (stage 1), V(mu), error bound (tile epilogue)
+    double* pre = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(kexpr) + SMEM_KEXPR);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t tile0 = (int64_t)blockIdx.x * TP;
@@ -215,6 +218,19 @@ gp_tile_kernel(const __grid_constant__ slb_sweep cfg, const gp_args a) {
         }
 #pragma unroll
         for (int c = 0; c < DIN; ++c) zraw[c * TP + tid] = z[c];
+    } else if (tid < 2 * TP && a.mode != MODE_PREDICT) {
+        // warps 2-3, concurrently: the terms of the decision that need only x
+        const int p = tid - TP;
+        int64_t rel = tile0 + p;
+        if (rel > a.n - 1) rel = a.n - 1;
+        const int d = cfg.grid.ndim;
+        double x[SLB_MAX_DIM];
+        if (a.mode == MODE_SWEEP_GRID) {
+            grid_index_to_state(cfg.grid, a.idx_begin + rel, x);
+        } else {
+            for (int c = 0; c < d; ++c) x[c] = a.points[rel * d + c];
+        }
+        lyapunov_state_terms(cfg, x, &pre[p], &pre[TP + p]);
     }
     __syncthreads();
 
@@ -488,20 +504,34 @@ gp_tile_kernel(const __grid_constant__ slb_sweep cfg, const gp_args a) {
         t[0] = t_gen; t[1] = t_mma; t[2] = t_epi; t[3] = clock64() - t_start;
         t[4] = g_start; t[5] = g_end; t[6] = t_sync; t[7] = 0;
     }
-    // ---- tile epilogue
-    if (tid < TP && tile0 + tid < a.n) {
-        const int64_t rel = tile0 + tid;
-        double mu[SLB_MAX_OUT], er[SLB_MAX_OUT];
-        for (int o = 0; o < D; ++o) {
-            mu[o] = post[o * TP + tid];
-            er[o] = post[(SLB_MAX_OUT + o) * TP + tid];
+    // ---- tile epilogue: V(mu) on warps 0-1, the error bound on warps 2-3, then the decision
+    {
+        const int p = tid & (TP - 1);
+        const int64_t rel = tile0 + p;
+        const bool live = rel < a.n;
+        if (tid < 2 * TP && live) {
+            double mu[SLB_MAX_OUT], er[SLB_MAX_OUT];
+            for (int o = 0; o < D; ++o) {
+                mu[o] = post[o * TP + p];
+                er[o] = post[(SLB_MAX_OUT + o) * TP + p];
+            }
+            if (tid < TP) {
+                if (a.mean != nullptr) for (int o = 0; o < D; ++o) a.mean[rel * D + o] = mu[o];
+                if (a.err != nullptr) for (int o = 0; o < D; ++o) a.err[rel * D + o] = er[o];
+                if (a.mode != MODE_PREDICT) {
+                    double vm[1];
+                    eval_fn(cfg.lyapunov, mu, vm);
+                    pre[2 * TP + p] = vm[0];
+                }
+            } else if (a.mode != MODE_PREDICT) {
+                pre[3 * TP + p] = lyapunov_error_bound(cfg, mu, er);
+            }
         }
-        if (a.mean != nullptr) for (int o = 0; o < D; ++o) a.mean[rel * D + o] = mu[o];
-        if (a.err != nullptr) for (int o = 0; o < D; ++o) a.err[rel * D + o] = er[o];
-        if (a.mode != MODE_PREDICT) {
-            double x[SLB_MAX_DIM];
-            for (int c = 0; c < cfg.grid.ndim; ++c) x[c] = zraw[c * TP + tid];
-            const slb_decision r = lyapunov_decide(cfg, x, mu, er);
+        if (a.mode == MODE_PREDICT) return;
+        __syncthreads();
+        if (tid < TP && live) {
+            const slb_decision r =
+                lyapunov_combine(pre[p], pre[TP + p], pre[2 * TP + p], pre[3 * TP + p]);
             a.negative[rel] = r.negative ? 1 : 0;
             if (a.values != nullptr) a.values[rel] = r.vx;
             if (a.decrease != nullptr) a.decrease[rel] = r.decrease;
