@@ -60,17 +60,24 @@ enum slb_fn_kind {
     SLB_FN_LYAPUNOV_NN = 7,    /* LyapunovNetwork             examples/utilities.py:48-104  */
     SLB_FN_MLP = 8             /* NeuralNetwork (inference)   functions.py:1702-1729        */
 };
-/* post-ops, applied in this order: saturate -> abs -> norm1 -> out_scale */
+/* post-ops, applied in this order: saturate -> abs -> norm1 | maxabs -> out_scale */
 #define SLB_FLAG_SATURATE 1u   /* Saturation  functions.py:349-354                     */
 #define SLB_FLAG_ABS      2u   /* tf.abs(fun(x))     (notebook Lipschitz lambdas)      */
 #define SLB_FLAG_NORM1    4u   /* tf.norm(., ord=1, axis=1, keepdims=True)             */
 #define SLB_FLAG_PROJECT  8u   /* Triangulation(project=True) functions.py:1479-1485  */
 #define SLB_FLAG_SCALE   16u   /* multiply by out_scale (MultipliedFunction / __neg__) */
+#define SLB_FLAG_GRADIENT 32u  /* TRIANGULATION with one output column: return the d partial
+                                  derivatives of the piecewise-linear interpolant instead of its
+                                  value (Triangulation.gradient, functions.py:1260-1326, 1506-1510);
+                                  out_dim = d                                              */
+#define SLB_FLAG_MAXABS  64u   /* tf.reduce_max(tf.abs(.), axis=1, keepdims=True): the
+                                  Lipschitz lambda of examples/inverted_pendulum.ipynb cell 14;
+                                  applied after saturate, reduces to 1 column              */
 
 typedef struct slb_function {
     int32_t kind;
     int32_t in_dim;
-    int32_t out_dim;            /* before NORM1 (which reduces to 1 column)            */
+    int32_t out_dim;            /* before NORM1 / MAXABS (which reduce to 1 column)    */
     uint32_t flags;
     double  out_scale;
     double  lower, upper;       /* saturation bounds                                   */

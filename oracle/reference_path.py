@@ -25,6 +25,7 @@ import scipy.spatial
 __all__ = [
     "config", "DimensionError", "GridWorld", "LinearSystem", "QuadraticFunction",
     "Saturation", "ConstantFunction", "ScaledFunction", "AbsFunction", "Norm1Function",
+    "MaxAbsFunction",
     "RBF", "Matern12", "Matern32", "Matern52", "Linear", "Constant", "Bias", "White", "Add", "Prod",
     "LinearMean", "GPRCached", "GaussianProcess", "FunctionStack", "Triangulation",
     "InvertedPendulum", "CartPole", "LyapunovNetwork", "NeuralNetwork", "Lyapunov",
@@ -268,6 +269,17 @@ class Norm1Function(object):
 
     def __call__(self, *inputs):
         return _row_norm1(self.fun(*inputs))
+
+
+class MaxAbsFunction(object):
+    """``tf.reduce_max(tf.abs(fun(x)), axis=1, keepdims=True)``
+    (``examples/inverted_pendulum.ipynb`` cell 14)."""
+
+    def __init__(self, fun):
+        self.fun = fun
+
+    def __call__(self, *inputs):
+        return np.max(np.abs(self.fun(*inputs)), axis=1, keepdims=True)
 
 
 def _row_norm1(values):
@@ -664,6 +676,30 @@ class Triangulation(object):
         for k in range(1, w.shape[1]):
             acc = acc + w[:, k, None] * vals[:, k, :]
         return acc
+
+    def gradient(self, points):
+        """``functions.py:1260-1326`` (``_get_weights_gradient`` + ``gradient``): per point the
+        weights ``[d, d+1]`` are ``[-sum_c H[k, c], H[k, 0], ..., H[k, d-1]]`` of the simplex the
+        point falls in; ``grad[i, l, k] = sum_v weights[i, k, v] * values[corner_v, l]``, the
+        output axis squeezed for one column.  Pinned by ``tests/test_functions.py:582-624``."""
+        points = np.atleast_2d(np.asarray(points, dtype=np.float64))
+        ids = self.find_simplex(points)
+        corners = self.simplices(ids)
+        planes = self.hyperplanes[ids % self.nsimplex_unit]          # [B, d, d]
+        d = self.input_dim
+        hs = planes[:, :, 0]
+        for c in range(1, d):
+            hs = hs + planes[:, :, c]
+        vals = self._parameters[corners]                             # [B, d+1, out]
+        res = (-hs)[:, None, :] * vals[:, 0, :, None]                # [B, out, d]
+        for c in range(d):
+            res = res + planes[:, None, :, c] * vals[:, c + 1, :, None]
+        if res.shape[1] == 1:
+            res = res[:, 0, :]
+        return res
+
+    def gradient_function(self):
+        return lambda *inputs: self.gradient(hstack_inputs(inputs))
 
 
 # --------------------------------------------------------------------------- plants / Lyapunov NN

@@ -363,6 +363,19 @@ SLB_DEV void eval_triangulation(const slb_function& f, const double* xin, double
     double acc = w[1];
     for (int c = 2; c <= d; ++c) acc = f64add(acc, w[c]);
     w[0] = f64sub(1.0, acc);
+    if (f.flags & SLB_FLAG_GRADIENT) {
+        // Triangulation.gradient (:1260-1326): weights[k][0] = -sum_c H[k][c], weights[k][1 + c] =
+        // H[k][c]; d/dx_k = sum_v weights[k][v] * value[vertex v]   (one output column)
+        for (int k = 0; k < d; ++k) {
+            double hs = H[k * d];
+            for (int c = 1; c < d; ++c) hs = f64add(hs, H[k * d + c]);
+            double v = f64mul(-hs, f.matrix[simp[0] + corner]);
+            for (int c = 0; c < d; ++c)
+                v = f64add(v, f64mul(H[k * d + c], f.matrix[simp[c + 1] + corner]));
+            out[k] = v;
+        }
+        return;
+    }
     // gather vertex values and combine  (:1494-1499)
     const int od = f.out_dim;
     for (int o = 0; o < od; ++o) {
@@ -539,6 +552,12 @@ SLB_EVAL_ATTR int eval_fn(const slb_function& f, const double* in, double* out) 
     if (f.flags & SLB_FLAG_NORM1) {
         double acc = out[0];
         for (int o = 1; o < od; ++o) acc = f64add(acc, out[o]);
+        out[0] = acc;
+        od = 1;
+    }
+    if (f.flags & SLB_FLAG_MAXABS) {
+        double acc = fabs(out[0]);
+        for (int o = 1; o < od; ++o) acc = fmax(acc, fabs(out[o]));
         out[0] = acc;
         od = 1;
     }

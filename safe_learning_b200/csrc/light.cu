@@ -38,6 +38,10 @@ int slb_validate_grid(const slb_grid* g, bool need_points) {
 }
 
 int slb_validate_function(const slb_function* f, const char* what, int expect_in) {
+    SLB_CHECK(!(f->flags & SLB_FLAG_GRADIENT) || f->kind == SLB_FN_TRIANGULATION,
+              "%s: the gradient flag is only defined for Triangulation", what);
+    SLB_CHECK(!((f->flags & SLB_FLAG_NORM1) && (f->flags & SLB_FLAG_MAXABS)),
+              "%s: norm1 and maxabs reductions are exclusive", what);
     switch (f->kind) {
     case SLB_FN_NONE:
         return 0;
@@ -64,6 +68,9 @@ int slb_validate_function(const slb_function* f, const char* what, int expect_in
                   f->in_dim, f->grid.ndim);
         SLB_CHECK(f->out_dim >= 1 && f->out_dim <= SLB_MAX_OUT, "%s: Triangulation out_dim %d",
                   what, f->out_dim);
+        SLB_CHECK(!(f->flags & SLB_FLAG_GRADIENT) || f->out_dim == f->grid.ndim,
+                  "%s: Triangulation gradient needs one value column and out_dim = ndim (%d), got %d",
+                  what, f->grid.ndim, f->out_dim);
         break;
     case SLB_FN_PENDULUM:
         SLB_CHECK(f->in_dim == 3 && f->out_dim == 2, "%s: pendulum must map 3 -> 2", what);
@@ -602,7 +609,7 @@ int slb_eval_function(void* stream, const slb_function* fn, const double* points
     SLB_CHECK(n >= 0, "slb_eval_function: negative n");
     if (n == 0) return 0;
     SLB_CHECK(points_dev && out_dev, "slb_eval_function: null buffer");
-    int ncols = (fn->flags & SLB_FLAG_NORM1) ? 1 : fn->out_dim;
+    int ncols = (fn->flags & (SLB_FLAG_NORM1 | SLB_FLAG_MAXABS)) ? 1 : fn->out_dim;
     if (fn->kind == SLB_FN_QUADRATIC || fn->kind == SLB_FN_LYAPUNOV_NN) ncols = 1;
     eval_function_kernel<<<blocks_for(n), LT, 0, (cudaStream_t)stream>>>(*fn, points_dev, n, out_dev,
                                                                         ncols);

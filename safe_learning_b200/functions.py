@@ -29,7 +29,8 @@ config = Configuration()
 
 __all__ = ["DimensionError", "GridWorld", "Function", "DeterministicFunction",
            "UncertainFunction", "ConstantFunction", "LinearSystem", "QuadraticFunction",
-           "Saturation", "AbsFunction", "Norm1Function", "ScaledFunction", "Triangulation",
+           "Saturation", "AbsFunction", "Norm1Function", "MaxAbsFunction", "ScaledFunction",
+           "Triangulation", "TriangulationGradient",
            "Kernel", "RBF", "Matern12", "Matern32", "Matern52", "Linear", "Constant", "Bias",
            "White", "Sum", "Add", "Product", "Prod", "kernels", "Likelihood", "GPRCached", "GPR",
            "GaussianProcess", "FunctionStack",
@@ -192,8 +193,8 @@ class Function(object):
         if pts.dim() != 2 or pts.shape[1] != desc.in_dim:
             raise DimensionError("%s expects %d input columns, got shape %s"
                                  % (type(self).__name__, desc.in_dim, tuple(pts.shape)))
-        ncols = 1 if (desc.flags & nat.FLAG_NORM1 or desc.kind == nat.FN_QUADRATIC) \
-            else desc.out_dim
+        ncols = 1 if (desc.flags & (nat.FLAG_NORM1 | nat.FLAG_MAXABS)
+                      or desc.kind == nat.FN_QUADRATIC) else desc.out_dim
         out = dev.empty((pts.shape[0], ncols))
         nat.check(lib.slb_eval_function(dev.stream(), desc, pts.data_ptr(), pts.shape[0],
                                         out.data_ptr()), "slb_eval_function")
@@ -290,7 +291,7 @@ class QuadraticFunction(DeterministicFunction):
 class _PostOp(DeterministicFunction):
     """A post-operation fused onto a wrapped function's descriptor.  The kernels apply
     saturate -> abs -> norm1 -> scale in that order (``slb200.h``), so wrappers must be
-    nested in that order."""
+    nested in that order (``MaxAbsFunction`` takes the place of norm1)."""
 
     _order = 0
 
@@ -362,6 +363,23 @@ class Norm1Function(_PostOp):
     def descriptor(self):
         d = self.fun.descriptor()
         d.flags |= nat.FLAG_NORM1
+        return d
+
+
+class MaxAbsFunction(_PostOp):
+    """``tf.reduce_max(tf.abs(fun(x)), axis=1, keepdims=True)`` -- the Lipschitz lambda of
+    ``examples/inverted_pendulum.ipynb`` cell 14 (around ``value_function.gradient``), as a
+    fusable object."""
+
+    _order = 3
+
+    def __init__(self, fun, name="maxabs"):
+        super().__init__(fun, name)
+        self.output_dim = 1
+
+    def descriptor(self):
+        d = self.fun.descriptor()
+        d.flags |= nat.FLAG_MAXABS
         return d
 
 
@@ -522,6 +540,43 @@ class Triangulation(DeterministicFunction):
         d.corner_simplex = self._corner_dev.data_ptr() if self.input_dim > 1 else None
         d.nsimplex = self.tri.nsimplex_unit
         d.grid = self.discretization.descriptor(need_points=True)
+        return d
+
+    def gradient_function(self):
+        """The gradient of the interpolant as a fusable function object (one value column)."""
+        return TriangulationGradient(self)
+
+    def gradient(self, points):
+        """``Triangulation.gradient`` (``functions.py:1302-1326, 1506-1510``): the partial
+        derivatives of the piecewise-linear interpolant, numpy ``[n, d]``."""
+        return self.gradient_function()(points)
+
+
+class TriangulationGradient(DeterministicFunction):
+    """``x -> d Triangulation(x) / dx`` (piecewise constant; ``functions.py:1260-1326``), evaluated
+    by the same simplex lookup as the value (``SLB_FLAG_GRADIENT``)."""
+
+    def __init__(self, triangulation, name="triangulation_gradient"):
+        super().__init__(name)
+        if not isinstance(triangulation, Triangulation):
+            raise TypeError("TriangulationGradient wraps a Triangulation")
+        self.triangulation = triangulation
+        self.input_dim = self.output_dim = triangulation.input_dim
+
+    @property
+    def parameters(self):
+        return self.triangulation.parameters
+
+    @property
+    def version(self):
+        return ("grad", self.triangulation.version)
+
+    def descriptor(self):
+        d = self.triangulation.descriptor()
+        if d.out_dim != 1:
+            raise DimensionError("the fused gradient needs a Triangulation with one value column")
+        d.flags |= nat.FLAG_GRADIENT
+        d.out_dim = self.input_dim
         return d
 
 

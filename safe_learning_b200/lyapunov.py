@@ -312,8 +312,15 @@ class Lyapunov(object):
             cfg.lv_const = float(lv)
         lf = self._lipschitz_dynamics
         if callable(lf):
-            raise NotImplementedError("state-dependent lipschitz_dynamics is not fused in this "
-                                      "build; pass a float")
+            # the notebooks pass constants as lambdas (`lambda x: norm(A, 1) + ...`,
+            # lyapunov_function_learning.ipynb cell 13): accept a callable that is constant
+            grid = self.discretization
+            probe = grid.index_to_state(np.array([0, grid.nindex // 2, grid.nindex - 1]))
+            vals = np.asarray(lf(probe), dtype=np.float64).ravel()
+            if vals.size == 0 or not np.all(vals == vals[0]):
+                raise NotImplementedError("state-dependent lipschitz_dynamics is not fused in "
+                                          "this build; pass a float or a constant callable")
+            lf = vals[0]
         cfg.lf_const = float(lf)
         cfg.tau = float(self.tau)
         return cfg

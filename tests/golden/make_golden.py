@@ -1,7 +1,7 @@
 """Generate golden fixtures by executing the UNMODIFIED reference (/root/reference) on the
 numpy-backed TF1 / gpflow API shims in ``tf1_shim/`` (build container only).
 
-    python tests/golden/make_golden.py [grid|gp|gp_kernels|lyapunov|policy ...]   # rewrites tests/golden/*.npz
+    python tests/golden/make_golden.py [grid|gp|gp_kernels|lyapunov|policy|tri_gradient ...]   # rewrites tests/golden/*.npz
 
 Each fixture stores the raw inputs and the reference's outputs; tests/test_golden_fixtures.py
 rebuilds the numpy oracle (CPU tests) and the CUDA product (GPU tests) from the same inputs
@@ -262,6 +262,54 @@ def gen_grid_triangulation(out):
     print("grid/triangulation fixtures written")
 
 
+def gen_triangulation_gradient(out):
+    """Triangulation.gradient (functions.py:1260-1326, 1506-1510) on 1-D / 2-D / 3-D grids, and a
+    Lyapunov sweep with V = -value table and L_V = max |gradient| as in
+    examples/inverted_pendulum.ipynb cell 14."""
+    rng = np.random.default_rng(17)
+    res = {}
+    with tf.Session():
+        for tag, limits, num in (("g1", [[-1.0, 1.5]], [6]), ("g2", [[-1.0, 1.5], [0.0, 2.0]], [5, 4]),
+                                 ("g3", [[-1, 1], [0, 2], [-0.5, 0.5]], [4, 3, 5])):
+            grid = sl.GridWorld(limits, num)
+            lo, hi = grid.limits[:, 0], grid.limits[:, 1]
+            inside = rng.uniform(lo, hi, (200, grid.ndim))
+            vals = rng.normal(size=(grid.nindex, 1))
+            tri = sl.Triangulation(grid, vals, name="tri_grad_%s" % tag)
+            res[tag + "_limits"], res[tag + "_num"] = grid.limits, grid.num_points
+            res[tag + "_inside"], res[tag + "_vals"] = inside, vals
+            res[tag + "_gradient"] = tri.gradient(inside).eval()
+        # Lyapunov sweep: V = -(value table) on a coarse triangulation, L_V(x) = max_k |dV/dx_k|
+        # upstream quirk: a query exactly ON a vertex can land in a simplex of the cell that does not
+        # contain that vertex ((x - offset) % unit_maxes rounds to ~unit_maxes instead of 0), and the
+        # value is then extrapolated from the wrong plane -- the interpolant does not reproduce its
+        # own vertex values on e.g. a 25 x 21 grid.  Pinned as is.
+        qgrid = sl.GridWorld([[-1, 1], [-1, 1]], [25, 21])
+        qvals = rng.normal(size=(qgrid.nindex, 1))
+        qtri = sl.Triangulation(qgrid, qvals, name="tri_quirk")
+        res["quirk_vals"] = qvals
+        res["quirk_at_vertices"] = qtri(qgrid.all_points).eval()
+        par = W.make_pendulum(num_points=[25, 21], M=90, tau_scale=1 / 400.)
+        vgrid = sl.GridWorld(par["limits"], [30, 26])
+        table = -np.sum(vgrid.all_points.dot(par["P"]) * vgrid.all_points, axis=1, keepdims=True)
+        value = sl.Triangulation(vgrid, table, name="value_table")
+        l_v = lambda x: tf.reduce_max(tf.abs(value.gradient(x)), axis=1, keepdims=True)  # noqa: E731
+        grid = sl.GridWorld(par["limits"], par["num_points"])
+        policy = sl.Saturation(sl.LinearSystem((-par["K"],), name="policy_g"), -1., 1.)
+        lyap = sl.Lyapunov(grid, -value, ref_gp_stack(par), par["L_dyn"], l_v, par["tau"], policy,
+                           par["initial"].copy())
+        res.update(flat_par(par, "lyap_par_"))
+        res["lyap_vgrid_num"], res["lyap_table"] = np.array([30, 26]), table
+        res["lyap_values"] = lyap.values.copy()
+        res.update({"lyap_sweep_" + k: v for k, v in sweep_outputs(lyap).items()})
+        lyap.update_safe_set()
+        res["lyap_safe_set"] = lyap.safe_set.copy()
+        res["lyap_c_max"] = np.array(lyap.feed_dict[lyap.c_max])
+    np.savez_compressed(os.path.join(out, "triangulation_gradient.npz"), **res)
+    print("triangulation gradient fixtures written; lyapunov safe", res["lyap_safe_set"].sum(), "/",
+          res["lyap_safe_set"].size)
+
+
 def gen_policy_iteration(out):
     res = {}
     par = W.make_pendulum(num_points=8, M=40, seed=9)
@@ -302,7 +350,8 @@ def gen_policy_iteration(out):
 
 if __name__ == "__main__":
     generators = {"grid": gen_grid_triangulation, "gp": gen_gp, "gp_kernels": gen_gp_kernels,
-                  "lyapunov": gen_lyapunov, "policy": gen_policy_iteration}
+                  "lyapunov": gen_lyapunov, "policy": gen_policy_iteration,
+                  "tri_gradient": gen_triangulation_gradient}
     for name in (sys.argv[1:] or list(generators)):     # "lyapunov:case1,case2" limits the cases
         name, _, only = name.partition(":")
         if only:

@@ -194,6 +194,48 @@ def test_lyapunov_fixture(kind, case):
         ns.config.gp_batch_size = old
 
 
+# ------------------------------------------------------------------ triangulation gradient
+@pytest.mark.parametrize("kind", KINDS)
+def test_triangulation_gradient_fixture(kind):
+    """Triangulation.gradient (functions.py:1260-1326), the upstream vertex-query quirk, and the
+    sweep of examples/inverted_pendulum.ipynb cell 14: V = -value table, L_V = max |dV/dx|."""
+    ns, _, which = backend(kind)
+    fix = load("triangulation_gradient.npz")
+    for tag in ("g1", "g2", "g3"):
+        grid = ns.GridWorld(fix[tag + "_limits"], fix[tag + "_num"])
+        tri = ns.Triangulation(grid, fix[tag + "_vals"])
+        assert_allclose(tri.gradient(fix[tag + "_inside"]), fix[tag + "_gradient"], rtol=1e-12,
+                        atol=1e-13)
+    qgrid = ns.GridWorld([[-1, 1], [-1, 1]], [25, 21])
+    qtri = ns.Triangulation(qgrid, fix["quirk_vals"])
+    assert_allclose(qtri(qgrid.all_points), fix["quirk_at_vertices"], rtol=1e-12, atol=1e-13)
+    assert np.abs(fix["quirk_at_vertices"] - fix["quirk_vals"]).max() > 1.0   # the quirk is real
+
+    par = par_from(fix, "lyap_par_")
+    grid, dynamics = W._build(ns, par, which)
+    vgrid = ns.GridWorld(par["limits"], fix["lyap_vgrid_num"])
+    value = ns.Triangulation(vgrid, fix["lyap_table"])
+    policy = ns.Saturation(ns.LinearSystem(-par["K"]), -1., 1.)
+    lyap = ns.Lyapunov(grid, ns.ScaledFunction(value, -1.0), dynamics, par["L_dyn"],
+                       ns.MaxAbsFunction(value.gradient_function()), par["tau"], policy,
+                       initial_set=par["initial"])
+    assert_allclose(lyap.values, fix["lyap_values"], rtol=1e-13, atol=1e-15)
+    lyap.values = fix["lyap_values"]
+    states = grid.all_points
+    if kind == "oracle":
+        dec, thr = lyap.decrease_and_threshold(states)
+    else:
+        _, det = lyap.compute_negative(want_details=True)
+        dec, thr = (det[k].cpu().numpy().reshape(-1, 1) for k in ("decrease", "threshold"))
+    assert_allclose(dec, fix["lyap_sweep_decrease"], rtol=RTOL, atol=1e-12)
+    assert_allclose(thr, fix["lyap_sweep_threshold"], rtol=1e-12, atol=0)
+    assert np.abs(fix["lyap_sweep_decrease"] - fix["lyap_sweep_threshold"]).min() > 1e-9
+    lyap.update_safe_set()
+    c_max = lyap.c_max if kind == "oracle" else lyap.feed_dict[lyap.c_max]
+    assert_array_equal(lyap.safe_set, fix["lyap_safe_set"])
+    assert c_max == float(fix["lyap_c_max"])
+
+
 # ------------------------------------------------------------------ policy iteration
 @pytest.mark.parametrize("kind", KINDS)
 def test_policy_iteration_fixture(kind):

@@ -167,6 +167,43 @@ def test_triangulation_vs_oracle(sl, dims, project):
     assert_allclose(t_gpu(inside), t_cpu(inside), rtol=1e-13, atol=1e-13)
 
 
+@pytest.mark.parametrize("dims", [1, 2, 3])
+def test_triangulation_gradient_vs_oracle(sl, dims):
+    """Triangulation.gradient (functions.py:1260-1326) and max |.| over it -- the Lipschitz lambda
+    of examples/inverted_pendulum.ipynb cell 14 -- incl. queries on vertices and outside."""
+    rng = np.random.default_rng(dims)
+    limits = [[-1.0, 1.5], [0.0, 2.0], [-0.5, 0.5]][:dims]
+    num = [7, 5, 4][:dims]
+    g_gpu, g_cpu = sl.GridWorld(limits, num), O.GridWorld(limits, num)
+    vals = rng.normal(size=(g_cpu.nindex, 1))
+    lo, hi = g_cpu.limits[:, 0], g_cpu.limits[:, 1]
+    pts = rng.uniform(lo, hi, (400, dims))
+    for project in (False, True):
+        t_gpu = sl.Triangulation(g_gpu, vals, project=project)
+        t_cpu = O.Triangulation(g_cpu, vals, project=project)
+        assert_allclose(t_gpu.gradient(pts), t_cpu.gradient(pts), rtol=1e-12, atol=1e-13)
+        lv_gpu = sl.MaxAbsFunction(t_gpu.gradient_function())
+        lv_cpu = O.MaxAbsFunction(t_cpu.gradient_function())
+        assert_array_equal(lv_gpu(pts), np.max(np.abs(t_gpu.gradient(pts)), axis=1, keepdims=True))
+        assert_allclose(lv_gpu(pts), lv_cpu(pts), rtol=1e-12, atol=1e-13)
+    with pytest.raises(sl.DimensionError):
+        sl.Triangulation(g_gpu, rng.normal(size=(g_cpu.nindex, 2))).gradient(pts)
+
+
+def test_constant_callable_lipschitz_dynamics(sl):
+    """The notebooks pass L_f as `lambda x: const` (lyapunov_function_learning.ipynb cell 13)."""
+    par = W.make_pendulum(num_points=[13, 11], M=40)
+    a, b = W.build_product(par), W.build_product(par)
+    const = float(par["L_dyn"])
+    b._lipschitz_dynamics = lambda x: const
+    a.update_safe_set()
+    b.update_safe_set()
+    assert_array_equal(a.safe_set, b.safe_set)
+    b._lipschitz_dynamics = lambda x: np.abs(x[:, [0]])
+    with pytest.raises(NotImplementedError):
+        b.update_safe_set()
+
+
 def test_neural_network_policy_vs_oracle(sl):
     """functions.py:1702-1729 inference (the 2-32-32-1 policy of inverted_pendulum.ipynb cell 9)
     and its use as the policy of a Lyapunov sweep."""
