@@ -290,7 +290,10 @@ def gen_triangulation_gradient(out):
         res["quirk_vals"] = qvals
         res["quirk_at_vertices"] = qtri(qgrid.all_points).eval()
         par = W.make_pendulum(num_points=[25, 21], M=90, tau_scale=1 / 400.)
-        vgrid = sl.GridWorld(par["limits"], [30, 26])
+        # the value table lives on a slightly larger, non-commensurate grid so that no state of the
+        # sweep sits on a simplex face (the gradient is discontinuous there and upstream's pick is
+        # scipy's order-dependent walk)
+        vgrid = sl.GridWorld(par["limits"] * np.array([[1.05, 1.08], [1.03, 1.06]]), [30, 26])
         table = -np.sum(vgrid.all_points.dot(par["P"]) * vgrid.all_points, axis=1, keepdims=True)
         value = sl.Triangulation(vgrid, table, name="value_table")
         l_v = lambda x: tf.reduce_max(tf.abs(value.gradient(x)), axis=1, keepdims=True)  # noqa: E731
@@ -300,6 +303,7 @@ def gen_triangulation_gradient(out):
                            par["initial"].copy())
         res.update(flat_par(par, "lyap_par_"))
         res["lyap_vgrid_num"], res["lyap_table"] = np.array([30, 26]), table
+        res["lyap_vgrid_limits"] = vgrid.limits
         res["lyap_values"] = lyap.values.copy()
         res.update({"lyap_sweep_" + k: v for k, v in sweep_outputs(lyap).items()})
         lyap.update_safe_set()
