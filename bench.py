@@ -337,7 +337,7 @@ def run_ours(args, rank, world, local_rank):
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-        "warmup": n_warm, "ms_per_step": ms_total / args.steps,
+        "warmup": args.warmup, "warmup_sweeps_run": n_warm, "ms_per_step": ms_total / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic", "config": workload_config(world), "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d),

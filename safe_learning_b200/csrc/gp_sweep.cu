@@ -560,12 +560,15 @@ __global__ void pack_factor_kernel(const double* __restrict__ Linv, int M, int n
 
 template <int DIN, bool TIMING, bool KEXPR>
 int launch_gp_tile(cudaStream_t st, const slb_sweep& cfg, const gp_args& a) {
-    static bool configured = false;
-    if (!configured) {
+    // the opt-in to > 48 KB of dynamic shared memory is a per-device function attribute
+    static bool configured[64] = {};
+    int device = 0;
+    SLB_CUDA(cudaGetDevice(&device));
+    if (device < 0 || device >= 64 || !configured[device]) {
         SLB_CUDA(cudaFuncSetAttribute(gp_tile_kernel<DIN, TIMING, KEXPR>,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)SMEM_TOTAL));
-        configured = true;
+        if (device >= 0 && device < 64) configured[device] = true;
     }
     const int64_t tiles = (a.n + TP - 1) / TP;
     gp_tile_kernel<DIN, TIMING, KEXPR><<<(unsigned)tiles, NT, SMEM_TOTAL, st>>>(cfg, a);
