@@ -302,3 +302,23 @@ def test_kernel_algebra_normal_form_and_descriptor():
         sl.Matern32(1, active_dims=[4]).fill(desc, 3)
     assert sl.RBF(3, lengthscales=[1., 2., 3.]).is_plain_rbf(3)
     assert not sl.RBF(2, active_dims=[0, 2]).is_plain_rbf(3)
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside ours) prints one JSON line
+    with the contract's keys, without touching CUDA or /root/reference."""
+    import json
+    import subprocess
+    proc = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference",
+                           "--steps", "1", "--warmup", "0"], stdout=subprocess.PIPE,
+                          stderr=subprocess.PIPE, text=True, timeout=600, cwd=ROOT)
+    assert proc.returncode == 0, proc.stderr[-2000:]
+    line = json.loads(proc.stdout.strip().splitlines()[-1])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step",
+                "higher_is_better", "scaling", "vs_baseline", "dtype", "data", "config", "e2e",
+                "cpu_baseline", "impl"):
+        assert key in line, key
+    assert line["impl"] == "reference" and line["steps"] == 1 and line["warmup"] == 0
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["value"] == line["value"]
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["value"] > 0 and "workload" in line["config"]
