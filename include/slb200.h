@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define SLB_ABI_VERSION 1
+#define SLB_ABI_VERSION 2   /* 2: slb_gp_factor.kernel (covariance expressions), GRADIENT / MAXABS flags */
 #define SLB_MAX_DIM 6   /* state dimension d                         */
 #define SLB_MAX_IN  8   /* GP input dimension d_in = d + m           */
 #define SLB_MAX_OUT 6   /* stacked one-output GPs (FunctionStack)    */

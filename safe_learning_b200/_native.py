@@ -23,6 +23,7 @@ FLAG_SATURATE, FLAG_ABS, FLAG_NORM1, FLAG_PROJECT, FLAG_SCALE, FLAG_GRADIENT, FL
     1, 2, 4, 8, 16, 32, 64
 K_RBF, K_MATERN12, K_MATERN32, K_MATERN52, K_LINEAR, K_CONSTANT, K_WHITE = range(7)
 SLB_MAX_KPRIM = 6
+ABI_VERSION = 2
 
 UINT64_MAX = (1 << 64) - 1
 INT64_MAX = (1 << 63) - 1
@@ -151,8 +152,10 @@ def load():
         fn = getattr(lib, name)          # AttributeError if the symbol is not exported
         fn.restype = res
         fn.argtypes = args
-    if lib.slb_abi_version() != 1:
-        raise NativeLibraryError("libslb200 ABI version %d != 1" % lib.slb_abi_version())
+    if lib.slb_abi_version() != ABI_VERSION:
+        raise NativeLibraryError("libslb200 ABI version %d != %d (rebuild: python -c 'import "
+                                 "__graft_entry__ as g; g.build()')"
+                                 % (lib.slb_abi_version(), ABI_VERSION))
     _check_layout(lib)
     _lib = lib
     return lib
