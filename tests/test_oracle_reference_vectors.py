@@ -212,3 +212,81 @@ def test_adaptive_closed_form_matches_batch_loop():
             assert lyap.c_max == values[order[position]]
     finally:
         O.config.gp_batch_size = old
+
+
+def test_triangulation_known_answers():
+    """/root/reference/safe_learning/tests/test_functions.py:457-655 (find_simplex, values,
+    projection, three dimensions, gradient, 1-D) restated against the oracle's Triangulation."""
+    # find_simplex :457-499
+    limits, num = [[-1, 1], [-1, 2]], [3, 7]
+    tri = O.Triangulation(O.GridWorld(limits, num))
+    assert tri.discretization.nrectangles == 12 and tri.input_dim == 2
+    assert tri.nsimplex_unit * tri.discretization.nrectangles == 24
+    assert_equal(tri.discretization.offset, np.array([-1, -1]))
+    assert_equal(tri.discretization.unit_maxes, np.array([2, 3]) / (np.array(num) - 1))
+    lower = int(np.squeeze(tri.triangulation.find_simplex(np.array([0, 0]))))
+    upper = 1 - lower
+    pts = np.array([[0, 0], [0.9, 0.45], [1.1, 0], [1.9, 2.9]]) + np.array(limits)[:, 0]
+    ids = tri.find_simplex(pts)
+    assert_equal(ids, np.array([lower, upper, 6 * 2 + lower, 11 * 2 + upper]))
+    assert_equal(np.sort(tri.simplices(ids), axis=1),
+                 np.array([[0, 1, 7], [1, 7, 8], [7, 8, 14], [13, 19, 20]]))
+    assert_equal(tri.find_simplex(np.array([[-100., -100.]])), lower)
+    assert_equal(tri.find_simplex(np.array([[100., 100.]])), 24 - 1 - lower)
+
+    # values and projection :501-546
+    eps = 1e-10
+    tri = O.Triangulation(O.GridWorld([[0, 1], [0, 1]], [2, 2]))
+    nodes = tri.discretization.state_to_index(np.array([[0, 0], [1, 0], [0, 1]]))
+    pts = np.array([[0, 0], [1 - eps, 0], [0, 1 - eps], [0.5 - eps, 0.5 - eps], [0, 0.5], [0.5, 0]])
+    vals = np.random.default_rng(0).random(tri.nindex)
+    tri.parameters = vals
+    want = np.array([vals[nodes[0]], vals[nodes[1]], vals[nodes[2]],
+                     0.5 * (vals[nodes[1]] + vals[nodes[2]]), 0.5 * (vals[nodes[0]] + vals[nodes[2]]),
+                     0.5 * (vals[nodes[0]] + vals[nodes[1]])])[:, None]
+    assert_allclose(tri(pts), want, atol=1e-7)
+    tri.parameters = np.array([0, 1, 1, 1])
+    assert_allclose(tri(np.array([[-0.5, -0.5]])), np.array([[-1]]))
+    tri.project = True
+    assert_allclose(tri(np.array([[-0.5, -0.5]])), np.array([[0]]))
+
+    # three dimensions :548-580
+    tri = O.Triangulation(O.GridWorld([[0, 1]] * 3, [2] * 3))
+    assert tri.input_dim == 3 and tri.discretization.nrectangles == 1 and tri.nsimplex_unit == 6
+    corners = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0], [0, 0, 1], [0, 1, 1], [1, 1, 0], [1, 0, 1],
+                        [1, 1, 1]], dtype=float)
+    tri.parameters = np.sum(tri.discretization.index_to_state(np.arange(8)), axis=1) / 3
+    pts = np.vstack((corners, np.array([[0, 0, 0.5], [0.5, 0, 0], [0, 0.5, 0], [0.5, 0.5, 0.5]])))
+    want = np.hstack((np.sum(corners, axis=1) / 3, np.array([1 / 6, 1 / 6, 1 / 6, 1 / 2])))
+    assert_allclose(tri(pts), want[:, None], atol=1e-5)
+
+    # gradient :582-624
+    tri = O.Triangulation(O.GridWorld([[0, 1], [0, 1]], [2, 2]))
+    nodes = tri.discretization.state_to_index(np.array([[0, 0], [1, 0], [0, 1], [1, 1]]))
+    vals = np.zeros(tri.nindex)
+    vals[nodes] = [1, 2, 3, 1]
+    tri.parameters = vals
+    assert_allclose(tri.gradient(np.array([[0.01, 0.01], [0.99, 0.99]])), np.array([[1, 2], [-2, -1]]))
+
+    # 1-D :626-655
+    tri = O.Triangulation(O.GridWorld([[0, 1]], 3), [0, 0.5, 0])
+    pts = np.array([[0, 0.2, 0.5, 0.6, 0.9, 1.]]).T
+    assert_equal(tri.find_simplex(pts), np.array([0, 0, 1, 1, 1, 1]))
+    assert_allclose(tri(pts), np.array([0, 0.2, 0.5, 0.4, 0.1, 0])[:, None])
+    assert_allclose(tri.gradient(pts), np.array([1, 1, -1, -1, -1, -1])[:, None])
+
+
+def test_unique_rows_and_perturb_actions():
+    """tests/test_utilities.py:86-91 (unique_rows) and the action perturbation grid of
+    lyapunov.py:609-651."""
+    a = np.array([[1, 1], [1, 2], [1, 3], [1, 2], [1, 3], [1, 4], [2, 3]])
+    assert_equal(O.unique_rows(a), np.array([[1, 1], [1, 2], [1, 3], [1, 4], [2, 3]]))
+    states = np.array([[0., 1.], [2., 3.]])
+    actions = np.array([[0.5], [-0.5]])
+    out = O.perturb_actions(states, actions, np.array([[-1.], [0.], [1.]]), limits=np.array([[-1., 1.]]))
+    want = np.array([[0., 1., -0.5], [0., 1., 0.5], [0., 1., 1.],
+                     [2., 3., -1.], [2., 3., -0.5], [2., 3., 0.5]])
+    # row order is np.unique's on the raw bytes (utilities.py:509-516), compare as a set of rows
+    assert_equal(out[np.lexsort(out.T[::-1])], want)
+    dup = O.perturb_actions(states, actions, np.array([[2.], [3.]]), limits=np.array([[-1., 1.]]))
+    assert_equal(dup[np.lexsort(dup.T[::-1])], np.array([[0., 1., 1.], [2., 3., 1.]]))
