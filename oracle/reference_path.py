@@ -31,7 +31,7 @@ __all__ = [
     "InvertedPendulum", "CartPole", "LyapunovNetwork", "NeuralNetwork", "Lyapunov",
     "PolicyIteration",
     "batchify", "dlqr", "hstack_inputs", "stable_value_order", "prefix_rule",
-    "perturb_actions", "get_safe_sample", "unique_rows",
+    "perturb_actions", "get_safe_sample", "unique_rows", "smallest_boundary_value",
 ]
 
 
@@ -1149,6 +1149,19 @@ class PolicyIteration(object):
 
 
 # --------------------------------------------------------------------------- safe sampling
+def smallest_boundary_value(fun, discretization):
+    """``lyapunov.py:22-56``: the smallest value of ``fun`` over the faces of the grid (per axis:
+    that axis at its two end points, all others at every grid coordinate).  Pinned by
+    ``tests/test_lyapunov.py:77-84``."""
+    min_value = np.inf
+    for i in range(discretization.ndim):
+        tmp = list(discretization.discrete_points)
+        tmp[i] = discretization.discrete_points[i][[0, -1]]
+        columns = (x.ravel() for x in np.meshgrid(*tmp, indexing="ij"))
+        min_value = min(min_value, float(np.min(fun(np.column_stack(list(columns))))))
+    return min_value
+
+
 def unique_rows(array):
     """``utilities.py:496-516``."""
     array = np.ascontiguousarray(array)

@@ -18,8 +18,8 @@ from . import _device as dev
 from . import _native as nat
 from .functions import Function, FunctionStack, GaussianProcess, UncertainFunction, config
 
-__all__ = ["Lyapunov", "get_safe_sample", "perturb_actions", "combine_fail_keys",
-           "combine_prefix_stats"]
+__all__ = ["Lyapunov", "get_safe_sample", "perturb_actions", "smallest_boundary_value",
+           "combine_fail_keys", "combine_prefix_stats"]
 
 
 def _unique_rows(array):
@@ -28,6 +28,24 @@ def _unique_rows(array):
     dtype = np.dtype((np.void, array.dtype.itemsize * array.shape[1]))
     _, idx = np.unique(array.view(dtype=dtype), return_index=True)
     return array[idx]
+
+
+def smallest_boundary_value(fun, discretization):
+    """Smallest value of ``fun`` on the faces of the grid (``lyapunov.py:22-56``): the level up to
+    which a Lyapunov candidate's sub-level sets stay inside the discretisation.  ``fun`` is a
+    fusable Function object (evaluated on the GPU) or any callable on numpy arrays."""
+    min_value = np.inf
+    for i in range(discretization.ndim):
+        tmp = list(discretization.discrete_points)
+        tmp[i] = discretization.discrete_points[i][[0, -1]]
+        columns = [x.ravel() for x in np.meshgrid(*tmp, indexing="ij")]
+        points = np.column_stack(columns)
+        if isinstance(fun, Function):
+            smallest = float(fun.evaluate_device(points).min().item())
+        else:
+            smallest = float(np.min(fun(points)))
+        min_value = min(min_value, smallest)
+    return min_value
 
 
 def perturb_actions(states, actions, perturbations, limits=None):

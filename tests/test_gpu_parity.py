@@ -204,6 +204,16 @@ def test_constant_callable_lipschitz_dynamics(sl):
         b.update_safe_set()
 
 
+def test_smallest_boundary_value(sl):
+    """lyapunov.py:22-56, known answer of tests/test_lyapunov.py:77-84 and a fused V."""
+    grid = sl.GridWorld([[-1.5, 1], [-1, 1.5]], [3, 3])
+    assert sl.smallest_boundary_value(lambda x: 2 * np.sum(np.abs(x), axis=1), grid) == 2.5
+    P = np.array([[1.3, 0.2], [0.2, 0.7]])
+    got = sl.smallest_boundary_value(sl.QuadraticFunction(P), sl.GridWorld([[-1, 2], [-1, 1]], [7, 9]))
+    want = O.smallest_boundary_value(O.QuadraticFunction(P), O.GridWorld([[-1, 2], [-1, 1]], [7, 9]))
+    assert got == want
+
+
 def test_neural_network_policy_vs_oracle(sl):
     """functions.py:1702-1729 inference (the 2-32-32-1 policy of inverted_pendulum.ipynb cell 9)
     and its use as the policy of a Lyapunov sweep."""

@@ -290,3 +290,9 @@ def test_unique_rows_and_perturb_actions():
     assert_equal(out[np.lexsort(out.T[::-1])], want)
     dup = O.perturb_actions(states, actions, np.array([[2.], [3.]]), limits=np.array([[-1., 1.]]))
     assert_equal(dup[np.lexsort(dup.T[::-1])], np.array([[0., 1., 1.], [2., 3., 1.]]))
+
+
+def test_smallest_boundary_value():
+    """tests/test_lyapunov.py:77-84."""
+    fun = lambda x: 2 * np.sum(np.abs(x), axis=1)  # noqa: E731
+    assert O.smallest_boundary_value(fun, O.GridWorld([[-1.5, 1], [-1, 1.5]], [3, 3])) == 2.5
