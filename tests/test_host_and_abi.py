@@ -322,3 +322,16 @@ def test_bench_reference_arm_contract():
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["value"] == line["value"]
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
     assert line["value"] > 0 and "workload" in line["config"]
+
+
+def test_host_array_helpers():
+    """utilities.py:252-296, 496-516 as shipped with the product (pure numpy, no GPU)."""
+    from safe_learning_b200 import utilities as U
+    assert_array_equal(U.combinations([np.array([1, 2]), np.array([5, 6, 7])]),
+                       np.array([[1, 5], [1, 6], [1, 7], [2, 5], [2, 6], [2, 7]]))
+    grid = U.linearly_spaced_combinations([(-1, 1), (0, 2)], [3, 2])
+    assert_array_equal(grid, np.array([[-1, 0], [-1, 2], [0, 0], [0, 2], [1, 0], [1, 2]], dtype=float))
+    assert U.linearly_spaced_combinations([(-1, 1)], 5).shape == (5, 1)
+    a = np.array([[1, 1], [1, 2], [1, 3], [1, 2], [1, 3], [1, 4], [2, 3]])
+    assert_array_equal(U.unique_rows(a), O.unique_rows(a))
+    assert_array_equal(U.unique_rows(a), np.array([[1, 1], [1, 2], [1, 3], [1, 4], [2, 3]]))
