@@ -28,12 +28,17 @@
 extern "C" {
 #endif
 
-#define SLB_ABI_VERSION 2   /* 2: slb_gp_factor.kernel (covariance expressions), GRADIENT / MAXABS flags */
+#define SLB_ABI_VERSION 3   /* 2: slb_gp_factor.kernel (covariance expressions), GRADIENT / MAXABS flags
+                               3: decision filter (slb_gp_factor.Whead, slb_lyapunov_sweep_filtered),
+                                  state-dependent lipschitz_dynamics, peer-memory key exchange
+                                  (slb_exchange), fixed-action Bellman tables                    */
 #define SLB_MAX_DIM 6   /* state dimension d                         */
 #define SLB_MAX_IN  8   /* GP input dimension d_in = d + m           */
 #define SLB_MAX_OUT 6   /* stacked one-output GPs (FunctionStack)    */
 #define SLB_MAX_ACT 2   /* action dimension m                        */
 #define SLB_TILE_POINTS 64  /* grid points per CTA tile of the GP kernels */
+#define SLB_HEAD_RANK 64    /* leading rows of L^-1 used by the decision filter's variance bound */
+#define SLB_MAX_RANKS 16    /* ranks of one peer-memory key exchange (one NVSwitch domain)       */
 
 /* ---- GridWorld (functions.py:579-817) ------------------------------------------- */
 typedef struct slb_grid {
@@ -148,6 +153,12 @@ typedef struct slb_gp_factor {
     double scale;               /* GPRCached _scale                functions.py:392     */
     double kss;                 /* (scale**2) * variance           functions.py:450     */
     slb_kernel kernel;          /* general covariance expression (num_prims > 0)        */
+    const double* Whead;        /* device [SLB_HEAD_RANK, SLB_HEAD_RANK], COLUMN-major, zero padded:
+                                   Whead[j * SLB_HEAD_RANK + i] = L^-1[i, j] for i, j < min(M,
+                                   SLB_HEAD_RANK).  a_i = sum_j L^-1[i,j] k_j for these rows gives
+                                   the posterior variance of the first rows of the training set
+                                   alone -- an upper bound of the full posterior variance -- used by
+                                   slb_lyapunov_sweep_filtered; may be NULL if that call is not used */
 } slb_gp_factor;
 
 typedef struct slb_gp_output {
@@ -181,6 +192,13 @@ typedef struct slb_sweep {
     double lv_const;            /* scalar lipschitz_lyapunov    lyapunov.py:246-263     */
     double lf_const;            /* scalar lipschitz_dynamics    lyapunov.py:227-244     */
     double tau;                 /* discretization constant      lyapunov.py:195         */
+    slb_function lipschitz_f;   /* state-dependent L_f(x) as a fused function (first column), or
+                                   kind NONE                    lyapunov.py:227-244, 287 */
+    const double* lf_values;    /* device, or NULL: L_f tabulated per flat grid index (an arbitrary
+                                   Python callable evaluated once by the host); entry for grid
+                                   index i is lf_values[i - lf_index_base].  Index-range sweeps only.
+                                   Precedence: lf_values, lipschitz_f, lf_const            */
+    int64_t lf_index_base;
 } slb_sweep;
 
 /* ---- one Bellman sweep: PolicyIteration.future_values (reinforcement_learning.py:65-114) */
@@ -196,6 +214,7 @@ typedef struct slb_bellman {
     int32_t _pad;
     double action[SLB_MAX_ACT];
 } slb_bellman;
+
 
 /* ---- result of the first-fail reduction (sort-free form of lyapunov.py:512-587) ------- */
 typedef struct slb_fail_key {
@@ -213,13 +232,26 @@ typedef struct slb_prefix_stats {
     uint64_t max_all;       /* order-preserving bits of max V over the range              */
 } slb_prefix_stats;
 
+/* ---- per-sweep key exchange between the ranks of one NVLink domain without a collective call:
+ *      every rank owns `slots` = slb_fail_key[2][world] in peer-mapped (symmetric) memory; after its
+ *      first-fail reduction a rank STORES its key into slot [parity][rank] of every peer (P2P
+ *      writes through NVLink) with the sweep's sequence number as the release flag, and the prefix
+ *      kernel of every rank waits for the `world` flags of the current sweep in its own copy.
+ *      Ranks must issue the same sequence of sweeps (like any collective).                        */
+typedef struct slb_exchange {
+    int32_t world;
+    int32_t rank;
+    slb_fail_key* slots[SLB_MAX_RANKS];  /* slots[r]: rank r's slot array as mapped in THIS process */
+    int64_t* seq_dev;                    /* local device int64 (zero-initialised): sweeps issued  */
+} slb_exchange;
+
 /* ---- library ---------------------------------------------------------------------------- */
 int         slb_abi_version(void);
 const char* slb_last_error(void);
 /* number of CUDA devices visible, or <0 with slb_last_error set */
 int         slb_device_count(void);
 /* sizeof() of the ABI structs in declaration order (grid, function, gp_factor, gp_output,
-   gp_stack, sweep, bellman, fail_key, prefix_stats); returns how many there are */
+   gp_stack, sweep, bellman, fail_key, prefix_stats, exchange); returns how many there are */
 int         slb_struct_sizes(int64_t* out, int32_t n);
 /* kernels this library has launched since load (bench.py's gpu_launches) */
 int64_t     slb_launch_count(void);
@@ -254,6 +286,20 @@ int slb_gp_predict(void* stream, const slb_gp_stack* gp, const double* points_de
 int slb_lyapunov_sweep(void* stream, const slb_sweep* cfg, int64_t idx_begin, int64_t idx_end,
                        uint8_t* negative_dev, double* values_dev, double* decrease_dev,
                        double* threshold_dev, double* mean_dev, double* err_dev);
+/* The same decision flags (and V) with a certified filter in front of the O(M^2) posterior:
+ * a thread-per-point kernel computes the exact GP mean (k . L^-T alpha), V(mu), L_V(mu) and an
+ * UPPER bound of every output's standard deviation -- first the prior's, then the posterior given
+ * only the first SLB_HEAD_RANK training rows (factor.Whead) -- and decides every point whose
+ * comparison `decrease < threshold` has the same outcome for all sigma in [0, bound] (with a
+ * 1e-6 relative guard band); the remaining points are compacted and go through the full fp64
+ * posterior (the kernel of slb_lyapunov_sweep).  Flags are identical to slb_lyapunov_sweep's.
+ * workspace_dev: >= slb_filter_workspace(n) bytes.  stats_dev: NULL or 4 int64 (device):
+ * {decided by mean + prior bound, decided by the head-rank bound, refined by the full posterior,
+ * points} accumulated over calls (the caller zeroes it). */
+int64_t slb_filter_workspace(int64_t n);
+int slb_lyapunov_sweep_filtered(void* stream, const slb_sweep* cfg, int64_t idx_begin,
+                                int64_t idx_end, uint8_t* negative_dev, double* values_dev,
+                                void* workspace_dev, int64_t* stats_dev);
 /* same on an explicit state list states_dev [n, d] (get_safe_sample-style callers) */
 int slb_lyapunov_points(void* stream, const slb_sweep* cfg, const double* states_dev, int64_t n,
                         uint8_t* negative_dev, double* values_dev, double* decrease_dev,
@@ -267,6 +313,15 @@ int64_t slb_first_fail_workspace(int64_t n);
 int slb_first_fail(void* stream, const double* values_dev, const uint8_t* negative_dev,
                    const uint8_t* initial_dev /* may be NULL */, int64_t n, int64_t idx_begin,
                    void* workspace_dev, slb_fail_key* result_dev);
+/* sharded form with the exchange fused into the two kernels: slb_first_fail_x pushes this rank's
+ * key to every peer, slb_apply_prefix_x waits for all keys of the sweep, reduces them (writing the
+ * winner to key_out_dev) and applies the prefix rule -- no collective call, no host round trip */
+int slb_first_fail_x(void* stream, const double* values_dev, const uint8_t* negative_dev,
+                     const uint8_t* initial_dev, int64_t n, int64_t idx_begin, void* workspace_dev,
+                     slb_fail_key* result_dev, const slb_exchange* xchg);
+int slb_apply_prefix_x(void* stream, const double* values_dev, const uint8_t* initial_dev,
+                       int64_t n, int64_t idx_begin, slb_fail_key* key_out_dev, uint8_t* safe_dev,
+                       void* workspace_dev, slb_prefix_stats* stats_dev, const slb_exchange* xchg);
 /* multi-GPU: lexicographic min (and n_ok sum) over `world` keys all-gathered by the caller
  * (the one collective of a sweep) -> out_dev; may alias gathered_dev[0] */
 int slb_combine_fail_keys(void* stream, const slb_fail_key* gathered_dev, int32_t world,

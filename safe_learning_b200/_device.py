@@ -75,3 +75,56 @@ def allgather_rows(row):
     out = torch.empty((world, row.numel()), dtype=row.dtype, device=row.device)
     dist.all_gather_into_tensor(out, row.view(1, -1).contiguous())
     return out
+
+
+# ---- peer-memory key exchange (slb_exchange): symmetric buffers over NVLink --------------------
+_EXCHANGE = {"tried": False, "struct": None, "keep": None, "error": None}
+
+
+def get_exchange():
+    """``slb_exchange`` of this process (one per process, shared by every sharded sweep), or None
+    when the ranks cannot map each other's memory (no NVLink peer access, CPU/gloo runs, or
+    ``SLB200_EXCHANGE=nccl``): callers then fall back to an NCCL all-gather of the keys.
+
+    Collective on first use: every rank allocates ``slb_fail_key[2][world]`` in symmetric memory
+    (``torch.distributed._symmetric_memory``: CUDA VMM allocations exchanged between the processes
+    of the NVSwitch domain), zeroes it, and all ranks rendezvous."""
+    import os
+    if _EXCHANGE["tried"]:
+        return _EXCHANGE["struct"]
+    _EXCHANGE["tried"] = True
+    rank, world = dist_info()
+    if world == 1 or world > _native.SLB_MAX_RANKS or not torch.cuda.is_available():
+        return None
+    if os.environ.get("SLB200_EXCHANGE", "peer") != "peer":
+        return None
+    import torch.distributed as dist
+    ok = 1
+    handle = buf = None
+    try:
+        import torch.distributed._symmetric_memory as symm_mem
+        buf = symm_mem.empty(2 * world * 4, dtype=torch.int64, device=device())
+        buf.zero_()
+        handle = symm_mem.rendezvous(buf, dist.group.WORLD)
+        ptrs = [int(p) for p in handle.buffer_ptrs]
+        if len(ptrs) != world or any(p == 0 for p in ptrs):
+            ok = 0
+    except Exception as exc:  # pragma: no cover - depends on the machine
+        _EXCHANGE["error"] = repr(exc)
+        ok = 0
+    # every rank must take the same path: agree (NCCL, once per process)
+    flag = torch.tensor([ok], dtype=torch.int32, device=device())
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if int(flag.item()) == 0:
+        return None
+    seq = torch.zeros(1, dtype=torch.int64, device=device())
+    x = _native.SlbExchange()
+    x.world, x.rank = world, rank
+    for r, p in enumerate(ptrs):
+        x.slots[r] = p
+    x.seq_dev = seq.data_ptr()
+    torch.cuda.synchronize()
+    dist.barrier()                      # every rank's slots are zero before anyone pushes
+    _EXCHANGE["struct"] = x
+    _EXCHANGE["keep"] = (buf, handle, seq)
+    return x

@@ -16,6 +16,8 @@ SLB_MAX_IN = 8
 SLB_MAX_OUT = 6
 SLB_MAX_ACT = 2
 SLB_TILE_POINTS = 64
+SLB_HEAD_RANK = 64
+SLB_MAX_RANKS = 16
 
 FN_NONE, FN_CONSTANT, FN_LINEAR, FN_QUADRATIC, FN_TRIANGULATION, FN_PENDULUM, FN_CARTPOLE, \
     FN_LYAPUNOV_NN, FN_MLP = range(9)
@@ -23,7 +25,7 @@ FLAG_SATURATE, FLAG_ABS, FLAG_NORM1, FLAG_PROJECT, FLAG_SCALE, FLAG_GRADIENT, FL
     1, 2, 4, 8, 16, 32, 64
 K_RBF, K_MATERN12, K_MATERN32, K_MATERN52, K_LINEAR, K_CONSTANT, K_WHITE = range(7)
 SLB_MAX_KPRIM = 6
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 UINT64_MAX = (1 << 64) - 1
 INT64_MAX = (1 << 63) - 1
@@ -61,7 +63,8 @@ class SlbKernel(C.Structure):
 class SlbGpFactor(C.Structure):
     _fields_ = [("M", C.c_int32), ("nrb", C.c_int32), ("Xs", C.c_void_p), ("Wpack", C.c_void_p),
                 ("lengthscales", C.c_double * SLB_MAX_IN), ("variance", C.c_double),
-                ("scale", C.c_double), ("kss", C.c_double), ("kernel", SlbKernel)]
+                ("scale", C.c_double), ("kss", C.c_double), ("kernel", SlbKernel),
+                ("Whead", C.c_void_p)]
 
 
 class SlbGpOutput(C.Structure):
@@ -78,7 +81,9 @@ class SlbGpStack(C.Structure):
 class SlbSweep(C.Structure):
     _fields_ = [("grid", SlbGrid), ("policy", SlbFunction), ("dynamics", SlbFunction),
                 ("gp", SlbGpStack), ("lyapunov", SlbFunction), ("lipschitz_v", SlbFunction),
-                ("lv_const", C.c_double), ("lf_const", C.c_double), ("tau", C.c_double)]
+                ("lv_const", C.c_double), ("lf_const", C.c_double), ("tau", C.c_double),
+                ("lipschitz_f", SlbFunction), ("lf_values", C.c_void_p),
+                ("lf_index_base", C.c_int64)]
 
 
 class SlbBellman(C.Structure):
@@ -98,8 +103,13 @@ class SlbPrefixStats(C.Structure):
                 ("max_all", C.c_uint64)]
 
 
+class SlbExchange(C.Structure):
+    _fields_ = [("world", C.c_int32), ("rank", C.c_int32),
+                ("slots", C.c_void_p * SLB_MAX_RANKS), ("seq_dev", C.c_void_p)]
+
+
 _STRUCTS = (SlbGrid, SlbFunction, SlbGpFactor, SlbGpOutput, SlbGpStack, SlbSweep, SlbBellman,
-            SlbFailKey, SlbPrefixStats)
+            SlbFailKey, SlbPrefixStats, SlbExchange)
 
 # SLB200_LIB lets a diagnostic run load an alternative build (A/B timing of kernel variants)
 LIB_PATH = os.environ.get("SLB200_LIB") or os.path.join(
@@ -123,7 +133,14 @@ SIGNATURES = {
                                      _dp, _dp]),
     "slb_lyapunov_points": (C.c_int, [_vp, C.POINTER(SlbSweep), _dp, _i64, _dp, _dp, _dp, _dp,
                                       _dp, _dp]),
+    "slb_filter_workspace": (C.c_int64, [_i64]),
+    "slb_lyapunov_sweep_filtered": (C.c_int, [_vp, C.POINTER(SlbSweep), _i64, _i64, _dp, _dp, _vp,
+                                              _vp]),
     "slb_first_fail_workspace": (C.c_int64, [_i64]),
+    "slb_first_fail_x": (C.c_int, [_vp, _dp, _dp, _dp, _i64, _i64, _vp, _vp,
+                                   C.POINTER(SlbExchange)]),
+    "slb_apply_prefix_x": (C.c_int, [_vp, _dp, _dp, _i64, _i64, _vp, _dp, _vp, _vp,
+                                     C.POINTER(SlbExchange)]),
     "slb_first_fail": (C.c_int, [_vp, _dp, _dp, _dp, _i64, _i64, _vp, _vp]),
     "slb_combine_fail_keys": (C.c_int, [_vp, _vp, _i32, _vp]),
     "slb_apply_prefix": (C.c_int, [_vp, _dp, _dp, _i64, _i64, _vp, _dp, _vp, _vp]),

@@ -18,7 +18,7 @@
 
 // ----------------------------------------------------------------------------- host side
 void slb_set_error(const char* fmt, ...);
-extern long long g_slb_launches;
+void slb_count_launch();
 
 #define SLB_CHECK(cond, ...)                                                     \
     do {                                                                         \
@@ -37,7 +37,7 @@ extern long long g_slb_launches;
 
 #define SLB_LAUNCH_CHECK()                                                       \
     do {                                                                         \
-        ++g_slb_launches;                                                        \
+        slb_count_launch();                                                      \
         SLB_CUDA(cudaGetLastError());                                            \
     } while (0)
 
@@ -574,8 +574,9 @@ struct slb_decision { double vx, decrease, threshold; bool negative; };
 // The decision of lyapunov.py:436-441 in three independent pieces (the tile kernel evaluates the
 // x-only piece while the GP runs, and the two mean-dependent pieces on different warps):
 // (1) V(x) and threshold(x) = -|L_V(x)|_1 (1 + L_f) tau                      :284-288
-SLB_DEV void lyapunov_state_terms(const slb_sweep& cfg, const double* x, double* vx_out,
-                                  double* threshold_out) {
+// `flat_index` is the point's flat grid index (for cfg.lf_values), or -1 for an explicit state.
+SLB_DEV void lyapunov_state_terms(const slb_sweep& cfg, const double* x, int64_t flat_index,
+                                  double* vx_out, double* threshold_out) {
     double tmp[SLB_MAX_OUT], vx[1];
     eval_fn(cfg.lyapunov, x, vx);
     *vx_out = vx[0];
@@ -590,7 +591,14 @@ SLB_DEV void lyapunov_state_terms(const slb_sweep& cfg, const double* x, double*
     } else {
         lvx = cfg.lv_const;
     }
-    *threshold_out = f64mul(f64mul(-lvx, f64add(1.0, cfg.lf_const)), cfg.tau);   // :288
+    double lf = cfg.lf_const;                                // lyapunov.py:227-244, :287
+    if (cfg.lf_values != nullptr && flat_index >= 0) {
+        lf = cfg.lf_values[flat_index - cfg.lf_index_base];
+    } else if (cfg.lipschitz_f.kind != SLB_FN_NONE) {
+        eval_fn(cfg.lipschitz_f, x, tmp);
+        lf = tmp[0];
+    }
+    *threshold_out = f64mul(f64mul(-lvx, f64add(1.0, lf)), cfg.tau);   // :288
 }
 
 // (2) sum_j L_V(mu)_j err_j, L_V evaluated at the predicted MEAN                :344-347
@@ -624,10 +632,10 @@ SLB_DEV slb_decision lyapunov_combine(double vx, double threshold, double vm, do
     return r;
 }
 
-SLB_DEV slb_decision lyapunov_decide(const slb_sweep& cfg, const double* x, const double* mu,
-                                     const double* err) {
+SLB_DEV slb_decision lyapunov_decide(const slb_sweep& cfg, const double* x, int64_t flat_index,
+                                     const double* mu, const double* err) {
     double vx, threshold, vm[1];
-    lyapunov_state_terms(cfg, x, &vx, &threshold);
+    lyapunov_state_terms(cfg, x, flat_index, &vx, &threshold);
     eval_fn(cfg.lyapunov, mu, vm);
     const double bound = err != nullptr ? lyapunov_error_bound(cfg, mu, err) : 0.0;
     return lyapunov_combine(vx, threshold, vm[0], bound);

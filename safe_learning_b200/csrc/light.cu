@@ -5,14 +5,18 @@
 //   GridWorld.index_to_state                    functions.py:714-731
 //   Bellman sweep / argmax / max|dV|            reinforcement_learning.py:65-114,135-140,213-279
 #include "common.cuh"
+#include "gp_mean.cuh"
 
 #include <stdarg.h>
 #include <stdio.h>
 #include <string.h>
 
+#include <atomic>
+
 // ----------------------------------------------------------------------------- plumbing
 static thread_local char g_err[512] = "";
-long long g_slb_launches = 0;
+static std::atomic<long long> g_slb_launches{0};
+void slb_count_launch() { g_slb_launches.fetch_add(1, std::memory_order_relaxed); }
 
 void slb_set_error(const char* fmt, ...) {
     va_list ap;
@@ -176,7 +180,7 @@ det_sweep_kernel(const __grid_constant__ slb_sweep cfg, const double* __restrict
     const int m = eval_fn(cfg.policy, z, u);
     for (int c = 0; c < m; ++c) z[d + c] = u[c];
     eval_fn(cfg.dynamics, z, mu);
-    const slb_decision r = lyapunov_decide(cfg, z, mu, nullptr);
+    const slb_decision r = lyapunov_decide(cfg, z, states != nullptr ? -1 : idx_begin + i, mu, nullptr);
     negative[i] = r.negative ? 1 : 0;
     if (values != nullptr) values[i] = r.vx;
     if (decrease != nullptr) decrease[i] = r.decrease;
@@ -264,17 +268,55 @@ first_fail_partial_kernel(const double* __restrict__ values, const uint8_t* __re
                             partial[blockIdx.x].nok = nok; }
 }
 
+// Peer-memory key exchange (slb_exchange, slb200.h).  The payload words are written with plain
+// system-scope stores, the sequence number behind a system-scope fence is the release flag.
+SLB_DEV void st_sys(int64_t* p, int64_t v) {
+    asm volatile("st.relaxed.sys.global.s64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+SLB_DEV void st_release_sys(int64_t* p, int64_t v) {
+    asm volatile("st.release.sys.global.s64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+SLB_DEV int64_t ld_sys(const int64_t* p) {
+    int64_t v;
+    asm volatile("ld.relaxed.sys.global.s64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+SLB_DEV int64_t ld_acquire_sys(const int64_t* p) {
+    int64_t v;
+    asm volatile("ld.acquire.sys.global.s64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
 __global__ void __launch_bounds__(FF_BLOCKS)
 first_fail_final_kernel(const ff_partial* __restrict__ partial, int nparts,
-                        slb_fail_key* __restrict__ result) {
+                        slb_fail_key* __restrict__ result, const slb_exchange x) {
+    __shared__ int64_t s_key[4];
     uint64_t kv = ~0ull;
     int64_t ki = INT64_MAX, nok = 0;
     if ((int)threadIdx.x < nparts) {
         kv = partial[threadIdx.x].kv; ki = partial[threadIdx.x].ki; nok = partial[threadIdx.x].nok;
     }
     ff_block_reduce(kv, ki, nok);
-    if (threadIdx.x == 0) { result->key_value = kv; result->key_index = ki; result->n_ok = nok;
-                            result->_pad = 0; }
+    if (threadIdx.x == 0) {
+        result->key_value = kv; result->key_index = ki; result->n_ok = nok; result->_pad = 0;
+        if (x.world > 1) {
+            const int64_t seq = *x.seq_dev + 1;       // sweeps issued by this rank, this one included
+            *x.seq_dev = seq;
+            s_key[0] = (int64_t)kv; s_key[1] = ki; s_key[2] = nok; s_key[3] = seq;
+        }
+    }
+    if (x.world <= 1) return;
+    __syncthreads();
+    // push: thread r stores this rank's key into slot [parity][rank] of rank r (its own included)
+    if ((int)threadIdx.x < x.world) {
+        const int64_t seq = s_key[3];
+        int64_t* slot = reinterpret_cast<int64_t*>(
+            x.slots[threadIdx.x] + (seq & 1) * x.world + x.rank);
+        st_sys(slot + 0, s_key[0]);
+        st_sys(slot + 1, s_key[1]);
+        st_sys(slot + 2, s_key[2]);
+        st_release_sys(slot + 3, seq);
+    }
 }
 
 // Lexicographic min over the per-rank keys gathered by the caller's all-gather.
@@ -292,12 +334,53 @@ __global__ void combine_fail_keys_kernel(const slb_fail_key* __restrict__ gather
     out->key_value = kv; out->key_index = ki; out->n_ok = nok; out->_pad = 0;
 }
 
+// X: the keys of all ranks arrive through peer memory (slb_exchange); every block waits for the
+// `world` release flags of the current sweep in this rank's own slot array (local HBM/L2), reduces
+// the keys (lexicographic min, n_ok sum) and block 0 publishes the winner to `key`.  A rank whose
+// peer does not show up within ~10 s gives up and marks the result (key->_pad = -1).
+template <bool X>
 __global__ void __launch_bounds__(LT)
 apply_prefix_kernel(const double* __restrict__ values, const uint8_t* __restrict__ initial, int64_t n,
-                    int64_t idx_begin, const slb_fail_key* __restrict__ key,
-                    uint8_t* __restrict__ safe, slb_prefix_stats* __restrict__ stats) {
-    const uint64_t kv = key->key_value;
-    const int64_t ki = key->key_index;
+                    int64_t idx_begin, slb_fail_key* __restrict__ key,
+                    uint8_t* __restrict__ safe, slb_prefix_stats* __restrict__ stats,
+                    const slb_exchange x) {
+    uint64_t kv;
+    int64_t ki;
+    if (X) {
+        __shared__ int64_t s_k[SLB_MAX_RANKS][3];
+        __shared__ int s_timeout;
+        if (threadIdx.x == 0) s_timeout = 0;
+        __syncthreads();
+        const int64_t seq = *x.seq_dev;
+        if ((int)threadIdx.x < x.world) {
+            const int64_t* slot = reinterpret_cast<const int64_t*>(
+                x.slots[x.rank] + (seq & 1) * x.world + threadIdx.x);
+            unsigned long long t0, t1;
+            asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t0));
+            while (ld_acquire_sys(slot + 3) != seq) {
+                asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t1));
+                if (t1 - t0 > 10000000000ull) { s_timeout = 1; break; }
+                __nanosleep(64);
+            }
+            s_k[threadIdx.x][0] = ld_sys(slot + 0);
+            s_k[threadIdx.x][1] = ld_sys(slot + 1);
+            s_k[threadIdx.x][2] = ld_sys(slot + 2);
+        }
+        __syncthreads();
+        kv = ~0ull; ki = INT64_MAX;
+        int64_t nok = 0;
+        for (int r = 0; r < x.world; ++r) {
+            nok += s_k[r][2];
+            if (key_less((uint64_t)s_k[r][0], s_k[r][1], kv, ki)) { kv = (uint64_t)s_k[r][0]; ki = s_k[r][1]; }
+        }
+        if (blockIdx.x == 0 && threadIdx.x == 0) {
+            key->key_value = kv; key->key_index = ki; key->n_ok = nok;
+            key->_pad = s_timeout ? -1 : seq;
+        }
+    } else {
+        kv = key->key_value;
+        ki = key->key_index;
+    }
     unsigned long long n_safe = 0, n_below = 0, max_below = 0, max_all = 0;
     for (int64_t i = (int64_t)blockIdx.x * LT + threadIdx.x; i < n; i += (int64_t)gridDim.x * LT) {
         const uint64_t v = value_key(values[i]);
@@ -327,106 +410,7 @@ apply_prefix_kernel(const double* __restrict__ values, const uint8_t* __restrict
 }
 
 // ---- Bellman sweep ------------------------------------------------------------------------
-// One factor with NO outputs on it: NO is a compile-time constant so the running dot products
-// stay in registers (a runtime-bounded loop over outputs would push them to local memory).
-constexpr int BCHUNK = 256;    // training rows staged per pass in the Bellman kernels
-
-template <int DIN, int NO>
-SLB_DEV void gp_mean_factor(const slb_gp_stack& gp, const slb_gp_factor& F, const int* outs,
-                            const double* z, double* mu, const double* exptab, double* stage) {
-    const bool general = F.kernel.num_prims > 0;     // covariance expression on the raw inputs
-    double zs[DIN];
-#pragma unroll
-    for (int c = 0; c < DIN; ++c) zs[c] = general ? z[c] : z[c] / F.lengthscales[c];
-    double dot[NO];
-    const double* gam[NO];
-#pragma unroll
-    for (int q = 0; q < NO; ++q) { dot[q] = 0.0; gam[q] = gp.outputs[outs[q]].gamma; }
-    const double* __restrict__ Xs = F.Xs;
-    const int M = F.M;
-    // The training inputs and gamma are staged chunk-wise in shared memory (one coalesced pass
-    // per block): every thread needs every row once, and read from global the first toucher
-    // of a row pays an L2 round trip inside the exp dependency chain.  All threads of the
-    // block take part (callers must not exit early).
-    double* xch = stage;                       // [BCHUNK][DIN]
-    double* gch = stage + BCHUNK * DIN;        // [NO][BCHUNK]
-    for (int c0 = 0; c0 < M; c0 += BCHUNK) {
-        const int nc = min(BCHUNK, M - c0);
-        __syncthreads();
-        for (int i = threadIdx.x; i < nc * DIN; i += blockDim.x) xch[i] = Xs[(size_t)c0 * DIN + i];
-#pragma unroll
-        for (int q = 0; q < NO; ++q)
-            for (int i = threadIdx.x; i < nc; i += blockDim.x) gch[q * BCHUNK + i] = gam[q][c0 + i];
-        __syncthreads();
-        // 4 independent exp chains per thread (the loop is bound by the fp64 pipe through exp)
-        for (int j0 = 0; j0 < nc; j0 += 4) {
-            double kv[4];
-            if (general) {
-                const double* xr[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) xr[u] = xch + min(j0 + u, nc - 1) * DIN;
-                kernel_expr_cross_n<DIN, 4>(F.kernel, zs, xr, exptab, kv);
-            } else {
-                double t2[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const double* xr = xch + min(j0 + u, nc - 1) * DIN;
-                    double acc = 0.0;
-#pragma unroll
-                    for (int c = 0; c < DIN; ++c) { const double df = zs[c] - xr[c]; acc = fma(df, df, acc); }
-                    t2[u] = acc;
-                }
-#pragma unroll
-                for (int u = 0; u < 4; ++u) kv[u] = F.variance * exp_neg_tab(-0.5 * t2[u], exptab);
-            }
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int j = min(j0 + u, nc - 1);
-                const double k = j0 + u >= nc ? 0.0 : kv[u];
-#pragma unroll
-                for (int q = 0; q < NO; ++q) dot[q] = fma(k, gch[q * BCHUNK + j], dot[q]);
-            }
-        }
-    }
-    const double s2 = f64mul(F.scale, F.scale);
-#pragma unroll
-    for (int q = 0; q < NO; ++q) {
-        const slb_gp_output& G = gp.outputs[outs[q]];
-        double mx = 0.0;
-        if (G.prior_mean != nullptr) {
-            mx = f64mul(z[0], G.prior_mean[0]);
-#pragma unroll
-            for (int c = 1; c < DIN; ++c) mx = f64add(mx, f64mul(z[c], G.prior_mean[c]));
-            mx = f64mul(F.scale, mx);
-        }
-        mu[outs[q]] = f64add(f64mul(s2, dot[q]), mx) / F.scale;
-    }
-}
-
-// mean of the GP stack at z (mean only, reinforcement_learning.py:98-99):
-//   mean_o = (scale^2 sum_j k_j gamma_o,j + scale m_o(z)) / scale,  gamma = L^-T alpha,
-// which equals a^T alpha of functions.py:441-442 up to rounding.
-template <int DIN>
-SLB_DEV void gp_mean_only(const slb_gp_stack& gp, const double* z, double* mu,
-                          const double* exptab, double* stage) {
-    for (int f = 0; f < gp.num_factors; ++f) {
-        const slb_gp_factor& F = gp.factors[f];
-        int outs[SLB_MAX_OUT];
-        int no = 0;
-        for (int o = 0; o < gp.num_outputs; ++o)
-            if (gp.outputs[o].factor == f) outs[no++] = o;
-        switch (no) {
-        case 1: gp_mean_factor<DIN, 1>(gp, F, outs, z, mu, exptab, stage); break;
-        case 2: gp_mean_factor<DIN, 2>(gp, F, outs, z, mu, exptab, stage); break;
-        case 3: gp_mean_factor<DIN, 3>(gp, F, outs, z, mu, exptab, stage); break;
-        case 4: gp_mean_factor<DIN, 4>(gp, F, outs, z, mu, exptab, stage); break;
-        case 5: gp_mean_factor<DIN, 5>(gp, F, outs, z, mu, exptab, stage); break;
-        case 6: gp_mean_factor<DIN, 6>(gp, F, outs, z, mu, exptab, stage); break;
-        default: break;
-        }
-    }
-}
-
+// (the mean-only GP loops live in gp_mean.cuh)
 template <int DIN>
 SLB_DEV double bellman_value(const slb_bellman& cfg, const double* x, const double* u, int m,
                              const double* exptab, double* stage) {
@@ -486,7 +470,8 @@ bellman_argmax_kernel(const __grid_constant__ slb_bellman cfg, int64_t idx_begin
         for (int c = 0; c < m; ++c) u[c] = actions[a * m + c];
         double v = bellman_value<DIN>(cfg, x, u, m, exptab, stage);
         if (constraint != nullptr && constraint[(int64_t)a * n + i] < 0.0) v = -INFINITY;  // :272-275
-        if (a == 0 || v > vmax) { vmax = v; arg = a; }      // np.argmax: first maximum (:278)
+        // np.argmax (:278): first maximum, and NaN counts as the maximum (first NaN wins)
+        if (a == 0 || v > vmax || (v != v && vmax == vmax)) { vmax = v; arg = a; }
     }
     if (valid) {
         best[i] = arg;
@@ -528,17 +513,19 @@ extern "C" {
 
 int slb_abi_version(void) { return SLB_ABI_VERSION; }
 const char* slb_last_error(void) { return g_err; }
-int64_t slb_launch_count(void) { return (int64_t)g_slb_launches; }
-void slb_note_graph_replay(int64_t kernels) { g_slb_launches += kernels; }
+int64_t slb_launch_count(void) { return (int64_t)g_slb_launches.load(); }
+void slb_note_graph_replay(int64_t kernels) { g_slb_launches.fetch_add(kernels); }
 
 /* sizeof of every ABI struct, for bindings to verify their mirror:
-   [grid, function, gp_factor, gp_output, gp_stack, sweep, bellman, fail_key, prefix_stats] */
+   [grid, function, gp_factor, gp_output, gp_stack, sweep, bellman, fail_key, prefix_stats,
+    exchange] */
 int slb_struct_sizes(int64_t* out, int32_t n) {
-    const int64_t sizes[9] = {sizeof(slb_grid), sizeof(slb_function), sizeof(slb_gp_factor),
-                              sizeof(slb_gp_output), sizeof(slb_gp_stack), sizeof(slb_sweep),
-                              sizeof(slb_bellman), sizeof(slb_fail_key), sizeof(slb_prefix_stats)};
-    for (int i = 0; i < n && i < 9; ++i) out[i] = sizes[i];
-    return 9;
+    const int64_t sizes[10] = {sizeof(slb_grid), sizeof(slb_function), sizeof(slb_gp_factor),
+                               sizeof(slb_gp_output), sizeof(slb_gp_stack), sizeof(slb_sweep),
+                               sizeof(slb_bellman), sizeof(slb_fail_key), sizeof(slb_prefix_stats),
+                               sizeof(slb_exchange)};
+    for (int i = 0; i < n && i < 10; ++i) out[i] = sizes[i];
+    return 10;
 }
 
 int slb_device_count(void) {
@@ -569,8 +556,63 @@ int slb_first_fail(void* stream, const double* values_dev, const uint8_t* negati
     first_fail_partial_kernel<<<nparts, LT, 0, st>>>(values_dev, negative_dev, initial_dev, n,
                                                      idx_begin, (ff_partial*)workspace_dev);
     SLB_LAUNCH_CHECK();
+    slb_exchange none;
+    memset(&none, 0, sizeof(none));
     first_fail_final_kernel<<<1, FF_BLOCKS, 0, st>>>((const ff_partial*)workspace_dev, nparts,
-                                                     result_dev);
+                                                     result_dev, none);
+    SLB_LAUNCH_CHECK();
+    return 0;
+}
+
+static int validate_exchange(const slb_exchange* x, const char* who) {
+    SLB_CHECK(x != nullptr, "%s: null exchange", who);
+    SLB_CHECK(x->world >= 1 && x->world <= SLB_MAX_RANKS && x->rank >= 0 && x->rank < x->world,
+              "%s: bad exchange (world %d, rank %d, at most %d ranks)", who, x->world, x->rank,
+              SLB_MAX_RANKS);
+    SLB_CHECK(x->seq_dev != nullptr, "%s: exchange without a sequence counter", who);
+    for (int r = 0; r < x->world; ++r)
+        SLB_CHECK(x->slots[r] != nullptr, "%s: exchange slot array of rank %d is not mapped", who, r);
+    return 0;
+}
+
+int slb_first_fail_x(void* stream, const double* values_dev, const uint8_t* negative_dev,
+                     const uint8_t* initial_dev, int64_t n, int64_t idx_begin, void* workspace_dev,
+                     slb_fail_key* result_dev, const slb_exchange* xchg) {
+    if (validate_exchange(xchg, "slb_first_fail_x")) return 1;
+    SLB_CHECK(n >= 0, "slb_first_fail_x: negative n");
+    SLB_CHECK(workspace_dev && result_dev, "slb_first_fail_x: null workspace/result");
+    SLB_CHECK(n == 0 || (values_dev && negative_dev), "slb_first_fail_x: null input");
+    const int64_t want = (n + LT - 1) / LT;
+    const int nparts = (int)(want < 1 ? 1 : (want > FF_BLOCKS ? FF_BLOCKS : want));
+    cudaStream_t st = (cudaStream_t)stream;
+    first_fail_partial_kernel<<<nparts, LT, 0, st>>>(values_dev, negative_dev, initial_dev, n,
+                                                     idx_begin, (ff_partial*)workspace_dev);
+    SLB_LAUNCH_CHECK();
+    first_fail_final_kernel<<<1, FF_BLOCKS, 0, st>>>((const ff_partial*)workspace_dev, nparts,
+                                                     result_dev, *xchg);
+    SLB_LAUNCH_CHECK();
+    return 0;
+}
+
+int slb_apply_prefix_x(void* stream, const double* values_dev, const uint8_t* initial_dev,
+                       int64_t n, int64_t idx_begin, slb_fail_key* key_out_dev, uint8_t* safe_dev,
+                       void* workspace_dev, slb_prefix_stats* stats_dev, const slb_exchange* xchg) {
+    (void)workspace_dev;
+    if (validate_exchange(xchg, "slb_apply_prefix_x")) return 1;
+    SLB_CHECK(n >= 0, "slb_apply_prefix_x: negative n");
+    SLB_CHECK(key_out_dev && stats_dev, "slb_apply_prefix_x: null key/stats");
+    SLB_CHECK(n == 0 || (values_dev && safe_dev), "slb_apply_prefix_x: null buffer");
+    cudaStream_t st = (cudaStream_t)stream;
+    SLB_CUDA(cudaMemsetAsync(stats_dev, 0, sizeof(slb_prefix_stats), st));
+    // a rank with an empty slab still takes part in the exchange (one block, no points)
+    const int64_t want = (n + LT - 1) / LT;
+    const unsigned blocks = (unsigned)(want > 2048 ? 2048 : (want < 1 ? 1 : want));
+    if (xchg->world > 1)
+        apply_prefix_kernel<true><<<blocks, LT, 0, st>>>(values_dev, initial_dev, n, idx_begin,
+                                                         key_out_dev, safe_dev, stats_dev, *xchg);
+    else
+        apply_prefix_kernel<false><<<blocks, LT, 0, st>>>(values_dev, initial_dev, n, idx_begin,
+                                                          key_out_dev, safe_dev, stats_dev, *xchg);
     SLB_LAUNCH_CHECK();
     return 0;
 }
@@ -595,8 +637,11 @@ int slb_apply_prefix(void* stream, const double* values_dev, const uint8_t* init
     if (n == 0) return 0;
     const int64_t want = (n + LT - 1) / LT;
     const unsigned blocks = (unsigned)(want > 2048 ? 2048 : want);
-    apply_prefix_kernel<<<blocks, LT, 0, st>>>(values_dev, initial_dev, n, idx_begin, key_dev,
-                                               safe_dev, stats_dev);
+    slb_exchange none;
+    memset(&none, 0, sizeof(none));
+    apply_prefix_kernel<false><<<blocks, LT, 0, st>>>(values_dev, initial_dev, n, idx_begin,
+                                                      const_cast<slb_fail_key*>(key_dev), safe_dev,
+                                                      stats_dev, none);
     SLB_LAUNCH_CHECK();
     return 0;
 }

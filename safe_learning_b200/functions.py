@@ -1097,7 +1097,8 @@ class Likelihood(object):
 class _Factor(object):
     """Device-resident Cholesky state of one (X, kernel, noise, scale) combination."""
 
-    __slots__ = ("key", "M", "nrb", "Xs", "L", "Linv", "Wpack", "appends", "plain")
+    __slots__ = ("key", "M", "nrb", "Xs", "L", "Linv", "Wpack", "Whead", "appends", "plain",
+                 "floor_rel")
 
 
 _FACTOR_CACHE = {}
@@ -1211,6 +1212,7 @@ class GPRCached(object):
                 fac.Xs = dev.zeros((0, din))
                 fac.L = fac.Linv = dev.zeros((0, 0))
                 fac.Wpack = dev.zeros((1,))
+                self._head(fac)
             else:
                 if fac.plain:
                     fac.Xs = dev.to_device(self._X / self.kern.lengthscales)
@@ -1229,12 +1231,36 @@ class GPRCached(object):
             _remember_factor(fac)
         self._finish_cache(fac)
 
-    @staticmethod
-    def _pack(fac):
+    def _pack(self, fac):
+        """Device tables derived from ``L^-1``: the DMMA-ordered packed factor, the column-major
+        head block of the decision filter (``slb_gp_factor.Whead``) and the certified lower
+        bound of the posterior variance that decides whether the filter may be used."""
         lib = nat.load()
         fac.Wpack = dev.empty((int(lib.slb_packed_len(fac.M)),))
         nat.check(lib.slb_pack_factor(dev.stream(), fac.Linv.data_ptr(), fac.M,
                                       fac.Wpack.data_ptr()), "slb_pack_factor")
+        self._head(fac)
+
+    def _head(self, fac):
+        R = nat.SLB_HEAD_RANK
+        r = min(fac.M, R)
+        fac.Whead = dev.zeros((R, R))
+        if r:
+            fac.Whead[:r, :r] = fac.Linv[:r, :r].T        # Whead[j, i] = L^-1[i, j]
+        # var(z) >= k(z,z) s / (M k(z,z) + s), s = noise variance (M noisy observations AT z are
+        # the most informative data set): relative to k(z,z) at least s / (M kmax + s).  When
+        # that is not far above fp64 rounding of the O(M^2) contraction the reference's
+        # "negative variance -> NaN -> unsafe" corner (functions.py:451) is reachable and the
+        # filter, which bounds the variance from above only, is not used.
+        if fac.M == 0:
+            fac.floor_rel = 1.0
+            return
+        noise = float(self.likelihood.variance)
+        if fac.plain:
+            kmax = float(self.kern.variance)
+        else:
+            kmax = float(self.kern.Kdiag_device(fac.Xs).max().item())
+        fac.floor_rel = noise / (fac.M * kmax + noise) if (kmax > 0 or noise > 0) else 0.0
 
     def _append_rows(self, x_new):
         """Rank-one growth of the cached factor for each appended observation (SURVEY.md 8f
@@ -1330,6 +1356,7 @@ class GPRCached(object):
         fac = self._factor
         f.M, f.nrb = fac.M, fac.nrb
         f.Xs, f.Wpack = fac.Xs.data_ptr(), fac.Wpack.data_ptr()
+        f.Whead = fac.Whead.data_ptr()
         f.scale = self._scale
         if fac.plain:
             for c, ls in enumerate(self.kern.lengthscales):
@@ -1347,6 +1374,12 @@ class GPRCached(object):
         o.alpha = self._alpha_dev.data_ptr()
         o.gamma = self._gamma_dev.data_ptr()
         o.prior_mean = None if self._prior_dev is None else self._prior_dev.data_ptr()
+
+
+    def variance_floor(self):
+        """Certified lower bound of posterior variance / prior variance (see ``_head``)."""
+        self._ensure()
+        return self._factor.floor_rel
 
 
 GPR = GPRCached     # the uncached gpflow.gpr.GPR of the notebooks maps onto the cached one
@@ -1409,6 +1442,9 @@ class GaussianProcess(UncertainFunction):
     def gp_stack(self):
         return _build_stack([self.gaussian_process], [self.beta])
 
+    def variance_floor(self):
+        return self.gaussian_process.variance_floor()
+
     @property
     def version(self):
         return (id(self.gaussian_process), self.gaussian_process.version, self.beta)
@@ -1446,6 +1482,9 @@ class FunctionStack(UncertainFunction):
     def gp_stack(self):
         return _build_stack([f.gaussian_process for f in self.functions],
                             [f.beta for f in self.functions])
+
+    def variance_floor(self):
+        return min(f.variance_floor() for f in self.functions)
 
     @property
     def version(self):

@@ -3,13 +3,18 @@
 Same constructor, attributes and methods as the reference; the work is one fused CUDA sweep
 (``slb_lyapunov_sweep``) + a sort-free prefix reduction (``slb_first_fail`` /
 ``slb_apply_prefix``) instead of a Python loop of 10 000-point ``Session.run`` calls.
+With GP dynamics the sweep runs behind a certified decision filter (``slb_lyapunov_sweep_filtered``,
+csrc/filter.cu): identical flags, the O(M^2) posterior only where the outcome depends on it.
 With ``torch.distributed`` initialised, the grid is sharded by contiguous flat-index range
-(one process per GPU) and the ranks exchange one 32-byte key per sweep.
+(one process per GPU) and the ranks exchange one 32-byte key per sweep -- through peer memory
+inside the reduction kernels (``slb_exchange``), without a collective call or a host round trip;
+``c_max`` and the statistics are resolved lazily when they are read.
 """
 
 from __future__ import annotations
 
 import os
+import zlib
 
 import numpy as np
 import torch
@@ -19,7 +24,7 @@ from . import _native as nat
 from .functions import Function, FunctionStack, GaussianProcess, UncertainFunction, config
 
 __all__ = ["Lyapunov", "get_safe_sample", "perturb_actions", "smallest_boundary_value",
-           "combine_fail_keys", "combine_prefix_stats"]
+           "combine_fail_keys", "combine_prefix_stats", "adaptive_as_written"]
 
 
 def _unique_rows(array):
@@ -128,6 +133,38 @@ class _CMax(object):
         return "<c_max>"
 
 
+class _FeedDict(dict):
+    """``lyapunov.feed_dict``: a dict whose ``c_max`` entry is resolved from the device when it is
+    read (the sweep itself never waits for the host)."""
+
+    def __init__(self, owner):
+        super().__init__()
+        self._owner = owner
+
+    def _sync(self):
+        self._owner._resolve_pending()
+
+    def __getitem__(self, key):
+        self._sync()
+        return dict.__getitem__(self, key)
+
+    def get(self, key, default=None):
+        self._sync()
+        return dict.get(self, key, default)
+
+    def items(self):
+        self._sync()
+        return dict.items(self)
+
+    def values(self):
+        self._sync()
+        return dict.values(self)
+
+    def copy(self):
+        self._sync()
+        return dict(self)
+
+
 def _as_function(obj, what):
     if isinstance(obj, Function):
         return obj
@@ -161,6 +198,60 @@ def _key_to_value(bits):
     return float(np.array([raw], dtype=np.uint64).view(np.float64)[0])
 
 
+def adaptive_as_written(values, negative, decrease, threshold, coef, initial, tau, batch,
+                        max_refinement, safety_factor):
+    """Host loop of the reference's adaptive branch, as written (``lyapunov.py:497-606`` with
+    ``:540-582``), over per-point quantities of the whole grid: ``negative``, ``decrease``,
+    ``threshold`` (at ``tau``) and ``coef = -L_V(x)(1 + L_f)`` so that ``threshold(x, tau / n) =
+    coef * (tau / n)``.  ``refined_safety_check`` (``:457-481``) compares the decrease of EVERY
+    state fed in the slice with the cell's own refined threshold, i.e. a cell passes iff the
+    largest decrease of the slice is below it.  Returns (safe [N] bool, refinement [N] int,
+    sorted position of c_max)."""
+    n_total = len(values)
+    order = np.argsort(values, kind="stable")
+    safe_s, refine_s = initial[order].copy(), initial[order].astype(int)
+    start = bound = refine_bound = 0
+    for start in range(0, n_total, batch):
+        sel = order[start:start + batch]
+        neg_b = negative[sel]
+        safe_b = safe_s[start:start + batch]            # views: edited in place
+        refine_b = refine_s[start:start + batch]
+        safe_b |= neg_b
+        refine_b[neg_b] = 1
+        bound = int(np.argmin(safe_b))
+        refine_bound = 0
+        if bound > 0 or not safe_b[0]:
+            with np.errstate(divide="ignore", invalid="ignore"):
+                ratio = safety_factor * threshold[sel[bound:]] / decrease[sel[bound:]]
+            ratio = np.where(np.isnan(ratio), 0.0, ratio)
+            refine_b[bound:] = np.ceil(np.maximum(ratio, 0))            # :445-455, :542-546
+            idx_safe = neg_b | initial[sel]
+            refine_b[idx_safe] = 1                                      # :548-551
+            to_check = ((refine_b >= 1) & (refine_b <= max_refinement))[bound:]
+            stop = len(to_check) if to_check.all() else int(np.argmin(to_check))
+            if stop > 0:
+                fed = sel[bound:bound + stop]
+                dec = decrease[fed]
+                worst = np.nan if np.isnan(dec).any() else dec.max()
+                with np.errstate(invalid="ignore"):
+                    thr = coef[fed] * (tau / refine_b[bound:bound + stop])
+                    refined = worst < thr                               # :474-478
+                refine_bound = len(refined) if refined.all() else int(np.argmin(refined))
+                safe_b[bound:bound + refine_bound] = True
+            if stop < len(to_check) or refine_bound < stop:
+                safe_b[bound + refine_bound:] = False
+                refine_b[bound + refine_bound:] = 0
+                break
+    position = start + bound + refine_bound - 1
+    safe = np.zeros(n_total, dtype=bool)
+    safe[order[safe_s]] = True
+    refinement = np.zeros(n_total, dtype=int)
+    refinement[order] = refine_s
+    safe[initial] = True
+    refinement[initial] = 1
+    return safe, refinement, position
+
+
 class Lyapunov(object):
     """See ``lyapunov.py:142-225`` for the parameters.
 
@@ -180,9 +271,15 @@ class Lyapunov(object):
         self._lipschitz_dynamics = lipschitz_dynamics
         self._lipschitz_lyapunov = lipschitz_lyapunov
         self.adaptive = adaptive
-        self.feed_dict = {}
+        self._pending = None              # sweep enqueued, c_max / statistics not read back yet
+        self._last_sweep = {}
+        self.feed_dict = _FeedDict(self)
         self.c_max = _CMax()
-        self.feed_dict[self.c_max] = 0.
+        dict.__setitem__(self.feed_dict, self.c_max, 0.)
+        # decision filter in front of the O(M^2) posterior: "auto" (on when every GP's certified
+        # variance floor is far above fp64 rounding), True, or False; SLB200_FILTER=0 disables it
+        self.filter = "auto"
+        self.refinement_mode = "mesh"     # or "reference": lyapunov.py:474-478 as written
 
         n = discretization.nindex
         self._begin, self._end = dev.shard_range(n)
@@ -202,7 +299,9 @@ class Lyapunov(object):
         self._initial_dev = None
         self._initial_token = None
         self._workspace = None
-        self.last_sweep = {}
+        self._filter_ws = None
+        self._filter_stats = None
+        self._lf_cache = None
         self.update_values()
 
     # ------------------------------------------------------------------ attributes
@@ -329,19 +428,55 @@ class Lyapunov(object):
         else:
             cfg.lv_const = float(lv)
         lf = self._lipschitz_dynamics
-        if callable(lf):
-            # the notebooks pass constants as lambdas (`lambda x: norm(A, 1) + ...`,
-            # lyapunov_function_learning.ipynb cell 13): accept a callable that is constant
-            grid = self.discretization
-            probe = grid.index_to_state(np.array([0, grid.nindex // 2, grid.nindex - 1]))
-            vals = np.asarray(lf(probe), dtype=np.float64).ravel()
-            if vals.size == 0 or not np.all(vals == vals[0]):
-                raise NotImplementedError("state-dependent lipschitz_dynamics is not fused in "
-                                          "this build; pass a float or a constant callable")
-            lf = vals[0]
-        cfg.lf_const = float(lf)
+        if isinstance(lf, Function):
+            cfg.lipschitz_f = lf.descriptor()              # state-dependent, fused
+        elif callable(lf):
+            # any Python callable (lyapunov.py:227-244; the notebooks pass lambdas, e.g.
+            # lyapunov_function_learning.ipynb cell 13): tabulated once on EVERY point of this
+            # rank's slab; a table that turns out constant collapses to the scalar
+            table = self._tabulate_lipschitz_dynamics(lf)
+            if table is None:
+                lf = self._lf_cache[2]
+                cfg.lf_const = float(lf)
+            else:
+                cfg.lf_values = table.data_ptr()
+                cfg.lf_index_base = self._begin
+        else:
+            cfg.lf_const = float(lf)
         cfg.tau = float(self.tau)
         return cfg
+
+    def _tabulate_lipschitz_dynamics(self, fn):
+        """L_f(x) of a Python callable on this rank's grid points -> device table [n_local], or
+        None if it is the same number everywhere (then ``_lf_cache[2]`` holds it)."""
+        token = (id(fn), self._begin, self._end)
+        if self._lf_cache is not None and self._lf_cache[0] == token:
+            return self._lf_cache[1]
+        grid = self.discretization
+        parts = []
+        for start in range(self._begin, self._end, 1 << 20):
+            idx = np.arange(start, min(start + (1 << 20), self._end))
+            vals = np.asarray(fn(grid.index_to_state(idx)), dtype=np.float64)
+            if vals.ndim == 2 and vals.shape[1] > 1:
+                raise ValueError("lipschitz_dynamics must return one value per state")
+            parts.append(np.broadcast_to(vals.reshape(-1) if vals.size > 1 else vals.reshape(1),
+                                         (len(idx),)).copy())
+        table = np.concatenate(parts) if parts else np.zeros(0)
+        constant = table.size == 0 or bool(np.all(table == table[0]))
+        rank, world = dev.dist_info()
+        if world > 1:                      # every rank must build the same kind of descriptor
+            import torch.distributed as dist
+            first = float(table[0]) if table.size else 0.0
+            pair = torch.tensor([first, -first, 0.0 if constant else 1.0], dtype=torch.float64,
+                                device=dev.device())
+            dist.all_reduce(pair, op=dist.ReduceOp.MAX)
+            lo, hi, varying = -float(pair[1]), float(pair[0]), float(pair[2])
+            constant = varying == 0.0 and lo == hi
+        if constant:
+            self._lf_cache = (token, None, float(table[0]) if table.size else 0.0)
+            return None
+        self._lf_cache = (token, dev.to_device(table), None)
+        return self._lf_cache[1]
 
     # ------------------------------------------------------------------ values
     def update_values(self):
@@ -369,9 +504,12 @@ class Lyapunov(object):
         """uint8 slab of the initial safe set (re-uploaded when the attribute changes)."""
         init = self.initial_safe_set
         if init is None:
+            self._initial_dev = self._initial_token = None
             return None
-        arr = np.asarray(init)
-        token = (id(init), arr.shape, arr.dtype.str)
+        arr = np.ascontiguousarray(init)
+        # keyed on the CONTENT (the reference re-reads the array on every update_safe_set,
+        # lyapunov.py:504-506; callers do edit it in place)
+        token = (arr.shape, arr.dtype.str, zlib.crc32(arr.view(np.uint8).reshape(-1)))
         if self._initial_dev is None or self._initial_token != token:
             mask = np.zeros(self.discretization.nindex, dtype=bool)
             mask[arr] = True
@@ -380,33 +518,81 @@ class Lyapunov(object):
             self._initial_token = token
         return self._initial_dev
 
+    def _filter_enabled(self, cfg):
+        """Whether the sweep goes through the decision filter (csrc/filter.cu)."""
+        if cfg.gp.num_outputs == 0 or self.filter is False:
+            return False
+        if os.environ.get("SLB200_FILTER", "1") == "0":
+            return False
+        if self.filter == "auto":
+            return self.dynamics.variance_floor() >= 1e-9
+        return True
+
     def compute_negative(self, want_details=False):
         """Run the fused sweep over this rank's index range.  Returns the device uint8 slab
         ``negative`` (and, if asked, a dict of device tensors: values, decrease, threshold,
-        mean, err)."""
-        lib = nat.load()
-        cfg = self.sweep_descriptor()
+        mean, err -- the details always come from the full posterior)."""
         n = self._end - self._begin
         if self._negative_dev is None or self._negative_dev.numel() != n:
             self._negative_dev = dev.empty((n,), torch.uint8)
+        if not want_details:
+            return self.compute_negative_range(self._begin, self._end, out=self._negative_dev)
+        lib = nat.load()
+        cfg = self.sweep_descriptor()
         details = {}
-        ptrs = [None] * 5
-        if want_details:
-            d = self.discretization.ndim
-            details["values"] = dev.empty((n,))
-            details["decrease"] = dev.empty((n,))
-            details["threshold"] = dev.empty((n,))
-            details["mean"] = dev.empty((n, d))
-            ptrs = [details[k].data_ptr() for k in ("values", "decrease", "threshold", "mean")]
-            if cfg.gp.num_outputs > 0:
-                details["err"] = dev.empty((n, d))
-                ptrs.append(details["err"].data_ptr())
-            else:
-                ptrs.append(None)
+        d = self.discretization.ndim
+        details["values"] = dev.empty((n,))
+        details["decrease"] = dev.empty((n,))
+        details["threshold"] = dev.empty((n,))
+        details["mean"] = dev.empty((n, d))
+        ptrs = [details[k].data_ptr() for k in ("values", "decrease", "threshold", "mean")]
+        if cfg.gp.num_outputs > 0:
+            details["err"] = dev.empty((n, d))
+            ptrs.append(details["err"].data_ptr())
+        else:
+            ptrs.append(None)
         nat.check(lib.slb_lyapunov_sweep(dev.stream(), cfg, self._begin, self._end,
                                          self._negative_dev.data_ptr(), *ptrs),
                   "slb_lyapunov_sweep")
-        return (self._negative_dev, details) if want_details else self._negative_dev
+        return self._negative_dev, details
+
+    def compute_negative_range(self, begin, end, out=None):
+        """``negative`` for the flat grid indices ``[begin, end)`` on the default path (filtered
+        when the dynamics are a GP, see ``filter``) -> device uint8 tensor."""
+        lib = nat.load()
+        cfg = self.sweep_descriptor()
+        n = end - begin
+        if out is None:
+            out = dev.empty((n,), torch.uint8)
+        if self._filter_enabled(cfg):
+            need = int(lib.slb_filter_workspace(n)) // 8 + 1
+            if self._filter_ws is None or self._filter_ws.numel() < need:
+                self._filter_ws = dev.empty((need,), torch.int64)
+            if self._filter_stats is None:
+                self._filter_stats = dev.zeros((4,), torch.int64)
+            nat.check(lib.slb_lyapunov_sweep_filtered(dev.stream(), cfg, begin, end,
+                                                      out.data_ptr(), None,
+                                                      self._filter_ws.data_ptr(),
+                                                      self._filter_stats.data_ptr()),
+                      "slb_lyapunov_sweep_filtered")
+        else:
+            nat.check(lib.slb_lyapunov_sweep(dev.stream(), cfg, begin, end, out.data_ptr(),
+                                             None, None, None, None, None), "slb_lyapunov_sweep")
+        return out
+
+    @property
+    def filter_stats(self):
+        """Counts since the last ``reset_filter_stats()`` (this rank): points decided by the mean
+        and the prior bound, by the head-rank variance bound, refined by the full posterior, and
+        all points that went through the filter."""
+        if self._filter_stats is None:
+            return {"prior": 0, "head": 0, "refined": 0, "points": 0}
+        a, b, c, n = (int(v) for v in self._filter_stats.cpu().numpy())
+        return {"prior": a, "head": b, "refined": c, "points": n}
+
+    def reset_filter_stats(self):
+        if self._filter_stats is not None:
+            self._filter_stats.zero_()
 
     def negative_at_points(self, points, tau=None):
         """The decision of ``lyapunov.py:436-441`` on an explicit device point list ``[n, d]``
@@ -484,15 +670,21 @@ class Lyapunov(object):
 
     def update_safe_set(self, can_shrink=True, max_refinement=1, safety_factor=1.,
                         parallel_iterations=1):
-        """Compute and update the safe set (``lyapunov.py:407-606``)."""
+        """Compute and update the safe set (``lyapunov.py:407-606``).
+
+        The call only ENQUEUES the sweep (fused decision kernel(s), first-fail reduction with the
+        inter-rank key exchange, prefix application); ``safe_set``, ``c_max`` (through
+        ``feed_dict``), ``_refinement`` and ``last_sweep`` synchronise when they are read."""
         adaptive = bool(self.adaptive and max_refinement > 1)
         if adaptive and not can_shrink:
             raise NotImplementedError("adaptive refinement with can_shrink=False is not "
                                       "implemented")
         safety_factor = max(float(safety_factor), 1.)
+        self._pending = None
+        if adaptive and self.refinement_mode == "reference":
+            return self._update_adaptive_as_written(max_refinement, safety_factor)
         lib = nat.load()
         n_local = self._end - self._begin
-        n_total = self.discretization.nindex
         initial = self._initial_device()
         if not can_shrink:
             return self._update_no_shrink(self.compute_negative())
@@ -507,19 +699,31 @@ class Lyapunov(object):
             self._safe_dev = dev.empty((n_local,), torch.uint8)
 
         self.__dict__["_adaptive_state"] = None
+        negb = None
         if adaptive:
             flags, n_req, negb = self._adaptive_ok(max_refinement, safety_factor, initial)
             self.__dict__["_adaptive_state"] = (n_req, negb)
+        xchg = dev.get_exchange() if world > 1 else None
 
         def enqueue():
             st = dev.stream()
             neg = flags if adaptive else self.compute_negative()
-            nat.check(lib.slb_first_fail(st, self._values_dev.data_ptr(), neg.data_ptr(),
-                                         dev.ptr(initial), n_local, self._begin,
-                                         self._workspace.data_ptr(), self._key_dev.data_ptr()),
-                      "slb_first_fail")
+            args = (st, self._values_dev.data_ptr(), neg.data_ptr(), dev.ptr(initial), n_local,
+                    self._begin, self._workspace.data_ptr(), self._key_dev.data_ptr())
+            if xchg is not None:
+                # the one exchange of the sweep: 32 bytes per rank stored into every peer's slot
+                # by the reduction kernel itself; the prefix kernel waits for them (light.cu)
+                nat.check(lib.slb_first_fail_x(*args, xchg), "slb_first_fail_x")
+                nat.check(lib.slb_apply_prefix_x(st, self._values_dev.data_ptr(), dev.ptr(initial),
+                                                 n_local, self._begin, self._key_dev.data_ptr(),
+                                                 self._safe_dev.data_ptr(),
+                                                 self._workspace.data_ptr(),
+                                                 self._stats_dev.data_ptr(), xchg),
+                          "slb_apply_prefix_x")
+                return
+            nat.check(lib.slb_first_fail(*args), "slb_first_fail")
             if world > 1:
-                # the one data-path collective of the sweep: 32 bytes per rank, reduced on device
+                # fallback without peer memory: NCCL all-gather of the keys, reduced on device
                 gathered = dev.allgather_rows(self._key_dev)
                 nat.check(lib.slb_combine_fail_keys(st, gathered.data_ptr(), world,
                                                     self._key_dev.data_ptr()),
@@ -529,12 +733,13 @@ class Lyapunov(object):
                                            self._safe_dev.data_ptr(), self._workspace.data_ptr(),
                                            self._stats_dev.data_ptr()), "slb_apply_prefix")
 
-        # Single GPU: the five launches of a sweep are captured once into a CUDA graph and replayed
-        # while nothing they depend on (function objects, GP state, buffers) has changed.
+        # Optional CUDA-graph replay of the launches of a sweep (no collective call inside when
+        # the keys travel through peer memory), while nothing they depend on has changed.
         token = None
-        if world == 1 and _USE_GRAPHS and not adaptive:
+        if _USE_GRAPHS and not adaptive and (world == 1 or xchg is not None):
             token = (self._descriptor_token(), self._values_dev.data_ptr(),
-                     0 if initial is None else initial.data_ptr(), n_local)
+                     0 if initial is None else initial.data_ptr(), n_local,
+                     self._filter_enabled(self.sweep_descriptor()))
         cached = self.__dict__.get("_sweep_graph")
         if token is not None and cached is not None and cached[0] == token:
             cached[1].replay()
@@ -550,14 +755,31 @@ class Lyapunov(object):
             self.__dict__["_sweep_graph_seen"] = token
             self.__dict__["_sweep_graph"] = None
             enqueue()
-        # single host read-back per sweep: key + statistics (64 bytes per rank)
+        self._pending = {"adaptive": adaptive, "negb": negb, "initial": initial}
+        self._safe_dirty = True
+        self._refinement = None      # materialised lazily from safe_set (0/1 in this branch)
+
+    def _resolve_pending(self):
+        """The single host read-back of a sweep (key + statistics, 64 bytes per rank), deferred
+        until ``c_max`` / ``last_sweep`` is read.  With several ranks this is a collective (like
+        reading ``safe_set``): every rank must read at the same point of the program."""
+        pending = self._pending
+        if pending is None:
+            return
+        self._pending = None
+        rank, world = dev.dist_info()
+        n_total = self.discretization.nindex
         if world > 1:
             host = dev.allgather_rows(self._ks_dev).cpu().numpy()
         else:
             host = self._ks_dev.cpu().numpy()[None, :]
+        if int(host[0, 3]) == -1:
+            raise RuntimeError("peer-memory key exchange timed out: a rank did not take part in "
+                               "the sweep (set SLB200_EXCHANGE=nccl to use NCCL instead)")
         key = (int(host[0, 0:1].view(np.uint64)[0]), int(host[0, 1]), int(host[0, 2]))
         n_safe, n_below, max_below, max_all = combine_prefix_stats(host[:, 4:8])
         failed = key[1] != nat.INT64_MAX
+        adaptive, negb, initial = pending["adaptive"], pending["negb"], pending["initial"]
         # c_max with the reference's index arithmetic (lyapunov.py:590-595, SURVEY.md Q4)
         if failed:
             position = n_below - 1
@@ -579,11 +801,61 @@ class Lyapunov(object):
             c_max = _key_to_value(max_below)
         else:
             c_max = self._kth_value(position)
-        self.feed_dict[self.c_max] = c_max
-        self.last_sweep = {"n_safe": n_safe, "first_fail_position": n_below if failed else None,
-                           "first_fail_index": key[1] if failed else None, "c_max": c_max}
-        self._safe_dirty = True
-        self._refinement = None      # materialised lazily from safe_set (0/1 in this branch)
+        dict.__setitem__(self.feed_dict, self.c_max, c_max)
+        self._last_sweep = {"n_safe": n_safe, "first_fail_position": n_below if failed else None,
+                            "first_fail_index": key[1] if failed else None, "c_max": c_max}
+
+    @property
+    def last_sweep(self):
+        self._resolve_pending()
+        return self._last_sweep
+
+    @last_sweep.setter
+    def last_sweep(self, value):
+        self._last_sweep = value
+
+    def _update_adaptive_as_written(self, max_refinement, safety_factor):
+        """``refinement_mode="reference"``: the adaptive branch exactly as the reference's graph and
+        host loop evaluate it (``lyapunov.py:457-481, 540-582``) -- ``refined_safety_check`` builds
+        the mesh but compares the OUTER ``decrease`` tensor of every state fed in the slice with
+        ``threshold(center, tau / n)``, so a cell counts as verified iff the LARGEST decrease of the
+        fed slice is below its own refined threshold, and initial-safe states are re-checked with
+        n = 1.  The per-point quantities (``negative``, ``decrease``, the threshold coefficient
+        ``-L_V(x)(1 + L_f)``) come from the fused sweep; the batch loop, which depends on
+        ``config.gp_batch_size`` and on sorted ranks, is replayed on the host over them."""
+        lib = nat.load()
+        neg, det = self.compute_negative(want_details=True)
+        # threshold(x, tau / n) = (-L_V(x) (1 + L_f)) * (tau / n): the coefficient is the sweep's
+        # threshold output for tau = 1 (a multiplication by 1.0 is exact)
+        cfg1 = nat.SlbSweep.from_buffer_copy(self.sweep_descriptor())
+        cfg1.tau = 1.0
+        n_local = self._end - self._begin
+        coef = dev.empty((n_local,))
+        scratch = dev.empty((n_local,), torch.uint8)
+        nat.check(lib.slb_lyapunov_sweep(dev.stream(), cfg1, self._begin, self._end,
+                                         scratch.data_ptr(), None, None, coef.data_ptr(), None,
+                                         None), "slb_lyapunov_sweep")
+        values = self._gather(self._values_dev).cpu().numpy()
+        negative = self._gather(neg).cpu().numpy().astype(bool)
+        decrease = self._gather(det["decrease"]).cpu().numpy()
+        threshold = self._gather(det["threshold"]).cpu().numpy()
+        coef = self._gather(coef).cpu().numpy()
+        n_total = self.discretization.nindex
+        initial = np.zeros(n_total, dtype=bool)
+        if self.initial_safe_set is not None:
+            initial[self.initial_safe_set] = True
+        safe, refinement, position = adaptive_as_written(
+            values, negative, decrease, threshold, coef, initial, self.tau,
+            int(config.gp_batch_size), max_refinement, safety_factor)
+        c_max = float(values[np.argsort(values, kind="stable")[position]])
+        self._safe_host = safe
+        self._safe_dirty = False
+        self._safe_dev = dev.to_device(safe[self._begin:self._end].astype(np.uint8), torch.uint8)
+        self._refinement = refinement
+        self.__dict__["_adaptive_state"] = None
+        dict.__setitem__(self.feed_dict, self.c_max, c_max)
+        self._last_sweep = {"n_safe": int(safe.sum()), "c_max": c_max,
+                            "first_fail_position": position + 1, "first_fail_index": None}
 
     # _refinement mirrors lyapunov.py:223-225, 531, 586, 601-606; without adaptive refinement
     # it is 1 exactly where the state is safe.
@@ -644,7 +916,7 @@ class Lyapunov(object):
             safe_s[p:stop] = False
             ref_s[p:stop] = 0
             position = p - 1
-        self.feed_dict[self.c_max] = float(values[order[position]].item())
+        dict.__setitem__(self.feed_dict, self.c_max, float(values[order[position]].item()))
         safe = torch.zeros_like(prev)
         safe[order] = safe_s
         refinement = torch.zeros_like(refine_prev)

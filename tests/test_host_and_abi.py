@@ -39,7 +39,7 @@ def test_header_symbols_exported(lib):
 
 def test_struct_layout_and_version(lib):
     from safe_learning_b200 import _native
-    assert lib.slb_abi_version() == _native.ABI_VERSION == 2
+    assert lib.slb_abi_version() == _native.ABI_VERSION == 3
     _native._check_layout(lib)
     assert lib.slb_packed_len(500) == 63 * 64 * 32
     assert lib.slb_packed_len(8) == 2 * 32
@@ -335,3 +335,69 @@ def test_host_array_helpers():
     a = np.array([[1, 1], [1, 2], [1, 3], [1, 2], [1, 3], [1, 4], [2, 3]])
     assert_array_equal(U.unique_rows(a), O.unique_rows(a))
     assert_array_equal(U.unique_rows(a), np.array([[1, 1], [1, 2], [1, 3], [1, 4], [2, 3]]))
+
+
+# ----------------------------------------------------------------- adaptive branch, as written
+@pytest.mark.parametrize("tau_scale,max_refinement,safety_factor,batch",
+                         [(1 / 30., 4, 2.0, 64), (1 / 60., 12, 4.0, 100), (1 / 30., 8, 1.0, 10000)])
+def test_adaptive_as_written_loop_matches_oracle(tau_scale, max_refinement, safety_factor, batch):
+    """The host replay of lyapunov.py:540-582 (refinement_mode="reference") over per-point arrays
+    equals the oracle running the reference loop state by state."""
+    import bench_workloads as W
+    from safe_learning_b200.lyapunov import adaptive_as_written
+    par = W.make_pendulum(num_points=[26, 21], M=40, tau_scale=tau_scale)
+    old = O.config.gp_batch_size
+    O.config.gp_batch_size = batch
+    try:
+        grid, dyn = W._build(O, par, "oracle")
+        policy = O.Saturation(O.LinearSystem(-par["K"]), -1., 1.)
+        cpu = O.Lyapunov(grid, O.QuadraticFunction(par["P"]), dyn, par["L_dyn"],
+                         O.AbsFunction(O.LinearSystem((2 * par["P"],))), par["tau"], policy,
+                         initial_set=par["initial"], adaptive=True)
+        states = grid.all_points
+        decrease, threshold = cpu.decrease_and_threshold(states)
+        coef = cpu.threshold(states, 1.0).ravel()
+        with np.errstate(invalid="ignore"):
+            negative = (decrease < threshold).ravel()
+        safe, refinement, position = adaptive_as_written(
+            cpu.values, negative, decrease.ravel(), np.ascontiguousarray(threshold).ravel(), coef,
+            par["initial"], par["tau"], batch, max_refinement, max(safety_factor, 1.))
+        cpu.update_safe_set(max_refinement=max_refinement, safety_factor=safety_factor,
+                            refinement_mode="reference")
+        assert_array_equal(safe, cpu.safe_set)
+        assert_array_equal(refinement, cpu._refinement)
+        assert cpu.values[O.stable_value_order(cpu.values)[position]] == cpu.c_max
+    finally:
+        O.config.gp_batch_size = old
+
+
+def test_filter_bounds_are_certified_on_the_oracle():
+    """The two facts the decision filter (csrc/filter.cu) rests on, checked with the oracle's own
+    arithmetic: (1) the variance given the first R training rows is the first R rows of the same
+    triangular solve and bounds the full posterior variance from above; (2) the mean through
+    gamma = L^-T alpha equals a . alpha.  Also records how much of the C2 workload each stage
+    decides (the numbers quoted in DESIGN.md)."""
+    import scipy.linalg as sla
+    import bench_workloads as W
+    par = W.make_pendulum(num_points=64, M=200, shared_hypers=False)
+    cpu = W.build_oracle(par)
+    states = cpu.discretization.all_points
+    z = np.hstack([states, cpu.policy(states)])
+    mean, err = cpu.dynamics(states, cpu.policy(states))
+    for j, f in enumerate(cpu.dynamics.functions):
+        gp = f.gaussian_process
+        L, X, s = np.asarray(gp.cholesky), np.asarray(gp.X), gp._scale
+        Kx = s ** 2 * gp.kern.K(X, z)
+        a = sla.solve_triangular(L, Kx, lower=True)
+        full = (s ** 2 * gp.kern.Kdiag(z) - np.sum(a * a, axis=0)) / s ** 2
+        assert_allclose(f.beta * np.sqrt(full), err[:, j], rtol=1e-9)
+        prev = gp.kern.Kdiag(z)
+        for R in (16, 64, 128, 200):
+            head = (s ** 2 * gp.kern.Kdiag(z) - np.sum(a[:R] * a[:R], axis=0)) / s ** 2
+            a_head = sla.solve_triangular(L[:R, :R], Kx[:R], lower=True)
+            assert_allclose(a_head, a[:R], rtol=1e-7, atol=1e-12)     # same rows of the solve
+            assert np.all(head <= prev * (1 + 1e-12)) and np.all(head >= full * (1 - 1e-12))
+            prev = head
+        gamma = sla.solve_triangular(L.T, np.asarray(gp.alpha), lower=False)
+        m_gamma = (Kx.T.dot(gamma) + s * gp._mean(z)) / s
+        assert_allclose(m_gamma[:, 0], mean[:, j], rtol=1e-7, atol=1e-12)
