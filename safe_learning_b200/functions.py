@@ -1381,6 +1381,39 @@ class GPRCached(object):
         self._ensure()
         return self._factor.floor_rel
 
+    # host copies of the cached tables ------------------------------------------------------
+    _CACHE_FIELDS = ("Xs", "Wpack", "Whead", "alpha", "gamma")
+
+    def export_cache(self, pinned=True):
+        """Host copies (torch CPU tensors, page-locked if ``pinned``) of the device tables a sweep
+        reads: scaled training inputs, packed ``L^-1``, its head block, ``alpha`` and ``gamma``
+        (what ``update_cache`` leaves in HBM, ``functions.py:395-415``).  Together with
+        ``import_cache`` this checkpoints / restores the cached state without a refit."""
+        self._ensure()
+        fac = self._factor
+        out = {}
+        for name, t in zip(self._CACHE_FIELDS, (fac.Xs, fac.Wpack, fac.Whead, self._alpha_dev,
+                                                self._gamma_dev)):
+            host = t.detach().cpu()
+            out[name] = host.pin_memory() if pinned and torch.cuda.is_available() else host
+        return out
+
+    def import_cache(self, tables):
+        """Copy tables produced by ``export_cache`` (same data set and hyper-parameters, hence same
+        shapes) back into the device buffers: asynchronous H2D copies on the current stream."""
+        self._ensure()
+        fac = self._factor
+        for name, dst in zip(self._CACHE_FIELDS, (fac.Xs, fac.Wpack, fac.Whead, self._alpha_dev,
+                                                  self._gamma_dev)):
+            src = tables[name]
+            if not isinstance(src, torch.Tensor):
+                src = torch.from_numpy(np.ascontiguousarray(src, dtype=np.float64))
+            if tuple(src.shape) != tuple(dst.shape):
+                raise DimensionError("import_cache: %s has shape %s, the cached table %s"
+                                     % (name, tuple(src.shape), tuple(dst.shape)))
+            dst.copy_(src, non_blocking=True)
+        return sum(int(tables[k].numel()) * 8 for k in self._CACHE_FIELDS)
+
 
 GPR = GPRCached     # the uncached gpflow.gpr.GPR of the notebooks maps onto the cached one
 
@@ -1445,6 +1478,12 @@ class GaussianProcess(UncertainFunction):
     def variance_floor(self):
         return self.gaussian_process.variance_floor()
 
+    def export_cache(self, pinned=True):
+        return [self.gaussian_process.export_cache(pinned)]
+
+    def import_cache(self, tables):
+        return self.gaussian_process.import_cache(tables[0])
+
     @property
     def version(self):
         return (id(self.gaussian_process), self.gaussian_process.version, self.beta)
@@ -1485,6 +1524,14 @@ class FunctionStack(UncertainFunction):
 
     def variance_floor(self):
         return min(f.variance_floor() for f in self.functions)
+
+    def export_cache(self, pinned=True):
+        """One table set per stacked GP (see ``GPRCached.export_cache``)."""
+        return [f.gaussian_process.export_cache(pinned) for f in self.functions]
+
+    def import_cache(self, tables):
+        """Restore every stacked GP's tables; returns the bytes copied host -> device."""
+        return sum(f.gaussian_process.import_cache(t) for f, t in zip(self.functions, tables))
 
     @property
     def version(self):

@@ -75,8 +75,7 @@ def test_c4_slab_64pow4_m2000_vs_oracle(sl):
     import torch
     from safe_learning_b200 import _device as dev
     from safe_learning_b200 import _native as nat
-    par = W.make_cartpole(num_points=64, M=2000, tau_scale=0.01)
-    par["initial"] = None
+    par = W.make_cartpole(num_points=64, M=2000, tau_scale=0.01, with_initial=False)
     gpu = W.build_product(par)
     n = gpu.discretization.nindex
     assert n == 64 ** 4

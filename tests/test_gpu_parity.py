@@ -199,9 +199,120 @@ def test_constant_callable_lipschitz_dynamics(sl):
     a.update_safe_set()
     b.update_safe_set()
     assert_array_equal(a.safe_set, b.safe_set)
-    b._lipschitz_dynamics = lambda x: np.abs(x[:, [0]])
-    with pytest.raises(NotImplementedError):
-        b.update_safe_set()
+
+
+def test_state_dependent_lipschitz_dynamics_vs_oracle(sl):
+    """lyapunov.py:227-244, 287: L_f(x) as an arbitrary Python callable (tabulated per grid index,
+    ADVICE r01: a callable that merely coincides at a few probe points must not pass as constant)
+    and as a fused Function object; threshold bit-exact, safe set identical to the oracle."""
+    par = W.make_pendulum(num_points=[29, 23], M=60, tau_scale=1 / 40.)
+    lf = lambda x: 0.5 + np.abs(x[:, [1]]) * (np.abs(x[:, [0]]) < 0.5)   # noqa: E731  even, flat at the corners
+    gpu, cpu = W.build_product(par), W.build_oracle(par)
+    gpu._lipschitz_dynamics = lf
+    cpu._lipschitz_dynamics = lf
+    det = _sweep_details(gpu)
+    states = cpu.discretization.all_points
+    assert_array_equal(det["threshold"], cpu.threshold(states).ravel())
+    _assert_negative_parity(gpu, cpu, det)
+    gpu.update_safe_set()
+    cpu.update_safe_set()
+    assert_array_equal(gpu.safe_set, cpu.safe_set)
+    assert gpu.feed_dict[gpu.c_max] == cpu.c_max
+    # the same dependence as a fused function object: L_f(x) = |x A^T| 1-norm
+    A = np.array([[0.3, -0.2], [0.1, 0.4]])
+    gpu2, cpu2 = W.build_product(par), W.build_oracle(par)
+    gpu2._lipschitz_dynamics = sl.Norm1Function(sl.LinearSystem(A))
+    cpu2._lipschitz_dynamics = O.Norm1Function(O.LinearSystem(A))
+    det2 = _sweep_details(gpu2)
+    assert_array_equal(det2["threshold"], cpu2.threshold(states).ravel())
+    gpu2.update_safe_set()
+    cpu2.update_safe_set()
+    assert_array_equal(gpu2.safe_set, cpu2.safe_set)
+
+
+def test_initial_safe_set_edited_in_place(sl):
+    """the reference re-reads ``initial_safe_set`` on every update_safe_set
+    (lyapunov.py:504-506); an in-place edit of the same array must reach the device."""
+    par = W.make_pendulum(num_points=[21, 17], M=40, tau_scale=0.0)
+    gpu, cpu = W.build_product(par), W.build_oracle(par)
+    for lyap in (gpu, cpu):
+        lyap.initial_safe_set = par["initial"].copy()
+    gpu.update_safe_set()
+    cpu.update_safe_set()
+    assert_array_equal(gpu.safe_set, cpu.safe_set)
+    for lyap in (gpu, cpu):
+        lyap.initial_safe_set[:5] = True          # same object, new content
+        lyap.update_safe_set()
+    assert_array_equal(gpu.safe_set, cpu.safe_set)
+    assert gpu.safe_set[:5].all()
+    for lyap in (gpu, cpu):
+        lyap.initial_safe_set = None
+        lyap.update_safe_set()
+    assert_array_equal(gpu.safe_set, cpu.safe_set)
+
+
+@pytest.mark.parametrize("tau_scale", [1.0, 1 / 8., 1 / 48., 0.0])
+@pytest.mark.parametrize("M", [0, 1, 8, 40, 64, 65, 100, 200, 256])
+def test_filtered_flags_equal_full_posterior(sl, M, tau_scale):
+    """The decision filter (csrc/filter.cu) must reproduce the full posterior's flags bit for bit
+    at every training-set size (M <= 64: the head bound is the whole posterior; M = 0: the prior)
+    and in every regime of tau (all fail ... most pass), incl. the guard-band hand-over."""
+    par = W.make_pendulum(num_points=[45, 37], M=max(M, 1), tau_scale=tau_scale, seed=M + 3)
+    if M == 0:
+        par["X"], par["Y"] = par["X"][:0], par["Y"][:0]
+    gpu = W.build_product(par)
+    assert gpu._filter_enabled(gpu.sweep_descriptor())
+    gpu.reset_filter_stats()
+    fast = gpu.compute_negative().cpu().numpy().copy()
+    stats = gpu.filter_stats
+    assert stats["points"] == gpu.discretization.nindex
+    assert stats["prior"] + stats["head"] + stats["refined"] == stats["points"]
+    gpu.filter = False
+    full = gpu.compute_negative().cpu().numpy()
+    assert_array_equal(fast, full)
+    if M and tau_scale > 0:
+        cpu = W.build_oracle(par)
+        assert_array_equal(full.astype(bool), cpu.full_grid_negative())
+
+
+def test_filter_is_not_used_below_the_variance_floor(sl):
+    """With (almost) noise-free data the reference's negative-variance -> NaN -> unsafe corner is
+    reachable; "auto" then keeps the full posterior."""
+    par = W.make_pendulum(num_points=[9, 9], M=30)
+    par["noise_variance"] = 1e-14
+    gpu = W.build_product(par)
+    assert gpu.dynamics.variance_floor() < 1e-9
+    assert not gpu._filter_enabled(gpu.sweep_descriptor())
+    gpu.filter = True
+    assert gpu._filter_enabled(gpu.sweep_descriptor())
+
+
+def test_adaptive_refinement_as_written_vs_oracle(sl):
+    """refinement_mode="reference": the adaptive branch exactly as upstream evaluates it
+    (lyapunov.py:457-481, 540-582), against the oracle's reference mode."""
+    old = (sl.config.gp_batch_size, O.config.gp_batch_size)
+    try:
+        sl.config.gp_batch_size = O.config.gp_batch_size = 64
+        for tau_scale, kwargs in ((1 / 30., dict(max_refinement=4, safety_factor=2.0)),
+                                  (1 / 60., dict(max_refinement=12, safety_factor=4.0))):
+            par = W.make_pendulum(num_points=[26, 21], M=90, tau_scale=tau_scale)
+            pair = []
+            for ns, kind in ((sl, "product"), (O, "oracle")):
+                grid, dyn = W._build(ns, par, kind)
+                policy = ns.Saturation(ns.LinearSystem(-par["K"]), -1., 1.)
+                pair.append(ns.Lyapunov(grid, ns.QuadraticFunction(par["P"]), dyn, par["L_dyn"],
+                                        ns.AbsFunction(ns.LinearSystem((2 * par["P"],))),
+                                        par["tau"], policy, initial_set=par["initial"],
+                                        adaptive=True))
+            gpu, cpu = pair
+            gpu.refinement_mode = "reference"
+            gpu.update_safe_set(**kwargs)
+            cpu.update_safe_set(refinement_mode="reference", **kwargs)
+            assert_array_equal(gpu.safe_set, cpu.safe_set)
+            assert_array_equal(gpu._refinement, cpu._refinement)
+            assert gpu.feed_dict[gpu.c_max] == cpu.c_max
+    finally:
+        sl.config.gp_batch_size, O.config.gp_batch_size = old
 
 
 def test_smallest_boundary_value(sl):
