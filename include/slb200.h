@@ -264,6 +264,10 @@ void        slb_note_graph_replay(int64_t kernels);
  * %globaltimer (ns) at tile start / end, cycles spent waiting at block barriers, 0;
  * pass NULL to switch it off (default) */
 int         slb_debug_phase_timing(void* buffer_dev);
+/* diagnostics / tuning: the refine pass of slb_lyapunov_sweep_filtered uses 16-point tiles for
+ * lists of up to `upto16` points, 32-point tiles up to `upto32`, 64-point tiles beyond
+ * (defaults 16 * 148 and 32 * 148: one wave of CTAs on a B200) */
+int         slb_debug_refine_split(int64_t upto16, int64_t upto32);
 
 /* ---- GP factor packing (after GPRCached.update_cache, functions.py:395-415) ------------ */
 /* doubles needed for the packed L^-1 of an M-point GP */

@@ -1,7 +1,7 @@
 """Build libslb200.so in-tree with nvcc for sm_100a (no JIT cache, the .so travels with the repo).
 
 Every translation unit is compiled to an object file concurrently (the GP tile kernel is one unit
-per input dimension, ``gp_tile_inst.cu`` with ``-DSLB_TILE_DIN=k``), then linked; only units whose
+per input dimension and tile size, ``gp_tile_inst.cu`` with ``-DSLB_TILE_DIN=k -DSLB_TP=t``), then linked; only units whose
 sources changed are recompiled.
 """
 
@@ -19,8 +19,8 @@ OUTPUT = os.path.join(HERE, "libslb200.so")
 HEADER = os.path.join(HERE, "..", "include", "slb200.h")
 
 # (object name, source, extra flags, headers it depends on besides common.cuh / slb200.h)
-UNITS = [("gp_tile_%d.o" % d, "gp_tile_inst.cu", ["-DSLB_TILE_DIN=%d" % d], ["gp_tile.cuh", "gp_args.h"])
-         for d in range(1, 7)]
+UNITS = [("gp_tile_%d_%d.o" % (d, tp), "gp_tile_inst.cu", ["-DSLB_TILE_DIN=%d" % d, "-DSLB_TP=%d" % tp],
+          ["gp_tile.cuh", "gp_args.h"]) for d in range(1, 7) for tp in (64, 32, 16)]
 UNITS += [("gp_sweep.o", "gp_sweep.cu", [], ["gp_args.h"]),
           ("filter.o", "filter.cu", [], ["gp_mean.cuh"]),
           ("light.o", "light.cu", [], ["gp_mean.cuh"])]

@@ -126,6 +126,7 @@ SIGNATURES = {
     "slb_launch_count": (C.c_int64, []),
     "slb_note_graph_replay": (None, [_i64]),
     "slb_debug_phase_timing": (C.c_int, [_vp]),
+    "slb_debug_refine_split": (C.c_int, [_i64, _i64]),
     "slb_packed_len": (C.c_int64, [_i32]),
     "slb_pack_factor": (C.c_int, [_vp, _dp, _i32, _dp]),
     "slb_gp_predict": (C.c_int, [_vp, C.POINTER(SlbGpStack), _dp, _i64, _dp, _dp, _i32]),

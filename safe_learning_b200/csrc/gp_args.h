@@ -19,6 +19,7 @@ struct slb_gp_args {
     double* err;
     const int64_t* index_list;           // refine mode: the tile's points are index_list[rel]
     const unsigned long long* count;     // refine mode: number of list entries (read on the device)
+    int64_t count_min, count_max;        // refine mode: this launch works iff count_min < *count <= count_max
     long long* timing;      // diagnostics: [tile][warp][8]: cycles in {generate, contract, epilogue, total}, globaltimer ns {start, end}, cycles waiting at barriers, 0
 };
 

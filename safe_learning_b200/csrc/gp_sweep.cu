@@ -8,7 +8,9 @@
 #include "gp_args.h"
 
 #define SLB_DECLARE_TILE(d) \
-    int slb_gp_tile_launch_##d(cudaStream_t, const slb_sweep&, const slb_gp_args&, bool, bool);
+    int slb_gp_tile_launch_##d##_64(cudaStream_t, const slb_sweep&, const slb_gp_args&, bool, bool); \
+    int slb_gp_tile_launch_##d##_32(cudaStream_t, const slb_sweep&, const slb_gp_args&, bool, bool); \
+    int slb_gp_tile_launch_##d##_16(cudaStream_t, const slb_sweep&, const slb_gp_args&, bool, bool);
 SLB_DECLARE_TILE(1) SLB_DECLARE_TILE(2) SLB_DECLARE_TILE(3)
 SLB_DECLARE_TILE(4) SLB_DECLARE_TILE(5) SLB_DECLARE_TILE(6)
 #undef SLB_DECLARE_TILE
@@ -34,19 +36,22 @@ __global__ void pack_factor_kernel(const double* __restrict__ Linv, int M, int n
 }
 
 
-int dispatch_gp_tile(cudaStream_t st, const slb_sweep& cfg, const slb_gp_args& a) {
+// tp: points per CTA (64 for sweeps and point lists; 32 / 16 only in the refine pass)
+int dispatch_gp_tile(cudaStream_t st, const slb_sweep& cfg, const slb_gp_args& a, int tp = 64) {
     if (a.n <= 0) return 0;
-    SLB_CHECK(a.n <= (int64_t)0x7fffffff * SLB_TILE_POINTS, "too many points for one launch");
+    SLB_CHECK(a.n <= (int64_t)0x7fffffff * tp, "too many points for one launch");
     const bool timing = a.timing != nullptr;
     bool kexpr = false;
     for (int f = 0; f < cfg.gp.num_factors; ++f) kexpr |= cfg.gp.factors[f].kernel.num_prims > 0;
+#define SLB_TILE_CASE(d)                                                                   \
+    case d:                                                                                \
+        return tp == 64 ? slb_gp_tile_launch_##d##_64(st, cfg, a, kexpr, timing)           \
+             : tp == 32 ? slb_gp_tile_launch_##d##_32(st, cfg, a, kexpr, timing)           \
+                        : slb_gp_tile_launch_##d##_16(st, cfg, a, kexpr, timing);
     switch (cfg.gp.input_dim) {
-    case 1: return slb_gp_tile_launch_1(st, cfg, a, kexpr, timing);
-    case 2: return slb_gp_tile_launch_2(st, cfg, a, kexpr, timing);
-    case 3: return slb_gp_tile_launch_3(st, cfg, a, kexpr, timing);
-    case 4: return slb_gp_tile_launch_4(st, cfg, a, kexpr, timing);
-    case 5: return slb_gp_tile_launch_5(st, cfg, a, kexpr, timing);
-    case 6: return slb_gp_tile_launch_6(st, cfg, a, kexpr, timing);
+        SLB_TILE_CASE(1) SLB_TILE_CASE(2) SLB_TILE_CASE(3)
+        SLB_TILE_CASE(4) SLB_TILE_CASE(5) SLB_TILE_CASE(6)
+#undef SLB_TILE_CASE
     default:
         slb_set_error("GP input_dim %d not compiled (1..6)", cfg.gp.input_dim);
         return 1;
@@ -63,20 +68,44 @@ int slb_launch_det_sweep(cudaStream_t st, const slb_sweep& cfg, const double* st
 static long long* g_timing_buffer = nullptr;
 
 // The full posterior for the points the decision filter (filter.cu) could not decide: `list`
-// holds their indices relative to idx_begin, `count` (device) how many there are.  The grid covers
-// the worst case (every point undecided); CTAs beyond the list leave at once.
+// holds their indices relative to idx_begin, `count` (device) how many there are.  The list is
+// usually a small fraction of the grid -- too short to fill the 148 SMs with 64-point tiles, and a
+// tile's duration does not shrink with the list -- so the pass is launched once per tile size
+// (16, 32, 64 points per CTA) and only the launch whose range holds the list length does work;
+// the CTAs of the others (and those beyond the list) leave at once.  Measured tile times at
+// M = 500, two factors: see DESIGN.md section 3.5.
+static int64_t g_refine_split[2] = {16 * 148, 32 * 148};
+
 int slb_launch_refine(cudaStream_t st, const slb_sweep& cfg, int64_t n_max, int64_t idx_begin,
                       const int64_t* list, const unsigned long long* count, uint8_t* negative,
                       double* values) {
     slb_gp_args a;
     memset(&a, 0, sizeof(a));
-    a.n = n_max; a.idx_begin = idx_begin; a.mode = MODE_SWEEP_GRID;
+    a.idx_begin = idx_begin; a.mode = MODE_SWEEP_GRID;
     a.negative = negative; a.values = values;
     a.index_list = list; a.count = count;
-    return dispatch_gp_tile(st, cfg, a);
+    const int tps[3] = {16, 32, 64};
+    const int64_t lo[3] = {0, g_refine_split[0], g_refine_split[1]};
+    const int64_t hi[3] = {g_refine_split[0], g_refine_split[1], INT64_MAX};
+    for (int v = 0; v < 3; ++v) {
+        if (lo[v] >= hi[v] || lo[v] >= n_max) continue;
+        a.count_min = lo[v]; a.count_max = hi[v];
+        a.n = n_max < hi[v] ? n_max : hi[v];        // the grid never needs to cover more
+        if (v == 2) a.n = n_max;
+        const int rc = dispatch_gp_tile(st, cfg, a, tps[v]);
+        if (rc) return rc;
+    }
+    return 0;
 }
 
 extern "C" {
+
+/* diagnostics: list lengths up to which the refine pass uses 16- and 32-point tiles */
+int slb_debug_refine_split(int64_t upto16, int64_t upto32) {
+    g_refine_split[0] = upto16 < 0 ? 0 : upto16;
+    g_refine_split[1] = upto32 < g_refine_split[0] ? g_refine_split[0] : upto32;
+    return 0;
+}
 
 int slb_debug_phase_timing(void* buffer_dev) {
     g_timing_buffer = static_cast<long long*>(buffer_dev);

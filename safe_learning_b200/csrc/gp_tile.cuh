@@ -40,7 +40,13 @@
 
 namespace {
 
-constexpr int TP = SLB_TILE_POINTS;   // points per CTA
+#ifndef SLB_TP
+#define SLB_TP SLB_TILE_POINTS
+#endif
+constexpr int TP = SLB_TP;            // points per CTA: 64 for sweeps; 32 / 16 for the refine pass of
+                                      // the filtered sweep, whose short point list would otherwise
+                                      // fill only a fraction of the SMs (one translation unit each)
+static_assert(TP == 16 || TP == 32 || TP == 64, "TP must be 16, 32 or 64");
 constexpr int PANEL = 256;            // rows per i-panel, columns per j-panel
 // K-row tile layout in shared memory: k-steps are handled in PAIRS (8 rows of K).  Row j of a
 // panel lives at pair m = j / 8, half h = (j / 4) % 2, fragment row r = j % 4; element (j, p) is
@@ -100,7 +106,7 @@ SLB_DEV void mma_run(double (&acc)[RQ][NB][2], const double2* const (&ap)[RQ], i
 #define SLB_BGROUP 4
 #endif
     constexpr int RING = SLB_RING;
-    constexpr int BG = SLB_BGROUP;       // column blocks whose B fragments are loaded together
+    constexpr int BG = SLB_BGROUP < NB ? SLB_BGROUP : NB;   // column blocks whose B fragments are loaded together
     double2 ar[RING][RQ];
     const int m1m = m1 - 1;
 #pragma unroll
@@ -140,6 +146,55 @@ SLB_DEV void mma_run(double (&acc)[RQ][NB][2], const double2* const (&ap)[RQ], i
     }
 }
 
+// Sum the 2 NBT per-thread values v[2 nb + e] (column 8 nb + 2 (T%4) + e of the warp tile) over the 8
+// lanes that share T%4 (lane bits 4, 3, 2) and add them to red_q[column * NRED].  Reduce-scatter:
+// every step halves the values a lane still carries (send one half, keep and add the other) --
+// NBT = 8: 8+4+2 shuffles instead of 3 per value, every lane ends with two finished columns;
+// NBT = 4: one column per lane; NBT = 2: the last step is a plain exchange (half the lanes write).
+template <int NBT>
+SLB_DEV void row_lane_reduce(const double (&v)[2 * NBT], int lane, double* red_q) {
+    constexpr int NV = 2 * NBT;
+    const bool g2 = (lane & 16) != 0, g1 = (lane & 8) != 0, g0 = (lane & 4) != 0;
+    double w8[NV / 2], w4[NV / 4];
+#pragma unroll
+    for (int i = 0; i < NV / 2; ++i) {
+        const double send = g2 ? v[i] : v[i + NV / 2];
+        const double keep = g2 ? v[i + NV / 2] : v[i];
+        w8[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+#pragma unroll
+    for (int i = 0; i < NV / 4; ++i) {
+        const double send = g1 ? w8[i] : w8[i + NV / 4];
+        const double keep = g1 ? w8[i + NV / 4] : w8[i];
+        w4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+    if constexpr (NBT == 8) {
+        double w2[2];
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const double send = g0 ? w4[i] : w4[i + 2];
+            const double keep = g0 ? w4[i + 2] : w4[i];
+            w2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+        }
+        // value index 2g + e  <->  nb = g = lane / 4, column 8g + 2(T%4) + e
+        double* slot = red_q + (8 * (lane >> 2) + 2 * (lane & 3)) * NRED;
+        slot[0] += w2[0];
+        slot[NRED] += w2[1];
+    } else if constexpr (NBT == 4) {
+        const double send = g0 ? w4[0] : w4[1];
+        const double keep = g0 ? w4[1] : w4[0];
+        const double w1 = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+        // value index g = lane / 4  <->  nb = g / 2, e = g % 2
+        const int g = lane >> 2;
+        red_q[(8 * (g >> 1) + 2 * (lane & 3) + (g & 1)) * NRED] += w1;
+    } else {
+        static_assert(NBT == 2, "written for 8, 4 or 2 column blocks");
+        const double w1 = w4[0] + __shfl_xor_sync(0xffffffffu, w4[0], 4);
+        // value index 2 g2 + g1  <->  nb = g2, e = g1; the g0 = 1 lanes hold duplicates
+        if (!g0) red_q[(8 * (g2 ? 1 : 0) + 2 * (lane & 3) + (g1 ? 1 : 0)) * NRED] += w1;
+    }
+}
+
 // KEXPR: at least one factor carries a covariance expression (slb_kernel) instead of the plain
 // RBF; the RBF-only instantiation keeps the lean generation loop.
 template <int DIN, bool TIMING, bool KEXPR>
@@ -166,7 +221,8 @@ gp_tile_kernel(const __grid_constant__ slb_sweep cfg, const slb_gp_args a) {
     int64_t npts = a.n;
     if (a.count != nullptr) {
         npts = (int64_t)*a.count;
-        if (tile0 >= npts) return;
+        // one launch per tile size; only the one whose range holds the list length does work
+        if (tile0 >= npts || npts <= a.count_min || npts > a.count_max) return;
     }
     const int D = cfg.gp.num_outputs;
     long long t_gen = 0, t_mma = 0, t_epi = 0, t_mark = 0, t_sync = 0, t_s0 = 0;
@@ -405,9 +461,9 @@ gp_tile_kernel(const __grid_constant__ slb_sweep cfg, const slb_gp_args a) {
                     for (int q = 0; q < RQ; ++q)
                         if (bq[q] >= pbeg) al[q] = __ldg(alpha + 8 * bq[q] + (lane >> 2));
                 }
-                // per-thread sums over this warp's row blocks: 16 values, column 8nb + 2(T%4) + e
-                static_assert(NB == 8, "butterfly below reduces 16 values over the 8 row lanes");
-                double v[16];
+                // per-thread sums over this warp's row blocks: 2 NB values, column 8nb + 2(T%4) + e
+                constexpr int NV = 2 * NB;
+                double v[NV];
 #pragma unroll
                 for (int nb = 0; nb < NB; ++nb) {
 #pragma unroll
@@ -421,32 +477,7 @@ gp_tile_kernel(const __grid_constant__ slb_sweep cfg, const slb_gp_args a) {
                         v[nb * 2 + e] = t;
                     }
                 }
-                // reduce-scatter over the 8 lanes that share T%4 (lane bits 4,3,2): 8+4+2
-                // shuffles instead of 3 per value; every lane ends with two finished columns
-                const bool g2 = (lane & 16) != 0, g1 = (lane & 8) != 0, g0 = (lane & 4) != 0;
-                double w8[8], w4[4], w2[2];
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const double send = g2 ? v[i] : v[i + 8];
-                    const double keep = g2 ? v[i + 8] : v[i];
-                    w8[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-                }
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const double send = g1 ? w8[i] : w8[i + 4];
-                    const double keep = g1 ? w8[i + 4] : w8[i];
-                    w4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-                }
-#pragma unroll
-                for (int i = 0; i < 2; ++i) {
-                    const double send = g0 ? w4[i] : w4[i + 2];
-                    const double keep = g0 ? w4[i + 2] : w4[i];
-                    w2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-                }
-                // value index 2g + e  <->  nb = g = lane / 4, column 8g + 2(T%4) + e
-                double* slot = red + (warp * TP + 8 * (lane >> 2) + 2 * (lane & 3)) * NRED + qty;
-                slot[0] += w2[0];
-                slot[NRED] += w2[1];
+                row_lane_reduce<NB>(v, lane, red + (size_t)warp * TP * NRED + qty);
                 ++qty;
             }
             __syncwarp();

@@ -31,12 +31,30 @@ def test_c2_bench_shape_vs_oracle(sl):
     for _ in range(2):                       # the second call replays cached descriptors
         gpu.update_safe_set()
     cpu.update_safe_set()
-    assert par["initial"].sum() < cpu.safe_set.sum() < cpu.safe_set.size
+    # (with tau = sum(unit_maxes) / 2 the first point outside the initial set fails: the safe set
+    # stays the initial one -- the benchmark still decides every grid point)
+    assert par["initial"].sum() <= cpu.safe_set.sum() < cpu.safe_set.size
     assert_array_equal(gpu.safe_set, cpu.safe_set)
     assert gpu.feed_dict[gpu.c_max] == cpu.c_max
     assert gpu.last_sweep["n_safe"] == int(cpu.safe_set.sum())
     # the flags of the default (filtered) sweep equal the full-posterior flags everywhere
     assert_array_equal(gpu.compute_negative().cpu().numpy().astype(bool), det["negative"])
+
+
+def test_c2_bench_shape_growing_safe_set_vs_oracle(sl):
+    """Same shape with a finer discretisation constant (tau / 64): 59% of the points satisfy the
+    decrease condition, the safe set grows far beyond the initial one and the filter has to hand
+    ~6% of the grid to the full posterior."""
+    par = W.make_pendulum(num_points=[256, 256], M=500, shared_hypers=False, tau_scale=1 / 64.)
+    gpu, cpu = W.build_product(par), W.build_oracle(par)
+    det = _sweep_details(gpu)
+    _assert_negative_parity(gpu, cpu, det)
+    assert_array_equal(gpu.compute_negative().cpu().numpy().astype(bool), det["negative"])
+    gpu.update_safe_set()
+    cpu.update_safe_set()
+    assert 4 * par["initial"].sum() < cpu.safe_set.sum() < cpu.safe_set.size
+    assert_array_equal(gpu.safe_set, cpu.safe_set)
+    assert gpu.feed_dict[gpu.c_max] == cpu.c_max
 
 
 def test_c2_shared_factor_bench_shape_vs_oracle(sl):

@@ -275,6 +275,28 @@ def test_filtered_flags_equal_full_posterior(sl, M, tau_scale):
         assert_array_equal(full.astype(bool), cpu.full_grid_negative())
 
 
+@pytest.mark.parametrize("split,label", [((0, 0), "64-point tiles"), ((0, 1 << 40), "32-point tiles"),
+                                         ((1 << 40, 1 << 40), "16-point tiles")])
+def test_refine_pass_tile_sizes(sl, split, label):
+    """The refine pass of the filtered sweep picks its tile size from the list length; every tile
+    size (forced through slb_debug_refine_split) must reproduce the full posterior's flags, with
+    M across a panel boundary and a ragged list length."""
+    from safe_learning_b200 import _native as nat
+    lib = nat.load()
+    try:
+        lib.slb_debug_refine_split(*split)
+        for M, num in ((300, [67, 59]), (40, [45, 37])):
+            par = W.make_pendulum(num_points=num, M=M, tau_scale=1 / 64., seed=11)
+            gpu = W.build_product(par)
+            gpu.reset_filter_stats()
+            fast = gpu.compute_negative().cpu().numpy().copy()
+            assert gpu.filter_stats["refined"] > 20, label
+            gpu.filter = False
+            assert_array_equal(fast, gpu.compute_negative().cpu().numpy(), err_msg=label)
+    finally:
+        lib.slb_debug_refine_split(16 * 148, 32 * 148)
+
+
 def test_filter_is_not_used_below_the_variance_floor(sl):
     """With (almost) noise-free data the reference's negative-variance -> NaN -> unsafe corner is
     reachable; "auto" then keeps the full posterior."""
