@@ -28,16 +28,19 @@
 extern "C" {
 #endif
 
-#define SLB_ABI_VERSION 3   /* 2: slb_gp_factor.kernel (covariance expressions), GRADIENT / MAXABS flags
+#define SLB_ABI_VERSION 4   /* 2: slb_gp_factor.kernel (covariance expressions), GRADIENT / MAXABS flags
                                3: decision filter (slb_gp_factor.Whead, slb_lyapunov_sweep_filtered),
                                   state-dependent lipschitz_dynamics, peer-memory key exchange
-                                  (slb_exchange), fixed-action Bellman tables                    */
+                                  (slb_exchange), fixed-action Bellman tables
+                               4: filter tables staged by TMA bulk copies (slb_gp_factor.Xf / Xhead /
+                                  head_rows / hmax, slb_gp_output.gamma_f / gamma_l1): pivoted head
+                                  subset, computed error bound of the filter's mean               */
 #define SLB_MAX_DIM 6   /* state dimension d                         */
 #define SLB_MAX_IN  8   /* GP input dimension d_in = d + m           */
 #define SLB_MAX_OUT 6   /* stacked one-output GPs (FunctionStack)    */
 #define SLB_MAX_ACT 2   /* action dimension m                        */
 #define SLB_TILE_POINTS 64  /* grid points per CTA tile of the GP kernels */
-#define SLB_HEAD_RANK 64    /* leading rows of L^-1 used by the decision filter's variance bound */
+#define SLB_HEAD_RANK 64    /* size of the training subset behind the decision filter's variance bound */
 #define SLB_MAX_RANKS 16    /* ranks of one peer-memory key exchange (one NVSwitch domain)       */
 
 /* ---- GridWorld (functions.py:579-817) ------------------------------------------- */
@@ -153,12 +156,20 @@ typedef struct slb_gp_factor {
     double scale;               /* GPRCached _scale                functions.py:392     */
     double kss;                 /* (scale**2) * variance           functions.py:450     */
     slb_kernel kernel;          /* general covariance expression (num_prims > 0)        */
+    /* ---- tables of the decision filter (slb_lyapunov_sweep_filtered); may be NULL / 0 if that
+       call is not used.  The posterior variance given ANY subset S of the training set is an upper
+       bound of the full posterior variance; the host picks up to SLB_HEAD_RANK points in pivoted-
+       Cholesky (greedy max-variance) order and factors them on their own:                        */
     const double* Whead;        /* device [SLB_HEAD_RANK, SLB_HEAD_RANK], COLUMN-major, zero padded:
-                                   Whead[j * SLB_HEAD_RANK + i] = L^-1[i, j] for i, j < min(M,
-                                   SLB_HEAD_RANK).  a_i = sum_j L^-1[i,j] k_j for these rows gives
-                                   the posterior variance of the first rows of the training set
-                                   alone -- an upper bound of the full posterior variance -- used by
-                                   slb_lyapunov_sweep_filtered; may be NULL if that call is not used */
+                                   Whead[j * SLB_HEAD_RANK + i] = L_S^-1[i, j], L_S = chol(scale^2
+                                   (K(X_S) + noise I))                                   */
+    const double* Xhead;        /* device [head_rows, d_in]: the subset's inputs, scaled like Xs */
+    int32_t head_rows;          /* |S| = min(M, SLB_HEAD_RANK)                           */
+    int32_t _pad2;
+    const double* Xf;           /* device [4 ceil(M/4), w], zero padded, 16-byte aligned (TMA bulk
+                                   copies): kernel.num_prims == 0: w = d_in + 1, row j =
+                                   (Xs[j, :], -|Xs[j, :]|^2 / 2); otherwise w = d_in, the raw X  */
+    double hmax;                /* max_j |Xs[j, :]|^2 / 2 (rounding bound of the expanded distance) */
 } slb_gp_factor;
 
 typedef struct slb_gp_output {
@@ -170,6 +181,11 @@ typedef struct slb_gp_output {
                                                                     functions.py:405-409 */
     const double* gamma;        /* device [M]: L^-T alpha (mean-only Bellman path)      */
     const double* prior_mean;   /* device [d_in] linear prior-mean row, or NULL         */
+    const double* gamma_f;      /* device [4 ceil(M/4)], zero padded, 16-byte aligned: the filter's
+                                   mean weights, scale^2 gamma (times the RBF variance when
+                                   kernel.num_prims == 0, whose kernel values are then <= 1)   */
+    double gamma_l1;            /* >= sum_i (|L^-1|^T |alpha|)_i in the units of gamma_f: bounds the
+                                   rounding error of every way of summing the mean (filter)    */
 } slb_gp_output;
 
 typedef struct slb_gp_stack {
@@ -275,6 +291,13 @@ int64_t slb_packed_len(int32_t M);
 /* Linv_dev [M,M] row-major lower-triangular -> Wpack_dev (slb_packed_len(M) doubles) */
 int slb_pack_factor(void* stream, const double* Linv_dev, int32_t M, double* Wpack_dev);
 
+/* head subset of the decision filter: the first r <= min(M, SLB_HEAD_RANK) pivots of the pivoted
+ * Cholesky factorisation of the symmetric positive semi-definite kernel_dev [M, M] (greedy: the
+ * training point with the largest variance given those already chosen; ties: lowest index)
+ * -> picks_dev [r] (int64).  scratch_dev: M * (r + 1) doubles. */
+int slb_pivoted_subset(void* stream, const double* kernel_dev, int32_t M, int32_t r,
+                       int64_t* picks_dev, double* scratch_dev);
+
 /* ---- GP posterior on an explicit point list: GaussianProcess.__call__ / FunctionStack
  *      (functions.py:278-291, 417-458, 507-515).  points_dev [n, d_in] (already [x,u]
  *      concatenated, utilities.py:143); mean_dev, err_dev [n, D];
@@ -291,12 +314,14 @@ int slb_lyapunov_sweep(void* stream, const slb_sweep* cfg, int64_t idx_begin, in
                        uint8_t* negative_dev, double* values_dev, double* decrease_dev,
                        double* threshold_dev, double* mean_dev, double* err_dev);
 /* The same decision flags (and V) with a certified filter in front of the O(M^2) posterior:
- * a thread-per-point kernel computes the exact GP mean (k . L^-T alpha), V(mu), L_V(mu) and an
- * UPPER bound of every output's standard deviation -- first the prior's, then the posterior given
- * only the first SLB_HEAD_RANK training rows (factor.Whead) -- and decides every point whose
- * comparison `decrease < threshold` has the same outcome for all sigma in [0, bound] (with a
- * 1e-6 relative guard band); the remaining points are compacted and go through the full fp64
- * posterior (the kernel of slb_lyapunov_sweep).  Flags are identical to slb_lyapunov_sweep's.
+ * a thread-per-point kernel computes the GP mean (k . L^-T alpha, with a computed error bound),
+ * V(mu), L_V(mu) and an UPPER bound of every output's standard deviation -- first the prior's,
+ * then (one warp per remaining point) the posterior given only a head subset of at most
+ * SLB_HEAD_RANK training points (factor.Whead / Xhead) -- and decides every point whose
+ * comparison `decrease < threshold` has the same outcome for all sigma in [0, bound] (guard band:
+ * 1e-6 relative + the mean's error bound); the remaining points are compacted and go through the
+ * full fp64 posterior (the kernel of slb_lyapunov_sweep).  Flags are identical to
+ * slb_lyapunov_sweep's.
  * workspace_dev: >= slb_filter_workspace(n) bytes.  stats_dev: NULL or 4 int64 (device):
  * {decided by mean + prior bound, decided by the head-rank bound, refined by the full posterior,
  * points} accumulated over calls (the caller zeroes it). */

@@ -25,7 +25,7 @@ FLAG_SATURATE, FLAG_ABS, FLAG_NORM1, FLAG_PROJECT, FLAG_SCALE, FLAG_GRADIENT, FL
     1, 2, 4, 8, 16, 32, 64
 K_RBF, K_MATERN12, K_MATERN32, K_MATERN52, K_LINEAR, K_CONSTANT, K_WHITE = range(7)
 SLB_MAX_KPRIM = 6
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 UINT64_MAX = (1 << 64) - 1
 INT64_MAX = (1 << 63) - 1
@@ -64,12 +64,14 @@ class SlbGpFactor(C.Structure):
     _fields_ = [("M", C.c_int32), ("nrb", C.c_int32), ("Xs", C.c_void_p), ("Wpack", C.c_void_p),
                 ("lengthscales", C.c_double * SLB_MAX_IN), ("variance", C.c_double),
                 ("scale", C.c_double), ("kss", C.c_double), ("kernel", SlbKernel),
-                ("Whead", C.c_void_p)]
+                ("Whead", C.c_void_p), ("Xhead", C.c_void_p), ("head_rows", C.c_int32),
+                ("_pad2", C.c_int32), ("Xf", C.c_void_p), ("hmax", C.c_double)]
 
 
 class SlbGpOutput(C.Structure):
     _fields_ = [("factor", C.c_int32), ("_pad", C.c_int32), ("beta", C.c_double),
-                ("alpha", C.c_void_p), ("gamma", C.c_void_p), ("prior_mean", C.c_void_p)]
+                ("alpha", C.c_void_p), ("gamma", C.c_void_p), ("prior_mean", C.c_void_p),
+                ("gamma_f", C.c_void_p), ("gamma_l1", C.c_double)]
 
 
 class SlbGpStack(C.Structure):
@@ -129,6 +131,7 @@ SIGNATURES = {
     "slb_debug_refine_split": (C.c_int, [_i64, _i64]),
     "slb_packed_len": (C.c_int64, [_i32]),
     "slb_pack_factor": (C.c_int, [_vp, _dp, _i32, _dp]),
+    "slb_pivoted_subset": (C.c_int, [_vp, _dp, _i32, _i32, _vp, _dp]),
     "slb_gp_predict": (C.c_int, [_vp, C.POINTER(SlbGpStack), _dp, _i64, _dp, _dp, _i32]),
     "slb_lyapunov_sweep": (C.c_int, [_vp, C.POINTER(SlbSweep), _i64, _i64, _dp, _dp, _dp, _dp,
                                      _dp, _dp]),

@@ -4,39 +4,50 @@
 //     negative = V(mu) - V(x) + sum_j L_V(mu)_j beta_j sigma_j  <  -L_V(x) (1 + L_f) tau
 // and all of its cost is sigma_j = sqrt(k** - |L^-1 k|^2): M^2 flops per point and Cholesky factor,
 // against M for the mean mu = k . (L^-T alpha).  But the comparison is monotone in every sigma_j, and
-//     0 <= sigma_j <= sigma_j given ANY subset of the training set <= prior sigma_j,
-// where the posterior given the first R rows of the training set is just the first R rows of the
-// same triangular solve (L is lower triangular): sum_{i<R} a_i^2 <= sum_{i<M} a_i^2.  So:
-//   stage 1  (filter_mean_kernel) exact mean (all M kernel values, one exp each -- the cost of a
-//            Bellman sweep), V(mu), L_V(mu); decide every point whose outcome is the same for
-//            sigma = 0 and the prior sigma; the rest is compacted into list A with its terms;
-//   stage 2  (filter_head_kernel, over list A) the head rows a_i = sum_j L^-1[i,j] k_j,
-//            i < R = SLB_HEAD_RANK, thread per point in registers; decide with the tighter bound;
+//     0 <= sigma_j <= sigma_j given ANY subset of the training set <= prior sigma_j.  So:
+//   stage 1  (filter_mean_kernel, thread per point) the posterior mean from all M kernel values
+//            (one exp each -- the cost of a Bellman sweep), V(mu), L_V(mu); decide every point
+//            whose outcome is the same for sigma = 0 and the prior sigma; the rest is compacted
+//            into list A with its terms;
+//   stage 2  (filter_head_kernel, warp per point of list A) the posterior variance given a HEAD
+//            SUBSET of at most SLB_HEAD_RANK training points (chosen by the host in pivoted-
+//            Cholesky order, its own small factor: slb_gp_factor.Whead / Xhead); decide with
+//            the tighter bound;
 //   rest     compacted into list B for the full fp64 posterior (gp_tile_kernel, gp_sweep.cu).
-// A point is only decided when the outcome holds with a guard band of 1e-6 relative to the
-// magnitudes involved (five orders above the rounding differences between two fp64 evaluation
-// orders of the posterior; the GP tolerance of the parity contract is 1e-5), anything with a NaN
-// goes to the full path, so the flags equal those of slb_lyapunov_sweep bit for bit.
-// On the C2 workload (256 x 256, M = 500) 90.7% of the points are decided by the mean alone, 8%
-// by the head-rank bound and 1.3% are refined (tools/filter_probe.py reproduces this on the CPU).
+// Certification.  A point is only decided when the outcome holds with a guard band that covers
+// (a) 1e-6 relative to the magnitudes involved (five orders above the rounding differences between
+// two fp64 evaluation orders of the posterior; the GP tolerance of the parity contract is 1e-5) and
+// (b) a computed bound of the error of stage 1's mean: it is summed as k . gamma with a kernel
+// value accurate to EPS_K relative (expanded squared distance, table-driven exp with a cubic
+// remainder -- tools/exp_neg_fast_check.c), so |mean error| <= (EPS_K + M 2^-52) sum_j |k_j
+// gamma_j| <= (...) |gamma|_1 (slb_gp_output.gamma_l1, k <= 1 after folding the variances into
+// gamma), entering the comparison through L_V(mu).  Anything non-finite goes to the full path, so
+// the flags equal those of slb_lyapunov_sweep bit for bit.
+// The training inputs / gamma slices are block-wide shared-memory landings: they are brought in
+// by TMA bulk copies (cp.async.bulk + mbarrier, bulk_copy.cuh), double buffered, issued by one
+// thread while the block works on the previous slice.
 #define SLB_EVAL_NOINLINE 1
 #include "common.cuh"
-#include "gp_mean.cuh"
+
+#include <atomic>
+
+#include "bulk_copy.cuh"
+#include "exp2_tab512.cuh"
 
 namespace {
 
-constexpr int FT = 64;                 // threads per CTA = points per CTA (1024 CTAs at 256 x 256,
-                                       // 8 resident per SM: single wave, 98.8% balanced)
+constexpr int FT = 64;                 // stage 1: threads per CTA = points per CTA (1024 CTAs at
+                                       // 256 x 256, 7 resident per SM: single wave, 98.8% balanced)
 constexpr int HR = SLB_HEAD_RANK;
-constexpr int HB = 16;                 // column block of the head-row update (static row ranges)
-constexpr int HH = HR / 2;             // rows per pass of the head solve (accumulators in registers)
+constexpr int HT = 128;                // stage 2: threads per CTA (4 warps, one list entry each)
+constexpr int HEAD_CTAS = 148 * 4;
 constexpr int64_t CHUNK = 1 << 22;     // points per pass of the three stages (bounds the workspace)
+constexpr double EPS_K = 1.0e-13;      // certified relative error of exp_neg_fast incl. its argument
 
 // terms of one undecided point, carried from stage 1 to stage 2
-struct filter_side { double dec0, thr, guard, coef[SLB_MAX_OUT]; };
+struct filter_side { double dec0, thr, guard, coef[SLB_MAX_OUT], z[SLB_MAX_IN]; };
 
 struct filter_args {
-    const double* points;              // explicit states [n, d] or nullptr (grid index range)
     int64_t n;
     int64_t idx_begin;
     uint8_t* negative;
@@ -46,6 +57,8 @@ struct filter_args {
     int64_t* list_b;                   // undecided after stage 2 -> full posterior
     unsigned long long* counts;        // [0] entries of list_a, [1] entries of list_b
     unsigned long long* stats;         // nullptr or [4], see slb200.h
+    int chunk_rows;                    // training rows per staged slice (multiple of 8)
+    int max_outputs_per_factor;
 };
 
 // outcome for err_j = beta_j sigma_j with sigma_j in [0, shi_j]:  +1 decided negative (True),
@@ -81,23 +94,203 @@ SLB_DEV void count_stat(bool hit, unsigned long long* slot) {
     if (ballot != 0 && (threadIdx.x & 31) == 0) atomicAdd(slot, (unsigned long long)__popc(ballot));
 }
 
-SLB_DEV void load_state(const slb_sweep& cfg, const filter_args& a, int64_t rel, double* z) {
-    const int d = cfg.grid.ndim;
-    if (a.points != nullptr) {
-        for (int c = 0; c < d; ++c) z[c] = a.points[rel * d + c];
+// exp(x) for -700 < x <= 0 (+ rounding) to 3.3e-14 relative (tools/exp_neg_fast_check.c):
+// x = (512 q + i) ln2/512 + r, |r| <= ln2/1024;  exp(x) = 2^q T[i] (1 + r + r^2/2 + r^3/6).
+// 7 fp64 operations (exp_neg_tab: 11).  `far` is set for x <= -700 (incl. -inf): the caller drops
+// the term (the value is unspecified then).  NaN arguments are excluded by the caller.
+SLB_DEV double exp_neg_fast(double x, const double* __restrict__ tab, bool& far) {
+    const double MAGIC = 6755399441055744.0;                           // 1.5 * 2^52
+    const double t = fma(x, 738.6598609351493, MAGIC);                 // 512 / ln2
+    const int n = __double2loint(t);
+    const double nd = t - MAGIC;
+    const double r = fma(nd, -0.0013538030870311431, x);               // ln2 / 512
+    double q = fma(r, 1.0 / 6.0, 0.5);
+    q = q * r;
+    const double p = fma(q, r, r);                                     // e^r - 1
+    const double T = tab[n & 511];
+    const double v = fma(T, p, T);
+    far = (unsigned)__double2hiint(x) > 0xC085E000u;                   // x < -700.0
+    return __hiloint2double(__double2hiint(v) + ((n >> 9) << 20), __double2loint(v));
+}
+
+// ---- stage 1: mean, prior bound -----------------------------------------------------------------
+// Staged slices: per factor the rows [c0, c0 + rows) of Xf (plain RBF: [x / l, -|x / l|^2 / 2],
+// width DIN + 1; covariance expressions: the raw inputs, width DIN) and of gamma_f of every output on
+// the factor.  Buffer b of slice t = t & 1; its mbarrier completes when the bytes have landed.
+struct mean_pipe {
+    uint64_t* bar;                     // [2]
+    double* xbuf;                      // [2][C * (DIN + 1)]
+    double* gbuf;                      // [2][nomax * C]
+    int C, xstride, gstride;
+    int t;                             // slices consumed so far
+    int pf, pc0;                       // producer: factor and first row of the NEXT slice to issue
+};
+
+SLB_DEV int padded_rows(int M) { return (M + 3) & ~3; }
+
+SLB_DEV int first_factor_with_data(const slb_gp_stack& gp, int f) {
+    while (f < gp.num_factors && gp.factors[f].M == 0) ++f;
+    return f;
+}
+
+// thread 0: issue the producer's next slice into buffer `b` and advance
+template <int DIN>
+SLB_DEV void issue_slice(const slb_gp_stack& gp, mean_pipe& P, int b) {
+    if (P.pf >= gp.num_factors) return;
+    const slb_gp_factor& F = gp.factors[P.pf];
+    const int Mp = padded_rows(F.M);
+    const int rows = min(P.C, Mp - P.pc0);
+    const int W = F.kernel.num_prims > 0 ? DIN : DIN + 1;
+    int no = 0;
+    for (int o = 0; o < gp.num_outputs; ++o) no += gp.outputs[o].factor == P.pf;
+    const unsigned xbytes = (unsigned)(rows * W * sizeof(double));
+    const unsigned gbytes = (unsigned)(rows * sizeof(double));
+    slb_bulk::mbar_arrive_expect_tx(P.bar + b, xbytes + no * gbytes);
+    slb_bulk::copy_g2s(P.xbuf + b * P.xstride, F.Xf + (size_t)P.pc0 * W, xbytes, P.bar + b);
+    int q = 0;
+    for (int o = 0; o < gp.num_outputs; ++o) {
+        if (gp.outputs[o].factor != P.pf) continue;
+        slb_bulk::copy_g2s(P.gbuf + b * P.gstride + q * P.C, gp.outputs[o].gamma_f + P.pc0, gbytes,
+                           P.bar + b);
+        ++q;
+    }
+    P.pc0 += P.C;
+    if (P.pc0 >= Mp) { P.pf = first_factor_with_data(gp, P.pf + 1); P.pc0 = 0; }
+}
+
+template <int W>
+SLB_DEV void load_row(const double* __restrict__ p, double (&r)[W]) {
+    if constexpr (W % 2 == 0) {
+#pragma unroll
+        for (int c = 0; c < W; c += 2) {
+            const double2 v = *reinterpret_cast<const double2*>(p + c);
+            r[c] = v.x; r[c + 1] = v.y;
+        }
     } else {
-        grid_index_to_state(cfg.grid, a.idx_begin + rel, z);
+#pragma unroll
+        for (int c = 0; c < W; ++c) r[c] = p[c];
     }
 }
 
-// ---- stage 1: exact mean, prior bound ---------------------------------------------------------
+// one factor with NO outputs on it (compile-time, so the running dot products stay in registers)
+template <int DIN, int NO>
+SLB_DEV void mean_factor(const slb_gp_stack& gp, int f, const int* outs, const double* z, double* mu,
+                         double* mean_err, const double* tab512, const double* tab64, mean_pipe& P) {
+    const slb_gp_factor& F = gp.factors[f];
+    const bool general = F.kernel.num_prims > 0;
+    double zs[DIN];
+    double zz = 0.0;
+#pragma unroll
+    for (int c = 0; c < DIN; ++c) {
+        zs[c] = general ? z[c] : z[c] / F.lengthscales[c];
+        zz = fma(zs[c], zs[c], zz);
+    }
+    zz *= -0.5;
+    double dot[NO];
+#pragma unroll
+    for (int q = 0; q < NO; ++q) dot[q] = 0.0;
+    double kbound = general ? 0.0 : 1.0;       // max_i |k_i| (plain RBF: variances live in gamma_f)
+    const int Mp = padded_rows(F.M);
+    for (int c0 = 0; c0 < Mp; c0 += P.C) {
+        const int rows = min(P.C, Mp - c0);
+        const int b = P.t & 1;
+        if (threadIdx.x == 0) issue_slice<DIN>(gp, P, b ^ 1);         // next slice, other buffer
+        slb_bulk::mbar_wait(P.bar + b, (P.t >> 1) & 1);
+        const double* __restrict__ xb = P.xbuf + b * P.xstride;
+        const double* __restrict__ gb = P.gbuf + b * P.gstride;
+        if (!general) {
+            // k_j = exp(-|zs - xs_j|^2 / 2) = exp(h_j + zs . xs_j + zz), h_j = -|xs_j|^2 / 2 staged
+            // with the row; variance and scale^2 are folded into gamma_f.  4 independent chains.
+            constexpr int W = DIN + 1;
+            for (int j0 = 0; j0 < rows; j0 += 4) {
+                double arg[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    double row[W];
+                    load_row<W>(xb + (j0 + u) * W, row);
+                    double acc = row[DIN] + zz;
+#pragma unroll
+                    for (int c = 0; c < DIN; ++c) acc = fma(zs[c], row[c], acc);
+                    arg[u] = acc;
+                }
+                double g[NO][4];
+#pragma unroll
+                for (int q = 0; q < NO; ++q) load_row<4>(gb + q * P.C + j0, g[q]);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    bool far;
+                    const double k = exp_neg_fast(arg[u], tab512, far);
+#pragma unroll
+                    for (int q = 0; q < NO; ++q)
+                        if (!far) dot[q] = fma(k, g[q][u], dot[q]);
+                }
+            }
+        } else {
+            for (int j0 = 0; j0 < rows; j0 += 4) {
+                const double* xr[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) xr[u] = xb + (j0 + u) * DIN;
+                double kv[4];
+                kernel_expr_cross_n<DIN, 4>(F.kernel, zs, xr, tab64, kv);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    kbound = fmax(kbound, fabs(kv[u]));
+#pragma unroll
+                    for (int q = 0; q < NO; ++q) dot[q] = fma(kv[u], gb[q * P.C + j0 + u], dot[q]);
+                }
+            }
+        }
+        __syncthreads();                       // every thread is done with buffer b
+        ++P.t;
+    }
+#pragma unroll
+    for (int q = 0; q < NO; ++q) {
+        const slb_gp_output& G = gp.outputs[outs[q]];
+        double mx = 0.0;
+        if (G.prior_mean != nullptr) {
+            mx = f64mul(z[0], G.prior_mean[0]);
+#pragma unroll
+            for (int c = 1; c < DIN; ++c) mx = f64add(mx, f64mul(z[c], G.prior_mean[c]));
+            mx = f64mul(F.scale, mx);
+        }
+        mu[outs[q]] = f64add(dot[q], mx) / F.scale;
+        // |mean - exact| <= eps sum_i |k_i| (|L^-1|^T |alpha|)_i <= eps kbound gamma_l1: kernel
+        // values to EPS_K (+ the expanded distance's rounding), the M-term sums here, in gamma
+        // itself and in the a . alpha form of the full posterior each to (M + 2) 2^-53
+        const double eps = (general ? 4.5e-16 : EPS_K + 4.5e-16 * (-zz + F.hmax)) +
+                           7e-16 * (F.M + 8);
+        mean_err[outs[q]] = eps * kbound * G.gamma_l1 / F.scale;
+    }
+}
+
 template <int DIN>
-__global__ void __launch_bounds__(FT, 8)
+__global__ void __launch_bounds__(FT, 7)
 filter_mean_kernel(const __grid_constant__ slb_sweep cfg, const filter_args a) {
-    __shared__ double exptab[64];
-    __shared__ double stage[BCHUNK * (DIN + SLB_MAX_OUT)];
-    load_exp_table(exptab);
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);             // [2]
+    double* tab512 = reinterpret_cast<double*>(smem_raw + 16);
+    double* tab64 = tab512 + 512;
+    mean_pipe P;
+    P.bar = bar;
+    P.C = a.chunk_rows;
+    P.xstride = P.C * (DIN + 1);
+    P.gstride = P.C * a.max_outputs_per_factor;
+    P.xbuf = tab64 + 64;
+    P.gbuf = P.xbuf + 2 * P.xstride;
+    P.t = 0;
+    P.pf = first_factor_with_data(cfg.gp, 0);
+    P.pc0 = 0;
+    if (threadIdx.x == 0) {
+        slb_bulk::mbar_init(bar + 0, 1);
+        slb_bulk::mbar_init(bar + 1, 1);
+        slb_bulk::fence_barrier_init();
+        slb_bulk::fence_proxy_async();
+        issue_slice<DIN>(cfg.gp, P, 0);                                 // slice 0 -> buffer 0
+    }
+    for (int i = threadIdx.x; i < 512; i += FT) tab512[i] = c_exp2_tab512[i];
+    load_exp_table(tab64);
     __syncthreads();
+
     const int64_t rel0 = (int64_t)blockIdx.x * FT + threadIdx.x;
     const bool valid = rel0 < a.n;
     const int64_t rel = valid ? rel0 : a.n - 1;   // every thread stays for the block barriers
@@ -105,26 +298,45 @@ filter_mean_kernel(const __grid_constant__ slb_sweep cfg, const filter_args a) {
     const int D = cfg.gp.num_outputs;
 
     // ---- x, V(x), threshold(x), u = policy(x)           (lyapunov.py:436, 284-288)
-    double z[SLB_MAX_IN];
-    load_state(cfg, a, rel, z);
     filter_side t;
+    grid_index_to_state(cfg.grid, a.idx_begin + rel, t.z);
     double vx;
-    lyapunov_state_terms(cfg, z, a.points != nullptr ? -1 : a.idx_begin + rel, &vx, &t.thr);
+    lyapunov_state_terms(cfg, t.z, a.idx_begin + rel, &vx, &t.thr);
     {
         double u[SLB_MAX_OUT];
-        const int m = eval_fn(cfg.policy, z, u);
-        for (int c = 0; c < m; ++c) z[d + c] = u[c];
+        const int m = eval_fn(cfg.policy, t.z, u);
+        for (int c = 0; c < m; ++c) t.z[d + c] = u[c];
     }
+    // the expanded squared distance needs moderate magnitudes; NaN / huge inputs -> full path
+    bool sane = true;
+#pragma unroll
+    for (int c = 0; c < DIN; ++c) sane &= fabs(t.z[c]) < 1e100;
 
-    // ---- exact posterior mean of every output (functions.py:439-442 as k . L^-T alpha)
+    // ---- posterior mean of every output (functions.py:439-442 as k . L^-T alpha)
     double mu[SLB_MAX_OUT];
-    gp_mean_only<DIN>(cfg.gp, z, mu, exptab, stage);
+    double mean_err[SLB_MAX_OUT];
+    for (int f = 0; f < cfg.gp.num_factors; ++f) {
+        int outs[SLB_MAX_OUT];
+        int no = 0;
+        for (int o = 0; o < D; ++o)
+            if (cfg.gp.outputs[o].factor == f) outs[no++] = o;
+        switch (no) {
+        case 1: mean_factor<DIN, 1>(cfg.gp, f, outs, t.z, mu, mean_err, tab512, tab64, P); break;
+        case 2: mean_factor<DIN, 2>(cfg.gp, f, outs, t.z, mu, mean_err, tab512, tab64, P); break;
+        case 3: mean_factor<DIN, 3>(cfg.gp, f, outs, t.z, mu, mean_err, tab512, tab64, P); break;
+        case 4: mean_factor<DIN, 4>(cfg.gp, f, outs, t.z, mu, mean_err, tab512, tab64, P); break;
+        case 5: mean_factor<DIN, 5>(cfg.gp, f, outs, t.z, mu, mean_err, tab512, tab64, P); break;
+        case 6: mean_factor<DIN, 6>(cfg.gp, f, outs, t.z, mu, mean_err, tab512, tab64, P); break;
+        default: break;
+        }
+    }
 
     // ---- V(mu), L_V(mu) and the coefficient of every sigma_j          (lyapunov.py:344-352)
     double vm[1];
     eval_fn(cfg.lyapunov, mu, vm);
     t.dec0 = f64sub(vm[0], vx);
     double lvmu = 0.0;                      // sum_j |L_V(mu)_j mu_j|: scale of V's sensitivity to mu
+    double lverr = 0.0;                     // sum_j |L_V(mu)_j| mean_err_j
     {
         double lv[SLB_MAX_OUT];
         int nl = 1;
@@ -133,18 +345,18 @@ filter_mean_kernel(const __grid_constant__ slb_sweep cfg, const filter_args a) {
         for (int j = 0; j < SLB_MAX_OUT; ++j) {
             const double l = j < D ? (nl == 1 ? lv[0] : lv[j]) : 0.0;
             t.coef[j] = j < D ? l * cfg.gp.outputs[j].beta : 0.0;
-            if (j < D) lvmu += fabs(l * mu[j]);
+            if (j < D) { lvmu += fabs(l * mu[j]); lverr += fabs(l) * mean_err[j]; }
         }
     }
-    t.guard = 1e-6 * (fabs(vm[0]) + fabs(vx) + fabs(t.thr) + lvmu) + 1e-300;
+    t.guard = 1e-6 * (fabs(vm[0]) + fabs(vx) + fabs(t.thr) + lvmu) + 4.0 * lverr + 1e-300;
 
     // ---- sigma_j <= prior sigma_j     (functions.py:450 without data)
     double shi[SLB_MAX_OUT];
     for (int j = 0; j < D; ++j) {
         const slb_gp_factor& F = cfg.gp.factors[cfg.gp.outputs[j].factor];
-        shi[j] = sqrt(F.kernel.num_prims > 0 ? kernel_expr_diag<DIN>(F.kernel, z) : F.variance);
+        shi[j] = sqrt(F.kernel.num_prims > 0 ? kernel_expr_diag<DIN>(F.kernel, t.z) : F.variance);
     }
-    const int outcome = decide(t, shi, D);
+    const int outcome = sane ? decide(t, shi, D) : -1;
     const bool undecided = valid && outcome < 0;
     if (valid) {
         a.negative[rel] = outcome > 0 ? 1 : 0;
@@ -158,149 +370,109 @@ filter_mean_kernel(const __grid_constant__ slb_sweep cfg, const filter_args a) {
     }
 }
 
-// ---- stage 2: head rows of the triangular solve, thread per point -----------------------------
-// acc[i - ROW0] += W[i, j] k_j for rows ROW0 .. ROW0 + HH - 1 and the columns of block B, rows
-// below the block's first column only (W is lower triangular).  W is the zero-padded column-major
-// head block: column j holds rows contiguously, 2 doubles per LDG.128, same address in all lanes.
-template <int DIN, int ROW0, int B>
-SLB_DEV void head_cols(double (&acc)[HH], const slb_gp_factor& F, bool general, const double* zs,
-                       const double* xhead, int rows, double s2, const double* exptab) {
-    constexpr int I0 = (HB * B > ROW0) ? HB * B : ROW0;      // first row this block touches
-    const double* __restrict__ Wt = F.Whead;
-#pragma unroll 1
-    for (int jj = 0; jj < HB; jj += 4) {
-        const int j0 = HB * B + jj;
-        if (j0 >= rows) break;
-        double kv[4];
-        if (general) {
-            const double* xr[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) xr[u] = xhead + min(j0 + u, rows - 1) * DIN;
-            kernel_expr_cross_n<DIN, 4>(F.kernel, zs, xr, exptab, kv);
-        } else {
-            double t2[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const double* xr = xhead + min(j0 + u, rows - 1) * DIN;
-                double a2 = 0.0;
-#pragma unroll
-                for (int c = 0; c < DIN; ++c) { const double df = zs[c] - xr[c]; a2 = fma(df, df, a2); }
-                t2[u] = a2;
-            }
-#pragma unroll
-            for (int u = 0; u < 4; ++u) kv[u] = F.variance * exp_neg_tab(-0.5 * t2[u], exptab);
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const double k = j0 + u < rows ? s2 * kv[u] : 0.0;       // functions.py:438 (scale^2 K)
-            const double2* col = reinterpret_cast<const double2*>(Wt + (size_t)(j0 + u) * HR);
-#pragma unroll
-            for (int i = I0; i < ROW0 + HH; i += 2) {
-                const double2 w = __ldg(col + (i >> 1));
-                acc[i - ROW0] = fma(w.x, k, acc[i - ROW0]);
-                acc[i + 1 - ROW0] = fma(w.y, k, acc[i + 1 - ROW0]);
-            }
-        }
-    }
-}
-
-// upper bound of the latent variance of factor F at z from its first min(M, HR) training rows:
-// (scale^2 k** - sum_{i < R} a_i^2) / scale^2   (functions.py:450-451, 456 restricted to R rows).
-// Two passes of HH rows each keep the accumulators in registers at 8 CTAs per SM.
+// ---- stage 2: variance given the head subset, one warp per undecided point ------------------------
+// Lane l owns rows l and l + 32 of the head solve a = W k (W = L_S^-1 of the subset's own Cholesky
+// factor, column-major and zero padded: row index contiguous, so a column is two coalesced 256-byte
+// loads served by L1); the kernel values k_j of the HR subset points are computed two per lane and
+// exchanged through shared memory.
 template <int DIN>
-SLB_DEV double head_variance(const slb_gp_factor& F, const double* z, const double* exptab,
-                             const double* xhead) {
-    const bool general = F.kernel.num_prims > 0;
-    const int rows = min(F.M, HR);
-    double zs[DIN];
-#pragma unroll
-    for (int c = 0; c < DIN; ++c) zs[c] = general ? z[c] : z[c] / F.lengthscales[c];
-    const double s2 = f64mul(F.scale, F.scale);
-    static_assert(HR == 4 * HB && HH == 2 * HB, "head_cols instantiations below cover HR rows");
-    double ss = 0.0;
-    {
-        double acc[HH];
-#pragma unroll
-        for (int i = 0; i < HH; ++i) acc[i] = 0.0;
-        head_cols<DIN, 0, 0>(acc, F, general, zs, xhead, rows, s2, exptab);
-        head_cols<DIN, 0, 1>(acc, F, general, zs, xhead, rows, s2, exptab);
-#pragma unroll
-        for (int i = 0; i < HH; ++i) ss = fma(acc[i], acc[i], ss);
-    }
-    if (rows > HH) {
-        double acc[HH];
-#pragma unroll
-        for (int i = 0; i < HH; ++i) acc[i] = 0.0;
-        head_cols<DIN, HH, 0>(acc, F, general, zs, xhead, rows, s2, exptab);
-        head_cols<DIN, HH, 1>(acc, F, general, zs, xhead, rows, s2, exptab);
-        head_cols<DIN, HH, 2>(acc, F, general, zs, xhead, rows, s2, exptab);
-        head_cols<DIN, HH, 3>(acc, F, general, zs, xhead, rows, s2, exptab);
-#pragma unroll
-        for (int i = 0; i < HH; ++i) ss = fma(acc[i], acc[i], ss);
-    }
-    double kss = F.kss;
-    if (general) kss = s2 * kernel_expr_diag<DIN>(F.kernel, z);
-    return f64sub(kss, ss) / s2;
-}
-
-template <int DIN>
-__global__ void __launch_bounds__(FT, 8)
+__global__ void __launch_bounds__(HT)
 filter_head_kernel(const __grid_constant__ slb_sweep cfg, const filter_args a) {
     __shared__ double exptab[64];
-    __shared__ double xhead[SLB_MAX_OUT][HR * DIN];
-    const int64_t count = (int64_t)a.counts[0];
-    const int64_t k0 = (int64_t)blockIdx.x * FT;
-    if (k0 >= count) return;                      // the grid covers the worst case
+    __shared__ double kbuf[HT / 32][HR];
     load_exp_table(exptab);
-    const int nf = cfg.gp.num_factors;
-    for (int f = 0; f < nf; ++f) {
-        const slb_gp_factor& F = cfg.gp.factors[f];
-        const int rows = min(F.M, HR);
-        for (int i = threadIdx.x; i < rows * DIN; i += FT) xhead[f][i] = F.Xs[i];
-    }
     __syncthreads();
-    const bool valid = k0 + threadIdx.x < count;
-    const int64_t k = valid ? k0 + threadIdx.x : count - 1;
-    const int64_t rel = a.list_a[k];
-    const filter_side t = a.side_a[k];
-    const int d = cfg.grid.ndim;
+    const int64_t count = (int64_t)a.counts[0];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t nwarps = (int64_t)gridDim.x * (HT / 32);
     const int D = cfg.gp.num_outputs;
-    double z[SLB_MAX_IN];
-    load_state(cfg, a, rel, z);
-    {
-        double u[SLB_MAX_OUT];
-        const int m = eval_fn(cfg.policy, z, u);
-        for (int c = 0; c < m; ++c) z[d + c] = u[c];
-    }
-    double shi[SLB_MAX_OUT];
-    for (int j = 0; j < D; ++j) {
-        const slb_gp_factor& F = cfg.gp.factors[cfg.gp.outputs[j].factor];
-        shi[j] = sqrt(F.kernel.num_prims > 0 ? kernel_expr_diag<DIN>(F.kernel, z) : F.variance);
-    }
-    for (int f = 0; f < nf; ++f) {
-        const slb_gp_factor& F = cfg.gp.factors[f];
-        if (F.M == 0 || F.Whead == nullptr) continue;
-        const double s = sqrt(head_variance<DIN>(F, z, exptab, xhead[f]));   // NaN if negative
-        for (int j = 0; j < D; ++j)
-            if (cfg.gp.outputs[j].factor == f) shi[j] = s;
-    }
-    const int outcome = decide(t, shi, D);
-    const bool undecided = valid && outcome < 0;
-    if (valid && outcome >= 0) a.negative[rel] = outcome > 0 ? 1 : 0;
-    const long long slot = list_append(undecided, a.counts + 1);
-    if (undecided) a.list_b[slot] = rel;
-    if (a.stats != nullptr) {
-        count_stat(valid && !undecided, a.stats + 1);
-        count_stat(undecided, a.stats + 2);
+    double* kw = kbuf[warp];
+    for (int64_t k = (int64_t)blockIdx.x * (HT / 32) + warp; k < count; k += nwarps) {
+        const filter_side& t = a.side_a[k];
+        double z[DIN];
+#pragma unroll
+        for (int c = 0; c < DIN; ++c) z[c] = t.z[c];
+        double shi[SLB_MAX_OUT];
+        for (int j = 0; j < D; ++j) {
+            const slb_gp_factor& F = cfg.gp.factors[cfg.gp.outputs[j].factor];
+            shi[j] = sqrt(F.kernel.num_prims > 0 ? kernel_expr_diag<DIN>(F.kernel, z) : F.variance);
+        }
+        for (int f = 0; f < cfg.gp.num_factors; ++f) {
+            const slb_gp_factor& F = cfg.gp.factors[f];
+            const int rows = F.head_rows;
+            if (rows <= 0 || F.Whead == nullptr) continue;
+            const bool general = F.kernel.num_prims > 0;
+            const double s2 = f64mul(F.scale, F.scale);
+            double zs[DIN];
+#pragma unroll
+            for (int c = 0; c < DIN; ++c) zs[c] = general ? z[c] : z[c] / F.lengthscales[c];
+            // kernel values against the subset points lane and lane + 32 (functions.py:438)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int j = lane + 32 * h;
+                double kv = 0.0;
+                if (j < rows) {
+                    const double* xr = F.Xhead + (size_t)j * DIN;
+                    if (general) {
+                        kv = kernel_expr_cross<DIN>(F.kernel, zs, xr, exptab);
+                    } else {
+                        double a2 = 0.0;
+#pragma unroll
+                        for (int c = 0; c < DIN; ++c) { const double df = zs[c] - __ldg(xr + c); a2 = fma(df, df, a2); }
+                        kv = F.variance * exp_neg_tab(-0.5 * a2, exptab);
+                    }
+                    kv = s2 * kv;
+                }
+                kw[j] = kv;
+            }
+            __syncwarp();
+            double a_lo = 0.0, a_hi = 0.0;
+            const double* __restrict__ Wt = F.Whead;
+#pragma unroll 4
+            for (int j = 0; j < rows; ++j) {
+                const double kj = kw[j];
+                a_lo = fma(__ldg(Wt + (size_t)j * HR + lane), kj, a_lo);
+                a_hi = fma(__ldg(Wt + (size_t)j * HR + 32 + lane), kj, a_hi);
+            }
+            __syncwarp();
+            double ss = fma(a_lo, a_lo, a_hi * a_hi);
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, off);
+            double kss = F.kss;
+            if (general) kss = s2 * kernel_expr_diag<DIN>(F.kernel, z);
+            const double s = sqrt(f64sub(kss, ss) / s2);              // NaN if negative
+            for (int j = 0; j < D; ++j)
+                if (cfg.gp.outputs[j].factor == f) shi[j] = s;
+        }
+        if (lane == 0) {
+            const int outcome = decide(t, shi, D);
+            const int64_t rel = a.list_a[k];
+            if (outcome >= 0) {
+                a.negative[rel] = outcome > 0 ? 1 : 0;
+                if (a.stats != nullptr) atomicAdd(a.stats + 1, 1ull);
+            } else {
+                const unsigned long long slot = atomicAdd(a.counts + 1, 1ull);
+                a.list_b[slot] = rel;
+                if (a.stats != nullptr) atomicAdd(a.stats + 2, 1ull);
+            }
+        }
     }
 }
 
 template <int DIN>
-int launch_filter(cudaStream_t st, const slb_sweep& cfg, const filter_args& a) {
+int launch_filter(cudaStream_t st, const slb_sweep& cfg, const filter_args& a, size_t smem) {
+    static std::atomic<bool> configured[64];
+    int device = 0;
+    SLB_CUDA(cudaGetDevice(&device));
+    if (device < 0 || device >= 64 || !configured[device].load(std::memory_order_acquire)) {
+        SLB_CUDA(cudaFuncSetAttribute(filter_mean_kernel<DIN>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+        if (device >= 0 && device < 64) configured[device].store(true, std::memory_order_release);
+    }
     const int64_t blocks = (a.n + FT - 1) / FT;
-    filter_mean_kernel<DIN><<<(unsigned)blocks, FT, 0, st>>>(cfg, a);
+    filter_mean_kernel<DIN><<<(unsigned)blocks, FT, smem, st>>>(cfg, a);
     SLB_LAUNCH_CHECK();
-    filter_head_kernel<DIN><<<(unsigned)blocks, FT, 0, st>>>(cfg, a);
+    filter_head_kernel<DIN><<<HEAD_CTAS, HT, 0, st>>>(cfg, a);
     SLB_LAUNCH_CHECK();
     return 0;
 }
@@ -349,21 +521,45 @@ int slb_lyapunov_sweep_filtered(void* stream, const slb_sweep* cfg, int64_t idx_
               cfg->gp.num_outputs, d);
     SLB_CHECK(cfg->gp.input_dim == d + m, "GP input_dim %d != state %d + action %d",
               cfg->gp.input_dim, d, m);
-    for (int o = 0; o < cfg->gp.num_outputs; ++o)
-        SLB_CHECK(cfg->gp.outputs[o].gamma != nullptr, "filtered sweep: GP output %d has no gamma", o);
-    for (int f = 0; f < cfg->gp.num_factors; ++f)
-        SLB_CHECK(cfg->gp.factors[f].M == 0 || cfg->gp.factors[f].Whead != nullptr,
-                  "filtered sweep: GP factor %d has no head block (Whead)", f);
+    int nomax = 1;
+    for (int f = 0; f < cfg->gp.num_factors; ++f) {
+        const slb_gp_factor& F = cfg->gp.factors[f];
+        SLB_CHECK(F.M == 0 || (F.Xf != nullptr && F.Whead != nullptr && F.Xhead != nullptr),
+                  "filtered sweep: GP factor %d lacks the filter tables (Xf / Whead / Xhead)", f);
+        SLB_CHECK(F.head_rows >= 0 && F.head_rows <= SLB_HEAD_RANK && F.head_rows <= F.M,
+                  "filtered sweep: GP factor %d has %d head rows (0..min(M, %d))", f, F.head_rows,
+                  SLB_HEAD_RANK);
+        SLB_CHECK((reinterpret_cast<uintptr_t>(F.Xf) & 15) == 0,
+                  "filtered sweep: GP factor %d: Xf must be 16-byte aligned", f);
+        int no = 0;
+        for (int o = 0; o < cfg->gp.num_outputs; ++o) no += cfg->gp.outputs[o].factor == f;
+        if (no > nomax) nomax = no;
+    }
+    for (int o = 0; o < cfg->gp.num_outputs; ++o) {
+        const slb_gp_output& G = cfg->gp.outputs[o];
+        SLB_CHECK(cfg->gp.factors[G.factor].M == 0 ||
+                  (G.gamma_f != nullptr && (reinterpret_cast<uintptr_t>(G.gamma_f) & 15) == 0),
+                  "filtered sweep: GP output %d has no (16-byte aligned) gamma_f", o);
+        SLB_CHECK(G.gamma_l1 >= 0.0, "filtered sweep: GP output %d has no gamma_l1", o);
+    }
     cudaStream_t st = (cudaStream_t)stream;
     char* ws = static_cast<char*>(workspace_dev);
     const int64_t cap = n_all < CHUNK ? n_all : CHUNK;
     filter_args a;
-    a.points = nullptr;
     a.counts = reinterpret_cast<unsigned long long*>(ws);
     a.list_a = reinterpret_cast<int64_t*>(ws + 64);
     a.list_b = a.list_a + cap;
     a.side_a = reinterpret_cast<filter_side*>(a.list_b + cap);
     a.stats = reinterpret_cast<unsigned long long*>(stats_dev);
+    // rows per staged slice: two buffers of (d_in + 1 + outputs per factor) doubles per row within
+    // ~24 KB, so that 7 CTAs stay resident per SM
+    const int din = cfg->gp.input_dim;
+    int chunk_rows = (24 * 1024) / (2 * 8 * (din + 1 + nomax));
+    chunk_rows = chunk_rows >= 256 ? 256 : (chunk_rows & ~7);
+    a.chunk_rows = chunk_rows;
+    a.max_outputs_per_factor = nomax;
+    const size_t smem = 16 + (512 + 64) * sizeof(double) +
+                        (size_t)2 * chunk_rows * (din + 1 + nomax) * sizeof(double);
     for (int64_t off = 0; off < n_all; off += CHUNK) {
         const int64_t n = n_all - off < CHUNK ? n_all - off : CHUNK;
         SLB_CUDA(cudaMemsetAsync(a.counts, 0, 64, st));
@@ -371,15 +567,15 @@ int slb_lyapunov_sweep_filtered(void* stream, const slb_sweep* cfg, int64_t idx_
         a.negative = negative_dev + off;
         a.values = values_dev ? values_dev + off : nullptr;
         int rc;
-        switch (cfg->gp.input_dim) {
-        case 1: rc = launch_filter<1>(st, *cfg, a); break;
-        case 2: rc = launch_filter<2>(st, *cfg, a); break;
-        case 3: rc = launch_filter<3>(st, *cfg, a); break;
-        case 4: rc = launch_filter<4>(st, *cfg, a); break;
-        case 5: rc = launch_filter<5>(st, *cfg, a); break;
-        case 6: rc = launch_filter<6>(st, *cfg, a); break;
+        switch (din) {
+        case 1: rc = launch_filter<1>(st, *cfg, a, smem); break;
+        case 2: rc = launch_filter<2>(st, *cfg, a, smem); break;
+        case 3: rc = launch_filter<3>(st, *cfg, a, smem); break;
+        case 4: rc = launch_filter<4>(st, *cfg, a, smem); break;
+        case 5: rc = launch_filter<5>(st, *cfg, a, smem); break;
+        case 6: rc = launch_filter<6>(st, *cfg, a, smem); break;
         default:
-            slb_set_error("GP input_dim %d not compiled (1..6)", cfg->gp.input_dim);
+            slb_set_error("GP input_dim %d not compiled (1..6)", din);
             return 1;
         }
         if (rc) return rc;

@@ -197,7 +197,11 @@ SLB_DEV void row_lane_reduce(const double (&v)[2 * NBT], int lane, double* red_q
 
 // KEXPR: at least one factor carries a covariance expression (slb_kernel) instead of the plain
 // RBF; the RBF-only instantiation keeps the lean generation loop.
-template <int DIN, bool TIMING, bool KEXPR>
+// TPV (= TP) only makes the kernel's NAME unique per translation unit: the units for the three tile
+// sizes are compiled from this one source file, nvcc derives the prefix of internal-linkage
+// kernels from the file name, and equally named kernels of different modules were resolved to
+// the same device function (observed: the 64-point launch ran the 32-point code).
+template <int DIN, bool TIMING, bool KEXPR, int TPV>
 __global__ void __launch_bounds__(NT, CTAS_PER_SM)
 gp_tile_kernel(const __grid_constant__ slb_sweep cfg, const slb_gp_args a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -581,13 +585,13 @@ int launch_gp_tile(cudaStream_t st, const slb_sweep& cfg, const slb_gp_args& a) 
     int device = 0;
     SLB_CUDA(cudaGetDevice(&device));
     if (device < 0 || device >= 64 || !configured[device].load(std::memory_order_acquire)) {
-        SLB_CUDA(cudaFuncSetAttribute(gp_tile_kernel<DIN, TIMING, KEXPR>,
+        SLB_CUDA(cudaFuncSetAttribute(gp_tile_kernel<DIN, TIMING, KEXPR, TP>,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)SMEM_TOTAL));
         if (device >= 0 && device < 64) configured[device].store(true, std::memory_order_release);
     }
     const int64_t tiles = (a.n + TP - 1) / TP;
-    gp_tile_kernel<DIN, TIMING, KEXPR><<<(unsigned)tiles, NT, SMEM_TOTAL, st>>>(cfg, a);
+    gp_tile_kernel<DIN, TIMING, KEXPR, TP><<<(unsigned)tiles, NT, SMEM_TOTAL, st>>>(cfg, a);
     SLB_LAUNCH_CHECK();
     return 0;
 }

@@ -496,6 +496,66 @@ max_abs_diff_kernel(const double* __restrict__ a, const double* __restrict__ b, 
     if ((threadIdx.x & 31) == 0) atomicMax(result, bits);
 }
 
+// ---- head subset of the decision filter: first r pivots of the pivoted Cholesky factorisation ----
+// One CTA.  Step t: pivot = argmax of the remaining diagonal (ties: lowest index), column t of the
+// partial factor  low[:, t] = (K[:, pivot] - low[:, :t] low[pivot, :t]) / sqrt(diag[pivot]),
+// diag -= low[:, t]^2.  K is symmetric: its row `pivot` is read instead of the column (coalesced).
+constexpr int PV_THREADS = 1024;
+
+__global__ void __launch_bounds__(PV_THREADS)
+pivoted_subset_kernel(const double* __restrict__ K, int M, int r, int64_t* __restrict__ picks,
+                      double* __restrict__ low, double* __restrict__ diag) {
+    __shared__ double s_val[32];
+    __shared__ int s_idx[32];
+    __shared__ double s_prow[SLB_HEAD_RANK];
+    __shared__ int s_piv;
+    __shared__ double s_dpiv;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int i = tid; i < M; i += PV_THREADS) diag[i] = K[(size_t)i * M + i];
+    __syncthreads();
+    for (int t = 0; t < r; ++t) {
+        double bv = -INFINITY;
+        int bi = 0x7fffffff;
+        for (int i = tid; i < M; i += PV_THREADS) {
+            const double v = diag[i];
+            if (v > bv || (v == bv && i < bi)) { bv = v; bi = i; }
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            const double ov = __shfl_xor_sync(0xffffffffu, bv, off);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
+            if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+        }
+        if (lane == 0) { s_val[warp] = bv; s_idx[warp] = bi; }
+        __syncthreads();
+        if (warp == 0) {
+            bv = s_val[lane]; bi = s_idx[lane];
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+                const double ov = __shfl_xor_sync(0xffffffffu, bv, off);
+                const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
+                if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+            }
+            if (lane == 0) { s_piv = bi; s_dpiv = bv; picks[t] = bi; }
+        }
+        __syncthreads();
+        const int piv = s_piv;
+        if (tid < t) s_prow[tid] = low[(size_t)piv * r + tid];
+        __syncthreads();
+        const double inv = 1.0 / sqrt(fmax(s_dpiv, 2.2250738585072014e-308));
+        for (int i = tid; i < M; i += PV_THREADS) {
+            double col = K[(size_t)piv * M + i];
+            const double* li = low + (size_t)i * r;
+            for (int j = 0; j < t; ++j) col = fma(-li[j], s_prow[j], col);
+            col *= inv;
+            low[(size_t)i * r + t] = col;
+            const double d = diag[i];
+            diag[i] = (i == piv || d == -INFINITY) ? -INFINITY : d - col * col;
+        }
+        __syncthreads();
+    }
+}
+
 inline unsigned blocks_for(int64_t n) { return (unsigned)((n + LT - 1) / LT); }
 
 }  // namespace
@@ -775,6 +835,18 @@ int slb_max_abs_diff(void* stream, const double* a_dev, const double* b_dev, int
     const unsigned blocks = (unsigned)(want > 1024 ? 1024 : want);
     max_abs_diff_kernel<<<blocks, LT, 0, st>>>(a_dev, b_dev, n,
                                                reinterpret_cast<unsigned long long*>(result_dev));
+    SLB_LAUNCH_CHECK();
+    return 0;
+}
+
+int slb_pivoted_subset(void* stream, const double* kernel_dev, int32_t M, int32_t r,
+                       int64_t* picks_dev, double* scratch_dev) {
+    SLB_CHECK(M >= 0 && r >= 0 && r <= M && r <= SLB_HEAD_RANK,
+              "slb_pivoted_subset: need 0 <= r <= min(M, %d) (M %d, r %d)", SLB_HEAD_RANK, M, r);
+    if (r == 0) return 0;
+    SLB_CHECK(kernel_dev && picks_dev && scratch_dev, "slb_pivoted_subset: null buffer");
+    pivoted_subset_kernel<<<1, PV_THREADS, 0, (cudaStream_t)stream>>>(
+        kernel_dev, M, r, picks_dev, scratch_dev, scratch_dev + (size_t)M * r);
     SLB_LAUNCH_CHECK();
     return 0;
 }

@@ -1097,8 +1097,8 @@ class Likelihood(object):
 class _Factor(object):
     """Device-resident Cholesky state of one (X, kernel, noise, scale) combination."""
 
-    __slots__ = ("key", "M", "nrb", "Xs", "L", "Linv", "Wpack", "Whead", "appends", "plain",
-                 "floor_rel")
+    __slots__ = ("key", "M", "nrb", "Xs", "L", "Linv", "Wpack", "Whead", "Xhead", "head_rows",
+                 "Xf", "hmax", "appends", "plain", "floor_rel")
 
 
 _FACTOR_CACHE = {}
@@ -1143,6 +1143,8 @@ class GPRCached(object):
         self._factor = None
         self._alpha_dev = None
         self._gamma_dev = None
+        self._gamma_f_dev = None
+        self._gamma_l1 = 0.0
         self._prior_dev = None
         self._stale = True
         self._version = 0
@@ -1212,7 +1214,7 @@ class GPRCached(object):
                 fac.Xs = dev.zeros((0, din))
                 fac.L = fac.Linv = dev.zeros((0, 0))
                 fac.Wpack = dev.zeros((1,))
-                self._head(fac)
+                self._head(fac, None)
             else:
                 if fac.plain:
                     fac.Xs = dev.to_device(self._X / self.kern.lengthscales)
@@ -1220,47 +1222,101 @@ class GPRCached(object):
                 else:
                     fac.Xs = dev.to_device(self._X)
                     kernel = self.kern.K_device(fac.Xs)
-                kernel = kernel + torch.eye(M, dtype=torch.float64, device=kernel.device) \
+                kernel_noisy = kernel + torch.eye(M, dtype=torch.float64, device=kernel.device) \
                     * self.likelihood.variance
-                kernel = kernel * (self._scale ** 2)
-                fac.L = torch.linalg.cholesky(kernel)
+                kernel_noisy = kernel_noisy * (self._scale ** 2)
+                fac.L = torch.linalg.cholesky(kernel_noisy)
                 fac.Linv = torch.linalg.solve_triangular(
                     fac.L, torch.eye(M, dtype=torch.float64, device=kernel.device),
                     upper=False).contiguous()
-                self._pack(fac)
+                self._pack(fac, kernel)
             _remember_factor(fac)
         self._finish_cache(fac)
 
-    def _pack(self, fac):
-        """Device tables derived from ``L^-1``: the DMMA-ordered packed factor, the column-major
-        head block of the decision filter (``slb_gp_factor.Whead``) and the certified lower
-        bound of the posterior variance that decides whether the filter may be used."""
+    def _pack(self, fac, kernel=None, head_from=None):
+        """Device tables derived from ``L^-1``: the DMMA-ordered packed factor and the tables of
+        the decision filter (``_head``).  ``kernel``: ``K(X, X)`` without noise if the caller has
+        it; ``head_from``: an older factor of the same model whose head subset is kept."""
         lib = nat.load()
         fac.Wpack = dev.empty((int(lib.slb_packed_len(fac.M)),))
         nat.check(lib.slb_pack_factor(dev.stream(), fac.Linv.data_ptr(), fac.M,
                                       fac.Wpack.data_ptr()), "slb_pack_factor")
-        self._head(fac)
+        self._head(fac, kernel, head_from)
 
-    def _head(self, fac):
+    def _head(self, fac, kernel, head_from=None):
+        """Tables of the decision filter (``slb_lyapunov_sweep_filtered``, csrc/filter.cu).
+
+        * Head subset: the posterior variance given ANY subset S of the training set bounds the
+          full posterior variance from above.  S = the first ``min(M, SLB_HEAD_RANK)`` points in
+          pivoted-Cholesky order of ``K(X, X)`` (greedy: the point with the largest variance given
+          the ones already chosen), factored on its own: ``Whead = chol(scale^2 (K_SS + noise
+          I))^-1`` (stored transposed = column-major, zero padded), ``Xhead = Xs[S]``.  A factor
+          grown by ``append_data`` keeps the subset of the factor it grew from.
+        * ``Xf``: the training inputs as the filter's mean stage streams them (TMA bulk copies:
+          rows padded to a multiple of 4, 16-byte aligned); for the plain RBF each row carries
+          ``-|x / l|^2 / 2`` so that the squared distance expands into three FMAs.
+        * ``floor_rel``: certified lower bound of posterior variance / prior variance that
+          decides whether the filter may be used at all (``Lyapunov._filter_enabled``)."""
         R = nat.SLB_HEAD_RANK
-        r = min(fac.M, R)
+        M, din = fac.M, self._X.shape[1]
+        r = min(M, R)
         fac.Whead = dev.zeros((R, R))
-        if r:
-            fac.Whead[:r, :r] = fac.Linv[:r, :r].T        # Whead[j, i] = L^-1[i, j]
+        fac.Xhead = dev.zeros((max(r, 1), din))
+        fac.head_rows = r
+        Mp = max(4 * ((M + 3) // 4), 4)
+        width = din + 1 if fac.plain else din
+        fac.Xf = dev.zeros((Mp, width))
+        fac.hmax = 0.0
+        if M == 0:
+            fac.floor_rel = 1.0
+            return
+        fac.Xf[:M, :din] = fac.Xs
+        if fac.plain:
+            half = -0.5 * (fac.Xs * fac.Xs).sum(dim=1)
+            fac.Xf[:M, din] = half
+            fac.hmax = float(-half.min().item())
+        if head_from is not None and head_from.head_rows == r:
+            fac.Whead, fac.Xhead = head_from.Whead, head_from.Xhead
+        else:
+            if kernel is None:
+                kernel = self.kern.K_scaled(fac.Xs) if fac.plain else self.kern.K_device(fac.Xs)
+            subset = self._pivoted_subset(kernel, r)
+            fac.Xhead = fac.Xs.index_select(0, subset).contiguous()
+            k_ss = kernel.index_select(0, subset).index_select(1, subset)
+            k_ss = (k_ss + torch.eye(r, dtype=torch.float64, device=k_ss.device)
+                    * self.likelihood.variance) * (self._scale ** 2)
+            l_ss = torch.linalg.cholesky(k_ss)
+            linv = torch.linalg.solve_triangular(
+                l_ss, torch.eye(r, dtype=torch.float64, device=k_ss.device), upper=False)
+            fac.Whead[:r, :r] = linv.T                    # Whead[j, i] = L_S^-1[i, j]
         # var(z) >= k(z,z) s / (M k(z,z) + s), s = noise variance (M noisy observations AT z are
         # the most informative data set): relative to k(z,z) at least s / (M kmax + s).  When
         # that is not far above fp64 rounding of the O(M^2) contraction the reference's
         # "negative variance -> NaN -> unsafe" corner (functions.py:451) is reachable and the
-        # filter, which bounds the variance from above only, is not used.
-        if fac.M == 0:
-            fac.floor_rel = 1.0
-            return
+        # filter, which bounds the variance from above only, is not used.  Neither is it with
+        # non-finite or absurdly large inputs (the expanded distance needs moderate magnitudes).
         noise = float(self.likelihood.variance)
         if fac.plain:
             kmax = float(self.kern.variance)
         else:
             kmax = float(self.kern.Kdiag_device(fac.Xs).max().item())
         fac.floor_rel = noise / (fac.M * kmax + noise) if (kmax > 0 or noise > 0) else 0.0
+        if not bool(torch.isfinite(fac.Xs).all()) or float(fac.Xs.abs().max().item()) > 1e100:
+            fac.floor_rel = 0.0
+
+    @staticmethod
+    def _pivoted_subset(kernel, r):
+        """Indices of the first ``r`` pivots of the pivoted Cholesky factorisation of the symmetric
+        positive semi-definite ``kernel`` (device tensor [M, M]) -> int64 device tensor [r]: one
+        kernel launch (``slb_pivoted_subset``), no host synchronisation."""
+        lib = nat.load()
+        M = kernel.shape[0]
+        kernel = kernel.contiguous()
+        picks = dev.zeros((r,), torch.int64)
+        scratch = dev.empty((M * (r + 1),))
+        nat.check(lib.slb_pivoted_subset(dev.stream(), kernel.data_ptr(), M, r, picks.data_ptr(),
+                                         scratch.data_ptr()), "slb_pivoted_subset")
+        return picks
 
     def _append_rows(self, x_new):
         """Rank-one growth of the cached factor for each appended observation (SURVEY.md 8f
@@ -1312,7 +1368,7 @@ class GPRCached(object):
         fac.key, fac.M, fac.nrb = key, Xs.shape[0], (Xs.shape[0] + 7) // 8
         fac.Xs, fac.L, fac.Linv = Xs.contiguous(), L, Linv.contiguous()
         fac.appends, fac.plain = old.appends + len(x_new), old.plain
-        self._pack(fac)
+        self._pack(fac, None, head_from=old if old.head_rows == nat.SLB_HEAD_RANK else None)
         _remember_factor(fac)
         return fac
 
@@ -1346,6 +1402,15 @@ class GPRCached(object):
         padded[:M] = alpha[:, 0]
         self._alpha_dev = padded
         self._gamma_dev = gamma[:, 0].contiguous() if M else dev.zeros((1,))
+        # the filter's mean weights: scale^2 gamma, times the RBF variance on the plain path
+        # (whose kernel values are then <= 1), zero padded to the row count of Xf; and the bound
+        # sum_i (|L^-1|^T |alpha|)_i of everything that rounds when the mean is summed
+        fold = self._scale ** 2 * (float(self.kern.variance) if fac.plain else 1.0)
+        self._gamma_f_dev = dev.zeros((fac.Xf.shape[0],))
+        self._gamma_l1 = 0.0
+        if M:
+            self._gamma_f_dev[:M] = fold * gamma[:, 0]
+            self._gamma_l1 = abs(fold) * float((fac.Linv.abs().T @ alpha.abs()).sum().item())
         self._stale = False
         self._hyper_seen = self._hyper_state()
         self._version += 1
@@ -1356,7 +1421,8 @@ class GPRCached(object):
         fac = self._factor
         f.M, f.nrb = fac.M, fac.nrb
         f.Xs, f.Wpack = fac.Xs.data_ptr(), fac.Wpack.data_ptr()
-        f.Whead = fac.Whead.data_ptr()
+        f.Whead, f.Xhead, f.head_rows = fac.Whead.data_ptr(), fac.Xhead.data_ptr(), fac.head_rows
+        f.Xf, f.hmax = fac.Xf.data_ptr(), fac.hmax
         f.scale = self._scale
         if fac.plain:
             for c, ls in enumerate(self.kern.lengthscales):
@@ -1374,6 +1440,7 @@ class GPRCached(object):
         o.alpha = self._alpha_dev.data_ptr()
         o.gamma = self._gamma_dev.data_ptr()
         o.prior_mean = None if self._prior_dev is None else self._prior_dev.data_ptr()
+        o.gamma_f, o.gamma_l1 = self._gamma_f_dev.data_ptr(), self._gamma_l1
 
 
     def variance_floor(self):
@@ -1382,7 +1449,12 @@ class GPRCached(object):
         return self._factor.floor_rel
 
     # host copies of the cached tables ------------------------------------------------------
-    _CACHE_FIELDS = ("Xs", "Wpack", "Whead", "alpha", "gamma")
+    _CACHE_FIELDS = ("Xs", "Wpack", "Whead", "Xhead", "Xf", "alpha", "gamma", "gamma_f")
+
+    def _cache_tables(self):
+        fac = self._factor
+        return (fac.Xs, fac.Wpack, fac.Whead, fac.Xhead, fac.Xf, self._alpha_dev, self._gamma_dev,
+                self._gamma_f_dev)
 
     def export_cache(self, pinned=True):
         """Host copies (torch CPU tensors, page-locked if ``pinned``) of the device tables a sweep
@@ -1392,8 +1464,7 @@ class GPRCached(object):
         self._ensure()
         fac = self._factor
         out = {}
-        for name, t in zip(self._CACHE_FIELDS, (fac.Xs, fac.Wpack, fac.Whead, self._alpha_dev,
-                                                self._gamma_dev)):
+        for name, t in zip(self._CACHE_FIELDS, self._cache_tables()):
             host = t.detach().cpu()
             out[name] = host.pin_memory() if pinned and torch.cuda.is_available() else host
         return out
@@ -1403,8 +1474,7 @@ class GPRCached(object):
         shapes) back into the device buffers: asynchronous H2D copies on the current stream."""
         self._ensure()
         fac = self._factor
-        for name, dst in zip(self._CACHE_FIELDS, (fac.Xs, fac.Wpack, fac.Whead, self._alpha_dev,
-                                                  self._gamma_dev)):
+        for name, dst in zip(self._CACHE_FIELDS, self._cache_tables()):
             src = tables[name]
             if not isinstance(src, torch.Tensor):
                 src = torch.from_numpy(np.ascontiguousarray(src, dtype=np.float64))

@@ -98,10 +98,17 @@ def get_safe_sample(lyapunov, perturbations=None, limits=None, positive=False, n
     def evaluate(sa):
         mean, std = lyapunov.dynamics.predict_device(sa)
         bound = std.sum(dim=1, keepdim=True)
-        lv = lyapunov._lipschitz_lyapunov
-        lv = lv.evaluate_device(mean) if isinstance(lv, Function) else float(lv)
+        def on_mean(fn):
+            # fusable objects on the device; plain callables on the host (composed path)
+            if isinstance(fn, Function):
+                return fn.evaluate_device(mean)
+            if callable(fn):
+                out = np.asarray(fn(mean.cpu().numpy()), dtype=np.float64)
+                return dev.to_device(out.reshape(mean.shape[0], -1))
+            return float(fn)
+        lv = on_mean(lyapunov._lipschitz_lyapunov)
         error = (lv * std).sum(dim=1, keepdim=True)
-        future = lyapunov.lyapunov_function.evaluate_device(mean) + error
+        future = on_mean(lyapunov.lyapunov_function) + error
         return (future < c_max)[:, 0].cpu().numpy(), mean.cpu().numpy(), bound.cpu().numpy()
 
     maps_inside, mean, bound = evaluate(state_actions)
@@ -256,9 +263,19 @@ class Lyapunov(object):
     """See ``lyapunov.py:142-225`` for the parameters.
 
     ``lipschitz_lyapunov`` may be a float or a fusable Function (e.g. ``abs(LinearSystem(2P))``);
-    ``lipschitz_dynamics`` must be a float in this build.  With ``adaptive=True``,
-    ``update_safe_set(max_refinement=R)`` re-checks failing cells on a locally refined mesh
-    (``lyapunov.py:445-487, 540-582``, see ``_adaptive_ok``).
+    ``lipschitz_dynamics`` a float, a fusable Function or any callable of the states.  With
+    ``adaptive=True``, ``update_safe_set(max_refinement=R)`` re-checks failing cells on a locally
+    refined mesh (``lyapunov.py:445-487, 540-582``, see ``_adaptive_ok``).
+
+    ``policy``, ``lyapunov_function``, ``lipschitz_lyapunov`` (and deterministic ``dynamics``) may
+    also be ARBITRARY Python callables on numpy arrays, as the reference allows
+    (``lyapunov.py:227-263``, ``lyapunov_function_learning.ipynb`` cell 19).  A Python lambda
+    cannot be fused into a CUDA kernel, so such a sweep takes the *composed* path
+    (``_compute_negative_composed``): the GP posterior of every grid point still runs on the GPU
+    (``slb_gp_predict``), the user's callables are evaluated on the host on the arrays the
+    reference's graph would feed them, and the flags go back to the device for the first-fail
+    reduction / prefix rule.  Orders of magnitude slower than the fused sweep -- use the Function
+    objects where they exist.
     """
 
     def __init__(self, discretization, lyapunov_function, dynamics, lipschitz_dynamics,
@@ -389,6 +406,58 @@ class Lyapunov(object):
         v_dot, v_dot_error = self.v_decrease_confidence(states, next_states)
         return v_dot + v_dot_error
 
+    # ------------------------------------------------------------------ composed (callable) path
+    def _is_composed(self):
+        """True if a member is a plain Python callable, i.e. the sweep cannot be fused."""
+        def plain(obj):
+            return callable(obj) and not isinstance(obj, Function)
+        return (plain(self.policy) or plain(self.lyapunov_function)
+                or plain(self._lipschitz_lyapunov) or plain(self.dynamics))
+
+    def _negative_composed(self, states, tau=None, want_details=False):
+        """The graph of ``lyapunov.py:433-441`` on a numpy array of states with the members
+        called as the reference calls them: ``dynamics(states, policy(states))``,
+        ``v_decrease_bound``, ``threshold``, strict ``<`` (NaN compares false)."""
+        actions = np.asarray(self.policy(states), dtype=np.float64)
+        if actions.ndim == 1:
+            actions = actions.reshape(len(states), -1)
+        next_states = self.dynamics(states, actions)
+        decrease = self.v_decrease_bound(states, next_states)
+        threshold = self.threshold(states, tau)
+        with np.errstate(invalid="ignore"):
+            negative = np.squeeze(decrease < threshold, axis=1)
+        if not want_details:
+            return negative
+        mean, err = next_states if isinstance(next_states, (tuple, list)) else (next_states, None)
+        return negative, {"decrease": decrease[:, 0],
+                          "threshold": np.broadcast_to(threshold, decrease.shape)[:, 0],
+                          "mean": mean, "err": err}
+
+    def _compute_negative_composed(self, want_details=False):
+        grid = self.discretization
+        n = self._end - self._begin
+        flags = np.empty(n, dtype=bool)
+        parts = {}
+        chunk = 1 << 18
+        for start in range(0, n, chunk):
+            stop = min(start + chunk, n)
+            states = grid.index_to_state(np.arange(self._begin + start, self._begin + stop))
+            out = self._negative_composed(states, want_details=want_details)
+            if want_details:
+                out, det = out
+                for k, v in det.items():
+                    if v is not None:
+                        parts.setdefault(k, []).append(v)
+            flags[start:stop] = out
+        if self._negative_dev is None or self._negative_dev.numel() != n:
+            self._negative_dev = dev.empty((n,), torch.uint8)
+        self._negative_dev.copy_(dev.to_device(flags.astype(np.uint8), torch.uint8))
+        if not want_details:
+            return self._negative_dev
+        details = {k: dev.to_device(np.concatenate(v)) for k, v in parts.items()}
+        details["values"] = self._values_dev
+        return self._negative_dev, details
+
     # ------------------------------------------------------------------ descriptor
     def _descriptor_token(self):
         def tok(obj):
@@ -483,8 +552,16 @@ class Lyapunov(object):
         """``values = V(all grid points)`` (``lyapunov.py:305-322``), computed on the device
         from flat indices in chunks (coordinates are never materialised for the full grid)."""
         lib = nat.load()
-        fn = _as_function(self.lyapunov_function, "lyapunov_function")
         n = self._end - self._begin
+        if not isinstance(self.lyapunov_function, Function) and callable(self.lyapunov_function):
+            grid = self.discretization
+            parts = [np.asarray(self.lyapunov_function(grid.index_to_state(
+                np.arange(s0, min(s0 + (1 << 20), self._end)))), dtype=np.float64).reshape(-1)
+                for s0 in range(self._begin, self._end, 1 << 20)]
+            self._values_dev = dev.to_device(np.concatenate(parts) if parts else np.zeros(0))
+            self._values_host = None
+            return
+        fn = _as_function(self.lyapunov_function, "lyapunov_function")
         out = dev.empty((n,))
         grid = self.discretization.descriptor()
         chunk = 1 << 22
@@ -533,6 +610,8 @@ class Lyapunov(object):
         ``negative`` (and, if asked, a dict of device tensors: values, decrease, threshold,
         mean, err -- the details always come from the full posterior)."""
         n = self._end - self._begin
+        if self._is_composed():
+            return self._compute_negative_composed(want_details)
         if self._negative_dev is None or self._negative_dev.numel() != n:
             self._negative_dev = dev.empty((n,), torch.uint8)
         if not want_details:
@@ -597,6 +676,9 @@ class Lyapunov(object):
     def negative_at_points(self, points, tau=None):
         """The decision of ``lyapunov.py:436-441`` on an explicit device point list ``[n, d]``
         (``slb_lyapunov_points``), optionally with another discretisation constant."""
+        if self._is_composed():
+            flags = self._negative_composed(points.cpu().numpy(), tau=tau)
+            return dev.to_device(flags.astype(np.uint8), torch.uint8)
         lib = nat.load()
         cfg = self.sweep_descriptor()
         if tau is not None and float(tau) != float(self.tau):
@@ -736,7 +818,8 @@ class Lyapunov(object):
         # Optional CUDA-graph replay of the launches of a sweep (no collective call inside when
         # the keys travel through peer memory), while nothing they depend on has changed.
         token = None
-        if _USE_GRAPHS and not adaptive and (world == 1 or xchg is not None):
+        if (_USE_GRAPHS and not adaptive and not self._is_composed()
+                and (world == 1 or xchg is not None)):
             token = (self._descriptor_token(), self._values_dev.data_ptr(),
                      0 if initial is None else initial.data_ptr(), n_local,
                      self._filter_enabled(self.sweep_descriptor()))
@@ -827,14 +910,22 @@ class Lyapunov(object):
         neg, det = self.compute_negative(want_details=True)
         # threshold(x, tau / n) = (-L_V(x) (1 + L_f)) * (tau / n): the coefficient is the sweep's
         # threshold output for tau = 1 (a multiplication by 1.0 is exact)
-        cfg1 = nat.SlbSweep.from_buffer_copy(self.sweep_descriptor())
-        cfg1.tau = 1.0
         n_local = self._end - self._begin
-        coef = dev.empty((n_local,))
-        scratch = dev.empty((n_local,), torch.uint8)
-        nat.check(lib.slb_lyapunov_sweep(dev.stream(), cfg1, self._begin, self._end,
-                                         scratch.data_ptr(), None, None, coef.data_ptr(), None,
-                                         None), "slb_lyapunov_sweep")
+        if self._is_composed():
+            grid = self.discretization
+            parts = [np.broadcast_to(self.threshold(grid.index_to_state(
+                np.arange(s0, min(s0 + (1 << 18), self._end))), 1.0),
+                (min(s0 + (1 << 18), self._end) - s0, 1))[:, 0]
+                for s0 in range(self._begin, self._end, 1 << 18)]
+            coef = dev.to_device(np.concatenate(parts) if parts else np.zeros(0))
+        else:
+            cfg1 = nat.SlbSweep.from_buffer_copy(self.sweep_descriptor())
+            cfg1.tau = 1.0
+            coef = dev.empty((n_local,))
+            scratch = dev.empty((n_local,), torch.uint8)
+            nat.check(lib.slb_lyapunov_sweep(dev.stream(), cfg1, self._begin, self._end,
+                                             scratch.data_ptr(), None, None, coef.data_ptr(),
+                                             None, None), "slb_lyapunov_sweep")
         values = self._gather(self._values_dev).cpu().numpy()
         negative = self._gather(neg).cpu().numpy().astype(bool)
         decrease = self._gather(det["decrease"]).cpu().numpy()

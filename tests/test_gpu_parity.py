@@ -230,6 +230,42 @@ def test_state_dependent_lipschitz_dynamics_vs_oracle(sl):
     assert_array_equal(gpu2.safe_set, cpu2.safe_set)
 
 
+def test_arbitrary_python_callables_vs_oracle(sl):
+    """lyapunov.py:227-263 and lyapunov_function_learning.ipynb cells 13-19: V, policy, L_V and
+    L_f given as plain Python callables on numpy arrays (the composed path: GP posterior on the
+    GPU, the callables on the host), against the oracle running the same lambdas and against the
+    fused path running the equivalent Function objects."""
+    par = W.make_pendulum(num_points=[41, 37], M=90, tau_scale=1 / 40.)
+    P, K = par["P"], par["K"]
+    v_fn = lambda x: np.sum(x.dot(P) * x, axis=1, keepdims=True)              # noqa: E731
+    pi_fn = lambda x: np.clip(x.dot(-K.T), -1., 1.)                            # noqa: E731
+    lv_fn = lambda x: np.abs(x.dot((2 * P).T))                                 # noqa: E731  two columns -> 1-norm in threshold
+    lf_fn = lambda x: np.full((len(x), 1), par["L_dyn"])                       # noqa: E731
+    fused, cpu = W.build_product(par), W.build_oracle(par)
+    gpu = sl.Lyapunov(fused.discretization, v_fn, fused.dynamics, lf_fn, lv_fn, par["tau"], pi_fn,
+                      initial_set=par["initial"])
+    ref = O.Lyapunov(cpu.discretization, v_fn, cpu.dynamics, lf_fn, lv_fn, par["tau"], pi_fn,
+                     initial_set=par["initial"])
+    assert gpu._is_composed() and not fused._is_composed()
+    assert_array_equal(gpu.values, ref.values)
+    det = _sweep_details(gpu)
+    _assert_negative_parity(gpu, ref, det)
+    for lyap in (gpu, ref, fused, cpu):
+        lyap.update_safe_set()
+    assert par["initial"].sum() < ref.safe_set.sum() < ref.safe_set.size
+    assert_array_equal(gpu.safe_set, ref.safe_set)
+    assert gpu.feed_dict[gpu.c_max] == ref.c_max
+    # the lambdas restate the Function objects: same safe set as the fused sweep
+    assert_array_equal(gpu.safe_set, fused.safe_set)
+    assert_array_equal(gpu.safe_set, cpu.safe_set)
+    # only some members are callables: a lambda policy with fused V / L_V
+    mixed = sl.Lyapunov(fused.discretization, fused.lyapunov_function, fused.dynamics,
+                        par["L_dyn"], fused._lipschitz_lyapunov, par["tau"], pi_fn,
+                        initial_set=par["initial"])
+    mixed.update_safe_set()
+    assert_array_equal(mixed.safe_set, cpu.safe_set)
+
+
 def test_initial_safe_set_edited_in_place(sl):
     """the reference re-reads ``initial_safe_set`` on every update_safe_set
     (lyapunov.py:504-506); an in-place edit of the same array must reach the device."""
@@ -295,6 +331,44 @@ def test_refine_pass_tile_sizes(sl, split, label):
             assert_array_equal(fast, gpu.compute_negative().cpu().numpy(), err_msg=label)
     finally:
         lib.slb_debug_refine_split(16 * 148, 32 * 148)
+
+
+def test_pivoted_head_subset_matches_greedy_selection(sl):
+    """slb_pivoted_subset (the head subset of the decision filter) against a numpy restatement of the
+    pivoted Cholesky factorisation: same pivots in the same order; and the subset's variance bound
+    is an upper bound of the full posterior variance at random points (what the filter relies on)."""
+    import torch
+    from safe_learning_b200 import _device as dev
+    from safe_learning_b200.functions import GPRCached
+    rng = np.random.default_rng(5)
+    X = rng.uniform(-1, 1, (137, 3))
+    K = np.exp(-0.5 * ((X[:, None, :] - X[None, :, :]) ** 2 / np.array([1.5, 1.2, 2.0]) ** 2).sum(-1))
+    r = 64
+    diag, low, ref = np.diag(K).copy(), np.zeros((len(X), r)), []
+    for t in range(r):
+        i = int(np.argmax(diag))
+        ref.append(i)
+        col = (K[i] - low[:, :t] @ low[i, :t]) / np.sqrt(diag[i])
+        low[:, t] = col
+        diag = diag - col * col
+        diag[ref] = -np.inf
+    picks = GPRCached._pivoted_subset(dev.to_device(K), r).cpu().numpy()
+    assert sorted(set(picks.tolist())) == sorted(picks.tolist()) and len(picks) == r
+    assert_array_equal(picks, np.array(ref))
+    par = W.make_pendulum(num_points=[9, 9], M=137)
+    gpu = W.build_product(par)
+    gp = gpu.dynamics.functions[0].gaussian_process
+    gp._ensure()
+    fac = gp._factor
+    assert fac.head_rows == 64
+    z = rng.uniform(-1, 1, (200, 3))
+    _, var = gpu.dynamics.functions[0].predict_device(z, want_var=True)
+    Xh = fac.Xhead.cpu().numpy()
+    zs = z / np.asarray(gp.kern.lengthscales)
+    kz = gp.kern.variance * np.exp(-0.5 * ((Xh[:, None, :] - zs[None, :, :]) ** 2).sum(-1))
+    a = fac.Whead.cpu().numpy().T[:64, :64] @ kz           # Whead[j, i] = L_S^-1[i, j]
+    bound = gp.kern.variance - (a * a).sum(axis=0)
+    assert (bound >= var.cpu().numpy()[:, 0] * (1 - 1e-9)).all()
 
 
 def test_filter_is_not_used_below_the_variance_floor(sl):
@@ -818,8 +892,8 @@ def test_discrete_policy_optimization_vs_oracle(sl):
 def test_errors_are_loud(sl):
     from safe_learning_b200 import _native as nat
     grid = sl.GridWorld([[-1, 1]], 3)
-    with pytest.raises(TypeError):
-        sl.Lyapunov(grid, lambda x: x, sl.LinearSystem(np.array([[1, 1.]])), 0.4, 0.3, 0.5,
+    with pytest.raises(TypeError):      # neither a Function object nor a callable
+        sl.Lyapunov(grid, "x^2", sl.LinearSystem(np.array([[1, 1.]])), 0.4, 0.3, 0.5,
                     sl.LinearSystem(np.array([[-.1]])))
     lyap = sl.Lyapunov(grid, sl.QuadraticFunction(np.array([[1.0]])),
                        sl.LinearSystem(np.array([[1, 1., 1.]])), 0.4, 0.3, 0.5,
