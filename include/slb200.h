@@ -163,10 +163,11 @@ typedef struct slb_gp_factor {
     const double* Whead;        /* device [SLB_HEAD_RANK, SLB_HEAD_RANK], COLUMN-major, zero padded:
                                    Whead[j * SLB_HEAD_RANK + i] = L_S^-1[i, j], L_S = chol(scale^2
                                    (K(X_S) + noise I))                                   */
-    const double* Xhead;        /* device [head_rows, d_in]: the subset's inputs, scaled like Xs */
+    const double* Xhead;        /* device [SLB_HEAD_RANK, d_in], zero padded: the subset's inputs,
+                                   scaled like Xs                                        */
     int32_t head_rows;          /* |S| = min(M, SLB_HEAD_RANK)                           */
     int32_t _pad2;
-    const double* Xf;           /* device [4 ceil(M/4), w], zero padded, 16-byte aligned (TMA bulk
+    const double* Xf;           /* device [8 ceil(M/8), w], zero padded, 16-byte aligned (TMA bulk
                                    copies): kernel.num_prims == 0: w = d_in + 1, row j =
                                    (Xs[j, :], -|Xs[j, :]|^2 / 2); otherwise w = d_in, the raw X  */
     double hmax;                /* max_j |Xs[j, :]|^2 / 2 (rounding bound of the expanded distance) */
@@ -181,7 +182,7 @@ typedef struct slb_gp_output {
                                                                     functions.py:405-409 */
     const double* gamma;        /* device [M]: L^-T alpha (mean-only Bellman path)      */
     const double* prior_mean;   /* device [d_in] linear prior-mean row, or NULL         */
-    const double* gamma_f;      /* device [4 ceil(M/4)], zero padded, 16-byte aligned: the filter's
+    const double* gamma_f;      /* device [8 ceil(M/8)], zero padded, 16-byte aligned: the filter's
                                    mean weights, scale^2 gamma (times the RBF variance when
                                    kernel.num_prims == 0, whose kernel values are then <= 1)   */
     double gamma_l1;            /* >= sum_i (|L^-1|^T |alpha|)_i in the units of gamma_f: bounds the
@@ -373,10 +374,15 @@ int slb_index_to_state(void* stream, const slb_grid* grid, int64_t idx_begin, in
 int slb_bellman_sweep(void* stream, const slb_bellman* cfg, int64_t idx_begin, int64_t idx_end,
                       double* out_dev);
 /* discrete_policy_optimization: actions_dev [n_actions, m]; constraint_dev [n_actions, n] or
- * NULL (value < 0 => -inf, :272-275); best_dev[i] = first argmax over actions (:278) */
+ * NULL (value < 0 => -inf, :272-275); best_dev[i] = first argmax over actions (:278, NaN counts as
+ * the maximum like np.argmax).  workspace_dev: NULL, or >= slb_bellman_argmax_workspace bytes: with
+ * GP dynamics on plain RBF factors the action is then factored out of the exponent (one kernel
+ * row per STATE, an [n_actions x M] x [M x states] fp64 tensor-core contraction per output)
+ * instead of n_actions sweeps; the workspace size is 0 when that path does not apply. */
+int64_t slb_bellman_argmax_workspace(const slb_bellman* cfg, int32_t n_actions);
 int slb_bellman_argmax(void* stream, const slb_bellman* cfg, int64_t idx_begin, int64_t idx_end,
                        const double* actions_dev, int32_t n_actions, const double* constraint_dev,
-                       int32_t* best_dev, double* best_value_dev);
+                       int32_t* best_dev, double* best_value_dev, void* workspace_dev);
 /* max_i |a_i - b_i| into result_dev[0] (value-iteration convergence test, test_rl.py:66-69) */
 int slb_max_abs_diff(void* stream, const double* a_dev, const double* b_dev, int64_t n,
                      double* result_dev);

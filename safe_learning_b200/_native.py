@@ -151,8 +151,9 @@ SIGNATURES = {
     "slb_eval_function": (C.c_int, [_vp, C.POINTER(SlbFunction), _dp, _i64, _dp]),
     "slb_index_to_state": (C.c_int, [_vp, C.POINTER(SlbGrid), _i64, _i64, _dp]),
     "slb_bellman_sweep": (C.c_int, [_vp, C.POINTER(SlbBellman), _i64, _i64, _dp]),
+    "slb_bellman_argmax_workspace": (C.c_int64, [C.POINTER(SlbBellman), _i32]),
     "slb_bellman_argmax": (C.c_int, [_vp, C.POINTER(SlbBellman), _i64, _i64, _dp, _i32, _dp, _dp,
-                                     _dp]),
+                                     _dp, _vp]),
     "slb_max_abs_diff": (C.c_int, [_vp, _dp, _dp, _i64, _dp]),
 }
 

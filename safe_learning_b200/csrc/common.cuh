@@ -277,6 +277,20 @@ SLB_DEV double kernel_expr_diag(const slb_kernel& K, const double* z) {
 
 // GridWorld.index_to_state (functions.py:714-731): ijk * unit_maxes + offset, two roundings.
 SLB_DEV void grid_index_to_state(const slb_grid& g, int64_t idx, double* x) {
+    if (g.nindex <= 0x7fffffffll) {        // 32-bit index arithmetic (same integers, ~5x fewer instructions)
+        unsigned rest = (unsigned)idx;
+#pragma unroll
+        for (int c = SLB_MAX_DIM - 1; c >= 0; --c) {
+            if (c < g.ndim) {
+                const unsigned n = (unsigned)g.num_points[c];
+                const unsigned q = rest / n;
+                const unsigned i = rest - q * n;
+                rest = q;
+                x[c] = f64add(f64mul((double)i, g.unit_maxes[c]), g.offset[c]);
+            }
+        }
+        return;
+    }
 #pragma unroll
     for (int c = SLB_MAX_DIM - 1; c >= 0; --c) {
         if (c < g.ndim) {

@@ -36,13 +36,24 @@
 
 namespace {
 
-constexpr int FT = 64;                 // stage 1: threads per CTA = points per CTA (1024 CTAs at
+#ifndef SLB_FT
+#define SLB_FT 64
+#endif
+#ifndef SLB_MEAN_MINB
+#define SLB_MEAN_MINB 7
+#endif
+#ifndef SLB_MEAN_UNROLL
+#define SLB_MEAN_UNROLL 4
+#endif
+constexpr int FT = SLB_FT;             // stage 1: threads per CTA = points per CTA (1024 CTAs at
                                        // 256 x 256, 7 resident per SM: single wave, 98.8% balanced)
+constexpr int MU = SLB_MEAN_UNROLL;    // independent exp chains per thread (rows per iteration)
 constexpr int HR = SLB_HEAD_RANK;
-constexpr int HT = 128;                // stage 2: threads per CTA (4 warps, one list entry each)
-constexpr int HEAD_CTAS = 148 * 4;
+constexpr int HT = 512;                // stage 2: threads per CTA (16 warps, one list entry each)
+constexpr int HEAD_CTAS = 148;         // one CTA per SM (it stages the head factors in shared memory)
 constexpr int64_t CHUNK = 1 << 22;     // points per pass of the three stages (bounds the workspace)
 constexpr double EPS_K = 1.0e-13;      // certified relative error of exp_neg_fast incl. its argument
+
 
 // terms of one undecided point, carried from stage 1 to stage 2
 struct filter_side { double dec0, thr, guard, coef[SLB_MAX_OUT], z[SLB_MAX_IN]; };
@@ -126,7 +137,7 @@ struct mean_pipe {
     int pf, pc0;                       // producer: factor and first row of the NEXT slice to issue
 };
 
-SLB_DEV int padded_rows(int M) { return (M + 3) & ~3; }
+SLB_DEV int padded_rows(int M) { return (M + 7) & ~7; }
 
 SLB_DEV int first_factor_with_data(const slb_gp_stack& gp, int f) {
     while (f < gp.num_factors && gp.factors[f].M == 0) ++f;
@@ -186,9 +197,9 @@ SLB_DEV void mean_factor(const slb_gp_stack& gp, int f, const int* outs, const d
         zz = fma(zs[c], zs[c], zz);
     }
     zz *= -0.5;
-    double dot[NO];
+    double dot[NO], dot2[NO];                  // two partial sums: half the loop-carried chain
 #pragma unroll
-    for (int q = 0; q < NO; ++q) dot[q] = 0.0;
+    for (int q = 0; q < NO; ++q) { dot[q] = 0.0; dot2[q] = 0.0; }
     double kbound = general ? 0.0 : 1.0;       // max_i |k_i| (plain RBF: variances live in gamma_f)
     const int Mp = padded_rows(F.M);
     for (int c0 = 0; c0 < Mp; c0 += P.C) {
@@ -202,10 +213,10 @@ SLB_DEV void mean_factor(const slb_gp_stack& gp, int f, const int* outs, const d
             // k_j = exp(-|zs - xs_j|^2 / 2) = exp(h_j + zs . xs_j + zz), h_j = -|xs_j|^2 / 2 staged
             // with the row; variance and scale^2 are folded into gamma_f.  4 independent chains.
             constexpr int W = DIN + 1;
-            for (int j0 = 0; j0 < rows; j0 += 4) {
-                double arg[4];
+            for (int j0 = 0; j0 < rows; j0 += MU) {
+                double arg[MU];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
+                for (int u = 0; u < MU; ++u) {
                     double row[W];
                     load_row<W>(xb + (j0 + u) * W, row);
                     double acc = row[DIN] + zz;
@@ -213,16 +224,21 @@ SLB_DEV void mean_factor(const slb_gp_stack& gp, int f, const int* outs, const d
                     for (int c = 0; c < DIN; ++c) acc = fma(zs[c], row[c], acc);
                     arg[u] = acc;
                 }
-                double g[NO][4];
+                double g[NO][MU];
 #pragma unroll
-                for (int q = 0; q < NO; ++q) load_row<4>(gb + q * P.C + j0, g[q]);
+                for (int q = 0; q < NO; ++q)
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
+                    for (int u = 0; u < MU; u += 4) load_row<4>(gb + q * P.C + j0 + u, *reinterpret_cast<double(*)[4]>(&g[q][u]));
+#pragma unroll
+                for (int u = 0; u < MU; ++u) {
                     bool far;
-                    const double k = exp_neg_fast(arg[u], tab512, far);
+                    double k = exp_neg_fast(arg[u], tab512, far);
+                    k = far ? 0.0 : k;
 #pragma unroll
-                    for (int q = 0; q < NO; ++q)
-                        if (!far) dot[q] = fma(k, g[q][u], dot[q]);
+                    for (int q = 0; q < NO; ++q) {
+                        if (u & 1) dot2[q] = fma(k, g[q][u], dot2[q]);
+                        else dot[q] = fma(k, g[q][u], dot[q]);
+                    }
                 }
             }
         } else {
@@ -245,6 +261,7 @@ SLB_DEV void mean_factor(const slb_gp_stack& gp, int f, const int* outs, const d
     }
 #pragma unroll
     for (int q = 0; q < NO; ++q) {
+        dot[q] += dot2[q];
         const slb_gp_output& G = gp.outputs[outs[q]];
         double mx = 0.0;
         if (G.prior_mean != nullptr) {
@@ -264,11 +281,11 @@ SLB_DEV void mean_factor(const slb_gp_stack& gp, int f, const int* outs, const d
 }
 
 template <int DIN>
-__global__ void __launch_bounds__(FT, 7)
+__global__ void __launch_bounds__(FT, SLB_MEAN_MINB)
 filter_mean_kernel(const __grid_constant__ slb_sweep cfg, const filter_args a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);             // [2]
-    double* tab512 = reinterpret_cast<double*>(smem_raw + 16);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);             // [2] slices, [2] exp tables
+    double* tab512 = reinterpret_cast<double*>(smem_raw + 32);
     double* tab64 = tab512 + 512;
     mean_pipe P;
     P.bar = bar;
@@ -283,12 +300,13 @@ filter_mean_kernel(const __grid_constant__ slb_sweep cfg, const filter_args a) {
     if (threadIdx.x == 0) {
         slb_bulk::mbar_init(bar + 0, 1);
         slb_bulk::mbar_init(bar + 1, 1);
+        slb_bulk::mbar_init(bar + 2, 1);
         slb_bulk::fence_barrier_init();
         slb_bulk::fence_proxy_async();
+        slb_bulk::mbar_arrive_expect_tx(bar + 2, 576 * sizeof(double));
+        slb_bulk::copy_g2s(tab512, g_exp_tables, 576 * sizeof(double), bar + 2);
         issue_slice<DIN>(cfg.gp, P, 0);                                 // slice 0 -> buffer 0
     }
-    for (int i = threadIdx.x; i < 512; i += FT) tab512[i] = c_exp2_tab512[i];
-    load_exp_table(tab64);
     __syncthreads();
 
     const int64_t rel0 = (int64_t)blockIdx.x * FT + threadIdx.x;
@@ -313,6 +331,7 @@ filter_mean_kernel(const __grid_constant__ slb_sweep cfg, const filter_args a) {
     for (int c = 0; c < DIN; ++c) sane &= fabs(t.z[c]) < 1e100;
 
     // ---- posterior mean of every output (functions.py:439-442 as k . L^-T alpha)
+    slb_bulk::mbar_wait(bar + 2, 0);              // exp tables have landed
     double mu[SLB_MAX_OUT];
     double mean_err[SLB_MAX_OUT];
     for (int f = 0; f < cfg.gp.num_factors; ++f) {
@@ -371,54 +390,103 @@ filter_mean_kernel(const __grid_constant__ slb_sweep cfg, const filter_args a) {
 }
 
 // ---- stage 2: variance given the head subset, one warp per undecided point ------------------------
-// Lane l owns rows l and l + 32 of the head solve a = W k (W = L_S^-1 of the subset's own Cholesky
-// factor, column-major and zero padded: row index contiguous, so a column is two coalesced 256-byte
-// loads served by L1); the kernel values k_j of the HR subset points are computed two per lane and
-// exchanged through shared memory.
+// One CTA per SM, 8 warps.  The head factors W = L_S^-1 (column-major, zero padded, 32 KB each) and
+// the subset's inputs are staged ONCE per CTA in shared memory by TMA bulk copies (read from
+// global memory per point they cost an L2/HBM round trip per column: measured 47 us for 5000
+// points); then every warp walks the list.  Lane l owns rows l and l + 32 of a = W k; the kernel
+// values k_j of the HR subset points are computed two per lane and exchanged through shared memory.
+constexpr int HW = HT / 32;            // warps per CTA
+
 template <int DIN>
-__global__ void __launch_bounds__(HT)
+__global__ void __launch_bounds__(HT, 1)
 filter_head_kernel(const __grid_constant__ slb_sweep cfg, const filter_args a) {
-    __shared__ double exptab[64];
-    __shared__ double kbuf[HT / 32][HR];
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);             // [1]
+    double* exptab = reinterpret_cast<double*>(smem_raw + 16);         // [64]
+    double* kbuf = exptab + 64;                                        // [HW][HR]
+    double* wbuf = kbuf + HW * HR;                                     // [nf][HR * HR]
+    const int nf = cfg.gp.num_factors;
+    double* xbuf = wbuf + (size_t)nf * HR * HR;                        // [nf][HR * DIN]
+    const int64_t count = (int64_t)a.counts[0];
+    if ((int64_t)blockIdx.x * HW >= count) return;                     // no list entry for this CTA
+    if (threadIdx.x == 0) {
+        slb_bulk::mbar_init(bar, 1);
+        slb_bulk::fence_barrier_init();
+        slb_bulk::fence_proxy_async();
+        unsigned bytes = 0;
+        for (int f = 0; f < nf; ++f)
+            if (cfg.gp.factors[f].head_rows > 0)
+                bytes += (unsigned)(HR * HR + HR * DIN) * sizeof(double);
+        slb_bulk::mbar_arrive_expect_tx(bar, bytes);
+        for (int f = 0; f < nf; ++f) {
+            const slb_gp_factor& F = cfg.gp.factors[f];
+            if (F.head_rows <= 0) continue;
+            slb_bulk::copy_g2s(wbuf + (size_t)f * HR * HR, F.Whead, HR * HR * sizeof(double), bar);
+            slb_bulk::copy_g2s(xbuf + (size_t)f * HR * DIN, F.Xhead, HR * DIN * sizeof(double), bar);
+        }
+    }
     load_exp_table(exptab);
     __syncthreads();
-    const int64_t count = (int64_t)a.counts[0];
+    slb_bulk::mbar_wait(bar, 0);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int64_t nwarps = (int64_t)gridDim.x * (HT / 32);
+    const int64_t nwarps = (int64_t)gridDim.x * HW;
     const int D = cfg.gp.num_outputs;
-    double* kw = kbuf[warp];
-    for (int64_t k = (int64_t)blockIdx.x * (HT / 32) + warp; k < count; k += nwarps) {
-        const filter_side& t = a.side_a[k];
+    double* kw = kbuf + warp * HR;
+    // One list entry = 17 doubles (filter_side) + its index: read with one coalesced load per warp,
+    // the NEXT entry while this one is processed (a dependent load per field cost two L2 / HBM
+    // round trips per point), fields handed out by shuffles.
+    static_assert(sizeof(filter_side) == 17 * sizeof(double), "lane <-> field map below");
+    const int64_t k_first = (int64_t)blockIdx.x * HW + warp;
+    double mine = 0.0;
+    int64_t rel_next = 0;
+    if (k_first < count) {
+        if (lane < 17) mine = reinterpret_cast<const double*>(a.side_a + k_first)[lane];
+        if (lane == 17) rel_next = a.list_a[k_first];
+    }
+    for (int64_t k = k_first; k < count; k += nwarps) {
+        const double cur = mine;
+        const int64_t rel = __shfl_sync(0xffffffffu, rel_next, 17);
+        if (k + nwarps < count) {
+            if (lane < 17) mine = reinterpret_cast<const double*>(a.side_a + k + nwarps)[lane];
+            if (lane == 17) rel_next = a.list_a[k + nwarps];
+        }
+        filter_side t;
+        t.dec0 = __shfl_sync(0xffffffffu, cur, 0);
+        t.thr = __shfl_sync(0xffffffffu, cur, 1);
+        t.guard = __shfl_sync(0xffffffffu, cur, 2);
+#pragma unroll
+        for (int j = 0; j < SLB_MAX_OUT; ++j) t.coef[j] = __shfl_sync(0xffffffffu, cur, 3 + j);
         double z[DIN];
 #pragma unroll
-        for (int c = 0; c < DIN; ++c) z[c] = t.z[c];
+        for (int c = 0; c < DIN; ++c) z[c] = __shfl_sync(0xffffffffu, cur, 3 + SLB_MAX_OUT + c);
         double shi[SLB_MAX_OUT];
         for (int j = 0; j < D; ++j) {
             const slb_gp_factor& F = cfg.gp.factors[cfg.gp.outputs[j].factor];
             shi[j] = sqrt(F.kernel.num_prims > 0 ? kernel_expr_diag<DIN>(F.kernel, z) : F.variance);
         }
-        for (int f = 0; f < cfg.gp.num_factors; ++f) {
+        for (int f = 0; f < nf; ++f) {
             const slb_gp_factor& F = cfg.gp.factors[f];
             const int rows = F.head_rows;
-            if (rows <= 0 || F.Whead == nullptr) continue;
+            if (rows <= 0) continue;
             const bool general = F.kernel.num_prims > 0;
             const double s2 = f64mul(F.scale, F.scale);
             double zs[DIN];
 #pragma unroll
             for (int c = 0; c < DIN; ++c) zs[c] = general ? z[c] : z[c] / F.lengthscales[c];
             // kernel values against the subset points lane and lane + 32 (functions.py:438)
+            const double* xh = xbuf + (size_t)f * HR * DIN;
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 const int j = lane + 32 * h;
                 double kv = 0.0;
                 if (j < rows) {
-                    const double* xr = F.Xhead + (size_t)j * DIN;
+                    const double* xr = xh + j * DIN;
                     if (general) {
                         kv = kernel_expr_cross<DIN>(F.kernel, zs, xr, exptab);
                     } else {
                         double a2 = 0.0;
 #pragma unroll
-                        for (int c = 0; c < DIN; ++c) { const double df = zs[c] - __ldg(xr + c); a2 = fma(df, df, a2); }
+                        for (int c = 0; c < DIN; ++c) { const double df = zs[c] - xr[c]; a2 = fma(df, df, a2); }
                         kv = F.variance * exp_neg_tab(-0.5 * a2, exptab);
                     }
                     kv = s2 * kv;
@@ -426,15 +494,19 @@ filter_head_kernel(const __grid_constant__ slb_sweep cfg, const filter_args a) {
                 kw[j] = kv;
             }
             __syncwarp();
-            double a_lo = 0.0, a_hi = 0.0;
-            const double* __restrict__ Wt = F.Whead;
+            // four independent partial sums per row: the FMA chain is the critical path
+            double al[2] = {0.0, 0.0}, ah[2] = {0.0, 0.0};
+            const double* __restrict__ Wt = wbuf + (size_t)f * HR * HR;
 #pragma unroll 4
-            for (int j = 0; j < rows; ++j) {
-                const double kj = kw[j];
-                a_lo = fma(__ldg(Wt + (size_t)j * HR + lane), kj, a_lo);
-                a_hi = fma(__ldg(Wt + (size_t)j * HR + 32 + lane), kj, a_hi);
+            for (int j = 0; j < HR; j += 2) {
+                const double2 kj = *reinterpret_cast<const double2*>(kw + j);
+                al[0] = fma(Wt[j * HR + lane], kj.x, al[0]);
+                ah[0] = fma(Wt[j * HR + 32 + lane], kj.x, ah[0]);
+                al[1] = fma(Wt[(j + 1) * HR + lane], kj.y, al[1]);
+                ah[1] = fma(Wt[(j + 1) * HR + 32 + lane], kj.y, ah[1]);
             }
             __syncwarp();
+            const double a_lo = al[0] + al[1], a_hi = ah[0] + ah[1];
             double ss = fma(a_lo, a_lo, a_hi * a_hi);
 #pragma unroll
             for (int off = 16; off > 0; off >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, off);
@@ -444,9 +516,8 @@ filter_head_kernel(const __grid_constant__ slb_sweep cfg, const filter_args a) {
             for (int j = 0; j < D; ++j)
                 if (cfg.gp.outputs[j].factor == f) shi[j] = s;
         }
+        const int outcome = decide(t, shi, D);
         if (lane == 0) {
-            const int outcome = decide(t, shi, D);
-            const int64_t rel = a.list_a[k];
             if (outcome >= 0) {
                 a.negative[rel] = outcome > 0 ? 1 : 0;
                 if (a.stats != nullptr) atomicAdd(a.stats + 1, 1ull);
@@ -467,12 +538,16 @@ int launch_filter(cudaStream_t st, const slb_sweep& cfg, const filter_args& a, s
     if (device < 0 || device >= 64 || !configured[device].load(std::memory_order_acquire)) {
         SLB_CUDA(cudaFuncSetAttribute(filter_mean_kernel<DIN>,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+        SLB_CUDA(cudaFuncSetAttribute(filter_head_kernel<DIN>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         if (device >= 0 && device < 64) configured[device].store(true, std::memory_order_release);
     }
     const int64_t blocks = (a.n + FT - 1) / FT;
     filter_mean_kernel<DIN><<<(unsigned)blocks, FT, smem, st>>>(cfg, a);
     SLB_LAUNCH_CHECK();
-    filter_head_kernel<DIN><<<HEAD_CTAS, HT, 0, st>>>(cfg, a);
+    const size_t head_smem = 16 + (64 + HW * HR) * sizeof(double) +
+                             (size_t)cfg.gp.num_factors * (HR * HR + HR * DIN) * sizeof(double);
+    filter_head_kernel<DIN><<<HEAD_CTAS, HT, head_smem, st>>>(cfg, a);
     SLB_LAUNCH_CHECK();
     return 0;
 }
@@ -554,11 +629,14 @@ int slb_lyapunov_sweep_filtered(void* stream, const slb_sweep* cfg, int64_t idx_
     // rows per staged slice: two buffers of (d_in + 1 + outputs per factor) doubles per row within
     // ~24 KB, so that 7 CTAs stay resident per SM
     const int din = cfg->gp.input_dim;
-    int chunk_rows = (24 * 1024) / (2 * 8 * (din + 1 + nomax));
+#ifndef SLB_MEAN_SMEM_KB
+#define SLB_MEAN_SMEM_KB 24
+#endif
+    int chunk_rows = (SLB_MEAN_SMEM_KB * 1024) / (2 * 8 * (din + 1 + nomax));
     chunk_rows = chunk_rows >= 256 ? 256 : (chunk_rows & ~7);
     a.chunk_rows = chunk_rows;
     a.max_outputs_per_factor = nomax;
-    const size_t smem = 16 + (512 + 64) * sizeof(double) +
+    const size_t smem = 32 + (512 + 64) * sizeof(double) +
                         (size_t)2 * chunk_rows * (din + 1 + nomax) * sizeof(double);
     for (int64_t off = 0; off < n_all; off += CHUNK) {
         const int64_t n = n_all - off < CHUNK ? n_all - off : CHUNK;

@@ -577,8 +577,12 @@ gp_tile_kernel(const __grid_constant__ slb_sweep cfg, const slb_gp_args a) {
     }
 }
 
-template <int DIN, bool TIMING, bool KEXPR>
+// TPV: see gp_tile_kernel -- nvcc emits templates of this unnamed namespace as WEAK symbols under a
+// prefix derived from the source file name, so the three tile-size units would otherwise share
+// one launch function (the first one linked: every refine pass ran with 64-point tiles).
+template <int DIN, bool TIMING, bool KEXPR, int TPV = TP>
 int launch_gp_tile(cudaStream_t st, const slb_sweep& cfg, const slb_gp_args& a) {
+    static_assert(TPV == TP, "TPV only disambiguates the symbol");
     // the opt-in to > 48 KB of dynamic shared memory is a per-device function attribute
     // (atomic flags: sweeps may be issued from several host threads)
     static std::atomic<bool> configured[64];

@@ -569,6 +569,13 @@ int slb_launch_det_sweep(cudaStream_t st, const slb_sweep& cfg, const double* st
     return 0;
 }
 
+// bellman_tile.cu
+bool slb_argmax_factorable(const slb_bellman& cfg, int m, int n_actions);
+int64_t slb_argmax_workspace_bytes(const slb_bellman& cfg, int n_actions);
+int slb_launch_argmax_factored(cudaStream_t st, const slb_bellman& cfg, int64_t idx_begin, int64_t n,
+                               const double* actions, int n_actions, int m, const double* constraint,
+                               int32_t* best, double* best_value, void* workspace);
+
 extern "C" {
 
 int slb_abi_version(void) { return SLB_ABI_VERSION; }
@@ -795,9 +802,15 @@ int slb_bellman_sweep(void* stream, const slb_bellman* cfg, int64_t idx_begin, i
     return 0;
 }
 
+int64_t slb_bellman_argmax_workspace(const slb_bellman* cfg, int32_t n_actions) {
+    if (cfg == nullptr || n_actions < 1) return 0;
+    const int m = cfg->policy.out_dim;
+    return slb_argmax_factorable(*cfg, m, n_actions) ? slb_argmax_workspace_bytes(*cfg, n_actions) : 0;
+}
+
 int slb_bellman_argmax(void* stream, const slb_bellman* cfg, int64_t idx_begin, int64_t idx_end,
                        const double* actions_dev, int32_t n_actions, const double* constraint_dev,
-                       int32_t* best_dev, double* best_value_dev) {
+                       int32_t* best_dev, double* best_value_dev, void* workspace_dev) {
     SLB_CHECK(cfg != nullptr && cfg->fixed_action, "slb_bellman_argmax: cfg.fixed_action must be set");
     int m;
     if (validate_bellman(cfg, &m)) return 1;
@@ -807,6 +820,10 @@ int slb_bellman_argmax(void* stream, const slb_bellman* cfg, int64_t idx_begin, 
     const int64_t n = idx_end - idx_begin;
     if (n == 0) return 0;
     SLB_CHECK(best_dev != nullptr, "slb_bellman_argmax: null output");
+    if (workspace_dev != nullptr && slb_argmax_factorable(*cfg, m, n_actions))
+        return slb_launch_argmax_factored((cudaStream_t)stream, *cfg, idx_begin, n, actions_dev,
+                                          n_actions, m, constraint_dev, best_dev, best_value_dev,
+                                          workspace_dev);
     const int din = cfg->grid.ndim + m;
 #define SLB_ARGMAX_CASE(D)                                                               \
     case D: bellman_argmax_kernel<D><<<blocks_for(n), LT, 0, (cudaStream_t)stream>>>(  \

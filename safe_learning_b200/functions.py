@@ -1261,9 +1261,9 @@ class GPRCached(object):
         M, din = fac.M, self._X.shape[1]
         r = min(M, R)
         fac.Whead = dev.zeros((R, R))
-        fac.Xhead = dev.zeros((max(r, 1), din))
+        fac.Xhead = dev.zeros((R, din))
         fac.head_rows = r
-        Mp = max(4 * ((M + 3) // 4), 4)
+        Mp = max(8 * ((M + 7) // 8), 8)
         width = din + 1 if fac.plain else din
         fac.Xf = dev.zeros((Mp, width))
         fac.hmax = 0.0
@@ -1281,7 +1281,7 @@ class GPRCached(object):
             if kernel is None:
                 kernel = self.kern.K_scaled(fac.Xs) if fac.plain else self.kern.K_device(fac.Xs)
             subset = self._pivoted_subset(kernel, r)
-            fac.Xhead = fac.Xs.index_select(0, subset).contiguous()
+            fac.Xhead[:r] = fac.Xs.index_select(0, subset)
             k_ss = kernel.index_select(0, subset).index_select(1, subset)
             k_ss = (k_ss + torch.eye(r, dtype=torch.float64, device=k_ss.device)
                     * self.likelihood.variance) * (self._scale ** 2)

@@ -45,6 +45,7 @@ class PolicyIteration(object):
         self.policy = policy
         self.feed_dict = {}
         self._storage = {}
+        self.factor_actions = True        # discrete_policy_optimization: see csrc/bellman_tile.cu
         self._grid = _triangulation_of(value_function).discretization
         self._begin, self._end = dev.shard_range(self._grid.nindex)
 
@@ -167,9 +168,14 @@ class PolicyIteration(object):
             cons_dev = dev.to_device(np.stack(rows))
         actions_dev = dev.to_device(actions)
         best = dev.empty((n,), torch.int32)
+        # factored path (csrc/bellman_tile.cu): one kernel row per state + a tensor-core contraction
+        # against the per-action table, when the library says it applies (workspace > 0)
+        need = int(lib.slb_bellman_argmax_workspace(cfg, n_opt)) if self.factor_actions else 0
+        scratch = dev.empty((need // 8 + 1,)) if need else None
         nat.check(lib.slb_bellman_argmax(dev.stream(), cfg, self._begin, self._end,
                                          actions_dev.data_ptr(), n_opt, dev.ptr(cons_dev),
-                                         best.data_ptr(), None), "slb_bellman_argmax")
+                                         best.data_ptr(), None, dev.ptr(scratch)),
+                  "slb_bellman_argmax")
         chosen = actions_dev[best.to(torch.int64)]            # [n, m]
         if m != 1 and dev.dist_info()[1] > 1:
             raise NotImplementedError("multi-GPU policy optimisation supports m == 1")

@@ -172,7 +172,34 @@ def shared():
                       "frac_of_fp64_peak": fl * n / (ms * 1e-3) * 1e-12 / PEAK_TF}))
 
 
+def argmax():
+    """discrete_policy_optimization at C3 size: 512 x 512 states, |A| = 101, GP-mean dynamics M=500;
+    the factored tensor-core path (csrc/bellman_tile.cu) against one sweep per action."""
+    par = W.make_pendulum(num_points=8, M=500)
+    grid = sl.GridWorld(par["limits"], 512)
+    _, dyn = W._build(sl, par, "product")
+    reward = sl.QuadraticFunction(-scipy.linalg.block_diag(np.diag([1., 2.]), 1.2 * np.eye(1)))
+    value = sl.Triangulation(grid, np.random.default_rng(0).normal(size=(grid.nindex, 1)), project=True)
+    policy = sl.Triangulation(grid, np.zeros((grid.nindex, 1)), project=True)
+    rl = sl.PolicyIteration(policy, dyn, reward, value, gamma=0.98)
+    actions = np.linspace(-1, 1, 101).reshape(-1, 1)
+    out = {}
+    for name, flag in (("factored", True), ("per_action_sweeps", False)):
+        rl.factor_actions = flag
+        ms = timed(lambda: rl.discrete_policy_optimization(actions), steps=3, warmup=1)
+        out[name] = {"ms": ms, "policy": policy.parameters[0].copy()}
+    same = float(np.mean(out["factored"]["policy"] == out["per_action_sweeps"]["policy"]))
+    n = grid.nindex
+    flops = 2.0 * n * 101 * 500 * 2
+    print(json.dumps({"bench": "discrete_policy_optimization", "grid": "512x512", "actions": 101,
+                      "M": 500, "factored_ms": out["factored"]["ms"],
+                      "per_action_sweeps_ms": out["per_action_sweeps"]["ms"],
+                      "speedup": out["per_action_sweeps"]["ms"] / out["factored"]["ms"],
+                      "factored_tflops": flops / (out["factored"]["ms"] * 1e-3) * 1e-12,
+                      "same_greedy_action_frac": same}))
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["bellman", "det", "det_linear", "c5", "shared", "c4", "nb"]
+    which = sys.argv[1:] or ["bellman", "det", "det_linear", "c5", "shared", "c4", "nb", "argmax"]
     for name in which:
         globals()[name]()
