@@ -314,6 +314,19 @@ def run_ours(args, rank, world, local_rank):
         fs = dict(zip(("prior", "head", "refined", "points"), (int(v) for v in t.cpu())))
     k_total, _ = timed(lyap.compute_negative, args.steps)
     filter_ms = k_total / args.steps
+    # stage times, live: the mean stage alone, then mean + head (diagnostic switch of the library;
+    # the flags of these timing runs are incomplete and not used)
+    lib = nat.load()
+    stage_ms = {}
+    if filtered:
+        for label, mask in (("mean", 0), ("mean_head", 1)):
+            lib.slb_debug_filter_stages(mask)
+            for _ in range(3):
+                lyap.compute_negative()
+            t_total, _ = timed(lyap.compute_negative, args.steps)
+            stage_ms[label] = t_total / args.steps
+        lib.slb_debug_filter_stages(3)
+        lyap.compute_negative()
 
     # ---- the full posterior for EVERY point (filter off): the round-1 step and the kernel the
     # algorithmic FLOP count of SURVEY.md section 8d describes
@@ -354,7 +367,8 @@ def run_ours(args, rank, world, local_rank):
     barrier()
     e_total = max_over_ranks(e_total)
     e2e_value = n_total * args.steps / (e_total * 1e-3)
-    h2d = h2d_box[0] + n_local                   # GP tables + this rank's slab of the mask
+    h2d = h2d_box[0]                             # GP tables (the mask is hashed on the host and
+                                                 # re-uploaded only when its content changed)
     d2h = n_local + 64                           # this rank's slab of the safe set + key/stats
     clocks = sampler.stop() if rank == 0 else None
 
@@ -420,10 +434,31 @@ def run_ours(args, rank, world, local_rank):
                         "frac": hbm_gbs / hbm_peak,
                         "note": "path is fp64-compute-bound (AI ~3e4 FLOP/B); HBM fraction "
                                 "reported for completeness"}}
-    # the filter pass evaluates D' M kernel entries (one fp64 exp each) per point: exp-bound on
-    # the fp64 pipe; peak = exp-only microbenchmark of round 1 (8.4e11 exp/s)
-    exp_rate = 2 * M_TRAIN * n_local / (filter_ms * 1e-3)
+    # The dominant kernel of the DEFAULT step is the filter's mean stage (filter_mean_kernel): per
+    # point and training row 3 d_in + 4 fp64 operations for the kernel entry and the dot product +
+    # one exp (F_B = D M (3 d_in + 4 + E_exp), E_exp = 1) on the fp64 pipe
+    # (DFMA shares the pipe and the peak of the DMMA tensor op: tools/fp64_peaks.cu).
     npts = max(fs["points"], 1)
+    mean_ms = stage_ms.get("mean")
+    roofline_filter = None
+    if mean_ms:
+        flops_mean = 2 * M_TRAIN * (3 * 3 + 4 + 1)
+        ach = flops_mean * n_local / (mean_ms * 1e-3) * 1e-12
+        roofline_filter = {
+            "bound": "tensor", "kernel": "filter_mean_kernel<3> (fp64 pipe: DFMA, the pipe and peak "
+                                         "of the DMMA tensor op): GP mean of every point, prior-variance decision",
+            "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,
+            "kernel_ms": mean_ms, "algorithmic_flops_per_point": flops_mean,
+            "executed_fp64_ops_per_entry": 12,
+            "exp_per_s": 2 * M_TRAIN * n_local / (mean_ms * 1e-3), "exp_peak_per_s": 8.4e11,
+            "exp_frac": 2 * M_TRAIN * n_local / (mean_ms * 1e-3) / 8.4e11,
+            "stage_ms": {"mean": mean_ms, "head": stage_ms["mean_head"] - mean_ms,
+                         "refine": filter_ms - stage_ms["mean_head"]},
+            "note": "stage times measured live with the library's stage switch (L2 flushed before "
+                    "each); E_exp = 1 charges one flop per exp although the table-driven exp executes "
+                    "7 fp64 operations, so the executed-operation utilisation of the pipe is about "
+                    "1.7x this fraction (ncu: profiles/r02_filter_mean_kernel_ncu.json)"}
+    exp_rate = 2 * M_TRAIN * n_local / (filter_ms * 1e-3)
     filter_info = {
         "enabled": bool(filtered),
         "decided_by_mean_and_prior_bound": fs["prior"] / npts,
@@ -453,7 +488,12 @@ def run_ours(args, rank, world, local_rank):
                 "ms_per_step_spread": spread(e_per),
                 "api": "FunctionStack.import_cache(pinned host tables), lyapunov.initial_safe_set = "
                        "numpy mask, update_safe_set(), lyapunov.safe_set (numpy), feed_dict[c_max]"},
-        "gpu_launches": int(launches), "roofline": roofline, "filter": filter_info,
+        "gpu_launches": int(launches),
+        # `roofline`: the dominant kernel of the timed (default, filtered) step; the kernel that carries
+        # the O(M^2) algorithmic cost of SURVEY.md section 8d is reported next to it
+        "roofline": roofline_filter if roofline_filter is not None else roofline,
+        "roofline_full_posterior": roofline,
+        "filter": filter_info,
         "full_posterior": {"value": n_total * args.steps / (f_total * 1e-3), "unit": UNIT,
                            "ms_per_step": f_total / args.steps,
                            "ms_per_step_spread": spread(f_per),

@@ -281,9 +281,17 @@ void        slb_note_graph_replay(int64_t kernels);
  * %globaltimer (ns) at tile start / end, cycles spent waiting at block barriers, 0;
  * pass NULL to switch it off (default) */
 int         slb_debug_phase_timing(void* buffer_dev);
+/* diagnostics (timing of the individual stages of slb_lyapunov_sweep_filtered; the flags are only
+ * complete with mask 3, the default): bit 0 runs the head stage, bit 1 the refine pass */
+int         slb_debug_filter_stages(int32_t mask);
+/* diagnostics: deterministic-dynamics sweeps of the LQR composition (d = 2, saturated linear policy,
+ * linear dynamics, quadratic V, constant / abs-linear L_V) take a specialised register-resident
+ * kernel; 0 switches back to the generic interpreter (A/B timing, parity tests). */
+int         slb_debug_det_fast(int32_t enable);
 /* diagnostics / tuning: the refine pass of slb_lyapunov_sweep_filtered uses 16-point tiles for
- * lists of up to `upto16` points, 32-point tiles up to `upto32`, 64-point tiles beyond
- * (defaults 16 * 148 and 32 * 148: one wave of CTAs on a B200) */
+ * lists of up to `upto16` points, 32-point tiles up to `upto32`, 64-point tiles beyond (defaults
+ * 16 * 18 and 32 * 148); with 16- and 32-point tiles the rows of a tile are additionally split
+ * over the CTAs a one-per-SM grid has to spare (up to 8 per tile) */
 int         slb_debug_refine_split(int64_t upto16, int64_t upto32);
 
 /* ---- GP factor packing (after GPRCached.update_cache, functions.py:395-415) ------------ */

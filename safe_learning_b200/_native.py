@@ -129,6 +129,8 @@ SIGNATURES = {
     "slb_note_graph_replay": (None, [_i64]),
     "slb_debug_phase_timing": (C.c_int, [_vp]),
     "slb_debug_refine_split": (C.c_int, [_i64, _i64]),
+    "slb_debug_det_fast": (C.c_int, [_i32]),
+    "slb_debug_filter_stages": (C.c_int, [_i32]),
     "slb_packed_len": (C.c_int64, [_i32]),
     "slb_pack_factor": (C.c_int, [_vp, _dp, _i32, _dp]),
     "slb_pivoted_subset": (C.c_int, [_vp, _dp, _i32, _i32, _vp, _dp]),

@@ -302,6 +302,18 @@ SLB_DEV void grid_index_to_state(const slb_grid& g, int64_t idx, double* x) {
     }
 }
 
+// fmod(a, b) for a >= 0, b > 0, a / b < 2^52 -- bit-identical to fmod (whose result is exact): the
+// quotient from one division (it can only come out one too large, when a / b rounds up to an
+// integer), the remainder by an exact fma.  CUDA's fmod is a long software loop; the Triangulation
+// lookup calls it once per dimension and dominated its cost.
+SLB_DEV double fmod_exact_pos(double a, double b) {
+    double q = floor(a / b);
+    double r = fma(-q, b, a);
+    if (r < 0.0) r = fma(-(q - 1.0), b, a);
+    else if (r >= b) r = fma(-(q + 1.0), b, a);
+    return r;
+}
+
 // ---- Triangulation (functions.py:1103-1158 lookup, :1473-1499 evaluation) ----------------
 SLB_DEV void eval_triangulation(const slb_function& f, const double* xin, double* out) {
     const slb_grid& g = f.grid;
@@ -331,7 +343,7 @@ SLB_DEV void eval_triangulation(const slb_function& f, const double* xin, double
         if (cen < lo) cen = lo;
         else if (cen > hi) { cen = hi; pattern |= 1 << c; }
         else all_clipped = false;
-        unit[c] = fmod(cen, g.unit_maxes[c]);
+        unit[c] = fmod_exact_pos(cen, g.unit_maxes[c]);
     }
     // simplex inside the unit cell: first simplex whose barycentric weights are all >= -tol
     int best = 0;
@@ -341,10 +353,20 @@ SLB_DEV void eval_triangulation(const slb_function& f, const double* xin, double
     for (int s = 0; s < f.nsimplex && !tabled; ++s) {
         const int64_t v0 = f.unit_simplices[s * (d + 1)];
         double o[SLB_MAX_DIM];
-        int64_t t = v0;
-        for (int c = d - 1; c >= 0; --c) {
-            o[c] = (double)(t % g.num_points[c]) * g.unit_maxes[c];
-            t /= g.num_points[c];
+        if (g.nindex <= 0x7fffffffll) {        // 32-bit index arithmetic (same integers)
+            unsigned t = (unsigned)v0;
+            for (int c = d - 1; c >= 0; --c) {
+                const unsigned n = (unsigned)g.num_points[c];
+                const unsigned qq = t / n;
+                o[c] = (double)(t - qq * n) * g.unit_maxes[c];
+                t = qq;
+            }
+        } else {
+            int64_t t = v0;
+            for (int c = d - 1; c >= 0; --c) {
+                o[c] = (double)(t % g.num_points[c]) * g.unit_maxes[c];
+                t /= g.num_points[c];
+            }
         }
         const double* H = f.hyperplanes + (size_t)s * d * d;
         double wsum = 0.0, wmin = 1e300;

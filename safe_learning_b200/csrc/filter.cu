@@ -33,6 +33,7 @@
 
 #include "bulk_copy.cuh"
 #include "exp2_tab512.cuh"
+#include "gp_args.h"
 
 namespace {
 
@@ -49,9 +50,10 @@ constexpr int FT = SLB_FT;             // stage 1: threads per CTA = points per 
                                        // 256 x 256, 7 resident per SM: single wave, 98.8% balanced)
 constexpr int MU = SLB_MEAN_UNROLL;    // independent exp chains per thread (rows per iteration)
 constexpr int HR = SLB_HEAD_RANK;
-constexpr int HT = 512;                // stage 2: threads per CTA (16 warps, one list entry each)
+constexpr int HT = 256;                // stage 2: threads per CTA (8 warps, 8 list entries each)
 constexpr int HEAD_CTAS = 148;         // one CTA per SM (it stages the head factors in shared memory)
 constexpr int64_t CHUNK = 1 << 22;     // points per pass of the three stages (bounds the workspace)
+constexpr int64_t WS_HEAD = 64 + SLB_SPLIT_TICKET_BYTES + (int64_t)SLB_SPLIT_PARTIAL_BYTES;   // bytes before the lists
 constexpr double EPS_K = 1.0e-13;      // certified relative error of exp_neg_fast incl. its argument
 
 
@@ -70,6 +72,8 @@ struct filter_args {
     unsigned long long* stats;         // nullptr or [4], see slb200.h
     int chunk_rows;                    // training rows per staged slice (multiple of 8)
     int max_outputs_per_factor;
+    int head_factors_staged;           // head stage: factors whose tables fit in shared memory (the
+                                       // others are read from global memory)
 };
 
 // outcome for err_j = beta_j sigma_j with sigma_j in [0, shi_j]:  +1 decided negative (True),
@@ -389,80 +393,69 @@ filter_mean_kernel(const __grid_constant__ slb_sweep cfg, const filter_args a) {
     }
 }
 
-// ---- stage 2: variance given the head subset, one warp per undecided point ------------------------
+// ---- stage 2: variance given the head subset, one warp per HP undecided points ---------------------
 // One CTA per SM, 8 warps.  The head factors W = L_S^-1 (column-major, zero padded, 32 KB each) and
 // the subset's inputs are staged ONCE per CTA in shared memory by TMA bulk copies (read from
 // global memory per point they cost an L2/HBM round trip per column: measured 47 us for 5000
-// points); then every warp walks the list.  Lane l owns rows l and l + 32 of a = W k; the kernel
-// values k_j of the HR subset points are computed two per lane and exchanged through shared memory.
+// points); then every warp walks the list in groups of HP = 8 points.  Lane l owns rows l and l + 32
+// of a = W k for all HP points (16 independent FMA chains): a column of W read from shared memory
+// serves 8 points -- one point per warp made the stage shared-memory-bandwidth bound (6.4 ms for
+// the 1.9 M list entries of a 2048 x 2048 grid).  The kernel values k_j of the HR subset points are
+// computed two per lane and point and exchanged through shared memory ([row][point]: one row's
+// HP values are four broadcast 128-bit loads); lane p < HP makes the decision of point p.
 constexpr int HW = HT / 32;            // warps per CTA
+constexpr int HP = 8;                  // list entries per warp iteration
 
 template <int DIN>
 __global__ void __launch_bounds__(HT, 1)
 filter_head_kernel(const __grid_constant__ slb_sweep cfg, const filter_args a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);             // [1]
+    unsigned* s_stat = reinterpret_cast<unsigned*>(smem_raw + 8);      // decided / undecided by this CTA
     double* exptab = reinterpret_cast<double*>(smem_raw + 16);         // [64]
-    double* kbuf = exptab + 64;                                        // [HW][HR]
-    double* wbuf = kbuf + HW * HR;                                     // [nf][HR * HR]
+    double* kbuf = exptab + 64;                                        // [HW][HR][HP]
+    double* wbuf = kbuf + HW * HR * HP;                                // [nf][HR * HR]
     const int nf = cfg.gp.num_factors;
-    double* xbuf = wbuf + (size_t)nf * HR * HR;                        // [nf][HR * DIN]
+    double* xbuf = wbuf + (size_t)a.head_factors_staged * HR * HR;     // [staged][HR * DIN]
     const int64_t count = (int64_t)a.counts[0];
-    if ((int64_t)blockIdx.x * HW >= count) return;                     // no list entry for this CTA
+    if ((int64_t)blockIdx.x * HW * HP >= count) return;                // no list entry for this CTA
     if (threadIdx.x == 0) {
         slb_bulk::mbar_init(bar, 1);
         slb_bulk::fence_barrier_init();
         slb_bulk::fence_proxy_async();
-        unsigned bytes = 0;
-        for (int f = 0; f < nf; ++f)
+        unsigned bytes = 64 * sizeof(double);
+        for (int f = 0; f < a.head_factors_staged; ++f)
             if (cfg.gp.factors[f].head_rows > 0)
                 bytes += (unsigned)(HR * HR + HR * DIN) * sizeof(double);
         slb_bulk::mbar_arrive_expect_tx(bar, bytes);
-        for (int f = 0; f < nf; ++f) {
+        slb_bulk::copy_g2s(exptab, g_exp_tables + 512, 64 * sizeof(double), bar);
+        for (int f = 0; f < a.head_factors_staged; ++f) {
             const slb_gp_factor& F = cfg.gp.factors[f];
             if (F.head_rows <= 0) continue;
             slb_bulk::copy_g2s(wbuf + (size_t)f * HR * HR, F.Whead, HR * HR * sizeof(double), bar);
             slb_bulk::copy_g2s(xbuf + (size_t)f * HR * DIN, F.Xhead, HR * DIN * sizeof(double), bar);
         }
     }
-    load_exp_table(exptab);
+    if (threadIdx.x < 2) s_stat[threadIdx.x] = 0;
     __syncthreads();
     slb_bulk::mbar_wait(bar, 0);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t ngroups = (count + HP - 1) / HP;
     const int64_t nwarps = (int64_t)gridDim.x * HW;
     const int D = cfg.gp.num_outputs;
-    double* kw = kbuf + warp * HR;
-    // One list entry = 17 doubles (filter_side) + its index: read with one coalesced load per warp,
-    // the NEXT entry while this one is processed (a dependent load per field cost two L2 / HBM
-    // round trips per point), fields handed out by shuffles.
-    static_assert(sizeof(filter_side) == 17 * sizeof(double), "lane <-> field map below");
-    const int64_t k_first = (int64_t)blockIdx.x * HW + warp;
-    double mine = 0.0;
-    int64_t rel_next = 0;
-    if (k_first < count) {
-        if (lane < 17) mine = reinterpret_cast<const double*>(a.side_a + k_first)[lane];
-        if (lane == 17) rel_next = a.list_a[k_first];
-    }
-    for (int64_t k = k_first; k < count; k += nwarps) {
-        const double cur = mine;
-        const int64_t rel = __shfl_sync(0xffffffffu, rel_next, 17);
-        if (k + nwarps < count) {
-            if (lane < 17) mine = reinterpret_cast<const double*>(a.side_a + k + nwarps)[lane];
-            if (lane == 17) rel_next = a.list_a[k + nwarps];
-        }
-        filter_side t;
-        t.dec0 = __shfl_sync(0xffffffffu, cur, 0);
-        t.thr = __shfl_sync(0xffffffffu, cur, 1);
-        t.guard = __shfl_sync(0xffffffffu, cur, 2);
-#pragma unroll
-        for (int j = 0; j < SLB_MAX_OUT; ++j) t.coef[j] = __shfl_sync(0xffffffffu, cur, 3 + j);
-        double z[DIN];
-#pragma unroll
-        for (int c = 0; c < DIN; ++c) z[c] = __shfl_sync(0xffffffffu, cur, 3 + SLB_MAX_OUT + c);
+    double* kw = kbuf + warp * HR * HP;
+    for (int64_t grp = (int64_t)blockIdx.x * HW + warp; grp < ngroups; grp += nwarps) {
+        // lane p < HP owns list entry grp * HP + p: its terms, its index and finally its decision
+        const int64_t k = grp * HP + min(lane, HP - 1);
+        const bool mine = lane < HP && k < count;
+        filter_side t = {};
+        int64_t rel = 0;
+        if (mine) { t = a.side_a[k]; rel = a.list_a[k]; }
         double shi[SLB_MAX_OUT];
         for (int j = 0; j < D; ++j) {
             const slb_gp_factor& F = cfg.gp.factors[cfg.gp.outputs[j].factor];
-            shi[j] = sqrt(F.kernel.num_prims > 0 ? kernel_expr_diag<DIN>(F.kernel, z) : F.variance);
+            shi[j] = mine ? sqrt(F.kernel.num_prims > 0 ? kernel_expr_diag<DIN>(F.kernel, t.z) : F.variance)
+                          : 0.0;
         }
         for (int f = 0; f < nf; ++f) {
             const slb_gp_factor& F = cfg.gp.factors[f];
@@ -470,65 +463,92 @@ filter_head_kernel(const __grid_constant__ slb_sweep cfg, const filter_args a) {
             if (rows <= 0) continue;
             const bool general = F.kernel.num_prims > 0;
             const double s2 = f64mul(F.scale, F.scale);
-            double zs[DIN];
+            const bool staged = f < a.head_factors_staged;
+            const double* xh = staged ? xbuf + (size_t)f * HR * DIN : F.Xhead;
+            // kernel values of every point of the group against subset points lane and lane + 32
+            // (functions.py:438); entries beyond the list reuse the last point (never decided)
 #pragma unroll
-            for (int c = 0; c < DIN; ++c) zs[c] = general ? z[c] : z[c] / F.lengthscales[c];
-            // kernel values against the subset points lane and lane + 32 (functions.py:438)
-            const double* xh = xbuf + (size_t)f * HR * DIN;
+            for (int p = 0; p < HP; ++p) {
+                double zs[DIN];
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int j = lane + 32 * h;
-                double kv = 0.0;
-                if (j < rows) {
-                    const double* xr = xh + j * DIN;
-                    if (general) {
-                        kv = kernel_expr_cross<DIN>(F.kernel, zs, xr, exptab);
-                    } else {
-                        double a2 = 0.0;
-#pragma unroll
-                        for (int c = 0; c < DIN; ++c) { const double df = zs[c] - xr[c]; a2 = fma(df, df, a2); }
-                        kv = F.variance * exp_neg_tab(-0.5 * a2, exptab);
-                    }
-                    kv = s2 * kv;
+                for (int c = 0; c < DIN; ++c) {
+                    const double zc = __shfl_sync(0xffffffffu, t.z[c], p);
+                    zs[c] = general ? zc : zc / F.lengthscales[c];
                 }
-                kw[j] = kv;
-            }
-            __syncwarp();
-            // four independent partial sums per row: the FMA chain is the critical path
-            double al[2] = {0.0, 0.0}, ah[2] = {0.0, 0.0};
-            const double* __restrict__ Wt = wbuf + (size_t)f * HR * HR;
-#pragma unroll 4
-            for (int j = 0; j < HR; j += 2) {
-                const double2 kj = *reinterpret_cast<const double2*>(kw + j);
-                al[0] = fma(Wt[j * HR + lane], kj.x, al[0]);
-                ah[0] = fma(Wt[j * HR + 32 + lane], kj.x, ah[0]);
-                al[1] = fma(Wt[(j + 1) * HR + lane], kj.y, al[1]);
-                ah[1] = fma(Wt[(j + 1) * HR + 32 + lane], kj.y, ah[1]);
-            }
-            __syncwarp();
-            const double a_lo = al[0] + al[1], a_hi = ah[0] + ah[1];
-            double ss = fma(a_lo, a_lo, a_hi * a_hi);
 #pragma unroll
-            for (int off = 16; off > 0; off >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, off);
-            double kss = F.kss;
-            if (general) kss = s2 * kernel_expr_diag<DIN>(F.kernel, z);
-            const double s = sqrt(f64sub(kss, ss) / s2);              // NaN if negative
-            for (int j = 0; j < D; ++j)
-                if (cfg.gp.outputs[j].factor == f) shi[j] = s;
-        }
-        const int outcome = decide(t, shi, D);
-        if (lane == 0) {
-            if (outcome >= 0) {
-                a.negative[rel] = outcome > 0 ? 1 : 0;
-                if (a.stats != nullptr) atomicAdd(a.stats + 1, 1ull);
-            } else {
-                const unsigned long long slot = atomicAdd(a.counts + 1, 1ull);
-                a.list_b[slot] = rel;
-                if (a.stats != nullptr) atomicAdd(a.stats + 2, 1ull);
+                for (int h = 0; h < 2; ++h) {
+                    const int j = lane + 32 * h;
+                    double kv = 0.0;
+                    if (j < rows) {
+                        const double* xr = xh + j * DIN;
+                        if (general) {
+                            kv = kernel_expr_cross<DIN>(F.kernel, zs, xr, exptab);
+                        } else {
+                            double a2 = 0.0;
+#pragma unroll
+                            for (int c = 0; c < DIN; ++c) { const double df = zs[c] - xr[c]; a2 = fma(df, df, a2); }
+                            kv = F.variance * exp_neg_tab(-0.5 * a2, exptab);
+                        }
+                        kv = s2 * kv;
+                    }
+                    kw[j * HP + p] = kv;
+                }
             }
+            __syncwarp();
+            double al[HP], ah[HP];
+#pragma unroll
+            for (int p = 0; p < HP; ++p) { al[p] = 0.0; ah[p] = 0.0; }
+            const double* __restrict__ Wt = staged ? wbuf + (size_t)f * HR * HR : F.Whead;
+#pragma unroll 2
+            for (int j = 0; j < HR; ++j) {
+                const double wl = Wt[j * HR + lane], wh = Wt[j * HR + 32 + lane];
+                double kj[HP];
+#pragma unroll
+                for (int p = 0; p < HP; p += 2) {
+                    const double2 v = *reinterpret_cast<const double2*>(kw + j * HP + p);
+                    kj[p] = v.x; kj[p + 1] = v.y;
+                }
+#pragma unroll
+                for (int p = 0; p < HP; ++p) {
+                    al[p] = fma(wl, kj[p], al[p]);
+                    ah[p] = fma(wh, kj[p], ah[p]);
+                }
+            }
+            __syncwarp();
+            // sum a^2 per point over the 64 rows: lane p ends up with point p's
+            double ssp = 0.0;
+#pragma unroll
+            for (int p = 0; p < HP; ++p) {
+                double ss = fma(al[p], al[p], ah[p] * ah[p]);
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, off);
+                if (lane == p) ssp = ss;
+            }
+            double kss = F.kss;
+            if (general && mine) kss = s2 * kernel_expr_diag<DIN>(F.kernel, t.z);
+            const double sdev = sqrt(f64sub(kss, ssp) / s2);          // NaN if negative
+            for (int j = 0; j < D; ++j)
+                if (cfg.gp.outputs[j].factor == f) shi[j] = sdev;
+        }
+        const int outcome = mine ? decide(t, shi, D) : 0;
+        const bool undecided = mine && outcome < 0;
+        if (mine && outcome >= 0) a.negative[rel] = outcome > 0 ? 1 : 0;
+        const long long slot = list_append(undecided, a.counts + 1);
+        if (undecided) a.list_b[slot] = rel;
+        const unsigned dec = __ballot_sync(0xffffffffu, mine && !undecided);
+        const unsigned und = __ballot_sync(0xffffffffu, undecided);
+        if (lane == 0) {
+            if (dec) atomicAdd(s_stat + 0, (unsigned)__popc(dec));
+            if (und) atomicAdd(s_stat + 1, (unsigned)__popc(und));
         }
     }
+    // one pair of global atomics per CTA (one per point serialised on the counter's L2 line)
+    __syncthreads();
+    if (a.stats != nullptr && threadIdx.x < 2 && s_stat[threadIdx.x] != 0)
+        atomicAdd(a.stats + 1 + threadIdx.x, (unsigned long long)s_stat[threadIdx.x]);
 }
+
+int g_filter_stages = 3;               // slb_debug_filter_stages: bit 0 head stage, bit 1 refine pass
 
 template <int DIN>
 int launch_filter(cudaStream_t st, const slb_sweep& cfg, const filter_args& a, size_t smem) {
@@ -545,9 +565,15 @@ int launch_filter(cudaStream_t st, const slb_sweep& cfg, const filter_args& a, s
     const int64_t blocks = (a.n + FT - 1) / FT;
     filter_mean_kernel<DIN><<<(unsigned)blocks, FT, smem, st>>>(cfg, a);
     SLB_LAUNCH_CHECK();
-    const size_t head_smem = 16 + (64 + HW * HR) * sizeof(double) +
-                             (size_t)cfg.gp.num_factors * (HR * HR + HR * DIN) * sizeof(double);
-    filter_head_kernel<DIN><<<HEAD_CTAS, HT, head_smem, st>>>(cfg, a);
+    if (!(g_filter_stages & 1)) return 0;
+    const size_t head_fixed = 16 + (64 + HW * HR * HP) * sizeof(double);
+    const size_t per_factor = (size_t)(HR * HR + HR * DIN) * sizeof(double);
+    filter_args ah = a;
+    ah.head_factors_staged = cfg.gp.num_factors;
+    while (ah.head_factors_staged > 0 && head_fixed + ah.head_factors_staged * per_factor > 226 * 1024)
+        --ah.head_factors_staged;
+    const size_t head_smem = head_fixed + ah.head_factors_staged * per_factor;
+    filter_head_kernel<DIN><<<HEAD_CTAS, HT, head_smem, st>>>(cfg, ah);
     SLB_LAUNCH_CHECK();
     return 0;
 }
@@ -557,15 +583,21 @@ int launch_filter(cudaStream_t st, const slb_sweep& cfg, const filter_args& a, s
 // gp_sweep.cu: the full posterior on the compacted list (count read on the device)
 int slb_launch_refine(cudaStream_t st, const slb_sweep& cfg, int64_t n_max, int64_t idx_begin,
                       const int64_t* list, const unsigned long long* count, uint8_t* negative,
-                      double* values);
+                      double* values, double* split_partial, int* split_ticket);
 
 extern "C" {
+
+int slb_debug_filter_stages(int32_t mask) {
+    g_filter_stages = mask;
+    return 0;
+}
 
 int64_t slb_filter_workspace(int64_t n) {
     if (n < 0) n = 0;
     if (n > CHUNK) n = CHUNK;     // longer ranges are swept in passes of CHUNK points
-    // [0] |list A|, [1] |list B| (uint64, 64 bytes reserved), list A, list B, terms of list A
-    return 64 + n * (int64_t)(2 * sizeof(int64_t) + sizeof(filter_side));
+    // [0] |list A|, [1] |list B| (uint64, 64 bytes reserved), tile tickets and partial sums of the
+    // row-split refine pass, list A, list B, terms of list A
+    return WS_HEAD + n * (int64_t)(2 * sizeof(int64_t) + sizeof(filter_side));
 }
 
 int slb_lyapunov_sweep_filtered(void* stream, const slb_sweep* cfg, int64_t idx_begin,
@@ -622,7 +654,9 @@ int slb_lyapunov_sweep_filtered(void* stream, const slb_sweep* cfg, int64_t idx_
     const int64_t cap = n_all < CHUNK ? n_all : CHUNK;
     filter_args a;
     a.counts = reinterpret_cast<unsigned long long*>(ws);
-    a.list_a = reinterpret_cast<int64_t*>(ws + 64);
+    int* tickets = reinterpret_cast<int*>(ws + 64);
+    double* partial = reinterpret_cast<double*>(ws + 64 + SLB_SPLIT_TICKET_BYTES);
+    a.list_a = reinterpret_cast<int64_t*>(ws + WS_HEAD);
     a.list_b = a.list_a + cap;
     a.side_a = reinterpret_cast<filter_side*>(a.list_b + cap);
     a.stats = reinterpret_cast<unsigned long long*>(stats_dev);
@@ -640,7 +674,7 @@ int slb_lyapunov_sweep_filtered(void* stream, const slb_sweep* cfg, int64_t idx_
                         (size_t)2 * chunk_rows * (din + 1 + nomax) * sizeof(double);
     for (int64_t off = 0; off < n_all; off += CHUNK) {
         const int64_t n = n_all - off < CHUNK ? n_all - off : CHUNK;
-        SLB_CUDA(cudaMemsetAsync(a.counts, 0, 64, st));
+        SLB_CUDA(cudaMemsetAsync(a.counts, 0, 64 + SLB_SPLIT_TICKET_BYTES, st));
         a.n = n; a.idx_begin = idx_begin + off;
         a.negative = negative_dev + off;
         a.values = values_dev ? values_dev + off : nullptr;
@@ -657,8 +691,10 @@ int slb_lyapunov_sweep_filtered(void* stream, const slb_sweep* cfg, int64_t idx_
             return 1;
         }
         if (rc) return rc;
+        if (!(g_filter_stages & 2)) continue;
         rc = slb_launch_refine(st, *cfg, n, idx_begin + off, a.list_b, a.counts + 1,
-                               negative_dev + off, values_dev ? values_dev + off : nullptr);
+                               negative_dev + off, values_dev ? values_dev + off : nullptr,
+                               partial, tickets);
         if (rc) return rc;
     }
     return 0;

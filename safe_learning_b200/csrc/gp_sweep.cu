@@ -74,11 +74,15 @@ static long long* g_timing_buffer = nullptr;
 // (16, 32, 64 points per CTA) and only the launch whose range holds the list length does work;
 // the CTAs of the others (and those beyond the list) leave at once.  Measured tile times at
 // M = 500, two factors: see DESIGN.md section 3.5.
-static int64_t g_refine_split[2] = {16 * 148, 32 * 148};
+static int64_t g_refine_split[2] = {16 * 18, 32 * 148};
 
+// Short lists (<= 32 x 148 points) additionally split every tile's ROWS over the CTAs the grid has
+// to spare (up to SLB_SPLIT_MAX groups of equal triangular area, gp_tile.cuh): the tile kernel's
+// duration is set by the M^2 / 2 contraction of one tile, so 525 points in 33 16-point tiles kept
+// 33 SMs busy for 88 us while 115 idled; split 8 ways a 32-point tile's share is ~8 times shorter.
 int slb_launch_refine(cudaStream_t st, const slb_sweep& cfg, int64_t n_max, int64_t idx_begin,
                       const int64_t* list, const unsigned long long* count, uint8_t* negative,
-                      double* values) {
+                      double* values, double* split_partial, int* split_ticket) {
     slb_gp_args a;
     memset(&a, 0, sizeof(a));
     a.idx_begin = idx_begin; a.mode = MODE_SWEEP_GRID;
@@ -91,7 +95,15 @@ int slb_launch_refine(cudaStream_t st, const slb_sweep& cfg, int64_t n_max, int6
         if (lo[v] >= hi[v] || lo[v] >= n_max) continue;
         a.count_min = lo[v]; a.count_max = hi[v];
         a.n = n_max < hi[v] ? n_max : hi[v];        // the grid never needs to cover more
-        if (v == 2) a.n = n_max;
+        a.split_partial = nullptr; a.split_ticket = nullptr; a.split_max = 1;
+        if (v < 2 && split_partial != nullptr) {
+            // at least one CTA per SM, so that short lists have CTAs to spread their rows over
+            if (a.n < (int64_t)148 * tps[v]) a.n = (int64_t)148 * tps[v];
+            if ((a.n + tps[v] - 1) / tps[v] <= SLB_SPLIT_ITEMS) {
+                a.split_partial = split_partial; a.split_ticket = split_ticket;
+                a.split_max = SLB_SPLIT_MAX;
+            }
+        }
         const int rc = dispatch_gp_tile(st, cfg, a, tps[v]);
         if (rc) return rc;
     }

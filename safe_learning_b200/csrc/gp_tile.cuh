@@ -219,15 +219,27 @@ gp_tile_kernel(const __grid_constant__ slb_sweep cfg, const slb_gp_args a) {
     double* pre = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(kexpr) + SMEM_KEXPR);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int64_t tile0 = (int64_t)blockIdx.x * TP;
+    int64_t tile_index = blockIdx.x;
+    int grp = 0, G = 1;                // row group of this CTA / groups per tile (split refine)
     // refine mode (slb_lyapunov_sweep_filtered): the point list was compacted by the filter
     // kernel, its length lives in device memory; CTAs beyond it leave before the first barrier
     int64_t npts = a.n;
     if (a.count != nullptr) {
         npts = (int64_t)*a.count;
         // one launch per tile size; only the one whose range holds the list length does work
-        if (tile0 >= npts || npts <= a.count_min || npts > a.count_max) return;
+        if (npts <= a.count_min || npts > a.count_max) return;
+        if (a.split_partial != nullptr) {
+            // short list: spread every tile's rows over as many CTAs as the grid has to spare
+            const int64_t ntiles = (npts + TP - 1) / TP;
+            const int64_t spare = (int64_t)gridDim.x / ntiles;
+            G = (int)(spare < 1 ? 1 : (spare > a.split_max ? a.split_max : spare));
+            if ((int64_t)blockIdx.x >= ntiles * G) return;
+            tile_index = blockIdx.x / G;
+            grp = blockIdx.x % G;
+        }
+        if (tile_index * TP >= npts) return;
     }
+    const int64_t tile0 = tile_index * TP;
     const int D = cfg.gp.num_outputs;
     long long t_gen = 0, t_mma = 0, t_epi = 0, t_mark = 0, t_sync = 0, t_s0 = 0;
     const long long t_start = TIMING ? clock64() : 0;
@@ -306,11 +318,43 @@ gp_tile_kernel(const __grid_constant__ slb_sweep cfg, const slb_gp_args a) {
     const int jg = tid / TP;                          // 0..NT/TP-1
     const double2* ks_lane = reinterpret_cast<const double2*>(Ks) + (lane & 3) * KSTR + (lane >> 2);
 
+    // ---- factor epilogue: mean and error bound of the outputs on factor f from tot[] (sum a^2, then
+    // a . alpha per output)                                     (functions.py:439-456, 514)
+    auto factor_epilogue = [&](int f, bool general, double s2) {
+        const slb_gp_factor& F = cfg.gp.factors[f];
+        if (tid < TP) {
+            int qty = 1;
+            for (int o = 0; o < D; ++o) {
+                const slb_gp_output& Go = cfg.gp.outputs[o];
+                if (Go.factor != f) continue;
+                double mx = 0.0;                                   // functions.py:439
+                if (Go.prior_mean != nullptr) {
+                    mx = f64mul(zraw[tid], Go.prior_mean[0]);
+                    for (int c = 1; c < DIN; ++c)
+                        mx = f64add(mx, f64mul(zraw[c * TP + tid], Go.prior_mean[c]));
+                    mx = f64mul(F.scale, mx);
+                }
+                const double fmean = f64add(tot[qty * TP + tid], mx) / F.scale;   // :442, :455
+                double kss = F.kss;
+                if (general) {
+                    double zt[DIN];
+#pragma unroll
+                    for (int c = 0; c < DIN; ++c) zt[c] = zraw[c * TP + tid];
+                    kss = s2 * kernel_expr_diag<DIN>(*kexpr, zt);
+                }
+                const double fvar = f64sub(kss, tot[tid]) / s2;                    // :450-451, :456
+                post[o * TP + tid] = fmean;
+                post[(SLB_MAX_OUT + o) * TP + tid] =
+                    a.want_var ? fvar : f64mul(Go.beta, sqrt(fvar));              // :514
+                ++qty;
+            }
+        }
+    };
+
     for (int f = 0; f < cfg.gp.num_factors; ++f) {
         const slb_gp_factor& F = cfg.gp.factors[f];
         const int M = F.M, nrb = F.nrb;
         const int nk4 = (M + 3) >> 2;
-        const int npan = (nrb + 31) >> 5;
         const double s2 = f64mul(F.scale, F.scale);
         const double variance = F.variance;
         const double* __restrict__ Xs = F.Xs;
@@ -334,20 +378,27 @@ gp_tile_kernel(const __grid_constant__ slb_sweep cfg, const slb_gp_args a) {
         __syncwarp();
         int resident = -1;
 
-        for (int ip = 0; ip < npan; ++ip) {
+        // row blocks of this CTA: all of them, or (split refine) the grp-th of G ranges of equal
+        // triangular area, boundaries at nrb sqrt(k / G)
+        int rlo = 0, rhi = nrb;
+        if (G > 1) {
+            rlo = __double2int_rd((double)nrb * sqrt((double)grp / (double)G));
+            rhi = grp + 1 == G ? nrb : __double2int_rd((double)nrb * sqrt((double)(grp + 1) / (double)G));
+        }
+        for (int pbeg = rlo; pbeg < rhi; pbeg += 32) {
             double acc[RQ][NB][2];
 #pragma unroll
             for (int q = 0; q < RQ; ++q)
 #pragma unroll
                 for (int nb = 0; nb < NB; ++nb) { acc[q][nb][0] = 0.0; acc[q][nb][1] = 0.0; }
 
-            const int pbeg = 32 * ip;
-            const int pend = min(pbeg + 32, nrb);
+            const int pend = min(pbeg + 32, rhi);
             int bq[RQ];
 #pragma unroll
             for (int q = 0; q < RQ; ++q) bq[q] = pend - 1 - wslot - NW * (RQ - 1 - q);
 
-            for (int jp = 0; jp <= ip; ++jp) {
+            const int jp_last = (pend - 1) >> 5;          // the j-panel holding the diagonal of row pend - 1
+            for (int jp = 0; jp <= jp_last; ++jp) {
                 const int nkp = min(64, nk4 - 64 * jp);
                 if (jp != resident) {
                     // ---- generation phase: K[j, p] for j in this panel (functions.py:438)
@@ -435,9 +486,9 @@ gp_tile_kernel(const __grid_constant__ slb_sweep cfg, const slb_gp_args a) {
                 const double2* ap[RQ];
 #pragma unroll
                 for (int q = 0; q < RQ; ++q) {
+                    // row block b needs the pairs of k-steps <= b: in j-panel jp that is b - 32 jp + 1
                     const bool valid = bq[q] >= pbeg;
-                    int me = valid ? npairs_mma : 0;
-                    if (valid && jp == ip) me = min(npairs_mma, bq[q] - pbeg + 1);
+                    const int me = valid ? min(npairs_mma, max(0, bq[q] - 32 * jp + 1)) : 0;
                     mend[q] = me;
                     const int64_t b = valid ? bq[q] : 0;
                     ap[q] = reinterpret_cast<const double2*>(F.Wpack) +
@@ -502,35 +553,46 @@ gp_tile_kernel(const __grid_constant__ slb_sweep cfg, const slb_gp_args a) {
         }
         __syncthreads();
 
-        // ---- factor epilogue: mean and error bound of the outputs on this factor
-        if (tid < TP) {
-            int qty = 1;
-            for (int o = 0; o < D; ++o) {
-                const slb_gp_output& G = cfg.gp.outputs[o];
-                if (G.factor != f) continue;
-                double mx = 0.0;                                   // functions.py:439
-                if (G.prior_mean != nullptr) {
-                    mx = f64mul(zraw[tid], G.prior_mean[0]);
-                    for (int c = 1; c < DIN; ++c)
-                        mx = f64add(mx, f64mul(zraw[c * TP + tid], G.prior_mean[c]));
-                    mx = f64mul(F.scale, mx);
-                }
-                const double fmean = f64add(tot[qty * TP + tid], mx) / F.scale;   // :442, :455
-                double kss = F.kss;
-                if (general) {
-                    double zt[DIN];
-#pragma unroll
-                    for (int c = 0; c < DIN; ++c) zt[c] = zraw[c * TP + tid];
-                    kss = s2 * kernel_expr_diag<DIN>(*kexpr, zt);
-                }
-                const double fvar = f64sub(kss, tot[tid]) / s2;                    // :450-451, :456
-                post[o * TP + tid] = fmean;
-                post[(SLB_MAX_OUT + o) * TP + tid] =
-                    a.want_var ? fvar : f64mul(G.beta, sqrt(fvar));               // :514
-                ++qty;
-            }
+        if (G > 1) {
+            // split refine: this CTA's share of the factor's sums; the tile is finished below
+            double* part = a.split_partial + ((size_t)blockIdx.x * SLB_MAX_OUT + f) * (NRED * TP);
+            for (int i = tid; i < NRED * TP; i += NT) part[i] = tot[i];
+            __syncthreads();
+            continue;
         }
+        factor_epilogue(f, general, s2);
         __syncthreads();
+    }
+
+    if (G > 1) {
+        // ---- split refine: the last CTA of the tile adds the partial sums in group order
+        __shared__ int s_ticket;
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) s_ticket = atomicAdd(a.split_ticket + tile_index, 1);
+        __syncthreads();
+        if (s_ticket != G - 1) return;
+        __threadfence();
+        if (tid == 0) a.split_ticket[tile_index] = 0;                  // ready for the next launch
+        for (int f = 0; f < cfg.gp.num_factors; ++f) {
+            const slb_gp_factor& F = cfg.gp.factors[f];
+            for (int i = tid; i < NRED * TP; i += NT) {
+                double sum = 0.0;
+                for (int g2 = 0; g2 < G; ++g2)
+                    sum += __ldcg(a.split_partial +
+                                  ((size_t)(tile_index * G + g2) * SLB_MAX_OUT + f) * (NRED * TP) + i);
+                tot[i] = sum;
+            }
+            const bool general = KEXPR && F.kernel.num_prims > 0;
+            if (general) {
+                const int* src = reinterpret_cast<const int*>(&F.kernel);
+                for (int i = tid; i < (int)(sizeof(slb_kernel) / sizeof(int)); i += NT)
+                    reinterpret_cast<int*>(kexpr)[i] = src[i];
+            }
+            __syncthreads();
+            factor_epilogue(f, general, f64mul(F.scale, F.scale));
+            __syncthreads();
+        }
     }
 
     if (TIMING && lane == 0) {

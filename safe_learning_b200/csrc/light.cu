@@ -188,6 +188,111 @@ det_sweep_kernel(const __grid_constant__ slb_sweep cfg, const double* __restrict
     if (mean != nullptr) for (int c = 0; c < d; ++c) mean[i * d + c] = mu[c];
 }
 
+// ---- deterministic-dynamics sweep, specialised ---------------------------------------------------
+// The same decision as det_sweep_kernel for the composition of the reference's LQR experiments
+// (deterministic variant of C2 / C5): d = 2, m = 1, policy = Saturation(
+// LinearSystem), dynamics = LinearSystem on [x, u], V = QuadraticFunction, L_V = a constant or
+// abs(LinearSystem) (one- or two-column), scalar L_f.  det_sweep_kernel interprets generic
+// descriptors through local-memory operand arrays (1.6 KB stack, 64-bit index division, one byte
+// written per thread: 7% of the HBM roofline); here the operands live in registers, the index
+// arithmetic is one 32-bit division per 8 points and the 8 flags leave as one 8-byte store.  The
+// arithmetic is eval_fn's, operation for operation (__dmul_rn / __dadd_rn, same order): bit-exact.
+struct det_fast_params {
+    const double* k;                   // policy row [2] (device)
+    const double* a;                   // dynamics rows on [x0, x1, u]: [2][3]
+    const double* p;                   // V's matrix [2][2]
+    const double* lv;                  // L_V rows [lv_kind][2] (lv_kind 1, 2)
+    double klo, khi;                   // saturation bounds
+    double lv_const, lf, tau;
+    int lv_kind;                       // 0: constant, 1: one abs-linear column, 2: two, 1-norm
+    int lv_abs;                        // columns pass through fabs (SLB_FLAG_ABS | NORM1)
+};
+
+SLB_DEV double quad2(const double (&p)[2][2], double x0, double x1) {
+    const double l0 = f64add(f64mul(x0, p[0][0]), f64mul(x1, p[1][0]));
+    const double l1 = f64add(f64mul(x0, p[0][1]), f64mul(x1, p[1][1]));
+    return f64add(f64mul(l0, x0), f64mul(l1, x1));
+}
+
+constexpr int DF_PTS = 8;              // points per thread (consecutive along the last grid axis)
+
+__global__ void __launch_bounds__(LT)
+det_sweep_fast_kernel(const __grid_constant__ slb_grid g, const det_fast_params qp, int64_t idx_begin,
+                      int64_t n, uint8_t* __restrict__ negative, double* __restrict__ values) {
+    const int64_t first = ((int64_t)blockIdx.x * LT + threadIdx.x) * DF_PTS;
+    if (first >= n) return;
+    // operand tables -> registers (warp-uniform loads, served by L1 after the first warp)
+    struct { double k[2], a[2][3], p[2][2], lv[2][2], klo, khi, lv_const, lf, tau; int lv_kind, lv_abs; } q;
+    q.k[0] = __ldg(qp.k); q.k[1] = __ldg(qp.k + 1);
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) q.a[r][c] = __ldg(qp.a + 3 * r + c);
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            q.p[r][c] = __ldg(qp.p + 2 * r + c);
+            q.lv[r][c] = r < qp.lv_kind ? __ldg(qp.lv + 2 * r + c) : 0.0;
+        }
+    }
+    q.klo = qp.klo; q.khi = qp.khi; q.lv_const = qp.lv_const; q.lf = qp.lf; q.tau = qp.tau;
+    q.lv_kind = qp.lv_kind; q.lv_abs = qp.lv_abs;
+    const unsigned n1 = (unsigned)g.num_points[1];
+    const unsigned flat = (unsigned)(idx_begin + first);
+    unsigned i0 = flat / n1, i1 = flat - i0 * n1;
+    unsigned long long flags = 0;
+    const int count = (int)min((int64_t)DF_PTS, n - first);
+#pragma unroll
+    for (int t = 0; t < DF_PTS; ++t) {
+        if (t < count) {
+            const double x0 = f64add(f64mul((double)i0, g.unit_maxes[0]), g.offset[0]);
+            const double x1 = f64add(f64mul((double)i1, g.unit_maxes[1]), g.offset[1]);
+            double u = f64add(f64mul(x0, q.k[0]), f64mul(x1, q.k[1]));
+            u = fmin(fmax(u, q.klo), q.khi);
+            const double m0 = f64add(f64add(f64mul(x0, q.a[0][0]), f64mul(x1, q.a[0][1])), f64mul(u, q.a[0][2]));
+            const double m1 = f64add(f64add(f64mul(x0, q.a[1][0]), f64mul(x1, q.a[1][1])), f64mul(u, q.a[1][2]));
+            const double vx = quad2(q.p, x0, x1);
+            const double vm = quad2(q.p, m0, m1);
+            double lvx = q.lv_const;
+            if (q.lv_kind >= 1) {
+                double c0 = f64add(f64mul(x0, q.lv[0][0]), f64mul(x1, q.lv[0][1]));
+                if (q.lv_abs) c0 = fabs(c0);
+                lvx = c0;
+                if (q.lv_kind == 2) {
+                    const double c1 = f64add(f64mul(x0, q.lv[1][0]), f64mul(x1, q.lv[1][1]));
+                    lvx = f64add(fabs(c0), fabs(c1));          // 1-norm of a vector-valued L_V (:284-286)
+                }
+            }
+            const double thr = f64mul(f64mul(-lvx, f64add(1.0, q.lf)), q.tau);
+            const double dec = f64add(f64sub(vm, vx), 0.0);     // lyapunov_combine with bound = 0
+            if (dec < thr) flags |= 1ull << (8 * t);
+            if (values != nullptr) values[first + t] = vx;
+            if (++i1 == n1) { i1 = 0; ++i0; }
+        }
+    }
+    if (count == DF_PTS && ((reinterpret_cast<uintptr_t>(negative) + first) & 7) == 0) {
+        *reinterpret_cast<unsigned long long*>(negative + first) = flags;
+    } else {
+        for (int t = 0; t < count; ++t) negative[first + t] = (uint8_t)((flags >> (8 * t)) & 1);
+    }
+}
+
+// host: does the sweep match the specialised composition?  Fills `q` from the device tables.
+bool det_fast_applicable(const slb_sweep& cfg, const double* states, const double* decrease,
+                         const double* threshold, const double* mean) {
+    if (states || decrease || threshold || mean) return false;
+    if (cfg.grid.ndim != 2 || cfg.grid.nindex > 0x7fffffffll) return false;
+    const slb_function& P = cfg.policy, &F = cfg.dynamics, &V = cfg.lyapunov, &L = cfg.lipschitz_v;
+    if (P.kind != SLB_FN_LINEAR || P.in_dim != 2 || P.out_dim != 1 || (P.flags & ~SLB_FLAG_SATURATE))
+        return false;
+    if (F.kind != SLB_FN_LINEAR || F.in_dim != 3 || F.out_dim != 2 || F.flags) return false;
+    if (V.kind != SLB_FN_QUADRATIC || V.in_dim != 2 || V.flags) return false;
+    if (cfg.lf_values != nullptr || cfg.lipschitz_f.kind != SLB_FN_NONE) return false;
+    if (L.kind == SLB_FN_NONE) return true;
+    if (L.kind != SLB_FN_LINEAR || L.in_dim != 2 || L.out_dim < 1 || L.out_dim > 2) return false;
+    // one column: plain or abs; two columns reduce with the 1-norm in threshold() either way
+    return (L.flags & ~(SLB_FLAG_ABS | SLB_FLAG_NORM1)) == 0;
+}
+
 __global__ void __launch_bounds__(LT)
 eval_function_kernel(const __grid_constant__ slb_function fn, const double* __restrict__ points,
                      int64_t n, double* __restrict__ out, int ncols) {
@@ -558,11 +663,32 @@ pivoted_subset_kernel(const double* __restrict__ K, int M, int r, int64_t* __res
 
 inline unsigned blocks_for(int64_t n) { return (unsigned)((n + LT - 1) / LT); }
 
+bool g_det_fast = true;           // slb_debug_det_fast: A/B against the generic interpreter
+
 }  // namespace
 
 int slb_launch_det_sweep(cudaStream_t st, const slb_sweep& cfg, const double* states, int64_t n,
                          int64_t idx_begin, uint8_t* negative, double* values, double* decrease,
                          double* threshold, double* mean) {
+    if (g_det_fast && det_fast_applicable(cfg, states, decrease, threshold, mean)) {
+        const slb_function& L = cfg.lipschitz_v;
+        det_fast_params q;
+        memset(&q, 0, sizeof(q));
+        q.k = cfg.policy.matrix; q.a = cfg.dynamics.matrix; q.p = cfg.lyapunov.matrix;
+        const bool sat = (cfg.policy.flags & SLB_FLAG_SATURATE) != 0;
+        q.klo = sat ? cfg.policy.lower : -INFINITY;
+        q.khi = sat ? cfg.policy.upper : INFINITY;
+        q.lv_const = cfg.lv_const; q.lf = cfg.lf_const; q.tau = cfg.tau;
+        if (L.kind != SLB_FN_NONE) {
+            q.lv = L.matrix;
+            q.lv_kind = L.out_dim;
+            q.lv_abs = (L.flags & (SLB_FLAG_ABS | SLB_FLAG_NORM1)) != 0;
+        }
+        const int64_t threads = (n + DF_PTS - 1) / DF_PTS;
+        det_sweep_fast_kernel<<<blocks_for(threads), LT, 0, st>>>(cfg.grid, q, idx_begin, n, negative, values);
+        SLB_LAUNCH_CHECK();
+        return 0;
+    }
     det_sweep_kernel<<<blocks_for(n), LT, 0, st>>>(cfg, states, n, idx_begin, negative, values,
                                                    decrease, threshold, mean);
     SLB_LAUNCH_CHECK();
@@ -799,6 +925,11 @@ int slb_bellman_sweep(void* stream, const slb_bellman* cfg, int64_t idx_begin, i
     }
 #undef SLB_BELLMAN_CASE
     SLB_LAUNCH_CHECK();
+    return 0;
+}
+
+int slb_debug_det_fast(int32_t enable) {
+    g_det_fast = enable != 0;
     return 0;
 }
 

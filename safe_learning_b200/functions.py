@@ -200,6 +200,19 @@ class Function(object):
                                         out.data_ptr()), "slb_eval_function")
         return out
 
+    # differentiable application (torch autograd) --------------------------------------------
+    def jacobian_device(self, points):
+        """d out / d in at device points [n, in] -> device tensor [n, out, in] (the reference gets
+        these from ``tf.gradients``; here every fusable object states its own)."""
+        raise NotImplementedError("%s has no device Jacobian" % type(self).__name__)
+
+    def torch(self, points):
+        """``fun(points)`` on a device tensor [n, in] as a node of torch's autograd graph: forward
+        = the fused CUDA evaluation, backward = ``grad_out @ jacobian_device(points)`` on the
+        device (``PolicyIteration.future_values`` with tensors, ``reinforcement_learning.py:65-114``
+        under ``tf.gradients`` in ``examples/inverted_pendulum.ipynb`` cell 17)."""
+        return _FusedApply.apply(points, self)
+
     # algebra (``functions.py:112-122``) --------------------------------------------------
     def __neg__(self):
         return ScaledFunction(self, -1.0)
@@ -217,6 +230,23 @@ class Function(object):
     def __add__(self, other):
         raise NotImplementedError("AddedFunction (functions.py:125-160) is outside the fused "
                                   "hot path of this build")
+
+
+class _FusedApply(torch.autograd.Function):
+    """Fused CUDA evaluation of a Function object inside torch's autograd graph."""
+
+    @staticmethod
+    def forward(ctx, points, fun):
+        points = points.detach().contiguous()
+        ctx.fun = fun
+        ctx.save_for_backward(points)
+        return fun.evaluate_device(points)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        (points,) = ctx.saved_tensors
+        jac = ctx.fun.jacobian_device(points)                       # [n, out, in]
+        return torch.einsum("no,noi->ni", grad_out.contiguous(), jac), None
 
 
 class DeterministicFunction(Function):
@@ -242,6 +272,9 @@ class ConstantFunction(DeterministicFunction):
             d.cparams[i] = float(v)
         return d
 
+    def jacobian_device(self, points):
+        return dev.zeros((points.shape[0], self.output_dim, self.input_dim))
+
 
 class LinearSystem(DeterministicFunction):
     """``y = [x, u] A^T`` (``functions.py:1546-1583``)."""
@@ -261,6 +294,10 @@ class LinearSystem(DeterministicFunction):
         d.kind, d.in_dim, d.out_dim = nat.FN_LINEAR, self.input_dim, self.output_dim
         d.matrix = self._matrix_dev.data_ptr()
         return d
+
+    def jacobian_device(self, points):
+        self.descriptor()
+        return self._matrix_dev.unsqueeze(0).expand(points.shape[0], -1, -1)
 
 
 class QuadraticFunction(DeterministicFunction):
@@ -286,6 +323,11 @@ class QuadraticFunction(DeterministicFunction):
         are given."""
         grad = LinearSystem((self.matrix + self.matrix.T).T)
         return grad if points is None else grad(points)
+
+    def jacobian_device(self, points):
+        self.descriptor()
+        sym = self._matrix_dev + self._matrix_dev.T
+        return (points @ sym).unsqueeze(1)                          # x (P + P^T)
 
 
 class _PostOp(DeterministicFunction):
@@ -333,6 +375,11 @@ class Saturation(_PostOp):
         d.lower, d.upper = self.lower, self.upper
         return d
 
+    def jacobian_device(self, points):
+        inner = self.fun.evaluate_device(points)
+        free = ((inner > self.lower) & (inner < self.upper)).to(torch.float64)
+        return self.fun.jacobian_device(points) * free.unsqueeze(2)   # tf.clip_by_value's gradient
+
 
 class AbsFunction(_PostOp):
     """``|fun(x)|`` element-wise -- the per-dimension Lipschitz lambda
@@ -350,6 +397,10 @@ class AbsFunction(_PostOp):
         d.flags |= nat.FLAG_ABS
         return d
 
+    def jacobian_device(self, points):
+        sign = torch.sign(self.fun.evaluate_device(points))
+        return self.fun.jacobian_device(points) * sign.unsqueeze(2)
+
 
 class Norm1Function(_PostOp):
     """``tf.norm(fun(x), ord=1, axis=1, keepdims=True)`` (same notebook cell)."""
@@ -364,6 +415,10 @@ class Norm1Function(_PostOp):
         d = self.fun.descriptor()
         d.flags |= nat.FLAG_NORM1
         return d
+
+    def jacobian_device(self, points):
+        sign = torch.sign(self.fun.evaluate_device(points))
+        return (self.fun.jacobian_device(points) * sign.unsqueeze(2)).sum(dim=1, keepdim=True)
 
 
 class MaxAbsFunction(_PostOp):
@@ -403,6 +458,9 @@ class ScaledFunction(_PostOp):
         d.flags |= nat.FLAG_SCALE
         d.out_scale = self.factor
         return d
+
+    def jacobian_device(self, points):
+        return self.fun.jacobian_device(points) * self.factor
 
 
 # =============================================================================== Triangulation
@@ -550,6 +608,15 @@ class Triangulation(DeterministicFunction):
         """``Triangulation.gradient`` (``functions.py:1302-1326, 1506-1510``): the partial
         derivatives of the piecewise-linear interpolant, numpy ``[n, d]``."""
         return self.gradient_function()(points)
+
+    def jacobian_device(self, points):
+        if self.output_dim != 1:
+            raise NotImplementedError("Jacobian of a multi-column Triangulation")
+        grad = self.gradient_function().evaluate_device(points)       # [n, d]
+        if self.project:      # clipped coordinates carry no gradient (tf.clip_by_value, :1479-1485)
+            lim = dev.to_device(np.asarray(self.discretization.limits, dtype=np.float64))
+            grad = grad * ((points >= lim[:, 0]) & (points <= lim[:, 1])).to(torch.float64)
+        return grad.unsqueeze(1)
 
 
 class TriangulationGradient(DeterministicFunction):
@@ -1415,6 +1482,29 @@ class GPRCached(object):
         self._hyper_seen = self._hyper_state()
         self._version += 1
 
+    # differentiable prediction -------------------------------------------------------------
+    def torch_predict(self, points):
+        """``build_predict`` (``functions.py:417-458``) on a device tensor [n, d_in] in torch
+        operations (cuBLAS / cuSOLVER on the cached factor), differentiable with respect to
+        ``points``: latent mean and variance, [n, 1] each."""
+        self._ensure()
+        fac, s = self._factor, self._scale
+        s2 = s * s
+        mx = 0.0
+        if self.mean_function is not None:
+            self.mean_function.descriptor()
+            mx = s * (points @ self.mean_function._matrix_dev.T)               # :439
+        kss = s2 * self.kern.Kdiag_device(points)                                # :450
+        if fac.M == 0:
+            return mx / s + 0.0 * points[:, :1], (kss / s2).unsqueeze(1)
+        x_train = dev.to_device(self._X)
+        kx = s2 * self.kern.K_device(x_train, points)                            # :438  [M, n]
+        a = torch.linalg.solve_triangular(fac.L, kx, upper=False)                # :441
+        alpha = self._alpha_dev[:fac.M].unsqueeze(1)
+        fmean = (a.T @ alpha + mx) / s                                           # :442, :455
+        fvar = (kss - (a * a).sum(dim=0)) / s2                                   # :451, :456
+        return fmean, fvar.unsqueeze(1)
+
     # descriptor pieces -------------------------------------------------------------------
     def fill_factor(self, f):
         self._ensure()
@@ -1565,6 +1655,11 @@ class GaussianProcess(UncertainFunction):
     def predict_device(self, points, want_var=False):
         return _gp_predict(self.gp_stack(), points, want_var)
 
+    def torch(self, points):
+        """(mean, beta * sigma) as differentiable torch tensors [n, 1] (``functions.py:507-515``)."""
+        mean, var = self.gaussian_process.torch_predict(points)
+        return mean, self.beta * torch.sqrt(var)
+
     def update_feed_dict(self):
         """Reference hook (``functions.py:517-523``): hyper-parameters travel in the
         descriptor here, so this only refreshes the cached factor."""
@@ -1613,6 +1708,11 @@ class FunctionStack(UncertainFunction):
 
     def predict_device(self, points, want_var=False):
         return _gp_predict(self.gp_stack(), points, want_var)
+
+    def torch(self, points):
+        """Stacked (mean, beta * sigma), [n, D] each, differentiable (``functions.py:278-291``)."""
+        parts = [f.torch(points) for f in self.functions]
+        return torch.cat([p[0] for p in parts], dim=1), torch.cat([p[1] for p in parts], dim=1)
 
     def add_data_point(self, x, y):
         for fun, yi in zip(self.functions, np.asarray(y).squeeze()):

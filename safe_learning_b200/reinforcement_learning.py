@@ -59,6 +59,8 @@ class PolicyIteration(object):
                       lagrange_multiplier=1.):
         """``r(x, u) + gamma V(mean f(x, u))`` [``- lambda (decrease - threshold)``]
         (``:65-114``); numpy in, numpy [n, 1] out."""
+        if isinstance(states, torch.Tensor) or isinstance(actions, torch.Tensor):
+            return self._future_values_torch(states, policy, actions, lyapunov, lagrange_multiplier)
         states = np.atleast_2d(np.asarray(states, dtype=np.float64))
         if actions is None:
             actions = (policy or self.policy)(states)
@@ -73,6 +75,39 @@ class PolicyIteration(object):
         if lyapunov is not None:
             decrease = lyapunov.v_decrease_bound(states, (next_states, var))
             updated = updated - lagrange_multiplier * (decrease - lyapunov.threshold(states))
+        return updated
+
+    def _future_values_torch(self, states, policy, actions, lyapunov, lagrange_multiplier):
+        """``future_values`` on device tensors as a differentiable torch expression (the reference
+        differentiates this graph with ``tf.gradients`` to optimise a parametric policy under the
+        Lyapunov penalty, ``examples/inverted_pendulum.ipynb`` cell 17): every fused function
+        object is one autograd node (CUDA evaluation forward, its device Jacobian backward,
+        ``Function.torch``), the GP mean / variance are torch operations on the cached Cholesky
+        factor.  ``policy`` may be any callable on tensors (e.g. a ``torch.nn.Module``); gradients
+        flow to ``actions`` / the policy's parameters and to ``states`` if they require them."""
+        states = dev.to_device(states) if not isinstance(states, torch.Tensor) else states
+        if actions is None:
+            fn = policy or self.policy
+            actions = fn.torch(states) if isinstance(fn, Function) else fn(states)
+        elif not isinstance(actions, torch.Tensor):
+            actions = dev.to_device(np.atleast_2d(np.asarray(actions, dtype=np.float64)))
+        actions = actions.expand(states.shape[0], actions.shape[1])
+        z = torch.cat((states, actions), dim=1)
+        err = None
+        if isinstance(self.dynamics, (FunctionStack, GaussianProcess)):
+            mean, err = self.dynamics.torch(z)                                   # :92, :98-99
+        else:
+            mean = self.dynamics.torch(z)
+        updated = self.reward_function.torch(z) + self.gamma * self.value_function.torch(mean)
+        if lyapunov is not None:                                                 # :107-112
+            v_fn, lv = lyapunov.lyapunov_function, lyapunov._lipschitz_lyapunov
+            decrease = v_fn.torch(mean) - v_fn.torch(states)
+            if err is not None:
+                lv_mu = lv.torch(mean) if isinstance(lv, Function) else float(lv)
+                decrease = decrease + (lv_mu * err).sum(dim=1, keepdim=True)
+            threshold = dev.to_device(np.broadcast_to(
+                lyapunov.threshold(states.detach().cpu().numpy()), (states.shape[0], 1)).copy())
+            updated = updated - lagrange_multiplier * (decrease - threshold)
         return updated
 
     # ------------------------------------------------------------------ fused sweeps

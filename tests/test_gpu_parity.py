@@ -646,6 +646,47 @@ def test_pendulum_sweep_vs_oracle(sl, shared):
     assert_array_equal(gpu._refinement, cpu._refinement)
 
 
+@pytest.mark.parametrize("lv_kind", ["abs2", "const", "norm1", "abs1"])
+@pytest.mark.parametrize("num", [[48, 48], [37, 29], [5, 3]])
+def test_deterministic_linear_sweep_specialised_kernel(sl, lv_kind, num):
+    """The register-resident kernel of the LQR composition with deterministic LinearSystem dynamics
+    (det_sweep_fast_kernel, light.cu): flags and V bit-identical to the generic interpreter and
+    to the oracle's arithmetic, ragged sizes (not multiples of 8 points per thread) included."""
+    from safe_learning_b200 import _native as nat
+    lib = nat.load()
+    par = W.make_pendulum(num_points=num, M=8, tau_scale=1 / 20.)
+    P = par["P"]
+    objs = []
+    for ns in (sl, O):
+        grid = ns.GridWorld(par["limits"], par["num_points"])
+        policy = ns.Saturation(ns.LinearSystem(-par["K"]), -1., 1.)
+        dyn = ns.LinearSystem((par["A_true"], par["B_true"]))
+        l_v = {"abs2": lambda: ns.AbsFunction(ns.LinearSystem((2 * P,))), "const": lambda: 0.7,
+               "norm1": lambda: ns.Norm1Function(ns.LinearSystem((2 * P,))),
+               "abs1": lambda: ns.AbsFunction(ns.LinearSystem((2 * P[[0]],)))}[lv_kind]()
+        objs.append(ns.Lyapunov(grid, ns.QuadraticFunction(P), dyn, par["L_dyn"], l_v, par["tau"],
+                                policy, initial_set=par["initial"]))
+    gpu, cpu = objs
+    fast = gpu.compute_negative().cpu().numpy().astype(bool)
+    nat.check(lib.slb_debug_det_fast(0), "slb_debug_det_fast")
+    try:
+        generic = gpu.compute_negative().cpu().numpy().astype(bool)
+    finally:
+        nat.check(lib.slb_debug_det_fast(1), "slb_debug_det_fast")
+    assert_array_equal(fast, generic)
+    states = cpu.discretization.all_points
+    nxt = cpu.dynamics(states, cpu.policy(states))
+    dec = cpu.v_decrease_bound(states, nxt).ravel()
+    thr = np.broadcast_to(cpu.threshold(states), (len(states), 1)).ravel()
+    assert_array_equal(fast, dec < thr)
+    assert 0 < fast.sum() < fast.size or min(num) < 8
+    gpu.update_safe_set()
+    cpu.update_safe_set()
+    assert_array_equal(gpu.values, cpu.values)
+    assert_array_equal(gpu.safe_set, cpu.safe_set)
+    assert gpu.feed_dict[gpu.c_max] == cpu.c_max
+
+
 def test_toy_1d_sweep_vs_oracle(sl):
     """C1: 101-point grid, M=50, V = |x| as a Triangulation on its own 3-point grid."""
     for tau in (1.0 / 101, 0.02, 0.2):
@@ -776,6 +817,39 @@ def test_future_values_lyapunov_penalty_vs_oracle(sl):
         assert_allclose(rl_gpu.future_values(states, lyapunov=gpu, lagrange_multiplier=lam),
                         rl_cpu.future_values(states, lyapunov=cpu, lagrange_multiplier=lam),
                         rtol=1e-8, atol=1e-10)
+
+
+def test_future_values_is_differentiable(sl):
+    """reinforcement_learning.py:65-114 under autodiff (inverted_pendulum.ipynb cell 17): the torch
+    form of future_values equals the numpy form, and its gradient with respect to the actions --
+    through the reward, the GP mean, the Triangulation value function and the Lyapunov penalty
+    with its beta * sigma term -- equals central differences of the numpy form."""
+    import torch
+    par = W.make_pendulum(num_points=[31, 29], M=60, tau_scale=1 / 30.)
+    rl, grid = _rl_objects(sl, par, "product", num=24)
+    rng = np.random.default_rng(2)
+    rl.value_function.parameters = rng.normal(size=(grid.nindex, 1))
+    lyap = W.build_product(par)
+    states = rng.uniform(-0.9, 0.9, (40, 2))
+    actions = rng.uniform(-0.6, 0.6, (40, 1))
+    for kwargs in (dict(), dict(lyapunov=lyap, lagrange_multiplier=0.7)):
+        a_t = torch.tensor(actions, dtype=torch.float64, device="cuda", requires_grad=True)
+        out = rl.future_values(torch.tensor(states, dtype=torch.float64, device="cuda"),
+                               actions=a_t, **kwargs)
+        ref = rl.future_values(states, actions=actions, **kwargs)
+        assert_allclose(out.detach().cpu().numpy(), ref, rtol=1e-9, atol=1e-12)
+        out.sum().backward()
+        h = 1e-6
+        fd = (rl.future_values(states, actions=actions + h, **kwargs)
+              - rl.future_values(states, actions=actions - h, **kwargs)) / (2 * h)
+        assert_allclose(a_t.grad.cpu().numpy(), fd, rtol=2e-4, atol=1e-6)
+    # a parametric torch policy: the gradient reaches its weights
+    net = torch.nn.Linear(2, 1, dtype=torch.float64, device="cuda")
+    s_t = torch.tensor(states, dtype=torch.float64, device="cuda")
+    loss = -rl.future_values(s_t, policy=lambda x: torch.tanh(net(x)), lyapunov=lyap).sum()
+    loss.backward()
+    assert net.weight.grad is not None and torch.isfinite(net.weight.grad).all()
+    assert float(net.weight.grad.abs().sum()) > 0
 
 
 def test_can_shrink_false_vs_oracle(sl):

@@ -95,13 +95,21 @@ def det_linear():
         dyn = sl.LinearSystem((par["A_true"], par["B_true"]))
         lyap = sl.Lyapunov(grid, sl.QuadraticFunction(par["P"]), dyn, par["L_dyn"],
                            abs(sl.LinearSystem((2 * par["P"],))), par["tau"], policy)
-        ms = timed(lyap.compute_negative, steps=10)
+        from safe_learning_b200 import _native as nat
+        lib = nat.load()
         n = grid.nindex
-        print(json.dumps({"bench": "deterministic_linear_sweep", "grid": "%dx%d" % (num, num),
-                          "kernel_ms": ms, "points_per_s": n / (ms * 1e-3),
-                          "hbm_algorithmic_gbs": n * 17 / (ms * 1e-3) * 1e-9,
-                          "hbm_frac_of_measured": n * 17 / (ms * 1e-3) * 1e-9 / HBM_GBS,
-                          "note": "writes 1 B flag per point (V not written); coordinates generated"}))
+        for fast in (1, 0):
+            lib.slb_debug_det_fast(fast)
+            ms = timed(lyap.compute_negative, steps=10)
+            print(json.dumps({"bench": "deterministic_linear_sweep", "grid": "%dx%d" % (num, num),
+                              "kernel": "det_sweep_fast_kernel (specialised)" if fast else
+                                        "det_sweep_kernel (generic interpreter)",
+                              "kernel_ms": ms, "points_per_s": n / (ms * 1e-3),
+                              "hbm_algorithmic_gbs": n * 17 / (ms * 1e-3) * 1e-9,
+                              "hbm_frac_of_measured": n * 17 / (ms * 1e-3) * 1e-9 / HBM_GBS,
+                              "note": "writes 1 B flag per point (V not written); coordinates "
+                                      "generated; 17 algorithmic B/pt"}))
+        lib.slb_debug_det_fast(1)
         del lyap
         torch.cuda.empty_cache()
 
@@ -121,17 +129,29 @@ def c4():
 
 
 def c5():
+    """Resolution x M points of the pendulum sweep on one GPU: the default (filtered) decision pass
+    and the full posterior for every point (the kernel the algorithmic FLOP count describes)."""
     for num, M in ((128, 100), (256, 100), (256, 200), (256, 500), (512, 500), (1024, 500),
-                   (256, 1000), (256, 2000), (128, 5000)):
+                   (2048, 500), (256, 1000), (256, 2000), (128, 5000)):
         par = W.make_pendulum(num_points=num, M=M)
         lyap = W.build_product(par)
+        lyap.reset_filter_stats()
+        lyap.compute_negative()
+        fs = lyap.filter_stats
         ms = timed(lyap.compute_negative, steps=5, warmup=2)
+        ms_step = timed(lyap.update_safe_set, steps=5, warmup=2)
+        lyap.filter = False
+        ms_full = timed(lyap.compute_negative, steps=3, warmup=1)
         n = lyap.discretization.nindex
         fl = algorithmic_flops_per_point(M, 3, 2, 2)
         print(json.dumps({"bench": "c5_gp_sweep", "grid": "%dx%d" % (num, num), "M": M,
-                          "kernel_ms": ms, "points_per_s": n / (ms * 1e-3),
-                          "tflops": fl * n / (ms * 1e-3) * 1e-12,
-                          "frac_of_fp64_peak": fl * n / (ms * 1e-3) * 1e-12 / PEAK_TF}))
+                          "decision_ms": ms, "update_safe_set_ms": ms_step,
+                          "points_per_s": n / (ms_step * 1e-3),
+                          "refined_frac": fs["refined"] / max(fs["points"], 1),
+                          "full_posterior_kernel_ms": ms_full,
+                          "full_posterior_points_per_s": n / (ms_full * 1e-3),
+                          "full_posterior_tflops": fl * n / (ms_full * 1e-3) * 1e-12,
+                          "full_posterior_frac_of_fp64_peak": fl * n / (ms_full * 1e-3) * 1e-12 / PEAK_TF}))
         del lyap
         torch.cuda.empty_cache()
 
