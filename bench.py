@@ -473,9 +473,13 @@ def run_ours(args, rank, world, local_rank):
                 "certified upper bound",
     }
 
-    # ---- CPU baseline, bounded sample, same run
-    cpu_par = W.make_pendulum(num_points=GRID, M=M_TRAIN, shared_hypers=False)
-    rate, cores, desc, _ = cpu_reference_rate(cpu_par, seconds_budget=20.0, steps=1, warmup=0)
+    # ---- CPU baseline, bounded sample, same run (rank 0 at N = 1 only: the N > 1 lines of a scaling
+    # run refer to the N = 1 line's baseline)
+    cpu_baseline = None
+    if world == 1:
+        cpu_par = W.make_pendulum(num_points=GRID, M=M_TRAIN, shared_hypers=False)
+        rate, cores, desc, _ = cpu_reference_rate(cpu_par, seconds_budget=20.0, steps=1, warmup=0)
+        cpu_baseline = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc}
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -503,8 +507,7 @@ def run_ours(args, rank, world, local_rank):
                       "value": n_total * n_cont / (c_total * 1e-3),
                       "note": "the timed step continued for ~1.5 s so that nvidia-smi samples "
                               "exist under load; `clocks` covers the timed region and this"},
-        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": desc},
+        "cpu_baseline": cpu_baseline,
         "safe_points": safe_points, "parity": parity, "exchange": exchange,
     }
     print(json.dumps(line))

@@ -602,6 +602,71 @@ SLB_EVAL_ATTR int eval_fn(const slb_function& f, const double* in, double* out) 
     return od;
 }
 
+// Fast path in front of eval_fn for the small linear-algebra objects that make up the per-point
+// prologue / epilogue of every sweep of the reference's experiments (policy = Saturation(LinearSystem),
+// V = QuadraticFunction, L_V = abs(LinearSystem)): in_dim <= 4, out_dim <= 2, operands in registers,
+// eval_fn's arithmetic operation for operation (bit-identical).  The generic interpreter costs a
+// call, local-memory operand arrays and runtime-bounded loops per evaluation: five of them made up
+// most of the 24 us floor of the filter's mean stage (M = 0: tools/mean_floor_probe.py).
+SLB_DEV int eval_fn_small(const slb_function& f, const double* in, double* out) {
+    const int n = f.in_dim;
+    if (f.kind == SLB_FN_LINEAR && n <= 4 && f.out_dim <= 2 &&
+        !(f.flags & (SLB_FLAG_MAXABS | SLB_FLAG_GRADIENT))) {
+        int od = f.out_dim;
+        double x[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) x[k] = k < n ? in[k] : 0.0;
+        double y[2];
+#pragma unroll
+        for (int o = 0; o < 2; ++o) {
+            if (o < od) {
+                const double* row = f.matrix + o * n;
+                double acc = f64mul(x[0], __ldg(row));
+#pragma unroll
+                for (int k = 1; k < 4; ++k)
+                    if (k < n) acc = f64add(acc, f64mul(x[k], __ldg(row + k)));
+                y[o] = acc;
+            } else {
+                y[o] = 0.0;
+            }
+        }
+        if (f.flags & SLB_FLAG_SATURATE) {
+            y[0] = fmin(fmax(y[0], f.lower), f.upper);
+            y[1] = fmin(fmax(y[1], f.lower), f.upper);
+        }
+        if (f.flags & (SLB_FLAG_ABS | SLB_FLAG_NORM1)) { y[0] = fabs(y[0]); y[1] = fabs(y[1]); }
+        if (f.flags & SLB_FLAG_NORM1) {
+            if (od == 2) y[0] = f64add(y[0], y[1]);
+            od = 1;
+        }
+        if (f.flags & SLB_FLAG_SCALE) { y[0] = f64mul(y[0], f.out_scale); y[1] = f64mul(y[1], f.out_scale); }
+        out[0] = y[0];
+        if (od == 2) out[1] = y[1];
+        return od;
+    }
+    if (f.kind == SLB_FN_QUADRATIC && n <= 4 && !(f.flags & ~SLB_FLAG_SCALE)) {
+        double x[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) x[k] = k < n ? in[k] : 0.0;
+        double total = 0.0;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            if (c < n) {
+                double lin = f64mul(x[0], __ldg(f.matrix + c));
+#pragma unroll
+                for (int r = 1; r < 4; ++r)
+                    if (r < n) lin = f64add(lin, f64mul(x[r], __ldg(f.matrix + r * n + c)));
+                const double prod = f64mul(lin, x[c]);
+                total = (c == 0) ? prod : f64add(total, prod);
+            }
+        }
+        if (f.flags & SLB_FLAG_SCALE) total = f64mul(total, f.out_scale);
+        out[0] = total;
+        return 1;
+    }
+    return eval_fn(f, in, out);
+}
+
 // The Lyapunov decision for one state (lyapunov.py:265-288, 324-376, 441).
 //   x [d]; mu [d] predicted mean; err [d] error bounds (beta*sigma) or nullptr when the
 //   dynamics are deterministic.  Returns negative = decrease < threshold (false on NaN).
@@ -614,11 +679,11 @@ struct slb_decision { double vx, decrease, threshold; bool negative; };
 SLB_DEV void lyapunov_state_terms(const slb_sweep& cfg, const double* x, int64_t flat_index,
                                   double* vx_out, double* threshold_out) {
     double tmp[SLB_MAX_OUT], vx[1];
-    eval_fn(cfg.lyapunov, x, vx);
+    eval_fn_small(cfg.lyapunov, x, vx);
     *vx_out = vx[0];
     double lvx;
     if (cfg.lipschitz_v.kind != SLB_FN_NONE) {               // :284-286 (1-norm of a vector lv)
-        const int nl = eval_fn(cfg.lipschitz_v, x, tmp);
+        const int nl = eval_fn_small(cfg.lipschitz_v, x, tmp);
         lvx = tmp[0];
         if (nl > 1) {
             lvx = fabs(tmp[0]);
@@ -631,7 +696,7 @@ SLB_DEV void lyapunov_state_terms(const slb_sweep& cfg, const double* x, int64_t
     if (cfg.lf_values != nullptr && flat_index >= 0) {
         lf = cfg.lf_values[flat_index - cfg.lf_index_base];
     } else if (cfg.lipschitz_f.kind != SLB_FN_NONE) {
-        eval_fn(cfg.lipschitz_f, x, tmp);
+        eval_fn_small(cfg.lipschitz_f, x, tmp);
         lf = tmp[0];
     }
     *threshold_out = f64mul(f64mul(-lvx, f64add(1.0, lf)), cfg.tau);   // :288
@@ -643,7 +708,7 @@ SLB_DEV double lyapunov_error_bound(const slb_sweep& cfg, const double* mu, cons
     double tmp[SLB_MAX_OUT];
     double bound;
     if (cfg.lipschitz_v.kind != SLB_FN_NONE) {
-        const int nl = eval_fn(cfg.lipschitz_v, mu, tmp);
+        const int nl = eval_fn_small(cfg.lipschitz_v, mu, tmp);
         if (nl == 1) {
             bound = f64mul(tmp[0], err[0]);
             for (int j = 1; j < d; ++j) bound = f64add(bound, f64mul(tmp[0], err[j]));
@@ -672,7 +737,7 @@ SLB_DEV slb_decision lyapunov_decide(const slb_sweep& cfg, const double* x, int6
                                      const double* mu, const double* err) {
     double vx, threshold, vm[1];
     lyapunov_state_terms(cfg, x, flat_index, &vx, &threshold);
-    eval_fn(cfg.lyapunov, mu, vm);
+    eval_fn_small(cfg.lyapunov, mu, vm);
     const double bound = err != nullptr ? lyapunov_error_bound(cfg, mu, err) : 0.0;
     return lyapunov_combine(vx, threshold, vm[0], bound);
 }

@@ -50,7 +50,7 @@ constexpr int FT = SLB_FT;             // stage 1: threads per CTA = points per 
                                        // 256 x 256, 7 resident per SM: single wave, 98.8% balanced)
 constexpr int MU = SLB_MEAN_UNROLL;    // independent exp chains per thread (rows per iteration)
 constexpr int HR = SLB_HEAD_RANK;
-constexpr int HT = 256;                // stage 2: threads per CTA (8 warps, 8 list entries each)
+constexpr int HT = 512;                // stage 2: threads per CTA (16 warps, 8 or 2 list entries each)
 constexpr int HEAD_CTAS = 148;         // one CTA per SM (it stages the head factors in shared memory)
 constexpr int64_t CHUNK = 1 << 22;     // points per pass of the three stages (bounds the workspace)
 constexpr int64_t WS_HEAD = 64 + SLB_SPLIT_TICKET_BYTES + (int64_t)SLB_SPLIT_PARTIAL_BYTES;   // bytes before the lists
@@ -326,7 +326,7 @@ filter_mean_kernel(const __grid_constant__ slb_sweep cfg, const filter_args a) {
     lyapunov_state_terms(cfg, t.z, a.idx_begin + rel, &vx, &t.thr);
     {
         double u[SLB_MAX_OUT];
-        const int m = eval_fn(cfg.policy, t.z, u);
+        const int m = eval_fn_small(cfg.policy, t.z, u);
         for (int c = 0; c < m; ++c) t.z[d + c] = u[c];
     }
     // the expanded squared distance needs moderate magnitudes; NaN / huge inputs -> full path
@@ -356,14 +356,14 @@ filter_mean_kernel(const __grid_constant__ slb_sweep cfg, const filter_args a) {
 
     // ---- V(mu), L_V(mu) and the coefficient of every sigma_j          (lyapunov.py:344-352)
     double vm[1];
-    eval_fn(cfg.lyapunov, mu, vm);
+    eval_fn_small(cfg.lyapunov, mu, vm);
     t.dec0 = f64sub(vm[0], vx);
     double lvmu = 0.0;                      // sum_j |L_V(mu)_j mu_j|: scale of V's sensitivity to mu
     double lverr = 0.0;                     // sum_j |L_V(mu)_j| mean_err_j
     {
         double lv[SLB_MAX_OUT];
         int nl = 1;
-        if (cfg.lipschitz_v.kind != SLB_FN_NONE) nl = eval_fn(cfg.lipschitz_v, mu, lv);
+        if (cfg.lipschitz_v.kind != SLB_FN_NONE) nl = eval_fn_small(cfg.lipschitz_v, mu, lv);
         else lv[0] = cfg.lv_const;
         for (int j = 0; j < SLB_MAX_OUT; ++j) {
             const double l = j < D ? (nl == 1 ? lv[0] : lv[j]) : 0.0;
@@ -404,7 +404,122 @@ filter_mean_kernel(const __grid_constant__ slb_sweep cfg, const filter_args a) {
 // computed two per lane and point and exchanged through shared memory ([row][point]: one row's
 // HP values are four broadcast 128-bit loads); lane p < HP makes the decision of point p.
 constexpr int HW = HT / 32;            // warps per CTA
-constexpr int HP = 8;                  // list entries per warp iteration
+constexpr int HP = 8;                  // list entries per warp iteration (long lists)
+constexpr int HP_SHORT = 2;            // ... when the list has fewer than HP entries per warp of the grid:
+                                       // the latency of one group is the whole stage then
+
+// one group of P list entries [g P, g P + P) on one warp
+template <int DIN, int P, bool ALL_STAGED>
+SLB_DEV void head_group(const slb_sweep& cfg, const filter_args& a, int64_t grp, int64_t count,
+                        const double* exptab, double* kw, const double* wbuf, const double* xbuf,
+                        unsigned* s_stat) {
+    const int lane = threadIdx.x & 31;
+    const int nf = cfg.gp.num_factors;
+    const int D = cfg.gp.num_outputs;
+    // lane p < P owns list entry grp * P + p: its terms, its index and finally its decision
+    const int64_t k = grp * P + min(lane, P - 1);
+    const bool mine = lane < P && k < count;
+    filter_side t = {};
+    int64_t rel = 0;
+    if (mine) { t = a.side_a[k]; rel = a.list_a[k]; }
+    double shi[SLB_MAX_OUT];
+    for (int j = 0; j < D; ++j) {
+        const slb_gp_factor& F = cfg.gp.factors[cfg.gp.outputs[j].factor];
+        shi[j] = mine ? sqrt(F.kernel.num_prims > 0 ? kernel_expr_diag<DIN>(F.kernel, t.z) : F.variance)
+                      : 0.0;
+    }
+    for (int f = 0; f < nf; ++f) {
+        const slb_gp_factor& F = cfg.gp.factors[f];
+        const int rows = F.head_rows;
+        if (rows <= 0) continue;
+        const bool general = F.kernel.num_prims > 0;
+        const double s2 = f64mul(F.scale, F.scale);
+        // ALL_STAGED: the tables are known to be in shared memory (LDS instead of generic loads)
+        const bool staged = ALL_STAGED || f < a.head_factors_staged;
+        const double* xh = xbuf + (size_t)f * HR * DIN;
+        if (!ALL_STAGED && !staged) xh = F.Xhead;
+        // kernel values of every point of the group against subset points lane and lane + 32
+        // (functions.py:438); entries beyond the list carry zeros (never decided)
+#pragma unroll
+        for (int p = 0; p < P; ++p) {
+            double zs[DIN];
+#pragma unroll
+            for (int c = 0; c < DIN; ++c) {
+                const double zc = __shfl_sync(0xffffffffu, t.z[c], p);
+                zs[c] = general ? zc : zc / F.lengthscales[c];
+            }
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int j = lane + 32 * h;
+                double kv = 0.0;
+                if (j < rows) {
+                    const double* xr = xh + j * DIN;
+                    if (general) {
+                        kv = kernel_expr_cross<DIN>(F.kernel, zs, xr, exptab);
+                    } else {
+                        double a2 = 0.0;
+#pragma unroll
+                        for (int c = 0; c < DIN; ++c) { const double df = zs[c] - xr[c]; a2 = fma(df, df, a2); }
+                        kv = F.variance * exp_neg_tab(-0.5 * a2, exptab);
+                    }
+                    kv = s2 * kv;
+                }
+                kw[j * P + p] = kv;
+            }
+        }
+        __syncwarp();
+        // short groups: two partial sums per row and point (even / odd columns) halve the dependent
+        // FMA chain; 8-point groups already carry 16 independent chains
+        constexpr int NS = P <= 2 ? 2 : 1;
+        double al[2][P], ah[2][P];
+#pragma unroll
+        for (int p = 0; p < P; ++p) { al[0][p] = al[1][p] = 0.0; ah[0][p] = ah[1][p] = 0.0; }
+        const double* Wt = wbuf + (size_t)f * HR * HR;
+        if (!ALL_STAGED && !staged) Wt = F.Whead;
+#pragma unroll 4
+        for (int j = 0; j < HR; ++j) {
+            const double wl = Wt[j * HR + lane], wh = Wt[j * HR + 32 + lane];
+            double kj[P];
+#pragma unroll
+            for (int p = 0; p < P; p += 2) {
+                const double2 v = *reinterpret_cast<const double2*>(kw + j * P + p);
+                kj[p] = v.x; kj[p + 1] = v.y;
+            }
+#pragma unroll
+            for (int p = 0; p < P; ++p) {
+                al[j & (NS - 1)][p] = fma(wl, kj[p], al[j & (NS - 1)][p]);
+                ah[j & (NS - 1)][p] = fma(wh, kj[p], ah[j & (NS - 1)][p]);
+            }
+        }
+        __syncwarp();
+        // sum a^2 per point over the 64 rows: lane p ends up with point p's
+        double ssp = 0.0;
+#pragma unroll
+        for (int p = 0; p < P; ++p) {
+            const double lo = al[0][p] + al[1][p], hi = ah[0][p] + ah[1][p];
+            double ss = fma(lo, lo, hi * hi);
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, off);
+            if (lane == p) ssp = ss;
+        }
+        double kss = F.kss;
+        if (general && mine) kss = s2 * kernel_expr_diag<DIN>(F.kernel, t.z);
+        const double sdev = sqrt(f64sub(kss, ssp) / s2);          // NaN if negative
+        for (int j = 0; j < D; ++j)
+            if (cfg.gp.outputs[j].factor == f) shi[j] = sdev;
+    }
+    const int outcome = mine ? decide(t, shi, D) : 0;
+    const bool undecided = mine && outcome < 0;
+    if (mine && outcome >= 0) a.negative[rel] = outcome > 0 ? 1 : 0;
+    const long long slot = list_append(undecided, a.counts + 1);
+    if (undecided) a.list_b[slot] = rel;
+    const unsigned dec = __ballot_sync(0xffffffffu, mine && !undecided);
+    const unsigned und = __ballot_sync(0xffffffffu, undecided);
+    if (lane == 0) {
+        if (dec) atomicAdd(s_stat + 0, (unsigned)__popc(dec));
+        if (und) atomicAdd(s_stat + 1, (unsigned)__popc(und));
+    }
+}
 
 template <int DIN>
 __global__ void __launch_bounds__(HT, 1)
@@ -414,11 +529,14 @@ filter_head_kernel(const __grid_constant__ slb_sweep cfg, const filter_args a) {
     unsigned* s_stat = reinterpret_cast<unsigned*>(smem_raw + 8);      // decided / undecided by this CTA
     double* exptab = reinterpret_cast<double*>(smem_raw + 16);         // [64]
     double* kbuf = exptab + 64;                                        // [HW][HR][HP]
-    double* wbuf = kbuf + HW * HR * HP;                                // [nf][HR * HR]
+    double* wbuf = kbuf + HW * HR * HP;                                // [staged][HR * HR]
     const int nf = cfg.gp.num_factors;
     double* xbuf = wbuf + (size_t)a.head_factors_staged * HR * HR;     // [staged][HR * DIN]
     const int64_t count = (int64_t)a.counts[0];
-    if ((int64_t)blockIdx.x * HW * HP >= count) return;                // no list entry for this CTA
+    const int64_t nwarps = (int64_t)gridDim.x * HW;
+    const bool short_list = count < nwarps * HP;
+    const int64_t ngroups = short_list ? (count + HP_SHORT - 1) / HP_SHORT : (count + HP - 1) / HP;
+    if ((int64_t)blockIdx.x * HW >= ngroups) return;                   // no group for this CTA
     if (threadIdx.x == 0) {
         slb_bulk::mbar_init(bar, 1);
         slb_bulk::fence_barrier_init();
@@ -439,107 +557,15 @@ filter_head_kernel(const __grid_constant__ slb_sweep cfg, const filter_args a) {
     if (threadIdx.x < 2) s_stat[threadIdx.x] = 0;
     __syncthreads();
     slb_bulk::mbar_wait(bar, 0);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int64_t ngroups = (count + HP - 1) / HP;
-    const int64_t nwarps = (int64_t)gridDim.x * HW;
-    const int D = cfg.gp.num_outputs;
+    const int warp = threadIdx.x >> 5;
     double* kw = kbuf + warp * HR * HP;
     for (int64_t grp = (int64_t)blockIdx.x * HW + warp; grp < ngroups; grp += nwarps) {
-        // lane p < HP owns list entry grp * HP + p: its terms, its index and finally its decision
-        const int64_t k = grp * HP + min(lane, HP - 1);
-        const bool mine = lane < HP && k < count;
-        filter_side t = {};
-        int64_t rel = 0;
-        if (mine) { t = a.side_a[k]; rel = a.list_a[k]; }
-        double shi[SLB_MAX_OUT];
-        for (int j = 0; j < D; ++j) {
-            const slb_gp_factor& F = cfg.gp.factors[cfg.gp.outputs[j].factor];
-            shi[j] = mine ? sqrt(F.kernel.num_prims > 0 ? kernel_expr_diag<DIN>(F.kernel, t.z) : F.variance)
-                          : 0.0;
-        }
-        for (int f = 0; f < nf; ++f) {
-            const slb_gp_factor& F = cfg.gp.factors[f];
-            const int rows = F.head_rows;
-            if (rows <= 0) continue;
-            const bool general = F.kernel.num_prims > 0;
-            const double s2 = f64mul(F.scale, F.scale);
-            const bool staged = f < a.head_factors_staged;
-            const double* xh = staged ? xbuf + (size_t)f * HR * DIN : F.Xhead;
-            // kernel values of every point of the group against subset points lane and lane + 32
-            // (functions.py:438); entries beyond the list reuse the last point (never decided)
-#pragma unroll
-            for (int p = 0; p < HP; ++p) {
-                double zs[DIN];
-#pragma unroll
-                for (int c = 0; c < DIN; ++c) {
-                    const double zc = __shfl_sync(0xffffffffu, t.z[c], p);
-                    zs[c] = general ? zc : zc / F.lengthscales[c];
-                }
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const int j = lane + 32 * h;
-                    double kv = 0.0;
-                    if (j < rows) {
-                        const double* xr = xh + j * DIN;
-                        if (general) {
-                            kv = kernel_expr_cross<DIN>(F.kernel, zs, xr, exptab);
-                        } else {
-                            double a2 = 0.0;
-#pragma unroll
-                            for (int c = 0; c < DIN; ++c) { const double df = zs[c] - xr[c]; a2 = fma(df, df, a2); }
-                            kv = F.variance * exp_neg_tab(-0.5 * a2, exptab);
-                        }
-                        kv = s2 * kv;
-                    }
-                    kw[j * HP + p] = kv;
-                }
-            }
-            __syncwarp();
-            double al[HP], ah[HP];
-#pragma unroll
-            for (int p = 0; p < HP; ++p) { al[p] = 0.0; ah[p] = 0.0; }
-            const double* __restrict__ Wt = staged ? wbuf + (size_t)f * HR * HR : F.Whead;
-#pragma unroll 2
-            for (int j = 0; j < HR; ++j) {
-                const double wl = Wt[j * HR + lane], wh = Wt[j * HR + 32 + lane];
-                double kj[HP];
-#pragma unroll
-                for (int p = 0; p < HP; p += 2) {
-                    const double2 v = *reinterpret_cast<const double2*>(kw + j * HP + p);
-                    kj[p] = v.x; kj[p + 1] = v.y;
-                }
-#pragma unroll
-                for (int p = 0; p < HP; ++p) {
-                    al[p] = fma(wl, kj[p], al[p]);
-                    ah[p] = fma(wh, kj[p], ah[p]);
-                }
-            }
-            __syncwarp();
-            // sum a^2 per point over the 64 rows: lane p ends up with point p's
-            double ssp = 0.0;
-#pragma unroll
-            for (int p = 0; p < HP; ++p) {
-                double ss = fma(al[p], al[p], ah[p] * ah[p]);
-#pragma unroll
-                for (int off = 16; off > 0; off >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, off);
-                if (lane == p) ssp = ss;
-            }
-            double kss = F.kss;
-            if (general && mine) kss = s2 * kernel_expr_diag<DIN>(F.kernel, t.z);
-            const double sdev = sqrt(f64sub(kss, ssp) / s2);          // NaN if negative
-            for (int j = 0; j < D; ++j)
-                if (cfg.gp.outputs[j].factor == f) shi[j] = sdev;
-        }
-        const int outcome = mine ? decide(t, shi, D) : 0;
-        const bool undecided = mine && outcome < 0;
-        if (mine && outcome >= 0) a.negative[rel] = outcome > 0 ? 1 : 0;
-        const long long slot = list_append(undecided, a.counts + 1);
-        if (undecided) a.list_b[slot] = rel;
-        const unsigned dec = __ballot_sync(0xffffffffu, mine && !undecided);
-        const unsigned und = __ballot_sync(0xffffffffu, undecided);
-        if (lane == 0) {
-            if (dec) atomicAdd(s_stat + 0, (unsigned)__popc(dec));
-            if (und) atomicAdd(s_stat + 1, (unsigned)__popc(und));
+        if (a.head_factors_staged == nf) {
+            if (short_list) head_group<DIN, HP_SHORT, true>(cfg, a, grp, count, exptab, kw, wbuf, xbuf, s_stat);
+            else head_group<DIN, HP, true>(cfg, a, grp, count, exptab, kw, wbuf, xbuf, s_stat);
+        } else {
+            if (short_list) head_group<DIN, HP_SHORT, false>(cfg, a, grp, count, exptab, kw, wbuf, xbuf, s_stat);
+            else head_group<DIN, HP, false>(cfg, a, grp, count, exptab, kw, wbuf, xbuf, s_stat);
         }
     }
     // one pair of global atomics per CTA (one per point serialised on the counter's L2 line)

@@ -506,11 +506,23 @@ apply_prefix_kernel(const double* __restrict__ values, const uint8_t* __restrict
         if (mb > max_below) max_below = mb;
         if (ma > max_all) max_all = ma;
     }
+    // block-level combine in shared memory, then four global atomics per block (one set per warp put
+    // 8192 same-address atomics behind a 64 K-point sweep)
+    __shared__ unsigned long long s_acc[4];
+    if (threadIdx.x < 4) s_acc[threadIdx.x] = 0ull;
+    __syncthreads();
     if ((threadIdx.x & 31) == 0) {
-        atomicAdd(reinterpret_cast<unsigned long long*>(&stats->n_safe), n_safe);
-        atomicAdd(reinterpret_cast<unsigned long long*>(&stats->n_below), n_below);
-        atomicMax(reinterpret_cast<unsigned long long*>(&stats->max_below), max_below);
-        atomicMax(reinterpret_cast<unsigned long long*>(&stats->max_all), max_all);
+        atomicAdd(&s_acc[0], n_safe);
+        atomicAdd(&s_acc[1], n_below);
+        atomicMax(&s_acc[2], max_below);
+        atomicMax(&s_acc[3], max_all);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        atomicAdd(reinterpret_cast<unsigned long long*>(&stats->n_safe), s_acc[0]);
+        atomicAdd(reinterpret_cast<unsigned long long*>(&stats->n_below), s_acc[1]);
+        atomicMax(reinterpret_cast<unsigned long long*>(&stats->max_below), s_acc[2]);
+        atomicMax(reinterpret_cast<unsigned long long*>(&stats->max_all), s_acc[3]);
     }
 }
 

@@ -11,6 +11,8 @@ for a in sys.argv:
         M = int(a[4:])
 par = W.make_pendulum(num_points=256, M=M, shared_hypers=shared)
 lyap = W.build_product(par)
+if "--filtered" not in sys.argv:
+    lyap.filter = False        # the full posterior for every point (the round-1 kernel profile)
 for _ in range(3):
     lyap.update_safe_set()
 torch.cuda.synchronize()
