@@ -345,9 +345,10 @@ def run_ours(args, rank, world, local_rank):
     lyap.filter = "auto"
 
     # ---- end-to-end arm through the public API: host buffers in, host buffers out, every step.
-    # In: the cached GP tables (FunctionStack.export_cache / import_cache, page-locked host copies
-    # -- what add_data_point leaves in HBM) and the initial safe set as a numpy mask.  Out: the
-    # safe set as a numpy array (lyapunov.safe_set) and c_max (lyapunov.feed_dict).
+    # In: the cached GP tables (FunctionStack.export_cache / import_cache: one page-locked host
+    # buffer mirroring one device arena -- what add_data_point leaves in HBM -- copied H2D every
+    # step) and the initial safe set as a numpy mask.  Out: the safe set as a numpy array
+    # (lyapunov.safe_set) and c_max (lyapunov.feed_dict), read back with one synchronisation.
     tables = lyap.dynamics.export_cache(pinned=True)
     init_mask = np.zeros(n_total, dtype=bool)
     init_mask[par["initial"]] = True
@@ -490,8 +491,9 @@ def run_ours(args, rank, world, local_rank):
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                 "d2h_bytes_per_step": int(d2h), "ms_per_step": e_total / args.steps,
                 "ms_per_step_spread": spread(e_per),
-                "api": "FunctionStack.import_cache(pinned host tables), lyapunov.initial_safe_set = "
-                       "numpy mask, update_safe_set(), lyapunov.safe_set (numpy), feed_dict[c_max]"},
+                "api": "FunctionStack.import_cache(page-locked host mirror of the GP tables: one H2D "
+                       "copy), lyapunov.initial_safe_set = numpy mask (hashed, re-uploaded when it "
+                       "changes), update_safe_set(), lyapunov.safe_set (numpy), feed_dict[c_max]"},
         "gpu_launches": int(launches),
         # `roofline`: the dominant kernel of the timed (default, filtered) step; the kernel that carries
         # the O(M^2) algorithmic cost of SURVEY.md section 8d is reported next to it

@@ -290,7 +290,7 @@ int         slb_debug_filter_stages(int32_t mask);
 int         slb_debug_det_fast(int32_t enable);
 /* diagnostics / tuning: the refine pass of slb_lyapunov_sweep_filtered uses 16-point tiles for
  * lists of up to `upto16` points, 32-point tiles up to `upto32`, 64-point tiles beyond (defaults
- * 16 * 18 and 32 * 148); with 16- and 32-point tiles the rows of a tile are additionally split
+ * 0 -- no 16-point launch -- and 32 * 148); with 16- and 32-point tiles the rows of a tile are additionally split
  * over the CTAs a one-per-SM grid has to spare (up to 8 per tile) */
 int         slb_debug_refine_split(int64_t upto16, int64_t upto32);
 

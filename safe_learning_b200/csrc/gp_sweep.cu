@@ -5,6 +5,8 @@
 
 #include <string.h>
 
+#include <stdlib.h>
+
 #include "gp_args.h"
 
 #define SLB_DECLARE_TILE(d) \
@@ -74,7 +76,7 @@ static long long* g_timing_buffer = nullptr;
 // (16, 32, 64 points per CTA) and only the launch whose range holds the list length does work;
 // the CTAs of the others (and those beyond the list) leave at once.  Measured tile times at
 // M = 500, two factors: see DESIGN.md section 3.5.
-static int64_t g_refine_split[2] = {16 * 18, 32 * 148};
+static int64_t g_refine_split[2] = {0, 32 * 148};   // 16-point tiles: diagnostics only (an empty launch costs ~3 us)
 
 // Short lists (<= 32 x 148 points) additionally split every tile's ROWS over the CTAs the grid has
 // to spare (up to SLB_SPLIT_MAX groups of equal triangular area, gp_tile.cuh): the tile kernel's
@@ -101,7 +103,12 @@ int slb_launch_refine(cudaStream_t st, const slb_sweep& cfg, int64_t n_max, int6
             if (a.n < (int64_t)148 * tps[v]) a.n = (int64_t)148 * tps[v];
             if ((a.n + tps[v] - 1) / tps[v] <= SLB_SPLIT_ITEMS) {
                 a.split_partial = split_partial; a.split_ticket = split_ticket;
-                a.split_max = SLB_SPLIT_MAX;
+                static const int split_max = [] {          // SLB200_SPLIT_MAX: A/B timing knob
+                    const char* e = getenv("SLB200_SPLIT_MAX");
+                    const int v = e ? atoi(e) : SLB_SPLIT_MAX;
+                    return v < 1 ? 1 : (v > SLB_SPLIT_MAX ? SLB_SPLIT_MAX : v);
+                }();
+                a.split_max = split_max;
             }
         }
         const int rc = dispatch_gp_tile(st, cfg, a, tps[v]);

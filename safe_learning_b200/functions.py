@@ -1577,6 +1577,62 @@ class GPRCached(object):
 
 GPR = GPRCached     # the uncached gpflow.gpr.GPR of the notebooks maps onto the cached one
 
+def _table_slots(gps):
+    """(owner, attribute) of every cached device table of a list of GPRCached models, each table
+    once (stacked GPs may share a factor)."""
+    slots, seen = [], set()
+    for gp in gps:
+        gp._ensure()
+        fac = gp._factor
+        for owner, names in ((fac, ("Xs", "Wpack", "Whead", "Xhead", "Xf")),
+                             (gp, ("_alpha_dev", "_gamma_dev", "_gamma_f_dev"))):
+            for name in names:
+                if (id(owner), name) not in seen:
+                    seen.add((id(owner), name))
+                    slots.append((owner, name))
+    return slots
+
+
+class PackedCache(object):
+    """All cached GP tables of a model (or stack) in ONE contiguous device arena with a page-locked
+    host mirror, so that checkpoint / restore is a single copy each way.  Building it re-homes the
+    tables into the arena (their device pointers change: descriptors are rebuilt)."""
+
+    ALIGN = 32                     # doubles: 256-byte table alignment (TMA bulk copies need 16 bytes)
+
+    def __init__(self, gps, pinned=True):
+        self.gps = list(gps)
+        self.slots = _table_slots(self.gps)
+        offsets, total = [], 0
+        for owner, name in self.slots:
+            offsets.append(total)
+            total += -(-max(getattr(owner, name).numel(), 1) // self.ALIGN) * self.ALIGN
+        self.arena = dev.zeros((total,))
+        self.views = []
+        for (owner, name), off in zip(self.slots, offsets):
+            old = getattr(owner, name)
+            view = self.arena[off:off + old.numel()].view(old.shape)
+            view.copy_(old)
+            setattr(owner, name, view)
+            self.views.append(view)
+        for gp in self.gps:
+            gp._version += 1       # the descriptors point at the old buffers
+        host = self.arena.cpu()
+        self.host = host.pin_memory() if pinned and torch.cuda.is_available() else host
+        self.nbytes = int(total) * 8
+        self.token = tuple(id(gp._factor) for gp in self.gps)
+
+    def valid(self):
+        return (self.token == tuple(id(gp._factor) for gp in self.gps)
+                and all(getattr(o, n) is v for (o, n), v in zip(self.slots, self.views)))
+
+    def restore(self):
+        """Host mirror -> device arena: one asynchronous H2D copy on the current stream."""
+        self.arena.copy_(self.host, non_blocking=True)
+        return self.nbytes
+
+
+
 
 def _build_stack(gps, betas):
     """slb_gp_stack for a list of GPRCached models (factor sharing by key)."""
@@ -1639,10 +1695,11 @@ class GaussianProcess(UncertainFunction):
         return self.gaussian_process.variance_floor()
 
     def export_cache(self, pinned=True):
-        return [self.gaussian_process.export_cache(pinned)]
+        """See ``FunctionStack.export_cache``."""
+        return PackedCache([self.gaussian_process], pinned)
 
     def import_cache(self, tables):
-        return self.gaussian_process.import_cache(tables[0])
+        return FunctionStack.import_cache(self, tables)
 
     @property
     def version(self):
@@ -1691,12 +1748,22 @@ class FunctionStack(UncertainFunction):
         return min(f.variance_floor() for f in self.functions)
 
     def export_cache(self, pinned=True):
-        """One table set per stacked GP (see ``GPRCached.export_cache``)."""
-        return [f.gaussian_process.export_cache(pinned) for f in self.functions]
+        """Checkpoint of everything a sweep reads from the cached GPs (scaled training inputs,
+        packed ``L^-1``, filter tables, ``alpha``, ``gamma`` -- what ``update_cache`` leaves in HBM,
+        ``functions.py:395-415``) as a ``PackedCache``: the tables are re-homed into one contiguous
+        device arena mirrored by one page-locked host buffer, so ``import_cache`` is a single H2D
+        copy.  (``GPRCached.export_cache`` gives per-table host tensors instead.)"""
+        return PackedCache([f.gaussian_process for f in self.functions], pinned)
 
     def import_cache(self, tables):
-        """Restore every stacked GP's tables; returns the bytes copied host -> device."""
-        return sum(f.gaussian_process.import_cache(t) for f, t in zip(self.functions, tables))
+        """Restore the cached tables from ``export_cache``'s result (same data set and hyper-
+        parameters); returns the bytes copied host -> device."""
+        if isinstance(tables, PackedCache):
+            if not tables.valid():
+                raise DimensionError("import_cache: the GP cache was refitted since export_cache")
+            return tables.restore()
+        gps = [f.gaussian_process for f in getattr(self, "functions", [self])]
+        return sum(gp.import_cache(t) for gp, t in zip(gps, tables))
 
     @property
     def version(self):

@@ -127,9 +127,11 @@ def get_safe_sample(lyapunov, perturbations=None, limits=None, positive=False, n
     return state_actions[maps_inside, :][[max_id]], bound_safe[max_id].squeeze()
 
 
-# CUDA-graph replay of the five launches of a sweep (opt-in): measured to give no gain, the
-# launches are already hidden behind the ~1.4 ms sweep kernel.
-_USE_GRAPHS = os.environ.get("SLB200_GRAPHS", "0") == "1"
+# CUDA-graph replay of the launches of a sweep (memsets + 8 kernels) while nothing they depend on
+# changes: the second sweep with an unchanged descriptor is captured, later ones replay it.  Measured
+# at C2 (profiles/r02_*): -9 us on the device step (0.219 -> 0.210 ms) and -32 us of host enqueue
+# time per sweep, which is what bounds the end-to-end step.  SLB200_GRAPHS=0 switches it off.
+_USE_GRAPHS = os.environ.get("SLB200_GRAPHS", "1") == "1"
 
 
 class _CMax(object):
@@ -326,9 +328,21 @@ class Lyapunov(object):
     def safe_set(self):
         """Boolean numpy array over the whole grid (gathers the device slabs on demand)."""
         if self._safe_dirty:
-            slab = self._safe_dev.to(torch.bool)
-            full = self._gather(slab).cpu().numpy()
-            self._safe_host = full
+            rank, world = dev.dist_info()
+            if world == 1:
+                # one synchronisation for both read-backs of a sweep: the safe set and the 64 bytes of
+                # key + statistics that c_max / last_sweep are resolved from
+                host = self._host_buffers()
+                host[0].copy_(self._safe_dev, non_blocking=True)
+                if self._pending is not None:
+                    host[1].copy_(self._ks_dev, non_blocking=True)
+                torch.cuda.current_stream().synchronize()
+                self._safe_host = host[0].numpy().astype(bool)
+                if self._pending is not None:
+                    self._resolve_pending(host[1].numpy()[None, :].copy())
+            else:
+                slab = self._safe_dev.to(torch.bool)
+                self._safe_host = self._gather(slab).cpu().numpy()
             self._safe_dirty = False
         return self._safe_host
 
@@ -842,7 +856,17 @@ class Lyapunov(object):
         self._safe_dirty = True
         self._refinement = None      # materialised lazily from safe_set (0/1 in this branch)
 
-    def _resolve_pending(self):
+    def _host_buffers(self):
+        """Page-locked landing buffers of the read-backs (safe slab, key + statistics)."""
+        n_local = self._end - self._begin
+        bufs = self.__dict__.get("_host_bufs")
+        if bufs is None or bufs[0].numel() != n_local:
+            bufs = (torch.empty(n_local, dtype=torch.uint8).pin_memory(),
+                    torch.empty(8, dtype=torch.int64).pin_memory())
+            self.__dict__["_host_bufs"] = bufs
+        return bufs
+
+    def _resolve_pending(self, host=None):
         """The single host read-back of a sweep (key + statistics, 64 bytes per rank), deferred
         until ``c_max`` / ``last_sweep`` is read.  With several ranks this is a collective (like
         reading ``safe_set``): every rank must read at the same point of the program."""
@@ -852,7 +876,9 @@ class Lyapunov(object):
         self._pending = None
         rank, world = dev.dist_info()
         n_total = self.discretization.nindex
-        if world > 1:
+        if host is not None:
+            pass                            # already on the host (read together with the safe set)
+        elif world > 1:
             host = dev.allgather_rows(self._ks_dev).cpu().numpy()
         else:
             host = self._ks_dev.cpu().numpy()[None, :]

@@ -266,6 +266,33 @@ def test_arbitrary_python_callables_vs_oracle(sl):
     assert_array_equal(mixed.safe_set, cpu.safe_set)
 
 
+def test_gp_cache_export_import_round_trip(sl):
+    """FunctionStack.export_cache / import_cache (the host-buffer side of bench.py's end-to-end arm):
+    the tables move into one device arena with a page-locked host mirror; wiping the arena and
+    restoring it with one H2D copy reproduces the sweep; a refit invalidates the checkpoint."""
+    import torch
+    par = W.make_pendulum(num_points=[33, 31], M=70, tau_scale=1 / 40.)
+    gpu, cpu = W.build_product(par), W.build_oracle(par)
+    gpu.update_safe_set()
+    cpu.update_safe_set()
+    before = gpu.safe_set.copy()
+    assert_array_equal(before, cpu.safe_set)
+    cache = gpu.dynamics.export_cache(pinned=True)
+    assert cache.valid() and cache.nbytes > 70 * 70 * 8
+    gpu.update_safe_set()                       # descriptors rebuilt on the re-homed tables
+    assert_array_equal(gpu.safe_set, before)
+    cache.arena.zero_()
+    copied = gpu.dynamics.import_cache(cache)
+    assert copied == cache.nbytes
+    gpu.update_safe_set()
+    assert_array_equal(gpu.safe_set, before)
+    assert gpu.feed_dict[gpu.c_max] == cpu.c_max
+    gpu.dynamics.add_data_point(np.array([[0.1, -0.2, 0.3]]), np.array([[0.05, -0.02]]))
+    gpu.update_safe_set()
+    with pytest.raises(sl.functions.DimensionError):
+        gpu.dynamics.import_cache(cache)
+
+
 def test_initial_safe_set_edited_in_place(sl):
     """the reference re-reads ``initial_safe_set`` on every update_safe_set
     (lyapunov.py:504-506); an in-place edit of the same array must reach the device."""

@@ -53,9 +53,17 @@ def test_sm100a_tensor_instructions_in_binary(lib):
     out = subprocess.run(["cuobjdump", "-lelf", _native.LIB_PATH], stdout=subprocess.PIPE,
                          text=True).stdout
     assert "sm_100a" in out
-    sass = subprocess.run("cuobjdump -sass %s | grep -c DMMA" % _native.LIB_PATH, shell=True,
-                          stdout=subprocess.PIPE, text=True).stdout
-    assert int(sass.strip()) >= 80
+    # one disassembly pass, counted with grep (the text is ~1 GB for the 40 instantiations)
+    counts = subprocess.run(
+        "cuobjdump -sass %s | grep -o -E 'DMMA|UBLKCP.S.G|SYNCS.ARRIVE.TRANS64|"
+        "SYNCS.PHASECHK.TRANS64.TRYWAIT' | sort | uniq -c" % _native.LIB_PATH, shell=True,
+        stdout=subprocess.PIPE, text=True).stdout
+    found = {line.split()[1]: int(line.split()[0]) for line in counts.strip().splitlines()}
+    assert found.get("DMMA", 0) >= 80
+    # the filter stages bring their tables into shared memory with TMA bulk copies tracked by
+    # mbarrier transaction counts (cp.async.bulk -> UBLKCP, expect_tx / try_wait -> SYNCS)
+    for mnemonic in ("UBLKCP.S.G", "SYNCS.ARRIVE.TRANS64", "SYNCS.PHASECHK.TRANS64.TRYWAIT"):
+        assert found.get(mnemonic, 0) >= 6, (mnemonic, found)
 
 
 def test_no_cpu_fallback_without_device(lib):
