@@ -26,8 +26,8 @@ UNITS = [("gp_tile_%d_%d.o" % (d, tp), "gp_tile_inst.cu",
           ["-DSLB_TILE_DIN=%d" % d, "-DSLB_TP=%d" % tp, "-DSLB_RING=%d" % RING[tp]],
           ["gp_tile.cuh", "gp_args.h"]) for d in range(1, 7) for tp in (64, 32, 16)]
 UNITS += [("gp_sweep.o", "gp_sweep.cu", [], ["gp_args.h"]),
-          ("filter.o", "filter.cu", [], ["bulk_copy.cuh", "exp2_tab512.cuh"]),
-          ("light.o", "light.cu", [], ["gp_mean.cuh"]),
+          ("filter.o", "filter.cu", [], ["bulk_copy.cuh", "exp2_tab512.cuh", "gp_mean_staged.cuh", "gp_args.h"]),
+          ("light.o", "light.cu", [], ["bulk_copy.cuh", "exp2_tab512.cuh", "gp_mean_staged.cuh"]),
           ("bellman_tile.o", "bellman_tile.cu", [], [])]
 SOURCES = sorted({u[1] for u in UNITS})
 

@@ -215,22 +215,34 @@ bellman_argmax_tile_kernel(const __grid_constant__ slb_bellman cfg, const argmax
 #pragma unroll
             for (int c = 0; c < DS; ++c) z[c] = xraw[c * BS + s];
             const int i_end = min(a.n_actions, 8 * (rb0 + nrbp));
+            // state part of every output's linear prior mean (the action terms follow per action, in
+            // the same left-to-right order as the unfactored path)
+            double mstate[SLB_MAX_OUT], scale[SLB_MAX_OUT];
+            const double* pm[SLB_MAX_OUT];
+            for (int o = 0; o < D; ++o) {
+                const slb_gp_output& G = cfg.gp.outputs[o];
+                scale[o] = cfg.gp.factors[G.factor].scale;
+                pm[o] = G.prior_mean;
+                mstate[o] = 0.0;
+                if (pm[o] != nullptr) {
+                    mstate[o] = f64mul(z[0], pm[o][0]);
+                    for (int c = 1; c < DS; ++c) mstate[o] = f64add(mstate[o], f64mul(z[c], pm[o][c]));
+                }
+            }
             for (int i = 8 * rb0 + g; i < i_end; i += 4) {
                 for (int c = 0; c < a.m; ++c) z[DS + c] = a.actions[i * a.m + c];
                 double mu[SLB_MAX_OUT], r[SLB_MAX_OUT], v[SLB_MAX_OUT];
                 for (int o = 0; o < D; ++o) {
-                    const slb_gp_output& G = cfg.gp.outputs[o];
-                    const double scale = cfg.gp.factors[G.factor].scale;
                     double mx = 0.0;
-                    if (G.prior_mean != nullptr) {
-                        mx = f64mul(z[0], G.prior_mean[0]);
-                        for (int c = 1; c < din; ++c) mx = f64add(mx, f64mul(z[c], G.prior_mean[c]));
-                        mx = f64mul(scale, mx);
+                    if (pm[o] != nullptr) {
+                        mx = mstate[o];
+                        for (int c = DS; c < din; ++c) mx = f64add(mx, f64mul(z[c], pm[o][c]));
+                        mx = f64mul(scale[o], mx);
                     }
                     const double dot = Cm[((size_t)o * 8 * BMAXRB + (i - 8 * rb0)) * BS + s];
-                    mu[o] = f64add(dot, mx) / scale;
+                    mu[o] = f64add(dot, mx) / scale[o];
                 }
-                eval_fn(cfg.reward, z, r);
+                eval_fn_small(cfg.reward, z, r);
                 eval_fn(cfg.value, mu, v);
                 double val = f64add(r[0], f64mul(cfg.gamma, v[0]));
                 if (a.constraint != nullptr && a.constraint[(int64_t)i * a.n + rel] < 0.0) val = -INFINITY;

@@ -31,8 +31,7 @@
 
 #include <atomic>
 
-#include "bulk_copy.cuh"
-#include "exp2_tab512.cuh"
+#include "gp_mean_staged.cuh"
 #include "gp_args.h"
 
 namespace {
@@ -43,18 +42,13 @@ namespace {
 #ifndef SLB_MEAN_MINB
 #define SLB_MEAN_MINB 7
 #endif
-#ifndef SLB_MEAN_UNROLL
-#define SLB_MEAN_UNROLL 4
-#endif
 constexpr int FT = SLB_FT;             // stage 1: threads per CTA = points per CTA (1024 CTAs at
                                        // 256 x 256, 7 resident per SM: single wave, 98.8% balanced)
-constexpr int MU = SLB_MEAN_UNROLL;    // independent exp chains per thread (rows per iteration)
 constexpr int HR = SLB_HEAD_RANK;
 constexpr int HT = 512;                // stage 2: threads per CTA (16 warps, 8 or 2 list entries each)
 constexpr int HEAD_CTAS = 148;         // one CTA per SM (it stages the head factors in shared memory)
 constexpr int64_t CHUNK = 1 << 22;     // points per pass of the three stages (bounds the workspace)
 constexpr int64_t WS_HEAD = 64 + SLB_SPLIT_TICKET_BYTES + (int64_t)SLB_SPLIT_PARTIAL_BYTES;   // bytes before the lists
-constexpr double EPS_K = 1.0e-13;      // certified relative error of exp_neg_fast incl. its argument
 
 
 // terms of one undecided point, carried from stage 1 to stage 2
@@ -109,208 +103,16 @@ SLB_DEV void count_stat(bool hit, unsigned long long* slot) {
     if (ballot != 0 && (threadIdx.x & 31) == 0) atomicAdd(slot, (unsigned long long)__popc(ballot));
 }
 
-// exp(x) for -700 < x <= 0 (+ rounding) to 3.3e-14 relative (tools/exp_neg_fast_check.c):
-// x = (512 q + i) ln2/512 + r, |r| <= ln2/1024;  exp(x) = 2^q T[i] (1 + r + r^2/2 + r^3/6).
-// 7 fp64 operations (exp_neg_tab: 11).  `far` is set for x <= -700 (incl. -inf): the caller drops
-// the term (the value is unspecified then).  NaN arguments are excluded by the caller.
-SLB_DEV double exp_neg_fast(double x, const double* __restrict__ tab, bool& far) {
-    const double MAGIC = 6755399441055744.0;                           // 1.5 * 2^52
-    const double t = fma(x, 738.6598609351493, MAGIC);                 // 512 / ln2
-    const int n = __double2loint(t);
-    const double nd = t - MAGIC;
-    const double r = fma(nd, -0.0013538030870311431, x);               // ln2 / 512
-    double q = fma(r, 1.0 / 6.0, 0.5);
-    q = q * r;
-    const double p = fma(q, r, r);                                     // e^r - 1
-    const double T = tab[n & 511];
-    const double v = fma(T, p, T);
-    far = (unsigned)__double2hiint(x) > 0xC085E000u;                   // x < -700.0
-    return __hiloint2double(__double2hiint(v) + ((n >> 9) << 20), __double2loint(v));
-}
-
-// ---- stage 1: mean, prior bound -----------------------------------------------------------------
-// Staged slices: per factor the rows [c0, c0 + rows) of Xf (plain RBF: [x / l, -|x / l|^2 / 2],
-// width DIN + 1; covariance expressions: the raw inputs, width DIN) and of gamma_f of every output on
-// the factor.  Buffer b of slice t = t & 1; its mbarrier completes when the bytes have landed.
-struct mean_pipe {
-    uint64_t* bar;                     // [2]
-    double* xbuf;                      // [2][C * (DIN + 1)]
-    double* gbuf;                      // [2][nomax * C]
-    int C, xstride, gstride;
-    int t;                             // slices consumed so far
-    int pf, pc0;                       // producer: factor and first row of the NEXT slice to issue
-};
-
-SLB_DEV int padded_rows(int M) { return (M + 7) & ~7; }
-
-SLB_DEV int first_factor_with_data(const slb_gp_stack& gp, int f) {
-    while (f < gp.num_factors && gp.factors[f].M == 0) ++f;
-    return f;
-}
-
-// thread 0: issue the producer's next slice into buffer `b` and advance
-template <int DIN>
-SLB_DEV void issue_slice(const slb_gp_stack& gp, mean_pipe& P, int b) {
-    if (P.pf >= gp.num_factors) return;
-    const slb_gp_factor& F = gp.factors[P.pf];
-    const int Mp = padded_rows(F.M);
-    const int rows = min(P.C, Mp - P.pc0);
-    const int W = F.kernel.num_prims > 0 ? DIN : DIN + 1;
-    int no = 0;
-    for (int o = 0; o < gp.num_outputs; ++o) no += gp.outputs[o].factor == P.pf;
-    const unsigned xbytes = (unsigned)(rows * W * sizeof(double));
-    const unsigned gbytes = (unsigned)(rows * sizeof(double));
-    slb_bulk::mbar_arrive_expect_tx(P.bar + b, xbytes + no * gbytes);
-    slb_bulk::copy_g2s(P.xbuf + b * P.xstride, F.Xf + (size_t)P.pc0 * W, xbytes, P.bar + b);
-    int q = 0;
-    for (int o = 0; o < gp.num_outputs; ++o) {
-        if (gp.outputs[o].factor != P.pf) continue;
-        slb_bulk::copy_g2s(P.gbuf + b * P.gstride + q * P.C, gp.outputs[o].gamma_f + P.pc0, gbytes,
-                           P.bar + b);
-        ++q;
-    }
-    P.pc0 += P.C;
-    if (P.pc0 >= Mp) { P.pf = first_factor_with_data(gp, P.pf + 1); P.pc0 = 0; }
-}
-
-template <int W>
-SLB_DEV void load_row(const double* __restrict__ p, double (&r)[W]) {
-    if constexpr (W % 2 == 0) {
-#pragma unroll
-        for (int c = 0; c < W; c += 2) {
-            const double2 v = *reinterpret_cast<const double2*>(p + c);
-            r[c] = v.x; r[c + 1] = v.y;
-        }
-    } else {
-#pragma unroll
-        for (int c = 0; c < W; ++c) r[c] = p[c];
-    }
-}
-
-// one factor with NO outputs on it (compile-time, so the running dot products stay in registers)
-template <int DIN, int NO>
-SLB_DEV void mean_factor(const slb_gp_stack& gp, int f, const int* outs, const double* z, double* mu,
-                         double* mean_err, const double* tab512, const double* tab64, mean_pipe& P) {
-    const slb_gp_factor& F = gp.factors[f];
-    const bool general = F.kernel.num_prims > 0;
-    double zs[DIN];
-    double zz = 0.0;
-#pragma unroll
-    for (int c = 0; c < DIN; ++c) {
-        zs[c] = general ? z[c] : z[c] / F.lengthscales[c];
-        zz = fma(zs[c], zs[c], zz);
-    }
-    zz *= -0.5;
-    double dot[NO], dot2[NO];                  // two partial sums: half the loop-carried chain
-#pragma unroll
-    for (int q = 0; q < NO; ++q) { dot[q] = 0.0; dot2[q] = 0.0; }
-    double kbound = general ? 0.0 : 1.0;       // max_i |k_i| (plain RBF: variances live in gamma_f)
-    const int Mp = padded_rows(F.M);
-    for (int c0 = 0; c0 < Mp; c0 += P.C) {
-        const int rows = min(P.C, Mp - c0);
-        const int b = P.t & 1;
-        if (threadIdx.x == 0) issue_slice<DIN>(gp, P, b ^ 1);         // next slice, other buffer
-        slb_bulk::mbar_wait(P.bar + b, (P.t >> 1) & 1);
-        const double* __restrict__ xb = P.xbuf + b * P.xstride;
-        const double* __restrict__ gb = P.gbuf + b * P.gstride;
-        if (!general) {
-            // k_j = exp(-|zs - xs_j|^2 / 2) = exp(h_j + zs . xs_j + zz), h_j = -|xs_j|^2 / 2 staged
-            // with the row; variance and scale^2 are folded into gamma_f.  4 independent chains.
-            constexpr int W = DIN + 1;
-            for (int j0 = 0; j0 < rows; j0 += MU) {
-                double arg[MU];
-#pragma unroll
-                for (int u = 0; u < MU; ++u) {
-                    double row[W];
-                    load_row<W>(xb + (j0 + u) * W, row);
-                    double acc = row[DIN] + zz;
-#pragma unroll
-                    for (int c = 0; c < DIN; ++c) acc = fma(zs[c], row[c], acc);
-                    arg[u] = acc;
-                }
-                double g[NO][MU];
-#pragma unroll
-                for (int q = 0; q < NO; ++q)
-#pragma unroll
-                    for (int u = 0; u < MU; u += 4) load_row<4>(gb + q * P.C + j0 + u, *reinterpret_cast<double(*)[4]>(&g[q][u]));
-#pragma unroll
-                for (int u = 0; u < MU; ++u) {
-                    bool far;
-                    double k = exp_neg_fast(arg[u], tab512, far);
-                    k = far ? 0.0 : k;
-#pragma unroll
-                    for (int q = 0; q < NO; ++q) {
-                        if (u & 1) dot2[q] = fma(k, g[q][u], dot2[q]);
-                        else dot[q] = fma(k, g[q][u], dot[q]);
-                    }
-                }
-            }
-        } else {
-            for (int j0 = 0; j0 < rows; j0 += 4) {
-                const double* xr[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) xr[u] = xb + (j0 + u) * DIN;
-                double kv[4];
-                kernel_expr_cross_n<DIN, 4>(F.kernel, zs, xr, tab64, kv);
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    kbound = fmax(kbound, fabs(kv[u]));
-#pragma unroll
-                    for (int q = 0; q < NO; ++q) dot[q] = fma(kv[u], gb[q * P.C + j0 + u], dot[q]);
-                }
-            }
-        }
-        __syncthreads();                       // every thread is done with buffer b
-        ++P.t;
-    }
-#pragma unroll
-    for (int q = 0; q < NO; ++q) {
-        dot[q] += dot2[q];
-        const slb_gp_output& G = gp.outputs[outs[q]];
-        double mx = 0.0;
-        if (G.prior_mean != nullptr) {
-            mx = f64mul(z[0], G.prior_mean[0]);
-#pragma unroll
-            for (int c = 1; c < DIN; ++c) mx = f64add(mx, f64mul(z[c], G.prior_mean[c]));
-            mx = f64mul(F.scale, mx);
-        }
-        mu[outs[q]] = f64add(dot[q], mx) / F.scale;
-        // |mean - exact| <= eps sum_i |k_i| (|L^-1|^T |alpha|)_i <= eps kbound gamma_l1: kernel
-        // values to EPS_K (+ the expanded distance's rounding), the M-term sums here, in gamma
-        // itself and in the a . alpha form of the full posterior each to (M + 2) 2^-53
-        const double eps = (general ? 4.5e-16 : EPS_K + 4.5e-16 * (-zz + F.hmax)) +
-                           7e-16 * (F.M + 8);
-        mean_err[outs[q]] = eps * kbound * G.gamma_l1 / F.scale;
-    }
-}
-
 template <int DIN>
 __global__ void __launch_bounds__(FT, SLB_MEAN_MINB)
 filter_mean_kernel(const __grid_constant__ slb_sweep cfg, const filter_args a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);             // [2] slices, [2] exp tables
-    double* tab512 = reinterpret_cast<double*>(smem_raw + 32);
-    double* tab64 = tab512 + 512;
     mean_pipe P;
-    P.bar = bar;
-    P.C = a.chunk_rows;
-    P.xstride = P.C * (DIN + 1);
-    P.gstride = P.C * a.max_outputs_per_factor;
-    P.xbuf = tab64 + 64;
-    P.gbuf = P.xbuf + 2 * P.xstride;
-    P.t = 0;
-    P.pf = first_factor_with_data(cfg.gp, 0);
-    P.pc0 = 0;
-    if (threadIdx.x == 0) {
-        slb_bulk::mbar_init(bar + 0, 1);
-        slb_bulk::mbar_init(bar + 1, 1);
-        slb_bulk::mbar_init(bar + 2, 1);
-        slb_bulk::fence_barrier_init();
-        slb_bulk::fence_proxy_async();
-        slb_bulk::mbar_arrive_expect_tx(bar + 2, 576 * sizeof(double));
-        slb_bulk::copy_g2s(tab512, g_exp_tables, 576 * sizeof(double), bar + 2);
-        issue_slice<DIN>(cfg.gp, P, 0);                                 // slice 0 -> buffer 0
-    }
+    double *tab512, *tab64;
+    mean_pipe_setup(P, smem_raw, DIN, a.chunk_rows, a.max_outputs_per_factor, cfg.gp, &tab512, &tab64);
+    uint64_t* bar = P.bar;
+    if (threadIdx.x == 0) mean_pipe_init(P, tab512);
+    mean_pipe_start<DIN>(cfg.gp, P);                                   // slice 0 -> buffer 0
     __syncthreads();
 
     const int64_t rel0 = (int64_t)blockIdx.x * FT + threadIdx.x;
@@ -338,21 +140,7 @@ filter_mean_kernel(const __grid_constant__ slb_sweep cfg, const filter_args a) {
     slb_bulk::mbar_wait(bar + 2, 0);              // exp tables have landed
     double mu[SLB_MAX_OUT];
     double mean_err[SLB_MAX_OUT];
-    for (int f = 0; f < cfg.gp.num_factors; ++f) {
-        int outs[SLB_MAX_OUT];
-        int no = 0;
-        for (int o = 0; o < D; ++o)
-            if (cfg.gp.outputs[o].factor == f) outs[no++] = o;
-        switch (no) {
-        case 1: mean_factor<DIN, 1>(cfg.gp, f, outs, t.z, mu, mean_err, tab512, tab64, P); break;
-        case 2: mean_factor<DIN, 2>(cfg.gp, f, outs, t.z, mu, mean_err, tab512, tab64, P); break;
-        case 3: mean_factor<DIN, 3>(cfg.gp, f, outs, t.z, mu, mean_err, tab512, tab64, P); break;
-        case 4: mean_factor<DIN, 4>(cfg.gp, f, outs, t.z, mu, mean_err, tab512, tab64, P); break;
-        case 5: mean_factor<DIN, 5>(cfg.gp, f, outs, t.z, mu, mean_err, tab512, tab64, P); break;
-        case 6: mean_factor<DIN, 6>(cfg.gp, f, outs, t.z, mu, mean_err, tab512, tab64, P); break;
-        default: break;
-        }
-    }
+    gp_mean_staged<DIN, true>(cfg.gp, t.z, mu, mean_err, tab512, tab64, P);
 
     // ---- V(mu), L_V(mu) and the coefficient of every sigma_j          (lyapunov.py:344-352)
     double vm[1];
@@ -692,12 +480,9 @@ int slb_lyapunov_sweep_filtered(void* stream, const slb_sweep* cfg, int64_t idx_
 #ifndef SLB_MEAN_SMEM_KB
 #define SLB_MEAN_SMEM_KB 24
 #endif
-    int chunk_rows = (SLB_MEAN_SMEM_KB * 1024) / (2 * 8 * (din + 1 + nomax));
-    chunk_rows = chunk_rows >= 256 ? 256 : (chunk_rows & ~7);
-    a.chunk_rows = chunk_rows;
+    a.chunk_rows = mean_chunk_rows(din, nomax, SLB_MEAN_SMEM_KB);
     a.max_outputs_per_factor = nomax;
-    const size_t smem = 32 + (512 + 64) * sizeof(double) +
-                        (size_t)2 * chunk_rows * (din + 1 + nomax) * sizeof(double);
+    const size_t smem = mean_smem_bytes(din, nomax, a.chunk_rows);
     for (int64_t off = 0; off < n_all; off += CHUNK) {
         const int64_t n = n_all - off < CHUNK ? n_all - off : CHUNK;
         SLB_CUDA(cudaMemsetAsync(a.counts, 0, 64 + SLB_SPLIT_TICKET_BYTES, st));

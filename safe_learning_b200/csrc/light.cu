@@ -5,7 +5,7 @@
 //   GridWorld.index_to_state                    functions.py:714-731
 //   Bellman sweep / argmax / max|dV|            reinforcement_learning.py:65-114,135-140,213-279
 #include "common.cuh"
-#include "gp_mean.cuh"
+#include "gp_mean_staged.cuh"
 
 #include <stdarg.h>
 #include <stdio.h>
@@ -527,16 +527,36 @@ apply_prefix_kernel(const double* __restrict__ values, const uint8_t* __restrict
 }
 
 // ---- Bellman sweep ------------------------------------------------------------------------
-// (the mean-only GP loops live in gp_mean.cuh)
+// The mean-only GP runs on the staged pipeline of gp_mean_staged.cuh (training rows and gamma streamed
+// through shared memory by TMA bulk copies, expanded squared distance, the <= 1 ulp table exp).
+struct bellman_smem {
+    mean_pipe P;
+    double* tab512;
+    double* tab64;
+};
+
+template <int DIN>
+SLB_DEV void bellman_setup(bellman_smem& S, unsigned char* smem_raw, const slb_bellman& cfg,
+                           int chunk_rows, int nomax) {
+    mean_pipe_setup(S.P, smem_raw, DIN, chunk_rows, nomax, cfg.gp, &S.tab512, &S.tab64);
+    if (threadIdx.x == 0) mean_pipe_init(S.P, S.tab512);
+    __syncthreads();
+    slb_bulk::mbar_wait(S.P.bar + 2, 0);                       // exp tables have landed
+}
+
 template <int DIN>
 SLB_DEV double bellman_value(const slb_bellman& cfg, const double* x, const double* u, int m,
-                             const double* exptab, double* stage) {
+                             bellman_smem& S) {
     const int d = cfg.grid.ndim;
-    double z[SLB_MAX_IN], mu[SLB_MAX_OUT], r[SLB_MAX_OUT], v[SLB_MAX_OUT];
+    double z[SLB_MAX_IN], mu[SLB_MAX_OUT], err[SLB_MAX_OUT], r[SLB_MAX_OUT], v[SLB_MAX_OUT];
     for (int c = 0; c < d; ++c) z[c] = x[c];
     for (int c = 0; c < m; ++c) z[d + c] = u[c];
-    if (cfg.gp.num_outputs > 0) gp_mean_only<DIN>(cfg.gp, z, mu, exptab, stage);
-    else eval_fn(cfg.dynamics, z, mu);
+    if (cfg.gp.num_outputs > 0) {
+        mean_pipe_start<DIN>(cfg.gp, S.P);
+        gp_mean_staged<DIN, false>(cfg.gp, z, mu, err, S.tab512, S.tab64, S.P);
+    } else {
+        eval_fn(cfg.dynamics, z, mu);
+    }
     eval_fn(cfg.reward, z, r);                               // :95
     eval_fn(cfg.value, mu, v);                               // :101
     return f64add(r[0], f64mul(cfg.gamma, v[0]));                // :104
@@ -545,11 +565,10 @@ SLB_DEV double bellman_value(const slb_bellman& cfg, const double* x, const doub
 template <int DIN>
 __global__ void __launch_bounds__(LT, 2)
 bellman_kernel(const __grid_constant__ slb_bellman cfg, int64_t idx_begin, int64_t n,
-               double* __restrict__ out) {
-    __shared__ double exptab[64];
-    __shared__ double stage[BCHUNK * (DIN + SLB_MAX_OUT)];
-    load_exp_table(exptab);
-    __syncthreads();
+               double* __restrict__ out, int chunk_rows, int nomax) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    bellman_smem S;
+    bellman_setup<DIN>(S, smem_raw, cfg, chunk_rows, nomax);
     const int64_t i0 = (int64_t)blockIdx.x * LT + threadIdx.x;
     const bool valid = i0 < n;
     const int64_t i = valid ? i0 : n - 1;       // every thread stays for the block barriers
@@ -562,7 +581,7 @@ bellman_kernel(const __grid_constant__ slb_bellman cfg, int64_t idx_begin, int64
     } else {
         m = eval_fn(cfg.policy, x, u);
     }
-    const double v = bellman_value<DIN>(cfg, x, u, m, exptab, stage);
+    const double v = bellman_value<DIN>(cfg, x, u, m, S);
     if (valid) out[i] = v;
 }
 
@@ -571,11 +590,10 @@ __global__ void __launch_bounds__(LT, 2)
 bellman_argmax_kernel(const __grid_constant__ slb_bellman cfg, int64_t idx_begin, int64_t n,
                       const double* __restrict__ actions, int n_actions, int m,
                       const double* __restrict__ constraint, int32_t* __restrict__ best,
-                      double* __restrict__ best_value) {
-    __shared__ double exptab[64];
-    __shared__ double stage[BCHUNK * (DIN + SLB_MAX_OUT)];
-    load_exp_table(exptab);
-    __syncthreads();
+                      double* __restrict__ best_value, int chunk_rows, int nomax) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    bellman_smem S;
+    bellman_setup<DIN>(S, smem_raw, cfg, chunk_rows, nomax);
     const int64_t i0 = (int64_t)blockIdx.x * LT + threadIdx.x;
     const bool valid = i0 < n;
     const int64_t i = valid ? i0 : n - 1;       // every thread stays for the block barriers
@@ -585,7 +603,7 @@ bellman_argmax_kernel(const __grid_constant__ slb_bellman cfg, int64_t idx_begin
     double vmax = 0.0;
     for (int a = 0; a < n_actions; ++a) {
         for (int c = 0; c < m; ++c) u[c] = actions[a * m + c];
-        double v = bellman_value<DIN>(cfg, x, u, m, exptab, stage);
+        double v = bellman_value<DIN>(cfg, x, u, m, S);
         if (constraint != nullptr && constraint[(int64_t)a * n + i] < 0.0) v = -INFINITY;  // :272-275
         // np.argmax (:278): first maximum, and NaN counts as the maximum (first NaN wins)
         if (a == 0 || v > vmax || (v != v && vmax == vmax)) { vmax = v; arg = a; }
@@ -883,6 +901,19 @@ int slb_index_to_state(void* stream, const slb_grid* grid, int64_t idx_begin, in
     return 0;
 }
 
+// slice size and dynamic shared memory of the Bellman kernels' mean pipeline (< 48 KB: no opt-in)
+static size_t bellman_stage_config(const slb_bellman& cfg, int din, int* chunk_rows, int* nomax) {
+    int most = 1;
+    for (int f = 0; f < cfg.gp.num_factors; ++f) {
+        int no = 0;
+        for (int o = 0; o < cfg.gp.num_outputs; ++o) no += cfg.gp.outputs[o].factor == f;
+        if (no > most) most = no;
+    }
+    *nomax = most;
+    *chunk_rows = mean_chunk_rows(din, most, 24);
+    return mean_smem_bytes(din, most, *chunk_rows);
+}
+
 static int validate_bellman(const slb_bellman* cfg, int* m_out) {
     SLB_CHECK(cfg != nullptr, "bellman: null config");
     if (slb_validate_grid(&cfg->grid, false)) return 1;
@@ -902,8 +933,14 @@ static int validate_bellman(const slb_bellman* cfg, int* m_out) {
         SLB_CHECK(cfg->gp.num_outputs == d && cfg->gp.input_dim == d + m,
                   "bellman: GP stack shape (%d outputs, %d inputs) does not match state %d + action %d",
                   cfg->gp.num_outputs, cfg->gp.input_dim, d, m);
-        for (int o = 0; o < cfg->gp.num_outputs; ++o)
-            SLB_CHECK(cfg->gp.outputs[o].gamma != nullptr, "bellman: GP output %d has no gamma", o);
+        for (int o = 0; o < cfg->gp.num_outputs; ++o) {
+            const slb_gp_output& G = cfg->gp.outputs[o];
+            const slb_gp_factor& F = cfg->gp.factors[G.factor];
+            SLB_CHECK(F.M == 0 || (G.gamma_f != nullptr && F.Xf != nullptr &&
+                                   (reinterpret_cast<uintptr_t>(G.gamma_f) & 15) == 0 &&
+                                   (reinterpret_cast<uintptr_t>(F.Xf) & 15) == 0),
+                      "bellman: GP output %d lacks the (16-byte aligned) staged tables Xf / gamma_f", o);
+        }
     } else {
         if (slb_validate_function(&cfg->dynamics, "dynamics", d + m)) return 1;
         SLB_CHECK(cfg->dynamics.kind != SLB_FN_NONE, "bellman: no dynamics given");
@@ -926,8 +963,10 @@ int slb_bellman_sweep(void* stream, const slb_bellman* cfg, int64_t idx_begin, i
     if (n == 0) return 0;
     SLB_CHECK(out_dev != nullptr, "slb_bellman_sweep: null output");
     const int din = cfg->grid.ndim + m;
+    int chunk_rows, nomax;
+    const size_t smem = bellman_stage_config(*cfg, din, &chunk_rows, &nomax);
 #define SLB_BELLMAN_CASE(D) \
-    case D: bellman_kernel<D><<<blocks_for(n), LT, 0, (cudaStream_t)stream>>>(*cfg, idx_begin, n, out_dev); break;
+    case D: bellman_kernel<D><<<blocks_for(n), LT, smem, (cudaStream_t)stream>>>(*cfg, idx_begin, n, out_dev, chunk_rows, nomax); break;
     switch (din) {
         SLB_BELLMAN_CASE(1) SLB_BELLMAN_CASE(2) SLB_BELLMAN_CASE(3) SLB_BELLMAN_CASE(4)
         SLB_BELLMAN_CASE(5) SLB_BELLMAN_CASE(6)
@@ -968,9 +1007,12 @@ int slb_bellman_argmax(void* stream, const slb_bellman* cfg, int64_t idx_begin, 
                                           n_actions, m, constraint_dev, best_dev, best_value_dev,
                                           workspace_dev);
     const int din = cfg->grid.ndim + m;
+    int chunk_rows, nomax;
+    const size_t smem = bellman_stage_config(*cfg, din, &chunk_rows, &nomax);
 #define SLB_ARGMAX_CASE(D)                                                               \
-    case D: bellman_argmax_kernel<D><<<blocks_for(n), LT, 0, (cudaStream_t)stream>>>(  \
-        *cfg, idx_begin, n, actions_dev, n_actions, m, constraint_dev, best_dev, best_value_dev); break;
+    case D: bellman_argmax_kernel<D><<<blocks_for(n), LT, smem, (cudaStream_t)stream>>>(  \
+        *cfg, idx_begin, n, actions_dev, n_actions, m, constraint_dev, best_dev, best_value_dev, \
+        chunk_rows, nomax); break;
     switch (din) {
         SLB_ARGMAX_CASE(1) SLB_ARGMAX_CASE(2) SLB_ARGMAX_CASE(3) SLB_ARGMAX_CASE(4)
         SLB_ARGMAX_CASE(5) SLB_ARGMAX_CASE(6)

@@ -17,4 +17,5 @@ timeout 400 ncu --set full --clock-control none --import-source on -k regex:gp_t
 timeout 900 python tools/bench_extra.py bellman argmax det det_linear c5 shared c4 nb > gpurun_out/r02_bench_extra.jsonl 2> gpurun_out/r02_extra.err; cut -c1-220 gpurun_out/r02_bench_extra.jsonl
 timeout 200 python tools/r02_probe.py > gpurun_out/r02_filter_probe.jsonl 2>> gpurun_out/r02_extra.err
 timeout 200 python tools/mean_floor_probe.py > gpurun_out/r02_mean_floor.jsonl 2>> gpurun_out/r02_extra.err
+timeout 200 python tools/e2e_breakdown.py > gpurun_out/r02_e2e_breakdown.json 2>> gpurun_out/r02_extra.err
 timeout 300 compute-sanitizer --tool racecheck python __graft_entry__.py --smoke 2>&1 | tail -3 > gpurun_out/r02_racecheck.txt; cat gpurun_out/r02_racecheck.txt
