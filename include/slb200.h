@@ -163,6 +163,10 @@ typedef struct slb_gp_factor {
     const double* Whead;        /* device [SLB_HEAD_RANK, SLB_HEAD_RANK], COLUMN-major, zero padded:
                                    Whead[j * SLB_HEAD_RANK + i] = L_S^-1[i, j], L_S = chol(scale^2
                                    (K(X_S) + noise I))                                   */
+    const double* Wheadp;       /* device, 16-byte aligned: the same L_S^-1 (zero padded to SLB_HEAD_RANK^2) in
+                                   DMMA.8x8x4 A-fragment order: for row block b (8 rows) and k-step s
+                                   (4 columns) 32 doubles, lane T <-> L_S^-1[8b + T/4, 4s + T%4], block
+                                   offset (b * (SLB_HEAD_RANK / 4) + s) * 32                */
     const double* Xhead;        /* device [SLB_HEAD_RANK, d_in], zero padded: the subset's inputs,
                                    scaled like Xs                                        */
     int32_t head_rows;          /* |S| = min(M, SLB_HEAD_RANK)                           */

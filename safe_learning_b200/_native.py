@@ -64,7 +64,8 @@ class SlbGpFactor(C.Structure):
     _fields_ = [("M", C.c_int32), ("nrb", C.c_int32), ("Xs", C.c_void_p), ("Wpack", C.c_void_p),
                 ("lengthscales", C.c_double * SLB_MAX_IN), ("variance", C.c_double),
                 ("scale", C.c_double), ("kss", C.c_double), ("kernel", SlbKernel),
-                ("Whead", C.c_void_p), ("Xhead", C.c_void_p), ("head_rows", C.c_int32),
+                ("Whead", C.c_void_p), ("Wheadp", C.c_void_p), ("Xhead", C.c_void_p),
+                ("head_rows", C.c_int32),
                 ("_pad2", C.c_int32), ("Xf", C.c_void_p), ("hmax", C.c_double)]
 
 

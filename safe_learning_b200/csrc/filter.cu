@@ -256,14 +256,49 @@ SLB_DEV void head_group(const slb_sweep& cfg, const filter_args& a, int64_t grp,
             }
         }
         __syncwarp();
+        double ssp = 0.0;                       // lane p: sum_i a_i^2 of point p
+        if constexpr (P == HP) {
+            // a = W k on the fp64 tensor pipe: W (64 x 64, lower triangular) pre-packed in DMMA
+            // A-fragment order (row block b, k-step s: slb_gp_factor.Wheadp), the HP = 8 points are
+            // the n dimension, k values [row][point] in shared memory are the B fragments as they
+            // lie.  Only the blocks on or below the diagonal (s <= 2 b + 1) are multiplied: 72 DMMAs.
+            const double* __restrict__ Wp = wbuf + (size_t)f * HR * HR;
+            if (!ALL_STAGED && !staged) Wp = F.Wheadp;
+            double acc[8][2];
+#pragma unroll
+            for (int b = 0; b < 8; ++b) { acc[b][0] = 0.0; acc[b][1] = 0.0; }
+#pragma unroll
+            for (int sk = 0; sk < 16; ++sk) {
+                const double bf = kw[(4 * sk + (lane & 3)) * HP + (lane >> 2)];
+#pragma unroll
+                for (int b = sk / 2; b < 8; ++b) {
+                    const double af = Wp[(b * 16 + sk) * 32 + lane];
+                    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                                 : "+d"(acc[b][0]), "+d"(acc[b][1]) : "d"(af), "d"(bf));
+                }
+            }
+            __syncwarp();
+            // lane T holds rows 8 b + T/4 of points 2 (T%4), 2 (T%4) + 1: square, sum over b, then over
+            // the 8 lanes that share T%4; lane p fetches point p's sum
+            double v0 = 0.0, v1 = 0.0;
+#pragma unroll
+            for (int b = 0; b < 8; ++b) { v0 = fma(acc[b][0], acc[b][0], v0); v1 = fma(acc[b][1], acc[b][1], v1); }
+#pragma unroll
+            for (int off = 4; off < 32; off <<= 1) {
+                v0 += __shfl_xor_sync(0xffffffffu, v0, off);
+                v1 += __shfl_xor_sync(0xffffffffu, v1, off);
+            }
+            const double s0 = __shfl_sync(0xffffffffu, v0, (lane >> 1) & 3);
+            const double s1 = __shfl_sync(0xffffffffu, v1, (lane >> 1) & 3);
+            ssp = (lane & 1) ? s1 : s0;
+        } else {
         // short groups: two partial sums per row and point (even / odd columns) halve the dependent
         // FMA chain; 8-point groups already carry 16 independent chains
         constexpr int NS = P <= 2 ? 2 : 1;
         double al[2][P], ah[2][P];
 #pragma unroll
         for (int p = 0; p < P; ++p) { al[0][p] = al[1][p] = 0.0; ah[0][p] = ah[1][p] = 0.0; }
-        const double* Wt = wbuf + (size_t)f * HR * HR;
-        if (!ALL_STAGED && !staged) Wt = F.Whead;
+        const double* Wt = F.Whead;            // column-major table (global / L2): reference path
 #pragma unroll 4
         for (int j = 0; j < HR; ++j) {
             const double wl = Wt[j * HR + lane], wh = Wt[j * HR + 32 + lane];
@@ -281,7 +316,6 @@ SLB_DEV void head_group(const slb_sweep& cfg, const filter_args& a, int64_t grp,
         }
         __syncwarp();
         // sum a^2 per point over the 64 rows: lane p ends up with point p's
-        double ssp = 0.0;
 #pragma unroll
         for (int p = 0; p < P; ++p) {
             const double lo = al[0][p] + al[1][p], hi = ah[0][p] + ah[1][p];
@@ -289,6 +323,7 @@ SLB_DEV void head_group(const slb_sweep& cfg, const filter_args& a, int64_t grp,
 #pragma unroll
             for (int off = 16; off > 0; off >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, off);
             if (lane == p) ssp = ss;
+        }
         }
         double kss = F.kss;
         if (general && mine) kss = s2 * kernel_expr_diag<DIN>(F.kernel, t.z);
@@ -322,8 +357,10 @@ filter_head_kernel(const __grid_constant__ slb_sweep cfg, const filter_args a) {
     double* xbuf = wbuf + (size_t)a.head_factors_staged * HR * HR;     // [staged][HR * DIN]
     const int64_t count = (int64_t)a.counts[0];
     const int64_t nwarps = (int64_t)gridDim.x * HW;
-    const bool short_list = count < nwarps * HP;
-    const int64_t ngroups = short_list ? (count + HP_SHORT - 1) / HP_SHORT : (count + HP - 1) / HP;
+    const bool short_list = false;     // every list takes 8-point DMMA groups (the 2-point FMA form of
+                                       // head_group is kept for reference / A-B timing)
+    const int64_t ngroups = (count + HP - 1) / HP;
+    (void)nwarps;
     if ((int64_t)blockIdx.x * HW >= ngroups) return;                   // no group for this CTA
     if (threadIdx.x == 0) {
         slb_bulk::mbar_init(bar, 1);
@@ -338,7 +375,7 @@ filter_head_kernel(const __grid_constant__ slb_sweep cfg, const filter_args a) {
         for (int f = 0; f < a.head_factors_staged; ++f) {
             const slb_gp_factor& F = cfg.gp.factors[f];
             if (F.head_rows <= 0) continue;
-            slb_bulk::copy_g2s(wbuf + (size_t)f * HR * HR, F.Whead, HR * HR * sizeof(double), bar);
+            slb_bulk::copy_g2s(wbuf + (size_t)f * HR * HR, F.Wheadp, HR * HR * sizeof(double), bar);
             slb_bulk::copy_g2s(xbuf + (size_t)f * HR * DIN, F.Xhead, HR * DIN * sizeof(double), bar);
         }
     }
@@ -445,8 +482,12 @@ int slb_lyapunov_sweep_filtered(void* stream, const slb_sweep* cfg, int64_t idx_
     int nomax = 1;
     for (int f = 0; f < cfg->gp.num_factors; ++f) {
         const slb_gp_factor& F = cfg->gp.factors[f];
-        SLB_CHECK(F.M == 0 || (F.Xf != nullptr && F.Whead != nullptr && F.Xhead != nullptr),
-                  "filtered sweep: GP factor %d lacks the filter tables (Xf / Whead / Xhead)", f);
+        SLB_CHECK(F.M == 0 || (F.Xf != nullptr && F.Whead != nullptr && F.Wheadp != nullptr &&
+                               F.Xhead != nullptr),
+                  "filtered sweep: GP factor %d lacks the filter tables (Xf / Whead / Wheadp / Xhead)", f);
+        SLB_CHECK(F.M == 0 || ((reinterpret_cast<uintptr_t>(F.Wheadp) & 15) == 0 &&
+                               (reinterpret_cast<uintptr_t>(F.Xhead) & 15) == 0),
+                  "filtered sweep: GP factor %d: Wheadp / Xhead must be 16-byte aligned", f);
         SLB_CHECK(F.head_rows >= 0 && F.head_rows <= SLB_HEAD_RANK && F.head_rows <= F.M,
                   "filtered sweep: GP factor %d has %d head rows (0..min(M, %d))", f, F.head_rows,
                   SLB_HEAD_RANK);

@@ -1164,7 +1164,7 @@ class Likelihood(object):
 class _Factor(object):
     """Device-resident Cholesky state of one (X, kernel, noise, scale) combination."""
 
-    __slots__ = ("key", "M", "nrb", "Xs", "L", "Linv", "Wpack", "Whead", "Xhead", "head_rows",
+    __slots__ = ("key", "M", "nrb", "Xs", "L", "Linv", "Wpack", "Whead", "Wheadp", "Xhead", "head_rows",
                  "Xf", "hmax", "appends", "plain", "floor_rel")
 
 
@@ -1329,6 +1329,7 @@ class GPRCached(object):
         r = min(M, R)
         fac.Whead = dev.zeros((R, R))
         fac.Xhead = dev.zeros((R, din))
+        fac.Wheadp = dev.zeros((R * R,))
         fac.head_rows = r
         Mp = max(8 * ((M + 7) // 8), 8)
         width = din + 1 if fac.plain else din
@@ -1342,8 +1343,9 @@ class GPRCached(object):
             half = -0.5 * (fac.Xs * fac.Xs).sum(dim=1)
             fac.Xf[:M, din] = half
             fac.hmax = float(-half.min().item())
+        fac.Wheadp = dev.zeros((R * R,))
         if head_from is not None and head_from.head_rows == r:
-            fac.Whead, fac.Xhead = head_from.Whead, head_from.Xhead
+            fac.Whead, fac.Wheadp, fac.Xhead = head_from.Whead, head_from.Wheadp, head_from.Xhead
         else:
             if kernel is None:
                 kernel = self.kern.K_scaled(fac.Xs) if fac.plain else self.kern.K_device(fac.Xs)
@@ -1356,6 +1358,10 @@ class GPRCached(object):
             linv = torch.linalg.solve_triangular(
                 l_ss, torch.eye(r, dtype=torch.float64, device=k_ss.device), upper=False)
             fac.Whead[:r, :r] = linv.T                    # Whead[j, i] = L_S^-1[i, j]
+            # the same matrix in DMMA A-fragment order (head stage of the filter): [b, s, T/4, T%4]
+            full = dev.zeros((R, R))
+            full[:r, :r] = linv
+            fac.Wheadp = full.reshape(R // 8, 8, R // 4, 4).permute(0, 2, 1, 3).contiguous().reshape(-1)
         # var(z) >= k(z,z) s / (M k(z,z) + s), s = noise variance (M noisy observations AT z are
         # the most informative data set): relative to k(z,z) at least s / (M kmax + s).  When
         # that is not far above fp64 rounding of the O(M^2) contraction the reference's
@@ -1512,6 +1518,7 @@ class GPRCached(object):
         f.M, f.nrb = fac.M, fac.nrb
         f.Xs, f.Wpack = fac.Xs.data_ptr(), fac.Wpack.data_ptr()
         f.Whead, f.Xhead, f.head_rows = fac.Whead.data_ptr(), fac.Xhead.data_ptr(), fac.head_rows
+        f.Wheadp = fac.Wheadp.data_ptr()
         f.Xf, f.hmax = fac.Xf.data_ptr(), fac.hmax
         f.scale = self._scale
         if fac.plain:
@@ -1539,12 +1546,12 @@ class GPRCached(object):
         return self._factor.floor_rel
 
     # host copies of the cached tables ------------------------------------------------------
-    _CACHE_FIELDS = ("Xs", "Wpack", "Whead", "Xhead", "Xf", "alpha", "gamma", "gamma_f")
+    _CACHE_FIELDS = ("Xs", "Wpack", "Whead", "Wheadp", "Xhead", "Xf", "alpha", "gamma", "gamma_f")
 
     def _cache_tables(self):
         fac = self._factor
-        return (fac.Xs, fac.Wpack, fac.Whead, fac.Xhead, fac.Xf, self._alpha_dev, self._gamma_dev,
-                self._gamma_f_dev)
+        return (fac.Xs, fac.Wpack, fac.Whead, fac.Wheadp, fac.Xhead, fac.Xf, self._alpha_dev,
+                self._gamma_dev, self._gamma_f_dev)
 
     def export_cache(self, pinned=True):
         """Host copies (torch CPU tensors, page-locked if ``pinned``) of the device tables a sweep
@@ -1584,7 +1591,7 @@ def _table_slots(gps):
     for gp in gps:
         gp._ensure()
         fac = gp._factor
-        for owner, names in ((fac, ("Xs", "Wpack", "Whead", "Xhead", "Xf")),
+        for owner, names in ((fac, ("Xs", "Wpack", "Whead", "Wheadp", "Xhead", "Xf")),
                              (gp, ("_alpha_dev", "_gamma_dev", "_gamma_f_dev"))):
             for name in names:
                 if (id(owner), name) not in seen:
