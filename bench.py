@@ -435,30 +435,73 @@ def run_ours(args, rank, world, local_rank):
                         "frac": hbm_gbs / hbm_peak,
                         "note": "path is fp64-compute-bound (AI ~3e4 FLOP/B); HBM fraction "
                                 "reported for completeness"}}
-    # The dominant kernel of the DEFAULT step is the filter's mean stage (filter_mean_kernel): per
-    # point and training row 3 d_in + 4 fp64 operations for the kernel entry and the dot product +
-    # one exp (F_B = D M (3 d_in + 4 + E_exp), E_exp = 1) on the fp64 pipe
-    # (DFMA shares the pipe and the peak of the DMMA tensor op: tools/fp64_peaks.cu).
+    # Rooflines of the three stages of the DEFAULT step (stage times measured live with the library's
+    # stage switch, L2 flushed before each); `roofline` is the stage that takes the most time.
+    #  * stage 1, fp32 screening kernel (filter_mean32_kernel): per point and training row d_in FFMA for the
+    #    exponent, one MUFU.EX2, one FFMA per output for the dot product -> bound by the SFU (16 ex2 per
+    #    clock and SM) and the fp32 issue rate; algorithmic flops F_B = D M (3 d_in + 4 + E_exp), E_exp = 1
+    #    (SURVEY.md section 8d), against the fp32 FFMA peak 148 SMs x 128 lanes x 2 x 1.965 GHz.
+    #  * stage 1, fp64 mean kernel (filter_mean_kernel, where screening does not apply): the same count on
+    #    the fp64 pipe (DFMA shares the pipe and the peak of the DMMA tensor op: tools/fp64_peaks.cu).
+    #  * head stage (filter_head_kernel): latency bound at C2 (one 8-point group per warp); reported as
+    #    points per second only.
+    #  * refine pass (gp_tile_kernel, 32-point row/factor-split tiles): the O(M^2) flops of the refined
+    #    points against the DMMA peak.
     npts = max(fs["points"], 1)
     mean_ms = stage_ms.get("mean")
     roofline_filter = None
+    stage_rooflines = None
     if mean_ms:
+        stage1 = int(lib.slb_filter_stage1(cfg))
+        head_ms = stage_ms["mean_head"] - mean_ms
+        refine_ms = filter_ms - stage_ms["mean_head"]
         flops_mean = 2 * M_TRAIN * (3 * 3 + 4 + 1)
         ach = flops_mean * n_local / (mean_ms * 1e-3) * 1e-12
-        roofline_filter = {
-            "bound": "tensor", "kernel": "filter_mean_kernel<3> (fp64 pipe: DFMA, the pipe and peak "
-                                         "of the DMMA tensor op): GP mean of every point, prior-variance decision",
-            "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,
-            "kernel_ms": mean_ms, "algorithmic_flops_per_point": flops_mean,
-            "executed_fp64_ops_per_entry": 12,
-            "exp_per_s": 2 * M_TRAIN * n_local / (mean_ms * 1e-3), "exp_peak_per_s": 8.4e11,
-            "exp_frac": 2 * M_TRAIN * n_local / (mean_ms * 1e-3) / 8.4e11,
-            "stage_ms": {"mean": mean_ms, "head": stage_ms["mean_head"] - mean_ms,
-                         "refine": filter_ms - stage_ms["mean_head"]},
-            "note": "stage times measured live with the library's stage switch (L2 flushed before "
-                    "each); E_exp = 1 charges one flop per exp although the table-driven exp executes "
-                    "7 fp64 operations, so the executed-operation utilisation of the pipe is about "
-                    "1.7x this fraction (ncu: profiles/r02_filter_mean_kernel_ncu.json)"}
+        exp_rate1 = 2 * M_TRAIN * n_local / (mean_ms * 1e-3)
+        sm_ghz = 1.965
+        if stage1 == 32:
+            fp32_peak = 148 * 128 * 2 * sm_ghz * 1e-3
+            mufu_peak = 148 * 16 * sm_ghz * 1e9
+            r_mean = {
+                "bound": "compute", "bound_detail": "neither HBM nor tensor cores: SFU (MUFU.EX2, 16 per "
+                "clock and SM) and fp32 issue rate; `peak` is the fp32 FFMA peak 148 x 128 x 2 x 1.965 GHz",
+                "kernel": "filter_mean32_kernel<3>: fp32 screening mean of every grid point (3 FFMA + "
+                          "MUFU.EX2 + 1 FFMA per kernel value) with a certified error bound, decision "
+                          "over the mean's error box and the prior variance",
+                "achieved": ach, "peak": fp32_peak, "unit": "TFLOP/s", "frac": ach / fp32_peak,
+                "kernel_ms": mean_ms, "algorithmic_flops_per_point": flops_mean,
+                "exp_per_s": exp_rate1, "exp_peak_per_s": mufu_peak, "exp_frac": exp_rate1 / mufu_peak,
+                "traffic": None}
+        else:
+            r_mean = {
+                "bound": "tensor", "kernel": "filter_mean_kernel<3> (fp64 pipe: DFMA, the pipe and peak "
+                                             "of the DMMA tensor op): GP mean of every point, prior-variance decision",
+                "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,
+                "kernel_ms": mean_ms, "algorithmic_flops_per_point": flops_mean,
+                "executed_fp64_ops_per_entry": 12,
+                "exp_per_s": exp_rate1, "exp_peak_per_s": 8.4e11, "exp_frac": exp_rate1 / 8.4e11,
+                "traffic": None}
+        ach_ref = flops_pt * fs["refined"] / max(refine_ms * 1e-3, 1e-9) * 1e-12
+        r_refine = {
+            "bound": "tensor", "kernel": "gp_tile_kernel<3, 32> on the refine list (fp64 DMMA.8x8x4; rows "
+                                         "and factors of every 32-point tile split over spare CTAs)",
+            "achieved": ach_ref, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach_ref / peak_tf,
+            "kernel_ms": refine_ms, "points": fs["refined"], "algorithmic_flops_per_point": flops_pt,
+            "traffic": None,
+            "note": "a few hundred points cannot fill 148 SMs: the pass is bound by the latency of one "
+                    "tile's serial chain (generation -> contraction -> reduction), not by the pipe"}
+        r_head = {"kernel": "filter_head_kernel<3>", "kernel_ms": head_ms,
+                  "points": fs["head"] + fs["refined"],
+                  "note": "one 8-point group per warp: latency bound at this list length"}
+        stage_rooflines = {"mean": r_mean, "head": r_head, "refine": r_refine}
+        roofline_filter = dict(r_refine if refine_ms > mean_ms else r_mean)
+        roofline_filter["stage_ms"] = {"mean": mean_ms, "head": head_ms, "refine": refine_ms}
+        roofline_filter["stage1"] = "fp32 screening" if stage1 == 32 else "fp64 mean"
+        roofline_filter["note"] = (
+            "dominant stage of the default step by time; stage times measured live with the library's "
+            "stage switch (L2 flushed before each); E_exp = 1 charges one flop per exp; all three stages: "
+            "`stage_rooflines`; the kernel carrying the O(M^2) cost over the whole grid: "
+            "`roofline_full_posterior`")
     exp_rate = 2 * M_TRAIN * n_local / (filter_ms * 1e-3)
     filter_info = {
         "enabled": bool(filtered),
@@ -499,6 +542,7 @@ def run_ours(args, rank, world, local_rank):
         # the O(M^2) algorithmic cost of SURVEY.md section 8d is reported next to it
         "roofline": roofline_filter if roofline_filter is not None else roofline,
         "roofline_full_posterior": roofline,
+        "stage_rooflines": stage_rooflines,
         "filter": filter_info,
         "full_posterior": {"value": n_total * args.steps / (f_total * 1e-3), "unit": UNIT,
                            "ms_per_step": f_total / args.steps,

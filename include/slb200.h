@@ -28,13 +28,15 @@
 extern "C" {
 #endif
 
-#define SLB_ABI_VERSION 4   /* 2: slb_gp_factor.kernel (covariance expressions), GRADIENT / MAXABS flags
+#define SLB_ABI_VERSION 5   /* 2: slb_gp_factor.kernel (covariance expressions), GRADIENT / MAXABS flags
                                3: decision filter (slb_gp_factor.Whead, slb_lyapunov_sweep_filtered),
                                   state-dependent lipschitz_dynamics, peer-memory key exchange
                                   (slb_exchange), fixed-action Bellman tables
                                4: filter tables staged by TMA bulk copies (slb_gp_factor.Xf / Xhead /
                                   head_rows / hmax, slb_gp_output.gamma_f / gamma_l1): pivoted head
-                                  subset, computed error bound of the filter's mean               */
+                                  subset, computed error bound of the filter's mean
+                               5: fp32 screening stage in front of the filter (slb_debug_screening_probe,
+                                  bit 2 of slb_debug_filter_stages); no structure changed           */
 #define SLB_MAX_DIM 6   /* state dimension d                         */
 #define SLB_MAX_IN  8   /* GP input dimension d_in = d + m           */
 #define SLB_MAX_OUT 6   /* stacked one-output GPs (FunctionStack)    */
@@ -286,8 +288,14 @@ void        slb_note_graph_replay(int64_t kernels);
  * pass NULL to switch it off (default) */
 int         slb_debug_phase_timing(void* buffer_dev);
 /* diagnostics (timing of the individual stages of slb_lyapunov_sweep_filtered; the flags are only
- * complete with mask 3, the default): bit 0 runs the head stage, bit 1 the refine pass */
+ * complete with bits 0 and 1 set -- 3, the default, or 7): bit 0 runs the head stage, bit 1 the
+ * refine pass; bit 2 forces the fp64 mean stage where the fp32 screening stage would run */
 int         slb_debug_filter_stages(int32_t mask);
+/* diagnostics: while both pointers are non-NULL, the fp32 screening stage of
+ * slb_lyapunov_sweep_filtered also writes, for every point of the swept range (row = index relative to
+ * idx_begin of the LAST pass), its screened mean [n, D] and the certified bound of its error [n, D]
+ * (+inf where the point is left to the fp64 stages); tests hold |mean - fp64 mean| <= bound */
+int         slb_debug_screening_probe(double* mu_dev, double* dm_dev);
 /* diagnostics: deterministic-dynamics sweeps of the LQR composition (d = 2, saturated linear policy,
  * linear dynamics, quadratic V, constant / abs-linear L_V) take a specialised register-resident
  * kernel; 0 switches back to the generic interpreter (A/B timing, parity tests). */
@@ -339,6 +347,10 @@ int slb_lyapunov_sweep(void* stream, const slb_sweep* cfg, int64_t idx_begin, in
  * {decided by mean + prior bound, decided by the head-rank bound, refined by the full posterior,
  * points} accumulated over calls (the caller zeroes it). */
 int64_t slb_filter_workspace(int64_t n);
+/* which first stage slb_lyapunov_sweep_filtered runs for this configuration: 32 = the fp32 screening
+ * kernel (plain RBF factors, quadratic V, constant / abs-linear L_V, tables fit the head stage's shared
+ * memory) followed by an fp64 mean on the undecided points; 64 = the fp64 mean kernel; 0 = no GP */
+int slb_filter_stage1(const slb_sweep* cfg);
 int slb_lyapunov_sweep_filtered(void* stream, const slb_sweep* cfg, int64_t idx_begin,
                                 int64_t idx_end, uint8_t* negative_dev, double* values_dev,
                                 void* workspace_dev, int64_t* stats_dev);

@@ -25,7 +25,7 @@ FLAG_SATURATE, FLAG_ABS, FLAG_NORM1, FLAG_PROJECT, FLAG_SCALE, FLAG_GRADIENT, FL
     1, 2, 4, 8, 16, 32, 64
 K_RBF, K_MATERN12, K_MATERN32, K_MATERN52, K_LINEAR, K_CONSTANT, K_WHITE = range(7)
 SLB_MAX_KPRIM = 6
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 UINT64_MAX = (1 << 64) - 1
 INT64_MAX = (1 << 63) - 1
@@ -132,6 +132,8 @@ SIGNATURES = {
     "slb_debug_refine_split": (C.c_int, [_i64, _i64]),
     "slb_debug_det_fast": (C.c_int, [_i32]),
     "slb_debug_filter_stages": (C.c_int, [_i32]),
+    "slb_debug_screening_probe": (C.c_int, [_dp, _dp]),
+    "slb_filter_stage1": (C.c_int, [C.POINTER(SlbSweep)]),
     "slb_packed_len": (C.c_int64, [_i32]),
     "slb_pack_factor": (C.c_int, [_vp, _dp, _i32, _dp]),
     "slb_pivoted_subset": (C.c_int, [_vp, _dp, _i32, _i32, _vp, _dp]),

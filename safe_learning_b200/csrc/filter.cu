@@ -30,6 +30,8 @@
 #include "common.cuh"
 
 #include <atomic>
+#include <string.h>
+#include <stdlib.h>
 
 #include "gp_mean_staged.cuh"
 #include "gp_args.h"
@@ -68,6 +70,15 @@ struct filter_args {
     int max_outputs_per_factor;
     int head_factors_staged;           // head stage: factors whose tables fit in shared memory (the
                                        // others are read from global memory)
+    int screened;                      // stage 1 was the fp32 screening kernel: list A entries carry only
+                                       // z, threshold and V(x) (in dec0); the head stage computes the
+                                       // fp64 mean and the terms that depend on it
+    int mean_off[SLB_MAX_OUT];         // screened: offset (doubles) of factor f's [Xf | gamma_f ...] block
+                                       // in the head stage's shared-memory copy
+    int mean_doubles;                  // screened: size of that copy
+    int prefetch_factors;              // head stage: warm L2 with the packed factors for the refine pass
+    double* probe_mu;                  // slb_debug_screening_probe: nullptr or [n, D] screened means ...
+    double* probe_dm;                  // ... and their certified error bounds (inf: point left to fp64)
 };
 
 // outcome for err_j = beta_j sigma_j with sigma_j in [0, shi_j]:  +1 decided negative (True),
@@ -101,6 +112,74 @@ SLB_DEV long long list_append(bool take, unsigned long long* counter) {
 SLB_DEV void count_stat(bool hit, unsigned long long* slot) {
     const unsigned ballot = __ballot_sync(0xffffffffu, hit);
     if (ballot != 0 && (threadIdx.x & 31) == 0) atomicAdd(slot, (unsigned long long)__popc(ballot));
+}
+
+// V(mu), L_V(mu) -> the terms of the comparison that depend on the mean: dec0 = V(mu) - V(x), the
+// coefficient of every sigma_j, and the guard band (1e-6 relative + the mean's own error bound
+// through L_V(mu), x 4)                                                      (lyapunov.py:344-352)
+SLB_DEV void mean_decision_terms(const slb_sweep& cfg, filter_side& t, double vx, const double* mu,
+                                 const double* mean_err) {
+    const int D = cfg.gp.num_outputs;
+    double vm[1];
+    eval_fn_small(cfg.lyapunov, mu, vm);
+    t.dec0 = f64sub(vm[0], vx);
+    double lvmu = 0.0;                      // sum_j |L_V(mu)_j mu_j|: scale of V's sensitivity to mu
+    double lverr = 0.0;                     // sum_j |L_V(mu)_j| mean_err_j
+    {
+        double lv[SLB_MAX_OUT];
+        int nl = 1;
+        if (cfg.lipschitz_v.kind != SLB_FN_NONE) nl = eval_fn_small(cfg.lipschitz_v, mu, lv);
+        else lv[0] = cfg.lv_const;
+        for (int j = 0; j < SLB_MAX_OUT; ++j) {
+            const double l = j < D ? (nl == 1 ? lv[0] : lv[j]) : 0.0;
+            t.coef[j] = j < D ? l * cfg.gp.outputs[j].beta : 0.0;
+            if (j < D) { lvmu += fabs(l * mu[j]); lverr += fabs(l) * mean_err[j]; }
+        }
+    }
+    t.guard = 1e-6 * (fabs(vm[0]) + fabs(vx) + fabs(t.thr) + lvmu) + 4.0 * lverr + 1e-300;
+}
+
+// The screening stage knows the mean only to within dm_j (certified, gp_mean_staged.cuh).  For the
+// function kinds it is enabled for -- V = x^T P x (QUADRATIC, optional scale), L_V constant or a
+// LINEAR map with abs / 1-norm / scale -- the change of the comparison over the box mu +- dm is
+// bounded in closed form:  |V(mu + e) - V(mu)| <= sum_i |((P + P^T) mu)_i| dm_i + sum_ij |P_ij| dm_i
+// dm_j;  |L_V(mu + e)_j - L_V(mu)_j| <= |scale| sum_i |A_ji| dm_i (all rows for the 1-norm), which
+// enters with beta_j sigma_j <= beta_j shi_j.  Returns the amount to add to the guard band.
+SLB_DEV double screening_slack(const slb_sweep& cfg, const double* mu, const double* dm,
+                               const double* shi) {
+    const int D = cfg.gp.num_outputs;
+    const slb_function& V = cfg.lyapunov;
+    const int n = V.in_dim;
+    double dv = 0.0;
+    for (int i = 0; i < n; ++i) {
+        double gi = 0.0;
+        for (int r = 0; r < n; ++r)
+            gi += mu[r] * (__ldg(V.matrix + r * n + i) + __ldg(V.matrix + i * n + r));
+        dv += fabs(gi) * dm[i];
+        for (int j = 0; j < n; ++j) dv += fabs(__ldg(V.matrix + i * n + j)) * dm[i] * dm[j];
+    }
+    if (V.flags & SLB_FLAG_SCALE) dv *= fabs(V.out_scale);
+    double dl = 0.0;
+    const slb_function& L = cfg.lipschitz_v;
+    if (L.kind == SLB_FN_LINEAR) {
+        const double sc = (L.flags & SLB_FLAG_SCALE) ? fabs(L.out_scale) : 1.0;
+        const int m = L.in_dim;
+        if ((L.flags & SLB_FLAG_NORM1) || L.out_dim == 1) {
+            double tot = 0.0;
+            for (int o = 0; o < L.out_dim; ++o)
+                for (int i = 0; i < m; ++i) tot += fabs(__ldg(L.matrix + o * m + i)) * dm[i];
+            double bs = 0.0;
+            for (int j = 0; j < D; ++j) bs += fabs(cfg.gp.outputs[j].beta) * shi[j];
+            dl = sc * tot * bs;
+        } else {
+            for (int j = 0; j < D; ++j) {
+                double row = 0.0;
+                for (int i = 0; i < m; ++i) row += fabs(__ldg(L.matrix + j * m + i)) * dm[i];
+                dl += sc * row * fabs(cfg.gp.outputs[j].beta) * shi[j];
+            }
+        }
+    }
+    return 1.000001 * (dv + dl);
 }
 
 template <int DIN>
@@ -142,24 +221,7 @@ filter_mean_kernel(const __grid_constant__ slb_sweep cfg, const filter_args a) {
     double mean_err[SLB_MAX_OUT];
     gp_mean_staged<DIN, true>(cfg.gp, t.z, mu, mean_err, tab512, tab64, P);
 
-    // ---- V(mu), L_V(mu) and the coefficient of every sigma_j          (lyapunov.py:344-352)
-    double vm[1];
-    eval_fn_small(cfg.lyapunov, mu, vm);
-    t.dec0 = f64sub(vm[0], vx);
-    double lvmu = 0.0;                      // sum_j |L_V(mu)_j mu_j|: scale of V's sensitivity to mu
-    double lverr = 0.0;                     // sum_j |L_V(mu)_j| mean_err_j
-    {
-        double lv[SLB_MAX_OUT];
-        int nl = 1;
-        if (cfg.lipschitz_v.kind != SLB_FN_NONE) nl = eval_fn_small(cfg.lipschitz_v, mu, lv);
-        else lv[0] = cfg.lv_const;
-        for (int j = 0; j < SLB_MAX_OUT; ++j) {
-            const double l = j < D ? (nl == 1 ? lv[0] : lv[j]) : 0.0;
-            t.coef[j] = j < D ? l * cfg.gp.outputs[j].beta : 0.0;
-            if (j < D) { lvmu += fabs(l * mu[j]); lverr += fabs(l) * mean_err[j]; }
-        }
-    }
-    t.guard = 1e-6 * (fabs(vm[0]) + fabs(vx) + fabs(t.thr) + lvmu) + 4.0 * lverr + 1e-300;
+    mean_decision_terms(cfg, t, vx, mu, mean_err);
 
     // ---- sigma_j <= prior sigma_j     (functions.py:450 without data)
     double shi[SLB_MAX_OUT];
@@ -181,6 +243,105 @@ filter_mean_kernel(const __grid_constant__ slb_sweep cfg, const filter_args a) {
     }
 }
 
+// ---- stage 1, fp32 screening variant ---------------------------------------------------------------
+// Same role as filter_mean_kernel with the mean from the fp32 scheme of gp_mean_staged.cuh (three FFMA
+// and one MUFU.EX2 per kernel value instead of twelve fp64 operations) and its certified error bound
+// dm: a point is decided when the comparison has the same outcome for every mean in mu +- dm and every
+// sigma between 0 and the prior's (screening_slack).  The undecided points go to list A with z,
+// threshold and V(x) only; the head stage recomputes their mean in fp64 (warp-cooperatively, on ~8% of
+// the grid at C2), so everything downstream of this kernel is the fp64 arithmetic of the other path.
+template <int DIN>
+__global__ void __launch_bounds__(FT, SLB_MEAN_MINB)
+filter_mean32_kernel(const __grid_constant__ slb_sweep cfg, const filter_args a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ double s_cen[SLB_MAX_IN];
+    constexpr int W32 = row32<DIN>::W;
+    mean_pipe P;
+    P.bar = reinterpret_cast<uint64_t*>(smem_raw);
+    P.C = a.chunk_rows;
+    P.xstride = P.C * (DIN + 1);
+    P.gstride = P.C * a.max_outputs_per_factor;
+    P.xbuf = reinterpret_cast<double*>(smem_raw + 32);
+    P.gbuf = P.xbuf + 2 * P.xstride;
+    P.t = 0;
+    mean32_bufs B;
+    B.red = P.gbuf + 2 * P.gstride;
+    B.xf = reinterpret_cast<float*>(B.red + 8 * (FT / 32) + 8);
+    B.g = B.xf + P.C * W32;
+    if (threadIdx.x == 0) {
+        slb_bulk::mbar_init(P.bar + 0, 1);
+        slb_bulk::mbar_init(P.bar + 1, 1);
+        slb_bulk::fence_barrier_init();
+        slb_bulk::fence_proxy_async();
+    }
+    mean_pipe_start<DIN>(cfg.gp, P);                                   // slice 0 -> buffer 0
+
+    const int64_t rel0 = (int64_t)blockIdx.x * FT + threadIdx.x;
+    const bool valid = rel0 < a.n;
+    const int64_t rel = valid ? rel0 : a.n - 1;   // every thread stays for the block barriers
+    const int d = cfg.grid.ndim;
+    const int D = cfg.gp.num_outputs;
+
+    // ---- x, V(x), threshold(x), u = policy(x)           (lyapunov.py:436, 284-288)
+    filter_side t;
+    grid_index_to_state(cfg.grid, a.idx_begin + rel, t.z);
+    double vx;
+    lyapunov_state_terms(cfg, t.z, a.idx_begin + rel, &vx, &t.thr);
+    {
+        double u[SLB_MAX_OUT];
+        const int m = eval_fn_small(cfg.policy, t.z, u);
+        for (int c = 0; c < m; ++c) t.z[d + c] = u[c];
+    }
+    bool sane = true;
+#pragma unroll
+    for (int c = 0; c < DIN; ++c) sane &= fabs(t.z[c]) < 1e100;
+    // the CTA's centre: the query point of its middle thread
+    if (threadIdx.x == FT / 2) {
+#pragma unroll
+        for (int c = 0; c < DIN; ++c) s_cen[c] = t.z[c];
+    }
+    __syncthreads();                              // centre visible; barriers initialised
+    double zcen[DIN];
+#pragma unroll
+    for (int c = 0; c < DIN; ++c) zcen[c] = s_cen[c];
+
+    double mu[SLB_MAX_OUT], dm[SLB_MAX_OUT];
+    gp_mean32_staged<DIN>(cfg.gp, t.z, zcen, mu, dm, sane, P, B);
+    if (a.probe_mu != nullptr && valid) {
+        for (int o = 0; o < D; ++o) {
+            a.probe_mu[rel * D + o] = mu[o];
+            a.probe_dm[rel * D + o] = sane ? dm[o] : __longlong_as_double(0x7ff0000000000000ll);
+        }
+    }
+
+    // ---- the comparison over mu +- dm and sigma_j in [0, prior sigma_j]
+    double zero[SLB_MAX_OUT];
+    for (int j = 0; j < SLB_MAX_OUT; ++j) zero[j] = 0.0;
+    mean_decision_terms(cfg, t, vx, mu, zero);
+    double shi[SLB_MAX_OUT];
+    for (int j = 0; j < D; ++j) shi[j] = sqrt(cfg.gp.factors[cfg.gp.outputs[j].factor].variance);
+    t.guard += screening_slack(cfg, mu, dm, shi);
+    const int outcome = sane ? decide(t, shi, D) : -1;
+    const bool undecided = valid && outcome < 0;
+    if (valid) {
+        a.negative[rel] = outcome > 0 ? 1 : 0;
+        if (a.values != nullptr) a.values[rel] = vx;
+    }
+    const long long slot = list_append(undecided, a.counts + 0);
+    if (undecided) {
+        filter_side* dst = a.side_a + slot;
+        dst->dec0 = vx;                           // the head stage rebuilds the mean-dependent terms
+        dst->thr = t.thr;
+#pragma unroll
+        for (int c = 0; c < DIN; ++c) dst->z[c] = t.z[c];
+        a.list_a[slot] = rel;
+    }
+    if (a.stats != nullptr) {
+        count_stat(valid && !undecided, a.stats + 0);
+        count_stat(valid, a.stats + 3);
+    }
+}
+
 // ---- stage 2: variance given the head subset, one warp per HP undecided points ---------------------
 // One CTA per SM, 8 warps.  The head factors W = L_S^-1 (column-major, zero padded, 32 KB each) and
 // the subset's inputs are staged ONCE per CTA in shared memory by TMA bulk copies (read from
@@ -196,11 +357,113 @@ constexpr int HP = 8;                  // list entries per warp iteration (long 
 constexpr int HP_SHORT = 2;            // ... when the list has fewer than HP entries per warp of the grid:
                                        // the latency of one group is the whole stage then
 
+// screened lists: fp64 mean of one factor's NO outputs at the lane's point.  L lanes (a power of two,
+// 4..32, consecutive in the warp) share a point: lane r of them takes rows r, r + L, ... of the
+// factor's shared-memory copy [Xf | gamma_f ...] and the parts are summed by log2(L) shuffles.  The
+// arithmetic of mean_factor<.., FAST = true>: expanded distance, exp_neg_fast, two partial sums.
+template <int DIN, int NO>
+SLB_DEV void head_mean_factor(const double* __restrict__ xf, int Mp, const double* zs, double zz, int r,
+                              int L, const double* __restrict__ tab512, double* dot) {
+    constexpr int W = DIN + 1;
+    const double* __restrict__ gm = xf + (size_t)Mp * W;
+    double d0[NO], d1[NO];
+#pragma unroll
+    for (int q = 0; q < NO; ++q) { d0[q] = 0.0; d1[q] = 0.0; }
+    for (int j = r; j < Mp; j += 4 * L) {
+        double arg[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int jc = min(j + L * u, Mp - 1);
+            double row[W];
+            load_row<W>(xf + jc * W, row);
+            double acc = row[DIN] + zz;
+#pragma unroll
+            for (int c = 0; c < DIN; ++c) acc = fma(zs[c], row[c], acc);
+            arg[u] = acc;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            bool far;
+            double k = exp_neg_fast(arg[u], tab512, far);
+            k = (far || j + L * u >= Mp) ? 0.0 : k;
+            const int jc = min(j + L * u, Mp - 1);
+#pragma unroll
+            for (int q = 0; q < NO; ++q) {
+                if (u & 1) d1[q] = fma(k, gm[q * Mp + jc], d1[q]);
+                else d0[q] = fma(k, gm[q * Mp + jc], d0[q]);
+            }
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < NO; ++q) {
+        double v = d0[q] + d1[q];
+        for (int off = L >> 1; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+        dot[q] = v;
+    }
+}
+
+// screened lists, once per round of the head kernel: the fp64 means of the points of ALL the CTA's
+// groups of the round, by all of its warps -- slot s = 8 w + p is entry p of warp w's group; L =
+// 512 / (number of slots) lanes per point, so a CTA with few groups (short lists: the stage's duration
+// is the latency of one group) still spreads the M exps per point and factor over all its threads.
+// Results: mu_s / merr_s [slot][SLB_MAX_OUT] in shared memory.
+template <int DIN>
+SLB_DEV void head_round_means(const slb_sweep& cfg, const filter_args& a, int64_t grp0, int64_t ngroups,
+                              int64_t count, const double* mbuf, const double* tab512, double* mu_s,
+                              double* merr_s) {
+    const int nf = cfg.gp.num_factors, D = cfg.gp.num_outputs;
+    // warp w's group this round is grp0 + w gridDim (increasing in w): active groups of the CTA
+    int64_t left = ngroups - grp0;
+    const int ng = left <= 0 ? 0 : (int)min((int64_t)HW, (left + gridDim.x - 1) / gridDim.x);
+    const int nslots = ng * HP;
+    const int L = nslots <= 16 ? 32 : nslots <= 32 ? 16 : nslots <= 64 ? 8 : 4;
+    const int r = threadIdx.x & (L - 1);
+    for (int slot = threadIdx.x / L; slot < nslots; slot += HT / L) {
+        const int64_t k = (grp0 + (int64_t)(slot / HP) * gridDim.x) * HP + (slot % HP);
+        double z[DIN];
+#pragma unroll
+        for (int c = 0; c < DIN; ++c) z[c] = k < count ? a.side_a[k].z[c] : 0.0;
+        for (int f = 0; f < nf; ++f) {
+            const slb_gp_factor& F = cfg.gp.factors[f];
+            int outs[SLB_MAX_OUT];
+            int no = 0;
+            for (int o = 0; o < D; ++o)
+                if (cfg.gp.outputs[o].factor == f) outs[no++] = o;
+            double zs[DIN];
+            double zz = 0.0;
+#pragma unroll
+            for (int c = 0; c < DIN; ++c) {
+                zs[c] = z[c] / F.lengthscales[c];
+                zz = fma(zs[c], zs[c], zz);
+            }
+            zz *= -0.5;
+            const int Mp = padded_rows(F.M);
+            const double* xf = mbuf + a.mean_off[f];
+            double dot[SLB_MAX_OUT];
+            switch (no) {
+            case 1: head_mean_factor<DIN, 1>(xf, Mp, zs, zz, r, L, tab512, dot); break;
+            case 2: head_mean_factor<DIN, 2>(xf, Mp, zs, zz, r, L, tab512, dot); break;
+            case 3: head_mean_factor<DIN, 3>(xf, Mp, zs, zz, r, L, tab512, dot); break;
+            case 4: head_mean_factor<DIN, 4>(xf, Mp, zs, zz, r, L, tab512, dot); break;
+            case 5: head_mean_factor<DIN, 5>(xf, Mp, zs, zz, r, L, tab512, dot); break;
+            case 6: head_mean_factor<DIN, 6>(xf, Mp, zs, zz, r, L, tab512, dot); break;
+            default: break;
+            }
+            if (r == 0) {
+                for (int q = 0; q < no; ++q)
+                    mean_output_finish<DIN>(F, cfg.gp.outputs[outs[q]], z, dot[q], zz, 1.0, false,
+                                            &mu_s[slot * SLB_MAX_OUT + outs[q]],
+                                            &merr_s[slot * SLB_MAX_OUT + outs[q]]);
+            }
+        }
+    }
+}
+
 // one group of P list entries [g P, g P + P) on one warp
 template <int DIN, int P, bool ALL_STAGED>
 SLB_DEV void head_group(const slb_sweep& cfg, const filter_args& a, int64_t grp, int64_t count,
                         const double* exptab, double* kw, const double* wbuf, const double* xbuf,
-                        unsigned* s_stat) {
+                        const double* mu_s, unsigned* s_stat) {
     const int lane = threadIdx.x & 31;
     const int nf = cfg.gp.num_factors;
     const int D = cfg.gp.num_outputs;
@@ -210,6 +473,20 @@ SLB_DEV void head_group(const slb_sweep& cfg, const filter_args& a, int64_t grp,
     filter_side t = {};
     int64_t rel = 0;
     if (mine) { t = a.side_a[k]; rel = a.list_a[k]; }
+    if constexpr (P == HP) {
+        if (a.screened) {
+            // stage 1 was the fp32 screening kernel: the fp64 means of the round are in shared memory
+            // (head_round_means); rebuild the terms of the comparison that depend on them
+            double mu[SLB_MAX_OUT], merr[SLB_MAX_OUT];
+            const double* ms = mu_s + (size_t)((threadIdx.x >> 5) * HP + min(lane, HP - 1)) * SLB_MAX_OUT;
+            for (int j = 0; j < SLB_MAX_OUT; ++j) {
+                mu[j] = j < D ? ms[j] : 0.0;
+                merr[j] = j < D ? ms[HW * HP * SLB_MAX_OUT + j] : 0.0;
+            }
+            const double vx = t.dec0;
+            mean_decision_terms(cfg, t, vx, mu, merr);
+        }
+    }
     double shi[SLB_MAX_OUT];
     for (int j = 0; j < D; ++j) {
         const slb_gp_factor& F = cfg.gp.factors[cfg.gp.outputs[j].factor];
@@ -228,14 +505,14 @@ SLB_DEV void head_group(const slb_sweep& cfg, const filter_args& a, int64_t grp,
         if (!ALL_STAGED && !staged) xh = F.Xhead;
         // kernel values of every point of the group against subset points lane and lane + 32
         // (functions.py:438); entries beyond the list carry zeros (never decided)
+        double zown[DIN];                       // this lane's point in the factor's units (one division
+#pragma unroll                                  // per lane and dimension instead of one per point)
+        for (int c = 0; c < DIN; ++c) zown[c] = general ? t.z[c] : t.z[c] / F.lengthscales[c];
 #pragma unroll
         for (int p = 0; p < P; ++p) {
             double zs[DIN];
 #pragma unroll
-            for (int c = 0; c < DIN; ++c) {
-                const double zc = __shfl_sync(0xffffffffu, t.z[c], p);
-                zs[c] = general ? zc : zc / F.lengthscales[c];
-            }
+            for (int c = 0; c < DIN; ++c) zs[c] = __shfl_sync(0xffffffffu, zown[c], p);
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 const int j = lane + 32 * h;
@@ -350,33 +627,65 @@ filter_head_kernel(const __grid_constant__ slb_sweep cfg, const filter_args a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);             // [1]
     unsigned* s_stat = reinterpret_cast<unsigned*>(smem_raw + 8);      // decided / undecided by this CTA
-    double* exptab = reinterpret_cast<double*>(smem_raw + 16);         // [64]
+    double* tab512 = reinterpret_cast<double*>(smem_raw + 16);         // [512] (screened lists: exp_neg_fast)
+    double* exptab = tab512 + 512;                                     // [64]
     double* kbuf = exptab + 64;                                        // [HW][HR][HP]
     double* wbuf = kbuf + HW * HR * HP;                                // [staged][HR * HR]
     const int nf = cfg.gp.num_factors;
     double* xbuf = wbuf + (size_t)a.head_factors_staged * HR * HR;     // [staged][HR * DIN]
+    double* mbuf = xbuf + (size_t)a.head_factors_staged * HR * DIN;    // screened: [Xf | gamma_f ...] per factor
     const int64_t count = (int64_t)a.counts[0];
     const int64_t nwarps = (int64_t)gridDim.x * HW;
     const bool short_list = false;     // every list takes 8-point DMMA groups (the 2-point FMA form of
                                        // head_group is kept for reference / A-B timing)
     const int64_t ngroups = (count + HP - 1) / HP;
-    (void)nwarps;
-    if ((int64_t)blockIdx.x * HW >= ngroups) return;                   // no group for this CTA
+    // groups are dealt round-robin over the CTAs (group g: CTA g % gridDim, warp g / gridDim): a short
+    // list spreads over all SMs instead of filling the 16 warps of the first few
+    // The refine pass that follows streams every factor's packed L^-1 (1 MB at M = 500); if it is
+    // not L2-resident by then (first sweep after a cache update, or evicted in between) its CTAs
+    // start with HBM round trips in lockstep.  Prefetch it into L2 from here, off the critical path.
+    if (a.prefetch_factors) {
+        for (int f = 0; f < nf; ++f) {
+            const slb_gp_factor& F = cfg.gp.factors[f];
+            const char* base = reinterpret_cast<const char*>(F.Wpack);
+            const size_t nbytes = (size_t)F.nrb * (F.nrb + 1) * 32 * sizeof(double);
+            for (size_t off = ((size_t)blockIdx.x * HT + threadIdx.x) * 128; off < nbytes;
+                 off += (size_t)gridDim.x * HT * 128)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(base + off));
+        }
+    }
+    if ((int64_t)blockIdx.x >= ngroups) return;                        // no group for this CTA
     if (threadIdx.x == 0) {
         slb_bulk::mbar_init(bar, 1);
         slb_bulk::fence_barrier_init();
         slb_bulk::fence_proxy_async();
-        unsigned bytes = 64 * sizeof(double);
+        unsigned bytes = 576 * sizeof(double);
         for (int f = 0; f < a.head_factors_staged; ++f)
             if (cfg.gp.factors[f].head_rows > 0)
                 bytes += (unsigned)(HR * HR + HR * DIN) * sizeof(double);
+        if (a.screened) bytes += (unsigned)a.mean_doubles * sizeof(double);
         slb_bulk::mbar_arrive_expect_tx(bar, bytes);
-        slb_bulk::copy_g2s(exptab, g_exp_tables + 512, 64 * sizeof(double), bar);
+        slb_bulk::copy_g2s(tab512, g_exp_tables, 576 * sizeof(double), bar);
         for (int f = 0; f < a.head_factors_staged; ++f) {
             const slb_gp_factor& F = cfg.gp.factors[f];
             if (F.head_rows <= 0) continue;
             slb_bulk::copy_g2s(wbuf + (size_t)f * HR * HR, F.Wheadp, HR * HR * sizeof(double), bar);
             slb_bulk::copy_g2s(xbuf + (size_t)f * HR * DIN, F.Xhead, HR * DIN * sizeof(double), bar);
+        }
+        if (a.screened) {
+            for (int f = 0; f < nf; ++f) {
+                const slb_gp_factor& F = cfg.gp.factors[f];
+                const int Mp = padded_rows(F.M);
+                if (Mp == 0) continue;
+                double* dst = mbuf + a.mean_off[f];
+                slb_bulk::copy_g2s(dst, F.Xf, (unsigned)(Mp * (DIN + 1)) * sizeof(double), bar);
+                dst += (size_t)Mp * (DIN + 1);
+                for (int o = 0; o < cfg.gp.num_outputs; ++o) {
+                    if (cfg.gp.outputs[o].factor != f) continue;
+                    slb_bulk::copy_g2s(dst, cfg.gp.outputs[o].gamma_f, (unsigned)Mp * sizeof(double), bar);
+                    dst += Mp;
+                }
+            }
         }
     }
     if (threadIdx.x < 2) s_stat[threadIdx.x] = 0;
@@ -384,13 +693,23 @@ filter_head_kernel(const __grid_constant__ slb_sweep cfg, const filter_args a) {
     slb_bulk::mbar_wait(bar, 0);
     const int warp = threadIdx.x >> 5;
     double* kw = kbuf + warp * HR * HP;
-    for (int64_t grp = (int64_t)blockIdx.x * HW + warp; grp < ngroups; grp += nwarps) {
+    double* mu_s = mbuf + a.mean_doubles;      // screened: [HW * HP][SLB_MAX_OUT] means, then their error bounds
+    // round: warp w takes group grp0 + w gridDim (every warp of the CTA makes the same number of rounds)
+    for (int64_t grp0 = blockIdx.x; grp0 < ngroups; grp0 += nwarps) {
+        const int64_t grp = grp0 + (int64_t)warp * gridDim.x;
+        if (a.screened) {
+            __syncthreads();                   // the previous round's readers of mu_s are done
+            head_round_means<DIN>(cfg, a, grp0, ngroups, count, mbuf, tab512, mu_s,
+                                  mu_s + HW * HP * SLB_MAX_OUT);
+            __syncthreads();
+        }
+        if (grp >= ngroups) continue;
         if (a.head_factors_staged == nf) {
-            if (short_list) head_group<DIN, HP_SHORT, true>(cfg, a, grp, count, exptab, kw, wbuf, xbuf, s_stat);
-            else head_group<DIN, HP, true>(cfg, a, grp, count, exptab, kw, wbuf, xbuf, s_stat);
+            if (short_list) head_group<DIN, HP_SHORT, true>(cfg, a, grp, count, exptab, kw, wbuf, xbuf, mu_s, s_stat);
+            else head_group<DIN, HP, true>(cfg, a, grp, count, exptab, kw, wbuf, xbuf, mu_s, s_stat);
         } else {
-            if (short_list) head_group<DIN, HP_SHORT, false>(cfg, a, grp, count, exptab, kw, wbuf, xbuf, s_stat);
-            else head_group<DIN, HP, false>(cfg, a, grp, count, exptab, kw, wbuf, xbuf, s_stat);
+            if (short_list) head_group<DIN, HP_SHORT, false>(cfg, a, grp, count, exptab, kw, wbuf, xbuf, mu_s, s_stat);
+            else head_group<DIN, HP, false>(cfg, a, grp, count, exptab, kw, wbuf, xbuf, mu_s, s_stat);
         }
     }
     // one pair of global atomics per CTA (one per point serialised on the counter's L2 line)
@@ -399,7 +718,61 @@ filter_head_kernel(const __grid_constant__ slb_sweep cfg, const filter_args a) {
         atomicAdd(a.stats + 1 + threadIdx.x, (unsigned long long)s_stat[threadIdx.x]);
 }
 
-int g_filter_stages = 3;               // slb_debug_filter_stages: bit 0 head stage, bit 1 refine pass
+double* g_probe_mu = nullptr;          // slb_debug_screening_probe
+double* g_probe_dm = nullptr;
+int g_filter_stages = 3;               // slb_debug_filter_stages: bit 0 head stage, bit 1 refine pass,
+                                       // bit 2 forces the fp64 mean stage (no fp32 screening)
+
+// The fp32 screening kernel needs closed-form bounds of V and L_V over a box of means
+// (screening_slack): plain RBF factors, V = QUADRATIC (optional scale) on the GP outputs, L_V constant
+// or LINEAR with abs / 1-norm / scale only.  Everything else keeps the fp64 mean stage.
+bool screening_applicable(const slb_sweep& cfg) {
+    if (g_filter_stages & 4) return false;
+    const int D = cfg.gp.num_outputs;
+    for (int f = 0; f < cfg.gp.num_factors; ++f)
+        if (cfg.gp.factors[f].kernel.num_prims > 0) return false;
+    const slb_function& V = cfg.lyapunov;
+    if (V.kind != SLB_FN_QUADRATIC || V.in_dim != D || (V.flags & ~(uint32_t)SLB_FLAG_SCALE)) return false;
+    const slb_function& L = cfg.lipschitz_v;
+    if (L.kind == SLB_FN_NONE) return true;
+    if (L.kind != SLB_FN_LINEAR || L.in_dim != D) return false;
+    if (L.flags & ~(uint32_t)(SLB_FLAG_ABS | SLB_FLAG_NORM1 | SLB_FLAG_SCALE)) return false;
+    return (L.flags & SLB_FLAG_NORM1) || L.out_dim == 1 || L.out_dim == D;
+}
+
+// Shared-memory plan of the head stage (one CTA per SM): which factors' head tables are staged, and --
+// when the fp32 screening kernel is stage 1 -- every factor's [Xf | gamma_f] next to them.  Screening
+// is only used when all of it fits (otherwise the fp64 mean stage runs, whose list entries are complete).
+void head_layout(const slb_sweep& cfg, int din, filter_args& ah, size_t& head_smem) {
+    const size_t head_fixed = 16 + (576 + HW * HR * HP) * sizeof(double);
+    const size_t per_factor = (size_t)(HR * HR + HR * din) * sizeof(double);
+    ah.head_factors_staged = cfg.gp.num_factors;
+    while (ah.head_factors_staged > 0 && head_fixed + ah.head_factors_staged * per_factor > 226 * 1024)
+        --ah.head_factors_staged;
+    head_smem = head_fixed + ah.head_factors_staged * per_factor;
+    ah.screened = 0;
+    ah.mean_doubles = 0;
+    static const int head_prefetch = [] {                  // SLB200_HEAD_PREFETCH=0: A/B timing knob
+        const char* e = getenv("SLB200_HEAD_PREFETCH");
+        return e ? (atoi(e) != 0) : 1;
+    }();
+    ah.prefetch_factors = ((g_filter_stages & 2) && head_prefetch) ? 1 : 0;
+    if (screening_applicable(cfg) && ah.head_factors_staged == cfg.gp.num_factors) {
+        int off = 0;
+        for (int f = 0; f < cfg.gp.num_factors; ++f) {
+            int no = 0;
+            for (int o = 0; o < cfg.gp.num_outputs; ++o) no += cfg.gp.outputs[o].factor == f;
+            ah.mean_off[f] = off;
+            off += ((cfg.gp.factors[f].M + 7) & ~7) * (din + 1 + no);
+        }
+        const size_t extra = ((size_t)off + 2 * HW * HP * SLB_MAX_OUT) * sizeof(double);
+        if (head_smem + extra <= 226 * 1024) {
+            ah.screened = 1;
+            ah.mean_doubles = off;
+            head_smem += extra;
+        }
+    }
+}
 
 template <int DIN>
 int launch_filter(cudaStream_t st, const slb_sweep& cfg, const filter_args& a, size_t smem) {
@@ -409,21 +782,26 @@ int launch_filter(cudaStream_t st, const slb_sweep& cfg, const filter_args& a, s
     if (device < 0 || device >= 64 || !configured[device].load(std::memory_order_acquire)) {
         SLB_CUDA(cudaFuncSetAttribute(filter_mean_kernel<DIN>,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+        SLB_CUDA(cudaFuncSetAttribute(filter_mean32_kernel<DIN>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
         SLB_CUDA(cudaFuncSetAttribute(filter_head_kernel<DIN>,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         if (device >= 0 && device < 64) configured[device].store(true, std::memory_order_release);
     }
     const int64_t blocks = (a.n + FT - 1) / FT;
-    filter_mean_kernel<DIN><<<(unsigned)blocks, FT, smem, st>>>(cfg, a);
+    filter_args ah = a;
+    size_t head_smem = 0;
+    head_layout(cfg, DIN, ah, head_smem);
+    ah.probe_mu = g_probe_mu;
+    ah.probe_dm = g_probe_dm;
+    if (ah.screened) {
+        const size_t smem32 = mean32_smem_bytes(DIN, a.max_outputs_per_factor, a.chunk_rows, FT / 32);
+        filter_mean32_kernel<DIN><<<(unsigned)blocks, FT, smem32, st>>>(cfg, ah);
+    } else {
+        filter_mean_kernel<DIN><<<(unsigned)blocks, FT, smem, st>>>(cfg, a);
+    }
     SLB_LAUNCH_CHECK();
     if (!(g_filter_stages & 1)) return 0;
-    const size_t head_fixed = 16 + (64 + HW * HR * HP) * sizeof(double);
-    const size_t per_factor = (size_t)(HR * HR + HR * DIN) * sizeof(double);
-    filter_args ah = a;
-    ah.head_factors_staged = cfg.gp.num_factors;
-    while (ah.head_factors_staged > 0 && head_fixed + ah.head_factors_staged * per_factor > 226 * 1024)
-        --ah.head_factors_staged;
-    const size_t head_smem = head_fixed + ah.head_factors_staged * per_factor;
     filter_head_kernel<DIN><<<HEAD_CTAS, HT, head_smem, st>>>(cfg, ah);
     SLB_LAUNCH_CHECK();
     return 0;
@@ -440,6 +818,21 @@ extern "C" {
 
 int slb_debug_filter_stages(int32_t mask) {
     g_filter_stages = mask;
+    return 0;
+}
+
+int slb_filter_stage1(const slb_sweep* cfg) {
+    if (cfg == nullptr || cfg->gp.num_outputs <= 0) return 0;
+    filter_args a;
+    memset(&a, 0, sizeof(a));
+    size_t smem = 0;
+    head_layout(*cfg, cfg->gp.input_dim, a, smem);
+    return a.screened ? 32 : 64;
+}
+
+int slb_debug_screening_probe(double* mu_dev, double* dm_dev) {
+    g_probe_mu = (mu_dev != nullptr && dm_dev != nullptr) ? mu_dev : nullptr;
+    g_probe_dm = g_probe_mu != nullptr ? dm_dev : nullptr;
     return 0;
 }
 
@@ -508,6 +901,7 @@ int slb_lyapunov_sweep_filtered(void* stream, const slb_sweep* cfg, int64_t idx_
     char* ws = static_cast<char*>(workspace_dev);
     const int64_t cap = n_all < CHUNK ? n_all : CHUNK;
     filter_args a;
+    memset(&a, 0, sizeof(a));
     a.counts = reinterpret_cast<unsigned long long*>(ws);
     int* tickets = reinterpret_cast<int*>(ws + 64);
     double* partial = reinterpret_cast<double*>(ws + 64 + SLB_SPLIT_TICKET_BYTES);

@@ -31,7 +31,7 @@ struct slb_gp_args {
     double* split_partial;
     int* split_ticket;
     int32_t split_max;
-    int32_t _pad;
+    int32_t split_factors;  // 1: with CTAs to spare, the factors of a tile go to separate CTAs before its rows are split
     long long* timing;      // diagnostics: [tile][warp][8]: cycles in {generate, contract, epilogue, total}, globaltimer ns {start, end}, cycles waiting at barriers, 0
 };
 

@@ -95,6 +95,27 @@ SLB_DEV void load_row(const double* __restrict__ p, double (&r)[W]) {
     }
 }
 
+// mean of one output from its finished dot product, and the bound of the mean's own error
+// (functions.py:439-442): shared by the thread-per-point stage and the head stage's recomputation
+template <int DIN>
+SLB_DEV void mean_output_finish(const slb_gp_factor& F, const slb_gp_output& G, const double* z,
+                                double dot, double zz, double kbound, bool general, double* mu,
+                                double* mean_err) {
+    double mx = 0.0;
+    if (G.prior_mean != nullptr) {
+        mx = f64mul(z[0], G.prior_mean[0]);
+#pragma unroll
+        for (int c = 1; c < DIN; ++c) mx = f64add(mx, f64mul(z[c], G.prior_mean[c]));
+        mx = f64mul(F.scale, mx);
+    }
+    *mu = f64add(dot, mx) / F.scale;
+    // |mean - exact| <= eps sum_i |k_i| (|L^-1|^T |alpha|)_i <= eps kbound gamma_l1: kernel
+    // values to EPS_K (+ the expanded distance's rounding), the M-term sums here, in gamma
+    // itself and in the a . alpha form of the full posterior each to (M + 2) 2^-53
+    const double eps = (general ? 4.5e-16 : EPS_K + 4.5e-16 * (-zz + F.hmax)) + 7e-16 * (F.M + 8);
+    *mean_err = eps * kbound * G.gamma_l1 / F.scale;
+}
+
 // one factor with NO outputs on it (compile-time, so the running dot products stay in registers)
 template <int DIN, int NO, bool FAST>
 SLB_DEV void mean_factor(const slb_gp_stack& gp, int f, const int* outs, const double* z, double* mu,
@@ -177,24 +198,9 @@ SLB_DEV void mean_factor(const slb_gp_stack& gp, int f, const int* outs, const d
         ++P.t;
     }
 #pragma unroll
-    for (int q = 0; q < NO; ++q) {
-        dot[q] += dot2[q];
-        const slb_gp_output& G = gp.outputs[outs[q]];
-        double mx = 0.0;
-        if (G.prior_mean != nullptr) {
-            mx = f64mul(z[0], G.prior_mean[0]);
-#pragma unroll
-            for (int c = 1; c < DIN; ++c) mx = f64add(mx, f64mul(z[c], G.prior_mean[c]));
-            mx = f64mul(F.scale, mx);
-        }
-        mu[outs[q]] = f64add(dot[q], mx) / F.scale;
-        // |mean - exact| <= eps sum_i |k_i| (|L^-1|^T |alpha|)_i <= eps kbound gamma_l1: kernel
-        // values to EPS_K (+ the expanded distance's rounding), the M-term sums here, in gamma
-        // itself and in the a . alpha form of the full posterior each to (M + 2) 2^-53
-        const double eps = (general ? 4.5e-16 : EPS_K + 4.5e-16 * (-zz + F.hmax)) +
-                           7e-16 * (F.M + 8);
-        mean_err[outs[q]] = eps * kbound * G.gamma_l1 / F.scale;
-    }
+    for (int q = 0; q < NO; ++q)
+        mean_output_finish<DIN>(F, gp.outputs[outs[q]], z, dot[q] + dot2[q], zz, kbound, general,
+                                &mu[outs[q]], &mean_err[outs[q]]);
 }
 
 // thread 0 of the block: barriers of the pipeline + the bulk copy of the exp tables (bar[2]); call
@@ -264,4 +270,221 @@ inline int mean_chunk_rows(int din, int nomax, int budget_kb) {
 }
 inline size_t mean_smem_bytes(int din, int nomax, int chunk_rows) {
     return 32 + (512 + 64) * sizeof(double) + (size_t)2 * chunk_rows * (din + 1 + nomax) * sizeof(double);
+}
+
+// ---- fp32 screening mean (filter.cu, filter_mean32_kernel) ---------------------------------------
+// The decision filter only needs the mean to within a bound it can certify, and at 12 fp64
+// operations per kernel value the fp64 mean stage is the largest part of a sweep.  Here the same
+// slices are converted, once per CTA, to fp32 rows CENTERED on a point of the CTA,
+//     xc_j = (xs_j - cs) s,  zc = (zs - cs) s,  s^2 = log2 e   (differences taken in fp64),
+// so that k_j = 2^(-|xc_j|^2/2 + zc . xc_j) 2^(-|zc|^2/2): three FFMA and one MUFU.EX2 per kernel
+// value, the last factor (E) applied once per point in fp64.  Error of the computed mean, with
+// u = 2^-24, Z = |zc|^2 / 2, t_j = |zc - xc_j|^2 / 2 (so k_j = 2^-t_j):
+//   argument: h_j rounds once, each of the DIN products carries two input roundings, each FFMA
+//     rounds once: |arg error| <= u (DIN + 2.01) (|h_j| + sum_c |zc_c xc_jc|) <= u (DIN + 2.01)
+//     (2 |h_j| + Z) <= u (DIN + 2.01) (4 t_j + 5 Z)      [|h_j| <= 2 t_j + 2 Z];
+//   2^x: ex2.approx.ftz.f32 to 2^-22 (PTX ISA), budgeted 8 u; gamma rounds to fp32: u;
+//   sums: F32_FLUSH terms per fp32 accumulator, then added into an fp64 sum: F32_FLUSH u;
+//   with k_j t_j <= 1 / (e ln 2) = 0.531 and k_j <= 1:
+//   |mean error| <= u [0.7 (DIN + 2.01) (2.13 + 5 Z) + 8 + 1 + F32_FLUSH + 2] sum_j |gamma_j| / scale
+// (0.7 > ln 2 turns the argument error into a relative error of 2^x; the last 2 covers the fp64
+// steps and the terms flushed to zero).  sum_j |gamma_j| is accumulated by the CTA while it
+// converts.  Points with Z > 40 (2^Z would leave the fp32 range) are left to the fp64 stages.
+constexpr int F32_FLUSH = 16;
+
+template <int DIN>
+struct row32 { static constexpr int W = DIN + 1 <= 2 ? 2 : (DIN + 1 <= 4 ? 4 : 8); };
+
+SLB_DEV float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+template <int W32>
+SLB_DEV void load_row32(const float* __restrict__ p, float (&r)[W32]) {
+    if constexpr (W32 == 2) {
+        const float2 v = *reinterpret_cast<const float2*>(p);
+        r[0] = v.x; r[1] = v.y;
+    } else {
+#pragma unroll
+        for (int c = 0; c < W32; c += 4) {
+            const float4 v = *reinterpret_cast<const float4*>(p + c);
+            r[c] = v.x; r[c + 1] = v.y; r[c + 2] = v.z; r[c + 3] = v.w;
+        }
+    }
+}
+
+// fp32 landing of the current slice, and the block's scratch for sum |gamma|
+struct mean32_bufs {
+    float* xf;                         // [C][row32<DIN>::W]
+    float* g;                          // [nomax][C]
+    double* red;                       // [SLB_MAX_OUT][warps per CTA]
+};
+
+// One plain-RBF factor with NO outputs: mu (fp32-screened) and dmu, the certified bound of its error.
+// `zcen`: the CTA's centre in input units (the same for every thread).  `ok` is cleared when the
+// point is out of the fp32 range of the scheme.
+template <int DIN, int NO>
+SLB_DEV void mean32_factor(const slb_gp_stack& gp, int f, const int* outs, const double* z,
+                           const double* zcen, double* mu, double* dmu, bool& ok, mean_pipe& P,
+                           const mean32_bufs& B) {
+    const slb_gp_factor& F = gp.factors[f];
+    constexpr int W = DIN + 1, W32 = row32<DIN>::W;
+    const double S = 1.2011224087864498;           // sqrt(log2 e)
+    double cs[DIN];
+    float zc[DIN];
+    double Z = 0.0;
+#pragma unroll
+    for (int c = 0; c < DIN; ++c) {
+        cs[c] = zcen[c] / F.lengthscales[c];
+        const double zsc = z[c] / F.lengthscales[c];
+        const double zcd = (zsc - cs[c]) * S;
+        zc[c] = (float)zcd;
+        Z = fma(zcd, zcd, Z);
+        // the fp64 roundings of the centring (1e-16 |zs|) stay far below u |zc| only for moderate inputs
+        if (!(fabs(zsc) < 1e6) || !(fabs(cs[c]) < 1e6)) ok = false;
+    }
+    Z *= 0.5;
+    float acc[NO][4];
+    double dot[NO], g1[NO];
+#pragma unroll
+    for (int q = 0; q < NO; ++q) {
+        dot[q] = 0.0; g1[q] = 0.0;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) acc[q][u] = 0.0f;
+    }
+    const int Mp = padded_rows(F.M);
+    for (int c0 = 0; c0 < Mp; c0 += P.C) {
+        const int rows = min(P.C, Mp - c0);
+        const int b = P.t & 1;
+        if (threadIdx.x == 0) issue_slice<DIN>(gp, P, b ^ 1);         // next slice, other buffer
+        slb_bulk::mbar_wait(P.bar + b, (P.t >> 1) & 1);
+        const double* __restrict__ xb = P.xbuf + b * P.xstride;
+        const double* __restrict__ gb = P.gbuf + b * P.gstride;
+        // ---- convert the slice: centred fp32 rows [xc, -|xc|^2 / 2], fp32 gammas
+        for (int r = threadIdx.x; r < rows; r += blockDim.x) {
+            double row[W];
+            load_row<W>(xb + r * W, row);
+            float o[W32];
+            double hh = 0.0;
+#pragma unroll
+            for (int c = 0; c < DIN; ++c) {
+                const double xcd = (row[c] - cs[c]) * S;
+                o[c] = (float)xcd;
+                hh = fma(xcd, xcd, hh);
+            }
+            o[DIN] = (float)(-0.5 * hh);
+#pragma unroll
+            for (int c = DIN + 1; c < W32; ++c) o[c] = 0.0f;
+            float* dst = B.xf + r * W32;
+            if constexpr (W32 == 2) {
+                *reinterpret_cast<float2*>(dst) = make_float2(o[0], o[1]);
+            } else {
+#pragma unroll
+                for (int c = 0; c < W32; c += 4)
+                    *reinterpret_cast<float4*>(dst + c) = make_float4(o[c], o[c + 1], o[c + 2], o[c + 3]);
+            }
+#pragma unroll
+            for (int q = 0; q < NO; ++q) {
+                const double gq = gb[q * P.C + r];
+                B.g[q * P.C + r] = (float)gq;
+                g1[q] += fabs(gq);
+            }
+        }
+        __syncthreads();                       // fp32 slice complete
+        // ---- kernel values and dot products: 4 independent chains, fp32 sums flushed into fp64
+        const float* __restrict__ xf = B.xf;
+        const float* __restrict__ gf = B.g;
+        for (int jb = 0; jb < rows; jb += 4 * F32_FLUSH) {
+            const int jend = min(jb + 4 * F32_FLUSH, rows);
+            for (int j0 = jb; j0 < jend; j0 += 4) {
+                float k[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    float row[W32];
+                    load_row32<W32>(xf + (j0 + u) * W32, row);
+                    float arg = row[DIN];
+#pragma unroll
+                    for (int c = 0; c < DIN; ++c) arg = fmaf(zc[c], row[c], arg);
+                    k[u] = ex2_approx(arg);
+                }
+#pragma unroll
+                for (int q = 0; q < NO; ++q) {
+                    const float4 g = *reinterpret_cast<const float4*>(gf + q * P.C + j0);
+                    acc[q][0] = fmaf(k[0], g.x, acc[q][0]);
+                    acc[q][1] = fmaf(k[1], g.y, acc[q][1]);
+                    acc[q][2] = fmaf(k[2], g.z, acc[q][2]);
+                    acc[q][3] = fmaf(k[3], g.w, acc[q][3]);
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < NO; ++q) {
+                dot[q] += ((double)acc[q][0] + (double)acc[q][1]) + ((double)acc[q][2] + (double)acc[q][3]);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) acc[q][u] = 0.0f;
+            }
+        }
+        __syncthreads();                       // every thread is done with the fp32 slice and buffer b
+        ++P.t;
+    }
+    // ---- sum_j |gamma_j| over the block (every thread converted a disjoint set of rows)
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+    for (int q = 0; q < NO; ++q) {
+        double v = g1[q];
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+        if (lane == 0) B.red[q * nw + warp] = v;
+    }
+    __syncthreads();
+    const double E = exp2(-Z);
+    const double u24 = 5.9604644775390625e-8;
+    const double epsrel = u24 * (0.7 * (DIN + 2.01) * (2.13 + 5.0 * Z) + 11.0 + F32_FLUSH);
+    if (!(Z <= 40.0)) ok = false;
+#pragma unroll
+    for (int q = 0; q < NO; ++q) {
+        double gsum = 0.0;
+        for (int w = 0; w < nw; ++w) gsum += B.red[q * nw + w];
+        const slb_gp_output& G = gp.outputs[outs[q]];
+        double mx = 0.0;
+        if (G.prior_mean != nullptr) {
+            mx = f64mul(z[0], G.prior_mean[0]);
+#pragma unroll
+            for (int c = 1; c < DIN; ++c) mx = f64add(mx, f64mul(z[c], G.prior_mean[c]));
+            mx = f64mul(F.scale, mx);
+        }
+        mu[outs[q]] = f64add(E * dot[q], mx) / F.scale;
+        // + the products that left the fp32 range downwards (each < 2^-126 in the scaled sum)
+        dmu[outs[q]] = (1.05 * epsrel * gsum + 1.3e-26 * Mp) / fabs(F.scale) + 1e-300;
+    }
+    __syncthreads();                           // B.red is reused by the next factor
+}
+
+template <int DIN>
+SLB_DEV void gp_mean32_staged(const slb_gp_stack& gp, const double* z, const double* zcen, double* mu,
+                              double* dmu, bool& ok, mean_pipe& P, const mean32_bufs& B) {
+    for (int f = 0; f < gp.num_factors; ++f) {
+        int outs[SLB_MAX_OUT];
+        int no = 0;
+        for (int o = 0; o < gp.num_outputs; ++o)
+            if (gp.outputs[o].factor == f) outs[no++] = o;
+        switch (no) {
+        case 1: mean32_factor<DIN, 1>(gp, f, outs, z, zcen, mu, dmu, ok, P, B); break;
+        case 2: mean32_factor<DIN, 2>(gp, f, outs, z, zcen, mu, dmu, ok, P, B); break;
+        case 3: mean32_factor<DIN, 3>(gp, f, outs, z, zcen, mu, dmu, ok, P, B); break;
+        case 4: mean32_factor<DIN, 4>(gp, f, outs, z, zcen, mu, dmu, ok, P, B); break;
+        case 5: mean32_factor<DIN, 5>(gp, f, outs, z, zcen, mu, dmu, ok, P, B); break;
+        case 6: mean32_factor<DIN, 6>(gp, f, outs, z, zcen, mu, dmu, ok, P, B); break;
+        default: break;
+        }
+    }
+}
+
+// shared memory of the fp32 screening kernel: [0, 32) mbarriers, the fp64 slice ring, the fp32 slice,
+// the block scratch (no exp tables)
+inline size_t mean32_smem_bytes(int din, int nomax, int chunk_rows, int warps) {
+    const int w32 = din + 1 <= 2 ? 2 : (din + 1 <= 4 ? 4 : 8);
+    return 32 + (size_t)2 * chunk_rows * (din + 1 + nomax) * sizeof(double) +
+           (size_t)chunk_rows * (w32 + nomax) * sizeof(float) + (size_t)(8 * warps + 8) * sizeof(double);
 }

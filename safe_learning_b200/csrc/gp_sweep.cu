@@ -90,6 +90,7 @@ int slb_launch_refine(cudaStream_t st, const slb_sweep& cfg, int64_t n_max, int6
     a.idx_begin = idx_begin; a.mode = MODE_SWEEP_GRID;
     a.negative = negative; a.values = values;
     a.index_list = list; a.count = count;
+    a.timing = g_timing_buffer;            // slb_debug_phase_timing: per-warp phase clocks of the refine CTAs
     const int tps[3] = {16, 32, 64};
     const int64_t lo[3] = {0, g_refine_split[0], g_refine_split[1]};
     const int64_t hi[3] = {g_refine_split[0], g_refine_split[1], INT64_MAX};
@@ -109,6 +110,11 @@ int slb_launch_refine(cudaStream_t st, const slb_sweep& cfg, int64_t n_max, int6
                     return v < 1 ? 1 : (v > SLB_SPLIT_MAX ? SLB_SPLIT_MAX : v);
                 }();
                 a.split_max = split_max;
+                static const int split_factors = [] {      // SLB200_SPLIT_FACTORS=0: A/B timing knob
+                    const char* e = getenv("SLB200_SPLIT_FACTORS");
+                    return e ? (atoi(e) != 0) : 1;
+                }();
+                a.split_factors = split_factors;
             }
         }
         const int rc = dispatch_gp_tile(st, cfg, a, tps[v]);

@@ -221,6 +221,8 @@ gp_tile_kernel(const __grid_constant__ slb_sweep cfg, const slb_gp_args a) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     int64_t tile_index = blockIdx.x;
     int grp = 0, G = 1;                // row group of this CTA / groups per tile (split refine)
+    int fsel = -1, FS = 1;             // split refine with spare CTAs left: this CTA's factor / factors
+                                       // dealt to separate CTAs (FS = 1: every CTA does all factors)
     // refine mode (slb_lyapunov_sweep_filtered): the point list was compacted by the filter
     // kernel, its length lives in device memory; CTAs beyond it leave before the first barrier
     int64_t npts = a.n;
@@ -231,11 +233,19 @@ gp_tile_kernel(const __grid_constant__ slb_sweep cfg, const slb_gp_args a) {
         if (a.split_partial != nullptr) {
             // short list: spread every tile's rows over as many CTAs as the grid has to spare
             const int64_t ntiles = (npts + TP - 1) / TP;
-            const int64_t spare = (int64_t)gridDim.x / ntiles;
+            int64_t spare = (int64_t)gridDim.x / ntiles;
+            // the factors of a stack are independent until the tile epilogue: with CTAs to spare they
+            // go to different CTAs first (half the generation phases and barriers in every CTA's
+            // serial chain), the rest of the spare CTAs splits the rows
+            const int nfac = cfg.gp.num_factors;
+            if (a.split_factors && nfac > 1 && spare >= 2 * nfac) { FS = nfac; spare /= nfac; }
             G = (int)(spare < 1 ? 1 : (spare > a.split_max ? a.split_max : spare));
-            if ((int64_t)blockIdx.x >= ntiles * G) return;
-            tile_index = blockIdx.x / G;
-            grp = blockIdx.x % G;
+            const int per_tile = G * FS;
+            if ((int64_t)blockIdx.x >= ntiles * per_tile) return;
+            tile_index = blockIdx.x / per_tile;
+            const int rem = (int)(blockIdx.x % per_tile);
+            grp = rem % G;
+            if (FS > 1) fsel = rem / G;
         }
         if (tile_index * TP >= npts) return;
     }
@@ -283,7 +293,7 @@ gp_tile_kernel(const __grid_constant__ slb_sweep cfg, const slb_gp_args a) {
                 for (int c = 0; c < d; ++c) x[c] = a.points[rel * d + c];
             }
             double u[SLB_MAX_OUT];
-            const int m = eval_fn(cfg.policy, x, u);
+            const int m = eval_fn_small(cfg.policy, x, u);
             for (int c = 0; c < d; ++c) z[c] = x[c];
             for (int c = 0; c < m; ++c) z[d + c] = u[c];
         }
@@ -351,7 +361,9 @@ gp_tile_kernel(const __grid_constant__ slb_sweep cfg, const slb_gp_args a) {
         }
     };
 
+    const bool split = G * FS > 1;
     for (int f = 0; f < cfg.gp.num_factors; ++f) {
+        if (fsel >= 0 && f != fsel) continue;      // another CTA of the tile owns this factor
         const slb_gp_factor& F = cfg.gp.factors[f];
         const int M = F.M, nrb = F.nrb;
         const int nk4 = (M + 3) >> 2;
@@ -553,7 +565,7 @@ gp_tile_kernel(const __grid_constant__ slb_sweep cfg, const slb_gp_args a) {
         }
         __syncthreads();
 
-        if (G > 1) {
+        if (split) {
             // split refine: this CTA's share of the factor's sums; the tile is finished below
             double* part = a.split_partial + ((size_t)blockIdx.x * SLB_MAX_OUT + f) * (NRED * TP);
             for (int i = tid; i < NRED * TP; i += NT) part[i] = tot[i];
@@ -564,23 +576,33 @@ gp_tile_kernel(const __grid_constant__ slb_sweep cfg, const slb_gp_args a) {
         __syncthreads();
     }
 
-    if (G > 1) {
+    if (split) {
         // ---- split refine: the last CTA of the tile adds the partial sums in group order
         __shared__ int s_ticket;
         __threadfence();
         __syncthreads();
         if (tid == 0) s_ticket = atomicAdd(a.split_ticket + tile_index, 1);
         __syncthreads();
-        if (s_ticket != G - 1) return;
+        if (s_ticket != G * FS - 1) {
+            if (TIMING && lane == 0) {             // row-group CTAs that do not finish the tile
+                long long* t = a.timing + ((size_t)blockIdx.x * NW + warp) * 8;
+                long long g_end;
+                asm volatile("mov.u64 %0, %globaltimer;" : "=l"(g_end));
+                t[0] = t_gen; t[1] = t_mma; t[2] = t_epi; t[3] = clock64() - t_start;
+                t[4] = g_start; t[5] = g_end; t[6] = t_sync; t[7] = 1;
+            }
+            return;
+        }
         __threadfence();
         if (tid == 0) a.split_ticket[tile_index] = 0;                  // ready for the next launch
         for (int f = 0; f < cfg.gp.num_factors; ++f) {
             const slb_gp_factor& F = cfg.gp.factors[f];
             for (int i = tid; i < NRED * TP; i += NT) {
                 double sum = 0.0;
+                // the CTAs that worked on factor f: all G * FS of the tile, or the G of its factor slot
+                const size_t cta0 = (size_t)tile_index * (G * FS) + (FS > 1 ? (size_t)f * G : 0);
                 for (int g2 = 0; g2 < G; ++g2)
-                    sum += __ldcg(a.split_partial +
-                                  ((size_t)(tile_index * G + g2) * SLB_MAX_OUT + f) * (NRED * TP) + i);
+                    sum += __ldcg(a.split_partial + ((cta0 + g2) * SLB_MAX_OUT + f) * (NRED * TP) + i);
                 tot[i] = sum;
             }
             const bool general = KEXPR && F.kernel.num_prims > 0;
@@ -619,7 +641,7 @@ gp_tile_kernel(const __grid_constant__ slb_sweep cfg, const slb_gp_args a) {
                 if (a.err != nullptr) for (int o = 0; o < D; ++o) a.err[rel * D + o] = er[o];
                 if (a.mode != MODE_PREDICT) {
                     double vm[1];
-                    eval_fn(cfg.lyapunov, mu, vm);
+                    eval_fn_small(cfg.lyapunov, mu, vm);
                     pre[2 * TP + p] = vm[0];
                 }
             } else if (a.mode != MODE_PREDICT) {

@@ -314,12 +314,24 @@ def test_initial_safe_set_edited_in_place(sl):
     assert_array_equal(gpu.safe_set, cpu.safe_set)
 
 
+@pytest.fixture(params=["fp32 screening", "fp64 mean stage"])
+def mean_stage(request):
+    """Stage 1 of the decision filter: the fp32 screening kernel (default where V is quadratic) or
+    the fp64 mean kernel (bit 2 of slb_debug_filter_stages forces it)."""
+    from safe_learning_b200 import _native as nat
+    lib = nat.load()
+    lib.slb_debug_filter_stages(3 if request.param == "fp32 screening" else 7)
+    yield request.param
+    lib.slb_debug_filter_stages(3)
+
+
 @pytest.mark.parametrize("tau_scale", [1.0, 1 / 8., 1 / 48., 0.0])
 @pytest.mark.parametrize("M", [0, 1, 8, 40, 64, 65, 100, 200, 256])
-def test_filtered_flags_equal_full_posterior(sl, M, tau_scale):
+def test_filtered_flags_equal_full_posterior(sl, M, tau_scale, mean_stage):
     """The decision filter (csrc/filter.cu) must reproduce the full posterior's flags bit for bit
     at every training-set size (M <= 64: the head bound is the whole posterior; M = 0: the prior)
-    and in every regime of tau (all fail ... most pass), incl. the guard-band hand-over."""
+    and in every regime of tau (all fail ... most pass), incl. the guard-band hand-over; with
+    either first stage."""
     par = W.make_pendulum(num_points=[45, 37], M=max(M, 1), tau_scale=tau_scale, seed=M + 3)
     if M == 0:
         par["X"], par["Y"] = par["X"][:0], par["Y"][:0]
@@ -336,6 +348,55 @@ def test_filtered_flags_equal_full_posterior(sl, M, tau_scale):
     if M and tau_scale > 0:
         cpu = W.build_oracle(par)
         assert_array_equal(full.astype(bool), cpu.full_grid_negative())
+
+
+@pytest.mark.parametrize("case", ["pendulum", "short lengthscales", "shared factor", "scaled targets",
+                                  "large noise-free gammas"])
+def test_screening_mean_error_is_within_its_certified_bound(sl, case):
+    """The fp32 screening stage decides points from a mean it only knows to within a bound it
+    computes (gp_mean_staged.cuh); slb_debug_screening_probe exposes mean and bound: the fp64
+    posterior mean must lie inside the bound at every point, and the flags must equal the full
+    posterior's in regimes where the bound is large."""
+    import torch
+    from safe_learning_b200 import _native as nat, _device as dev
+    lib = nat.load()
+    kw = dict(num_points=[61, 53], M=300, tau_scale=1 / 16., seed=7)
+    if case == "shared factor":
+        kw["shared_hypers"] = True
+    if case == "scaled targets":
+        kw["scale"] = 7.5
+    if case == "large noise-free gammas":
+        kw["noise_std"] = 2e-4
+    par = W.make_pendulum(**kw)
+    if case == "short lengthscales":
+        # |z - centre| / lengthscale reaches ~7 inside a CTA: large exponents of the split-off factor
+        # 2^(|zc|^2 / 2), argument errors of several thousand ulps -- all inside the computed bound
+        par["lengthscales"] = [[0.2, 0.15, 0.4], [0.25, 0.12, 0.3]]
+    gpu = W.build_product(par)
+    cpu = W.build_oracle(par)
+    desc = gpu.sweep_descriptor()
+    if not gpu._filter_enabled(desc):
+        pytest.skip("variance floor below the filter's limit for this case")
+    n, D = gpu.discretization.nindex, 2
+    mu = torch.zeros((n, D), dtype=torch.float64, device=dev.device())
+    dm = torch.full((n, D), -1.0, dtype=torch.float64, device=dev.device())
+    try:
+        lib.slb_debug_screening_probe(mu.data_ptr(), dm.data_ptr())
+        fast = gpu.compute_negative().cpu().numpy().copy()
+        torch.cuda.synchronize()
+    finally:
+        lib.slb_debug_screening_probe(None, None)
+    mu, dm = mu.cpu().numpy(), dm.cpu().numpy()
+    assert (dm >= 0).all(), "the screening stage did not run"
+    states = cpu.discretization.all_points
+    mean64, _ = gpu.dynamics(states, cpu.policy(states))
+    finite = np.isfinite(dm)
+    assert finite.mean() > 0.25, "most points left to the fp64 stages: %g" % finite.mean()
+    err = np.abs(mu - mean64)
+    assert (err[finite] <= dm[finite]).all(), "fp32 mean outside its certified bound: max ratio %g" % (
+        (err[finite] / dm[finite]).max())
+    gpu.filter = False
+    assert_array_equal(fast, gpu.compute_negative().cpu().numpy())
 
 
 @pytest.mark.parametrize("split,label", [((0, 0), "64-point tiles"), ((0, 1 << 40), "32-point tiles"),

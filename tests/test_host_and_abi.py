@@ -39,7 +39,7 @@ def test_header_symbols_exported(lib):
 
 def test_struct_layout_and_version(lib):
     from safe_learning_b200 import _native
-    assert lib.slb_abi_version() == _native.ABI_VERSION == 4
+    assert lib.slb_abi_version() == _native.ABI_VERSION == 5
     _native._check_layout(lib)
     assert lib.slb_packed_len(500) == 63 * 64 * 32
     assert lib.slb_packed_len(8) == 2 * 32
