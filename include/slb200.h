@@ -287,6 +287,14 @@ void        slb_note_graph_replay(int64_t kernels);
  * %globaltimer (ns) at tile start / end, cycles spent waiting at block barriers, 0;
  * pass NULL to switch it off (default) */
 int         slb_debug_phase_timing(void* buffer_dev);
+/* Records an event (owned by the library, one per device) on `stream` that every later launch reading
+ * the packed factors (slb_gp_factor.Wpack: the full posterior of slb_gp_predict / slb_lyapunov_sweep /
+ * slb_lyapunov_points and the refine pass of slb_lyapunov_sweep_filtered) waits for on ITS stream.  A
+ * caller that restores the GP tables from the host copies the packed factors -- 90% of the bytes -- on a
+ * second stream, calls this behind the copy, and enqueues the sweep at once: the filter stages do not
+ * read the packed factors and overlap the copy.  Under stream capture the wait is an external-event
+ * node (re-evaluated at every replay).  Single-threaded use like the other setters. */
+int         slb_record_factor_dependency(void* stream);
 /* diagnostics (timing of the individual stages of slb_lyapunov_sweep_filtered; the flags are only
  * complete with bits 0 and 1 set -- 3, the default, or 7): bit 0 runs the head stage, bit 1 the
  * refine pass; bit 2 forces the fp64 mean stage where the fp32 screening stage would run */

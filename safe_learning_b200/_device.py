@@ -128,3 +128,17 @@ def get_exchange():
     _EXCHANGE["struct"] = x
     _EXCHANGE["keep"] = (buf, handle, seq)
     return x
+
+
+_FACTOR_DEPENDENCY = [0]
+
+
+def note_factor_dependency():
+    """A restore registered an event the packed-factor launches wait for (functions.PackedCache):
+    CUDA graphs of sweeps captured before that have no wait node and must be re-captured."""
+    if _FACTOR_DEPENDENCY[0] == 0:
+        _FACTOR_DEPENDENCY[0] = 1
+
+
+def factor_dependency_epoch():
+    return _FACTOR_DEPENDENCY[0]

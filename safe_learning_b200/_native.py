@@ -129,6 +129,7 @@ SIGNATURES = {
     "slb_launch_count": (C.c_int64, []),
     "slb_note_graph_replay": (None, [_i64]),
     "slb_debug_phase_timing": (C.c_int, [_vp]),
+    "slb_record_factor_dependency": (C.c_int, [_vp]),
     "slb_debug_refine_split": (C.c_int, [_i64, _i64]),
     "slb_debug_det_fast": (C.c_int, [_i32]),
     "slb_debug_filter_stages": (C.c_int, [_i32]),

@@ -667,6 +667,21 @@ SLB_DEV int eval_fn_small(const slb_function& f, const double* in, double* out) 
     return eval_fn(f, in, out);
 }
 
+// The per-point prologue / epilogue of a sweep kernel reads a handful of small operands through
+// pointers of the descriptor (policy / V / L_V / L_f matrices, prior-mean rows), one dependent global
+// load after the other; after an L2 flush (or any eviction) each is an HBM round trip in every CTA's
+// serial chain.  Touch them all at once when the kernel starts.
+SLB_DEV void prefetch_descriptor_operands(const slb_sweep& cfg) {
+    const int i = threadIdx.x;
+    const void* p = nullptr;
+    if (i == 0) p = cfg.policy.matrix;
+    else if (i == 1) p = cfg.lyapunov.matrix;
+    else if (i == 2) p = cfg.lipschitz_v.matrix;
+    else if (i == 3) p = cfg.lipschitz_f.matrix;
+    else if (i < 4 + cfg.gp.num_outputs && i < 4 + SLB_MAX_OUT) p = cfg.gp.outputs[i - 4].prior_mean;
+    if (p != nullptr) asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+}
+
 // The Lyapunov decision for one state (lyapunov.py:265-288, 324-376, 441).
 //   x [d]; mu [d] predicted mean; err [d] error bounds (beta*sigma) or nullptr when the
 //   dynamics are deterministic.  Returns negative = decrease < threshold (false on NaN).

@@ -54,7 +54,9 @@ constexpr int64_t WS_HEAD = 64 + SLB_SPLIT_TICKET_BYTES + (int64_t)SLB_SPLIT_PAR
 
 
 // terms of one undecided point, carried from stage 1 to stage 2
-struct filter_side { double dec0, thr, guard, coef[SLB_MAX_OUT], z[SLB_MAX_IN]; };
+struct filter_side { double dec0, thr, guard, coef[SLB_MAX_OUT], z[SLB_MAX_IN], dm[SLB_MAX_OUT]; };
+// fp32 screening stage: dec0 = V(x), coef[j] = screened mean of output j, dm[j] = its certified bound
+// (the head stage rebuilds the mean-dependent terms from them, and from an fp64 mean where needed)
 
 struct filter_args {
     int64_t n;
@@ -186,6 +188,7 @@ template <int DIN>
 __global__ void __launch_bounds__(FT, SLB_MEAN_MINB)
 filter_mean_kernel(const __grid_constant__ slb_sweep cfg, const filter_args a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    prefetch_descriptor_operands(cfg);
     mean_pipe P;
     double *tab512, *tab64;
     mean_pipe_setup(P, smem_raw, DIN, a.chunk_rows, a.max_outputs_per_factor, cfg.gp, &tab512, &tab64);
@@ -255,6 +258,7 @@ __global__ void __launch_bounds__(FT, SLB_MEAN_MINB)
 filter_mean32_kernel(const __grid_constant__ slb_sweep cfg, const filter_args a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ double s_cen[SLB_MAX_IN];
+    prefetch_descriptor_operands(cfg);
     constexpr int W32 = row32<DIN>::W;
     mean_pipe P;
     P.bar = reinterpret_cast<uint64_t*>(smem_raw);
@@ -334,6 +338,10 @@ filter_mean32_kernel(const __grid_constant__ slb_sweep cfg, const filter_args a)
         dst->thr = t.thr;
 #pragma unroll
         for (int c = 0; c < DIN; ++c) dst->z[c] = t.z[c];
+        for (int j = 0; j < D; ++j) {
+            dst->coef[j] = mu[j];
+            dst->dm[j] = sane ? dm[j] : __longlong_as_double(0x7ff0000000000000ll);
+        }
         a.list_a[slot] = rel;
     }
     if (a.stats != nullptr) {
@@ -402,27 +410,27 @@ SLB_DEV void head_mean_factor(const double* __restrict__ xf, int Mp, const doubl
     }
 }
 
-// screened lists, once per round of the head kernel: the fp64 means of the points of ALL the CTA's
-// groups of the round, by all of its warps -- slot s = 8 w + p is entry p of warp w's group; L =
-// 512 / (number of slots) lanes per point, so a CTA with few groups (short lists: the stage's duration
-// is the latency of one group) still spreads the M exps per point and factor over all its threads.
+// screened lists, once per round of the head kernel: the fp64 means of the entries the round could not
+// decide from their screened means (`slots`: s = 8 w + p is entry p of warp w's group), by ALL warps of the
+// CTA -- L = 512 / (number of entries) lanes per point, so a CTA with few of them (short lists: the stage's
+// duration is the latency of one group) still spreads the M exps per point and factor over its threads.
 // Results: mu_s / merr_s [slot][SLB_MAX_OUT] in shared memory.
 template <int DIN>
-SLB_DEV void head_round_means(const slb_sweep& cfg, const filter_args& a, int64_t grp0, int64_t ngroups,
-                              int64_t count, const double* mbuf, const double* tab512, double* mu_s,
-                              double* merr_s) {
+SLB_DEV void head_round_means(const slb_sweep& cfg, const filter_args& a, const int* slots, int nneed,
+                              int64_t grp0, int64_t count, const double* mbuf, const double* tab512,
+                              double* mu_s, double* merr_s) {
     const int nf = cfg.gp.num_factors, D = cfg.gp.num_outputs;
-    // warp w's group this round is grp0 + w gridDim (increasing in w): active groups of the CTA
-    int64_t left = ngroups - grp0;
-    const int ng = left <= 0 ? 0 : (int)min((int64_t)HW, (left + gridDim.x - 1) / gridDim.x);
-    const int nslots = ng * HP;
-    const int L = nslots <= 16 ? 32 : nslots <= 32 ? 16 : nslots <= 64 ? 8 : 4;
+    const int L = nneed <= 16 ? 32 : nneed <= 32 ? 16 : nneed <= 64 ? 8 : 4;
     const int r = threadIdx.x & (L - 1);
-    for (int slot = threadIdx.x / L; slot < nslots; slot += HT / L) {
+    const int per_warp = 32 / L;
+    const int nloop = (nneed + per_warp - 1) / per_warp * per_warp;   // whole warps take part in the shuffles
+    for (int i = threadIdx.x / L; i < nloop; i += HT / L) {
+        const bool live = i < nneed;
+        const int slot = live ? slots[i] : 0;
         const int64_t k = (grp0 + (int64_t)(slot / HP) * gridDim.x) * HP + (slot % HP);
         double z[DIN];
 #pragma unroll
-        for (int c = 0; c < DIN; ++c) z[c] = k < count ? a.side_a[k].z[c] : 0.0;
+        for (int c = 0; c < DIN; ++c) z[c] = (live && k < count) ? a.side_a[k].z[c] : 0.0;
         for (int f = 0; f < nf; ++f) {
             const slb_gp_factor& F = cfg.gp.factors[f];
             int outs[SLB_MAX_OUT];
@@ -449,7 +457,7 @@ SLB_DEV void head_round_means(const slb_sweep& cfg, const filter_args& a, int64_
             case 6: head_mean_factor<DIN, 6>(xf, Mp, zs, zz, r, L, tab512, dot); break;
             default: break;
             }
-            if (r == 0) {
+            if (r == 0 && live) {
                 for (int q = 0; q < no; ++q)
                     mean_output_finish<DIN>(F, cfg.gp.outputs[outs[q]], z, dot[q], zz, 1.0, false,
                                             &mu_s[slot * SLB_MAX_OUT + outs[q]],
@@ -461,33 +469,18 @@ SLB_DEV void head_round_means(const slb_sweep& cfg, const filter_args& a, int64_
 
 // one group of P list entries [g P, g P + P) on one warp
 template <int DIN, int P, bool ALL_STAGED>
-SLB_DEV void head_group(const slb_sweep& cfg, const filter_args& a, int64_t grp, int64_t count,
-                        const double* exptab, double* kw, const double* wbuf, const double* xbuf,
-                        const double* mu_s, unsigned* s_stat) {
+SLB_DEV void head_group_bound(const slb_sweep& cfg, const filter_args& a, int64_t grp, int64_t count,
+                              const double* exptab, double* kw, const double* wbuf, const double* xbuf,
+                              filter_side& t, int64_t& rel, bool& mine, double* shi) {
     const int lane = threadIdx.x & 31;
     const int nf = cfg.gp.num_factors;
     const int D = cfg.gp.num_outputs;
     // lane p < P owns list entry grp * P + p: its terms, its index and finally its decision
     const int64_t k = grp * P + min(lane, P - 1);
-    const bool mine = lane < P && k < count;
-    filter_side t = {};
-    int64_t rel = 0;
+    mine = lane < P && k < count;
+    t = filter_side{};
+    rel = 0;
     if (mine) { t = a.side_a[k]; rel = a.list_a[k]; }
-    if constexpr (P == HP) {
-        if (a.screened) {
-            // stage 1 was the fp32 screening kernel: the fp64 means of the round are in shared memory
-            // (head_round_means); rebuild the terms of the comparison that depend on them
-            double mu[SLB_MAX_OUT], merr[SLB_MAX_OUT];
-            const double* ms = mu_s + (size_t)((threadIdx.x >> 5) * HP + min(lane, HP - 1)) * SLB_MAX_OUT;
-            for (int j = 0; j < SLB_MAX_OUT; ++j) {
-                mu[j] = j < D ? ms[j] : 0.0;
-                merr[j] = j < D ? ms[HW * HP * SLB_MAX_OUT + j] : 0.0;
-            }
-            const double vx = t.dec0;
-            mean_decision_terms(cfg, t, vx, mu, merr);
-        }
-    }
-    double shi[SLB_MAX_OUT];
     for (int j = 0; j < D; ++j) {
         const slb_gp_factor& F = cfg.gp.factors[cfg.gp.outputs[j].factor];
         shi[j] = mine ? sqrt(F.kernel.num_prims > 0 ? kernel_expr_diag<DIN>(F.kernel, t.z) : F.variance)
@@ -608,7 +601,11 @@ SLB_DEV void head_group(const slb_sweep& cfg, const filter_args& a, int64_t grp,
         for (int j = 0; j < D; ++j)
             if (cfg.gp.outputs[j].factor == f) shi[j] = sdev;
     }
-    const int outcome = mine ? decide(t, shi, D) : 0;
+}
+
+// a lane's final outcome: the flag of a decided point, list B for an undecided one (warp-collective)
+SLB_DEV void head_group_finish(const filter_args& a, bool mine, int outcome, int64_t rel, unsigned* s_stat) {
+    const int lane = threadIdx.x & 31;
     const bool undecided = mine && outcome < 0;
     if (mine && outcome >= 0) a.negative[rel] = outcome > 0 ? 1 : 0;
     const long long slot = list_append(undecided, a.counts + 1);
@@ -625,6 +622,7 @@ template <int DIN>
 __global__ void __launch_bounds__(HT, 1)
 filter_head_kernel(const __grid_constant__ slb_sweep cfg, const filter_args a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    prefetch_descriptor_operands(cfg);
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);             // [1]
     unsigned* s_stat = reinterpret_cast<unsigned*>(smem_raw + 8);      // decided / undecided by this CTA
     double* tab512 = reinterpret_cast<double*>(smem_raw + 16);         // [512] (screened lists: exp_neg_fast)
@@ -636,8 +634,6 @@ filter_head_kernel(const __grid_constant__ slb_sweep cfg, const filter_args a) {
     double* mbuf = xbuf + (size_t)a.head_factors_staged * HR * DIN;    // screened: [Xf | gamma_f ...] per factor
     const int64_t count = (int64_t)a.counts[0];
     const int64_t nwarps = (int64_t)gridDim.x * HW;
-    const bool short_list = false;     // every list takes 8-point DMMA groups (the 2-point FMA form of
-                                       // head_group is kept for reference / A-B timing)
     const int64_t ngroups = (count + HP - 1) / HP;
     // groups are dealt round-robin over the CTAs (group g: CTA g % gridDim, warp g / gridDim): a short
     // list spreads over all SMs instead of filling the 16 warps of the first few
@@ -652,6 +648,18 @@ filter_head_kernel(const __grid_constant__ slb_sweep cfg, const filter_args a) {
             for (size_t off = ((size_t)blockIdx.x * HT + threadIdx.x) * 128; off < nbytes;
                  off += (size_t)gridDim.x * HT * 128)
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(base + off));
+            // ... and the training inputs its generation phases stage panel by panel
+            const char* xs = reinterpret_cast<const char*>(F.Xs);
+            const size_t xbytes = (size_t)F.M * DIN * sizeof(double);
+            if (blockIdx.x == (unsigned)f)
+                for (size_t off = (size_t)threadIdx.x * 128; off < xbytes; off += (size_t)HT * 128)
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(xs + off));
+        }
+        if (blockIdx.x == gridDim.x - 1 && threadIdx.x < cfg.gp.num_outputs) {
+            const slb_gp_output& G = cfg.gp.outputs[threadIdx.x];
+            const size_t abytes = (size_t)cfg.gp.factors[G.factor].M * sizeof(double);
+            for (size_t off = 0; off < abytes; off += 128)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(G.alpha) + off));
         }
     }
     if ((int64_t)blockIdx.x >= ngroups) return;                        // no group for this CTA
@@ -689,28 +697,68 @@ filter_head_kernel(const __grid_constant__ slb_sweep cfg, const filter_args a) {
         }
     }
     if (threadIdx.x < 2) s_stat[threadIdx.x] = 0;
+    if (a.screened && threadIdx.x < 2)
+        reinterpret_cast<int*>(mbuf + a.mean_doubles + 2 * HW * HP * SLB_MAX_OUT)[threadIdx.x] = 0;
     __syncthreads();
     slb_bulk::mbar_wait(bar, 0);
     const int warp = threadIdx.x >> 5;
     double* kw = kbuf + warp * HR * HP;
-    double* mu_s = mbuf + a.mean_doubles;      // screened: [HW * HP][SLB_MAX_OUT] means, then their error bounds
+    double* mu_s = mbuf + a.mean_doubles;      // screened: [HW * HP][SLB_MAX_OUT] fp64 means, then their error bounds
+    double* merr_s = mu_s + HW * HP * SLB_MAX_OUT;
+    int* need_s = reinterpret_cast<int*>(merr_s + HW * HP * SLB_MAX_OUT);   // [2] counters (round parity), slots
     // round: warp w takes group grp0 + w gridDim (every warp of the CTA makes the same number of rounds)
-    for (int64_t grp0 = blockIdx.x; grp0 < ngroups; grp0 += nwarps) {
+    int round = 0;
+    for (int64_t grp0 = blockIdx.x; grp0 < ngroups; grp0 += nwarps, ++round) {
         const int64_t grp = grp0 + (int64_t)warp * gridDim.x;
+        const bool active = grp < ngroups;
+        const int lane = threadIdx.x & 31;
+        filter_side t;
+        int64_t rel = 0;
+        bool mine = false, need = false;
+        double shi[SLB_MAX_OUT];
+        double vx = 0.0;
+        int outcome = 0;
+        if (active) {
+            if (a.head_factors_staged == nf)
+                head_group_bound<DIN, HP, true>(cfg, a, grp, count, exptab, kw, wbuf, xbuf, t, rel, mine, shi);
+            else
+                head_group_bound<DIN, HP, false>(cfg, a, grp, count, exptab, kw, wbuf, xbuf, t, rel, mine, shi);
+            if (a.screened) {
+                // first with the screened mean and its error box (stage 1 left them in the entry): most
+                // entries are decided by the tighter variance bound alone
+                double mu[SLB_MAX_OUT], dm[SLB_MAX_OUT], zero[SLB_MAX_OUT];
+                for (int j = 0; j < SLB_MAX_OUT; ++j) { mu[j] = t.coef[j]; dm[j] = t.dm[j]; zero[j] = 0.0; }
+                vx = t.dec0;
+                mean_decision_terms(cfg, t, vx, mu, zero);
+                t.guard += screening_slack(cfg, mu, dm, shi);
+                outcome = mine ? decide(t, shi, cfg.gp.num_outputs) : 0;
+                need = mine && outcome < 0;
+                if (need) need_s[2 + atomicAdd(need_s + (round & 1), 1)] = warp * HP + lane;
+            } else {
+                outcome = mine ? decide(t, shi, cfg.gp.num_outputs) : 0;
+            }
+        }
         if (a.screened) {
-            __syncthreads();                   // the previous round's readers of mu_s are done
-            head_round_means<DIN>(cfg, a, grp0, ngroups, count, mbuf, tab512, mu_s,
-                                  mu_s + HW * HP * SLB_MAX_OUT);
+            if (threadIdx.x == 0) need_s[(round + 1) & 1] = 0;       // the next round's counter
             __syncthreads();
+            const int nneed = need_s[round & 1];
+            if (nneed > 0) {
+                // the rest gets its mean in fp64 (all warps), then the same comparison as the fp64 path
+                head_round_means<DIN>(cfg, a, need_s + 2, nneed, grp0, count, mbuf, tab512, mu_s, merr_s);
+                __syncthreads();
+                if (need) {
+                    double mu[SLB_MAX_OUT], merr[SLB_MAX_OUT];
+                    const int slot = warp * HP + lane;
+                    for (int j = 0; j < SLB_MAX_OUT; ++j) {
+                        mu[j] = mu_s[slot * SLB_MAX_OUT + j];
+                        merr[j] = merr_s[slot * SLB_MAX_OUT + j];
+                    }
+                    mean_decision_terms(cfg, t, vx, mu, merr);
+                    outcome = decide(t, shi, cfg.gp.num_outputs);
+                }
+            }
         }
-        if (grp >= ngroups) continue;
-        if (a.head_factors_staged == nf) {
-            if (short_list) head_group<DIN, HP_SHORT, true>(cfg, a, grp, count, exptab, kw, wbuf, xbuf, mu_s, s_stat);
-            else head_group<DIN, HP, true>(cfg, a, grp, count, exptab, kw, wbuf, xbuf, mu_s, s_stat);
-        } else {
-            if (short_list) head_group<DIN, HP_SHORT, false>(cfg, a, grp, count, exptab, kw, wbuf, xbuf, mu_s, s_stat);
-            else head_group<DIN, HP, false>(cfg, a, grp, count, exptab, kw, wbuf, xbuf, mu_s, s_stat);
-        }
+        if (active) head_group_finish(a, mine, outcome, rel, s_stat);
     }
     // one pair of global atomics per CTA (one per point serialised on the counter's L2 line)
     __syncthreads();
@@ -765,7 +813,8 @@ void head_layout(const slb_sweep& cfg, int din, filter_args& ah, size_t& head_sm
             ah.mean_off[f] = off;
             off += ((cfg.gp.factors[f].M + 7) & ~7) * (din + 1 + no);
         }
-        const size_t extra = ((size_t)off + 2 * HW * HP * SLB_MAX_OUT) * sizeof(double);
+        const size_t extra = ((size_t)off + 2 * HW * HP * SLB_MAX_OUT) * sizeof(double) +
+                             (size_t)(HW * HP + 4) * sizeof(int);
         if (head_smem + extra <= 226 * 1024) {
             ah.screened = 1;
             ah.mean_doubles = off;

@@ -286,7 +286,8 @@ inline size_t mean_smem_bytes(int din, int nomax, int chunk_rows) {
 //   2^x: ex2.approx.ftz.f32 to 2^-22 (PTX ISA), budgeted 8 u; gamma rounds to fp32: u;
 //   sums: F32_FLUSH terms per fp32 accumulator, then added into an fp64 sum: F32_FLUSH u;
 //   with k_j t_j <= 1 / (e ln 2) = 0.531 and k_j <= 1:
-//   |mean error| <= u [0.7 (DIN + 2.01) (2.13 + 5 Z) + 8 + 1 + F32_FLUSH + 2] sum_j |gamma_j| / scale
+//   |mean error| <= u [0.7 (DIN + 2.01) (2.13 + 5 Z) + 8 + 1 + F32_FLUSH + 2 + (8 + 0.7 Z)] sum_j |gamma_j| / scale
+// (the last bracket: E = 2^-Z also comes from ex2.approx, its argument rounded to fp32)
 // (0.7 > ln 2 turns the argument error into a relative error of 2^x; the last 2 covers the fp64
 // steps and the terms flushed to zero).  sum_j |gamma_j| is accumulated by the CTA while it
 // converts.  Points with Z > 40 (2^Z would leave the fp32 range) are left to the fp64 stages.
@@ -332,20 +333,29 @@ SLB_DEV void mean32_factor(const slb_gp_stack& gp, int f, const int* outs, const
     const slb_gp_factor& F = gp.factors[f];
     constexpr int W = DIN + 1, W32 = row32<DIN>::W;
     const double S = 1.2011224087864498;           // sqrt(log2 e)
+    // per CTA and factor: the centre in the factor's units and S / lengthscale (one division per
+    // dimension for the whole block instead of two per thread)
+    __syncthreads();                           // B.red of the previous factor has been read
+    if (threadIdx.x < DIN) {
+        B.red[threadIdx.x] = zcen[threadIdx.x] / F.lengthscales[threadIdx.x];
+        B.red[DIN + threadIdx.x] = S / F.lengthscales[threadIdx.x];
+    }
+    __syncthreads();
     double cs[DIN];
     float zc[DIN];
     double Z = 0.0;
 #pragma unroll
     for (int c = 0; c < DIN; ++c) {
-        cs[c] = zcen[c] / F.lengthscales[c];
-        const double zsc = z[c] / F.lengthscales[c];
-        const double zcd = (zsc - cs[c]) * S;
+        cs[c] = B.red[c];
+        // (z - centre) S / l: within 3e-16 relative of (z / l - cs) S, and the 1e-16 |cs| the rounded
+        // centre is off by stays below 1e-12 for the magnitudes admitted here -- four orders under u
+        const double zcd = (z[c] - zcen[c]) * B.red[DIN + c];
         zc[c] = (float)zcd;
         Z = fma(zcd, zcd, Z);
-        // the fp64 roundings of the centring (1e-16 |zs|) stay far below u |zc| only for moderate inputs
-        if (!(fabs(zsc) < 1e6) || !(fabs(cs[c]) < 1e6)) ok = false;
+        if (!(fabs(cs[c]) < 1e4) || !(fabs(zcd) < 1e4)) ok = false;
     }
     Z *= 0.5;
+    __syncthreads();                           // B.red is reused for sum |gamma| below
     float acc[NO][4];
     double dot[NO], g1[NO];
 #pragma unroll
@@ -438,9 +448,10 @@ SLB_DEV void mean32_factor(const slb_gp_stack& gp, int f, const int* outs, const
         if (lane == 0) B.red[q * nw + warp] = v;
     }
     __syncthreads();
-    const double E = exp2(-Z);
+    // E = 2^-Z on the SFU as well: relative error 2^-22 + ln2 u Z (the argument rounded to fp32)
+    const double E = (double)ex2_approx(-(float)Z);
     const double u24 = 5.9604644775390625e-8;
-    const double epsrel = u24 * (0.7 * (DIN + 2.01) * (2.13 + 5.0 * Z) + 11.0 + F32_FLUSH);
+    const double epsrel = u24 * (0.7 * (DIN + 2.01) * (2.13 + 5.0 * Z) + 11.0 + F32_FLUSH + 8.0 + 0.7 * Z);
     if (!(Z <= 40.0)) ok = false;
 #pragma unroll
     for (int q = 0; q < NO; ++q) {
@@ -458,7 +469,6 @@ SLB_DEV void mean32_factor(const slb_gp_stack& gp, int f, const int* outs, const
         // + the products that left the fp32 range downwards (each < 2^-126 in the scaled sum)
         dmu[outs[q]] = (1.05 * epsrel * gsum + 1.3e-26 * Mp) / fabs(F.scale) + 1e-300;
     }
-    __syncthreads();                           // B.red is reused by the next factor
 }
 
 template <int DIN>

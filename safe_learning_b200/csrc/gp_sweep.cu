@@ -38,9 +38,30 @@ __global__ void pack_factor_kernel(const double* __restrict__ Linv, int M, int n
 }
 
 
+// slb_record_factor_dependency: an event (owned by the library, one per device) that every launch
+// reading the packed factors has to wait for -- a restore of the GP tables whose large part, the
+// packed L^-1, is still in flight on another stream while the filter stages, which do not read it,
+// already run
+cudaEvent_t g_factor_event[64] = {};
+bool g_factor_pending[64] = {};
+
+int wait_for_factors(cudaStream_t st) {
+    int device = 0;
+    SLB_CUDA(cudaGetDevice(&device));
+    if (device < 0 || device >= 64 || !g_factor_pending[device]) return 0;
+    // under stream capture the wait becomes an external-event node: every replay of the graph
+    // waits for the event's latest record
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    SLB_CUDA(cudaStreamIsCapturing(st, &cs));
+    SLB_CUDA(cudaStreamWaitEvent(st, g_factor_event[device],
+                                 cs == cudaStreamCaptureStatusActive ? cudaEventWaitExternal : 0));
+    return 0;
+}
+
 // tp: points per CTA (64 for sweeps and point lists; 32 / 16 only in the refine pass)
 int dispatch_gp_tile(cudaStream_t st, const slb_sweep& cfg, const slb_gp_args& a, int tp = 64) {
     if (a.n <= 0) return 0;
+    if (wait_for_factors(st)) return 1;
     SLB_CHECK(a.n <= (int64_t)0x7fffffff * tp, "too many points for one launch");
     const bool timing = a.timing != nullptr;
     bool kexpr = false;
@@ -129,6 +150,17 @@ extern "C" {
 int slb_debug_refine_split(int64_t upto16, int64_t upto32) {
     g_refine_split[0] = upto16 < 0 ? 0 : upto16;
     g_refine_split[1] = upto32 < g_refine_split[0] ? g_refine_split[0] : upto32;
+    return 0;
+}
+
+int slb_record_factor_dependency(void* stream) {
+    int device = 0;
+    SLB_CUDA(cudaGetDevice(&device));
+    SLB_CHECK(device >= 0 && device < 64, "slb_record_factor_dependency: device %d unsupported", device);
+    if (g_factor_event[device] == nullptr)
+        SLB_CUDA(cudaEventCreateWithFlags(&g_factor_event[device], cudaEventDisableTiming));
+    SLB_CUDA(cudaEventRecord(g_factor_event[device], static_cast<cudaStream_t>(stream)));
+    g_factor_pending[device] = true;
     return 0;
 }
 

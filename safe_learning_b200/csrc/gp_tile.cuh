@@ -195,16 +195,11 @@ SLB_DEV void row_lane_reduce(const double (&v)[2 * NBT], int lane, double* red_q
     }
 }
 
-// KEXPR: at least one factor carries a covariance expression (slb_kernel) instead of the plain
-// RBF; the RBF-only instantiation keeps the lean generation loop.
-// TPV (= TP) only makes the kernel's NAME unique per translation unit: the units for the three tile
-// sizes are compiled from this one source file, nvcc derives the prefix of internal-linkage
-// kernels from the file name, and equally named kernels of different modules were resolved to
-// the same device function (observed: the 64-point launch ran the 32-point code).
-template <int DIN, bool TIMING, bool KEXPR, int TPV>
-__global__ void __launch_bounds__(NT, CTAS_PER_SM)
-gp_tile_kernel(const __grid_constant__ slb_sweep cfg, const slb_gp_args a) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+// One tile (or one row / factor share of it) on the calling CTA: the body of gp_tile_kernel.
+template <int DIN, bool TIMING, bool KEXPR>
+SLB_DEV void gp_tile_body(const slb_sweep& cfg, const slb_gp_args& a, unsigned char* smem_raw,
+                          const int64_t tile_index, const int64_t npts, const int grp, const int G,
+                          const int fsel, const int FS, const bool first_tile) {
     double* Ks = reinterpret_cast<double*>(smem_raw);
     double* zraw = Ks + (PANEL / 8) * 4 * KSTR * 2;   // [SLB_MAX_IN][TP]
     double* red = zraw + SLB_MAX_IN * TP;             // [NW][TP][NRED]
@@ -219,36 +214,10 @@ gp_tile_kernel(const __grid_constant__ slb_sweep cfg, const slb_gp_args a) {
     double* pre = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(kexpr) + SMEM_KEXPR);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    int64_t tile_index = blockIdx.x;
-    int grp = 0, G = 1;                // row group of this CTA / groups per tile (split refine)
-    int fsel = -1, FS = 1;             // split refine with spare CTAs left: this CTA's factor / factors
-                                       // dealt to separate CTAs (FS = 1: every CTA does all factors)
-    // refine mode (slb_lyapunov_sweep_filtered): the point list was compacted by the filter
-    // kernel, its length lives in device memory; CTAs beyond it leave before the first barrier
-    int64_t npts = a.n;
-    if (a.count != nullptr) {
-        npts = (int64_t)*a.count;
-        // one launch per tile size; only the one whose range holds the list length does work
-        if (npts <= a.count_min || npts > a.count_max) return;
-        if (a.split_partial != nullptr) {
-            // short list: spread every tile's rows over as many CTAs as the grid has to spare
-            const int64_t ntiles = (npts + TP - 1) / TP;
-            int64_t spare = (int64_t)gridDim.x / ntiles;
-            // the factors of a stack are independent until the tile epilogue: with CTAs to spare they
-            // go to different CTAs first (half the generation phases and barriers in every CTA's
-            // serial chain), the rest of the spare CTAs splits the rows
-            const int nfac = cfg.gp.num_factors;
-            if (a.split_factors && nfac > 1 && spare >= 2 * nfac) { FS = nfac; spare /= nfac; }
-            G = (int)(spare < 1 ? 1 : (spare > a.split_max ? a.split_max : spare));
-            const int per_tile = G * FS;
-            if ((int64_t)blockIdx.x >= ntiles * per_tile) return;
-            tile_index = blockIdx.x / per_tile;
-            const int rem = (int)(blockIdx.x % per_tile);
-            grp = rem % G;
-            if (FS > 1) fsel = rem / G;
-        }
-        if (tile_index * TP >= npts) return;
-    }
+    // small operands behind pointers / in the constant bank: start their (cold) loads now, they are
+    // consumed by stage 1 and by the first generation phase
+    prefetch_descriptor_operands(cfg);
+    const double exp_entry = c_exp2_tab[tid & 63];
     const int64_t tile0 = tile_index * TP;
     const int D = cfg.gp.num_outputs;
     long long t_gen = 0, t_mma = 0, t_epi = 0, t_mark = 0, t_sync = 0, t_s0 = 0;
@@ -262,7 +231,7 @@ gp_tile_kernel(const __grid_constant__ slb_sweep cfg, const slb_gp_args a) {
     // streaming latency, in lockstep, and run ~2x slower (measured: +15% on the whole sweep).
     // The first-wave CTAs therefore prefetch disjoint 128-byte lines of it into L2 while the
     // k-row generation phase runs; the demand loads then hit.
-    if (blockIdx.x < PREFETCH_CTAS) {
+    if (first_tile && blockIdx.x < PREFETCH_CTAS) {
         for (int f = 0; f < cfg.gp.num_factors; ++f) {
             const slb_gp_factor& F = cfg.gp.factors[f];
             const char* base = reinterpret_cast<const char*>(F.Wpack);
@@ -273,7 +242,7 @@ gp_tile_kernel(const __grid_constant__ slb_sweep cfg, const slb_gp_args a) {
         }
     }
 
-    load_exp_table(exptab);
+    if (tid < 64) exptab[tid] = exp_entry;
 
     // ---- stage 1: query points z = [x, policy(x)]  (lyapunov.py:436-437, utilities.py:143)
     if (tid < TP) {
@@ -661,6 +630,60 @@ gp_tile_kernel(const __grid_constant__ slb_sweep cfg, const slb_gp_args a) {
     }
 }
 
+// KEXPR: at least one factor carries a covariance expression (slb_kernel) instead of the plain
+// RBF; the RBF-only instantiation keeps the lean generation loop.
+// TPV (= TP) only makes the kernel's NAME unique per translation unit: the units for the three tile
+// sizes are compiled from this one source file, nvcc derives the prefix of internal-linkage
+// kernels from the file name, and equally named kernels of different modules were resolved to
+// the same device function (observed: the 64-point launch ran the 32-point code).
+template <int DIN, bool TIMING, bool KEXPR, int TPV>
+__global__ void __launch_bounds__(NT, CTAS_PER_SM)
+gp_tile_kernel(const __grid_constant__ slb_sweep cfg, const slb_gp_args a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    int64_t tile_index = blockIdx.x;
+    int64_t tile_end = tile_index + 1, tile_step = 1;
+    int grp = 0, G = 1;                // row group of this CTA / groups per tile (split refine)
+    int fsel = -1, FS = 1;             // split refine with spare CTAs left: this CTA's factor / factors
+                                       // dealt to separate CTAs (FS = 1: every CTA does all factors)
+    // refine mode (slb_lyapunov_sweep_filtered): the point list was compacted by the filter
+    // kernel, its length lives in device memory; CTAs beyond it leave before the first barrier
+    int64_t npts = a.n;
+    if (a.count != nullptr) {
+        npts = (int64_t)*a.count;
+        // one launch per tile size; only the one whose range holds the list length does work
+        if (npts <= a.count_min || npts > a.count_max) return;
+        const int64_t ntiles = (npts + TP - 1) / TP;
+        if (a.split_partial != nullptr) {
+            // short list: spread every tile's rows over as many CTAs as the grid has to spare
+            int64_t spare = (int64_t)gridDim.x / ntiles;
+            // the factors of a stack are independent until the tile epilogue: with CTAs to spare they
+            // go to different CTAs first (half the generation phases and barriers in every CTA's
+            // serial chain), the rest of the spare CTAs splits the rows
+            const int nfac = cfg.gp.num_factors;
+            if (a.split_factors && nfac > 1 && spare >= 2 * nfac) { FS = nfac; spare /= nfac; }
+            G = (int)(spare < 1 ? 1 : (spare > a.split_max ? a.split_max : spare));
+            const int per_tile = G * FS;
+            if ((int64_t)blockIdx.x >= ntiles * per_tile) return;
+            tile_index = blockIdx.x / per_tile;
+            tile_end = tile_index + 1;
+            const int rem = (int)(blockIdx.x % per_tile);
+            grp = rem % G;
+            if (FS > 1) fsel = rem / G;
+        } else {
+            // unsplit refine launches are persistent: the grid is one CTA per SM (the list length is
+            // not known to the host; a grid sized for the longest possible list cost 6 us of empty
+            // CTAs when it was not this launch's turn), every CTA walks the tiles in strides
+            tile_end = ntiles;
+            tile_step = gridDim.x;
+        }
+        if (tile_index * TP >= npts) return;
+    }
+    for (int64_t tile = tile_index; tile < tile_end; tile += tile_step) {
+        gp_tile_body<DIN, TIMING, KEXPR>(cfg, a, smem_raw, tile, npts, grp, G, fsel, FS, tile == tile_index);
+        if (tile + tile_step < tile_end) __syncthreads();     // shared memory is reused by the next tile
+    }
+}
+
 // TPV: see gp_tile_kernel -- nvcc emits templates of this unnamed namespace as WEAK symbols under a
 // prefix derived from the source file name, so the three tile-size units would otherwise share
 // one launch function (the first one linked: every refine pass ran with 64-point tiles).
@@ -678,7 +701,9 @@ int launch_gp_tile(cudaStream_t st, const slb_sweep& cfg, const slb_gp_args& a) 
                                       (int)SMEM_TOTAL));
         if (device >= 0 && device < 64) configured[device].store(true, std::memory_order_release);
     }
-    const int64_t tiles = (a.n + TP - 1) / TP;
+    int64_t tiles = (a.n + TP - 1) / TP;
+    // unsplit refine launches are persistent (see gp_tile_kernel): one CTA per SM
+    if (a.count != nullptr && a.split_partial == nullptr && tiles > PREFETCH_CTAS) tiles = PREFETCH_CTAS;
     gp_tile_kernel<DIN, TIMING, KEXPR, TP><<<(unsigned)tiles, NT, SMEM_TOTAL, st>>>(cfg, a);
     SLB_LAUNCH_CHECK();
     return 0;

@@ -1609,11 +1609,19 @@ class PackedCache(object):
 
     def __init__(self, gps, pinned=True):
         self.gps = list(gps)
-        self.slots = _table_slots(self.gps)
+        # the packed factors L^-1 (90% of the bytes; read by the O(M^2) posterior only) go last, so
+        # that restore() can send them on a second stream behind the tables the filter stages read
+        slots = _table_slots(self.gps)
+        self.slots = ([sl for sl in slots if sl[1] != "Wpack"] + [sl for sl in slots if sl[1] == "Wpack"])
         offsets, total = [], 0
+        self.split = None
         for owner, name in self.slots:
+            if name == "Wpack" and self.split is None:
+                self.split = total
             offsets.append(total)
             total += -(-max(getattr(owner, name).numel(), 1) // self.ALIGN) * self.ALIGN
+        if self.split is None:
+            self.split = total
         self.arena = dev.zeros((total,))
         self.views = []
         for (owner, name), off in zip(self.slots, offsets):
@@ -1628,14 +1636,32 @@ class PackedCache(object):
         self.host = host.pin_memory() if pinned and torch.cuda.is_available() else host
         self.nbytes = int(total) * 8
         self.token = tuple(id(gp._factor) for gp in self.gps)
+        self._side = None
 
     def valid(self):
         return (self.token == tuple(id(gp._factor) for gp in self.gps)
                 and all(getattr(o, n) is v for (o, n), v in zip(self.slots, self.views)))
 
-    def restore(self):
-        """Host mirror -> device arena: one asynchronous H2D copy on the current stream."""
-        self.arena.copy_(self.host, non_blocking=True)
+    def restore(self, overlap=True):
+        """Host mirror -> device arena, asynchronously.  With ``overlap`` (default, page-locked
+        mirror) the small tables travel on the current stream and the packed factors on a second
+        one; every launch that reads the packed factors waits for that copy inside the library
+        (``slb_record_factor_dependency``), so a sweep enqueued right after this call runs its filter
+        stages while the factors are still arriving.  Returns the bytes copied."""
+        total = self.arena.numel()
+        if not (overlap and self.host.is_pinned() and 0 < self.split < total):
+            self.arena.copy_(self.host, non_blocking=True)
+            return self.nbytes
+        cur = torch.cuda.current_stream()
+        if self._side is None:
+            self._side = torch.cuda.Stream()
+        self.arena[:self.split].copy_(self.host[:self.split], non_blocking=True)
+        self._side.wait_stream(cur)            # earlier readers of the factors on `cur` are done
+        with torch.cuda.stream(self._side):
+            self.arena[self.split:].copy_(self.host[self.split:], non_blocking=True)
+        nat.check(nat.load().slb_record_factor_dependency(self._side.cuda_stream),
+                  "slb_record_factor_dependency")
+        dev.note_factor_dependency()
         return self.nbytes
 
 

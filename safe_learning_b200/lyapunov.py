@@ -836,7 +836,7 @@ class Lyapunov(object):
                 and (world == 1 or xchg is not None)):
             token = (self._descriptor_token(), self._values_dev.data_ptr(),
                      0 if initial is None else initial.data_ptr(), n_local,
-                     self._filter_enabled(self.sweep_descriptor()))
+                     self._filter_enabled(self.sweep_descriptor()), dev.factor_dependency_epoch())
         cached = self.__dict__.get("_sweep_graph")
         if token is not None and cached is not None and cached[0] == token:
             cached[1].replay()

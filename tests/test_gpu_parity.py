@@ -1072,3 +1072,38 @@ def test_errors_are_loud(sl):
     with pytest.raises(NotImplementedError):      # expands to 8 primitives, the descriptor holds 6
         k = sl.RBF(2) + sl.Matern32(2)
         sl.GaussianProcess(sl.GPRCached(np.zeros((2, 2)), np.zeros((2, 1)), (k * k) * k))(np.zeros((1, 2)))
+
+
+@pytest.mark.parametrize("filtered", [True, False])
+def test_packed_restore_orders_the_factor_copy_behind_the_sweep(sl, filtered):
+    """PackedCache.restore sends the packed factors on a second stream and registers an event the
+    library waits for before any launch that reads them (slb_record_factor_dependency).  The copy is
+    held back by ~10 ms of busy-waiting on that stream while the device copy of the factors is
+    zeroed: the sweep (direct launches, then CUDA-graph replays) must still see the restored
+    factors."""
+    import torch
+    par = W.make_pendulum(num_points=[61, 53], M=200, tau_scale=1 / 16., seed=3)
+    gpu = W.build_product(par)
+    if not filtered:
+        gpu.filter = False
+    gpu.update_safe_set()
+    want = gpu.safe_set.copy()
+    if filtered:
+        gpu.reset_filter_stats()
+        gpu.compute_negative()
+        assert gpu.filter_stats["refined"] > 0
+    tables = gpu.dynamics.export_cache(pinned=True)
+    assert 0 < tables.split < tables.arena.numel()
+    gpu.dynamics.import_cache(tables)                 # creates the second stream
+    gpu.update_safe_set()
+    assert_array_equal(gpu.safe_set, want)
+    for trial in range(4):                            # trial >= 2: graph replays
+        tables.arena[tables.split:].zero_()
+        with torch.cuda.stream(tables._side):
+            torch.cuda._sleep(20000000)
+        gpu.dynamics.import_cache(tables)
+        gpu.update_safe_set()
+        assert_array_equal(gpu.safe_set, want, err_msg="trial %d" % trial)
+    cpu = W.build_oracle(par)
+    cpu.update_safe_set()
+    assert_array_equal(want, cpu.safe_set)

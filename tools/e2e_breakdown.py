@@ -33,3 +33,24 @@ for _ in range(30):
     lyap.dynamics.import_cache(tables); lyap.initial_safe_set = mask; lyap.update_safe_set(); s = lyap.safe_set; c = lyap.feed_dict[lyap.c_max]
     seg["whole_step_no_syncs"].append(time.perf_counter() - t0)
 print(json.dumps({k: round(1e6 * float(np.median(v)), 1) for k, v in seg.items()} | {"unit": "us (median of 30)"}))
+
+# host-only cost of each call (no synchronisation in between: what the enqueueing thread spends)
+host = {k: [] for k in ("import_cache", "set_initial", "update_safe_set", "safe_set", "c_max")}
+for _ in range(200):
+    t0 = time.perf_counter(); lyap.dynamics.import_cache(tables)
+    t1 = time.perf_counter(); lyap.initial_safe_set = mask
+    t2 = time.perf_counter(); lyap.update_safe_set()
+    t3 = time.perf_counter(); s = lyap.safe_set
+    t4 = time.perf_counter(); c = lyap.feed_dict[lyap.c_max]
+    t5 = time.perf_counter()
+    for k, v in zip(host, (t1 - t0, t2 - t1, t3 - t2, t4 - t3, t5 - t4)):
+        host[k].append(v)
+print(json.dumps({"host_only_us": {k: round(1e6 * float(np.median(v)), 1) for k, v in host.items()}}))
+if "--profile" in sys.argv:
+    import cProfile, pstats
+    def steps(n):
+        for _ in range(n):
+            lyap.dynamics.import_cache(tables); lyap.initial_safe_set = mask; lyap.update_safe_set()
+            s = lyap.safe_set; c = lyap.feed_dict[lyap.c_max]
+    pr = cProfile.Profile(); pr.enable(); steps(500); pr.disable()
+    st = pstats.Stats(pr); st.sort_stats("tottime").print_stats(28)
