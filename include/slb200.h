@@ -295,6 +295,13 @@ int         slb_debug_phase_timing(void* buffer_dev);
  * read the packed factors and overlap the copy.  Under stream capture the wait is an external-event
  * node (re-evaluated at every replay).  Single-threaded use like the other setters. */
 int         slb_record_factor_dependency(void* stream);
+/* Restore of a packed table arena (safe_learning_b200.functions.PackedCache: every cached GP table of a
+ * stack in one device buffer, mirrored by one page-locked host buffer, the packed factors last) in one
+ * call: bytes [0, split_bytes) are copied host -> device on `stream`, bytes [split_bytes, total_bytes)
+ * -- the packed factors -- on `side_stream` behind everything enqueued on `stream` so far, followed by
+ * slb_record_factor_dependency(side_stream).  side_stream NULL (or == stream): one stream, no event. */
+int         slb_restore_tables(void* dst_dev, const void* src_host, int64_t split_bytes, int64_t total_bytes,
+                               void* stream, void* side_stream);
 /* diagnostics (timing of the individual stages of slb_lyapunov_sweep_filtered; the flags are only
  * complete with bits 0 and 1 set -- 3, the default, or 7): bit 0 runs the head stage, bit 1 the
  * refine pass; bit 2 forces the fp64 mean stage where the fp32 screening stage would run */

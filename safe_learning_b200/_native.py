@@ -130,6 +130,7 @@ SIGNATURES = {
     "slb_note_graph_replay": (None, [_i64]),
     "slb_debug_phase_timing": (C.c_int, [_vp]),
     "slb_record_factor_dependency": (C.c_int, [_vp]),
+    "slb_restore_tables": (C.c_int, [_vp, _vp, _i64, _i64, _vp, _vp]),
     "slb_debug_refine_split": (C.c_int, [_i64, _i64]),
     "slb_debug_det_fast": (C.c_int, [_i32]),
     "slb_debug_filter_stages": (C.c_int, [_i32]),

@@ -149,36 +149,50 @@ SLB_DEV void mean_decision_terms(const slb_sweep& cfg, filter_side& t, double vx
 // enters with beta_j sigma_j <= beta_j shi_j.  Returns the amount to add to the guard band.
 SLB_DEV double screening_slack(const slb_sweep& cfg, const double* mu, const double* dm,
                                const double* shi) {
+    // straight-line for up to 4 outputs (screening_applicable): operands in registers, all matrix
+    // entries loaded at once -- this runs once per grid point in the screening kernel's epilogue
+    constexpr int NS = 4;
     const int D = cfg.gp.num_outputs;
     const slb_function& V = cfg.lyapunov;
     const int n = V.in_dim;
+    double m[NS], d[NS], bs[NS], P[NS][NS];
+#pragma unroll
+    for (int i = 0; i < NS; ++i) {
+        m[i] = i < n ? mu[i] : 0.0;
+        d[i] = i < n ? dm[i] : 0.0;
+        bs[i] = i < D ? fabs(cfg.gp.outputs[i].beta) * shi[i] : 0.0;
+#pragma unroll
+        for (int j = 0; j < NS; ++j) P[i][j] = (i < n && j < n) ? __ldg(V.matrix + i * n + j) : 0.0;
+    }
     double dv = 0.0;
-    for (int i = 0; i < n; ++i) {
+#pragma unroll
+    for (int i = 0; i < NS; ++i) {
         double gi = 0.0;
-        for (int r = 0; r < n; ++r)
-            gi += mu[r] * (__ldg(V.matrix + r * n + i) + __ldg(V.matrix + i * n + r));
-        dv += fabs(gi) * dm[i];
-        for (int j = 0; j < n; ++j) dv += fabs(__ldg(V.matrix + i * n + j)) * dm[i] * dm[j];
+#pragma unroll
+        for (int r = 0; r < NS; ++r) gi += m[r] * (P[r][i] + P[i][r]);
+        dv += fabs(gi) * d[i];
+#pragma unroll
+        for (int j = 0; j < NS; ++j) dv += fabs(P[i][j]) * d[i] * d[j];
     }
     if (V.flags & SLB_FLAG_SCALE) dv *= fabs(V.out_scale);
     double dl = 0.0;
     const slb_function& L = cfg.lipschitz_v;
     if (L.kind == SLB_FN_LINEAR) {
         const double sc = (L.flags & SLB_FLAG_SCALE) ? fabs(L.out_scale) : 1.0;
-        const int m = L.in_dim;
-        if ((L.flags & SLB_FLAG_NORM1) || L.out_dim == 1) {
-            double tot = 0.0;
-            for (int o = 0; o < L.out_dim; ++o)
-                for (int i = 0; i < m; ++i) tot += fabs(__ldg(L.matrix + o * m + i)) * dm[i];
-            double bs = 0.0;
-            for (int j = 0; j < D; ++j) bs += fabs(cfg.gp.outputs[j].beta) * shi[j];
-            dl = sc * tot * bs;
+        const int mi = L.in_dim, mo = L.out_dim;
+        double row[NS];                           // row[o] = sum_i |A_oi| dm_i
+#pragma unroll
+        for (int o = 0; o < NS; ++o) {
+            row[o] = 0.0;
+#pragma unroll
+            for (int i = 0; i < NS; ++i)
+                if (o < mo && i < mi) row[o] += fabs(__ldg(L.matrix + o * mi + i)) * d[i];
+        }
+        if ((L.flags & SLB_FLAG_NORM1) || mo == 1) {
+            dl = sc * (row[0] + row[1] + row[2] + row[3]) * (bs[0] + bs[1] + bs[2] + bs[3]);
         } else {
-            for (int j = 0; j < D; ++j) {
-                double row = 0.0;
-                for (int i = 0; i < m; ++i) row += fabs(__ldg(L.matrix + j * m + i)) * dm[i];
-                dl += sc * row * fabs(cfg.gp.outputs[j].beta) * shi[j];
-            }
+#pragma unroll
+            for (int j = 0; j < NS; ++j) dl += sc * row[j] * bs[j];
         }
     }
     return 1.000001 * (dv + dl);
@@ -188,6 +202,7 @@ template <int DIN>
 __global__ void __launch_bounds__(FT, SLB_MEAN_MINB)
 filter_mean_kernel(const __grid_constant__ slb_sweep cfg, const filter_args a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    pdl_launch_dependents();                      // the head stage may start staging its tables
     prefetch_descriptor_operands(cfg);
     mean_pipe P;
     double *tab512, *tab64;
@@ -258,6 +273,7 @@ __global__ void __launch_bounds__(FT, SLB_MEAN_MINB)
 filter_mean32_kernel(const __grid_constant__ slb_sweep cfg, const filter_args a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ double s_cen[SLB_MAX_IN];
+    pdl_launch_dependents();                      // the head stage may start staging its tables
     prefetch_descriptor_operands(cfg);
     constexpr int W32 = row32<DIN>::W;
     mean_pipe P;
@@ -622,6 +638,7 @@ template <int DIN>
 __global__ void __launch_bounds__(HT, 1)
 filter_head_kernel(const __grid_constant__ slb_sweep cfg, const filter_args a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    pdl_launch_dependents();                      // the refine launch may get its CTAs ready
     prefetch_descriptor_operands(cfg);
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);             // [1]
     unsigned* s_stat = reinterpret_cast<unsigned*>(smem_raw + 8);      // decided / undecided by this CTA
@@ -632,14 +649,10 @@ filter_head_kernel(const __grid_constant__ slb_sweep cfg, const filter_args a) {
     const int nf = cfg.gp.num_factors;
     double* xbuf = wbuf + (size_t)a.head_factors_staged * HR * HR;     // [staged][HR * DIN]
     double* mbuf = xbuf + (size_t)a.head_factors_staged * HR * DIN;    // screened: [Xf | gamma_f ...] per factor
-    const int64_t count = (int64_t)a.counts[0];
-    const int64_t nwarps = (int64_t)gridDim.x * HW;
-    const int64_t ngroups = (count + HP - 1) / HP;
-    // groups are dealt round-robin over the CTAs (group g: CTA g % gridDim, warp g / gridDim): a short
-    // list spreads over all SMs instead of filling the 16 warps of the first few
-    // The refine pass that follows streams every factor's packed L^-1 (1 MB at M = 500); if it is
-    // not L2-resident by then (first sweep after a cache update, or evicted in between) its CTAs
-    // start with HBM round trips in lockstep.  Prefetch it into L2 from here, off the critical path.
+    // ---- everything that does not depend on stage 1 first (the kernel is a programmatic dependent of
+    // it: this part overlaps stage 1's tail).  The refine pass that follows streams every factor's
+    // packed L^-1 (1 MB at M = 500); if it is not L2-resident by then (first sweep after a cache
+    // update, or evicted in between) its CTAs start with HBM round trips in lockstep: prefetch it.
     if (a.prefetch_factors) {
         for (int f = 0; f < nf; ++f) {
             const slb_gp_factor& F = cfg.gp.factors[f];
@@ -662,7 +675,6 @@ filter_head_kernel(const __grid_constant__ slb_sweep cfg, const filter_args a) {
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(G.alpha) + off));
         }
     }
-    if ((int64_t)blockIdx.x >= ngroups) return;                        // no group for this CTA
     if (threadIdx.x == 0) {
         slb_bulk::mbar_init(bar, 1);
         slb_bulk::fence_barrier_init();
@@ -700,7 +712,14 @@ filter_head_kernel(const __grid_constant__ slb_sweep cfg, const filter_args a) {
     if (a.screened && threadIdx.x < 2)
         reinterpret_cast<int*>(mbuf + a.mean_doubles + 2 * HW * HP * SLB_MAX_OUT)[threadIdx.x] = 0;
     __syncthreads();
-    slb_bulk::mbar_wait(bar, 0);
+    slb_bulk::mbar_wait(bar, 0);                  // also before leaving: the copies land in this CTA's memory
+    pdl_wait();                                   // ---- stage 1 has completed: its lists are visible
+    const int64_t count = (int64_t)a.counts[0];
+    const int64_t nwarps = (int64_t)gridDim.x * HW;
+    const int64_t ngroups = (count + HP - 1) / HP;
+    // groups are dealt round-robin over the CTAs (group g: CTA g % gridDim, warp g / gridDim): a short
+    // list spreads over all SMs instead of filling the 16 warps of the first few
+    if ((int64_t)blockIdx.x >= ngroups) return;                        // no group for this CTA
     const int warp = threadIdx.x >> 5;
     double* kw = kbuf + warp * HR * HP;
     double* mu_s = mbuf + a.mean_doubles;      // screened: [HW * HP][SLB_MAX_OUT] fp64 means, then their error bounds
@@ -780,11 +799,13 @@ bool screening_applicable(const slb_sweep& cfg) {
     for (int f = 0; f < cfg.gp.num_factors; ++f)
         if (cfg.gp.factors[f].kernel.num_prims > 0) return false;
     const slb_function& V = cfg.lyapunov;
+    if (D > 4) return false;                   // screening_slack is written out for up to 4 outputs
     if (V.kind != SLB_FN_QUADRATIC || V.in_dim != D || (V.flags & ~(uint32_t)SLB_FLAG_SCALE)) return false;
     const slb_function& L = cfg.lipschitz_v;
     if (L.kind == SLB_FN_NONE) return true;
     if (L.kind != SLB_FN_LINEAR || L.in_dim != D) return false;
     if (L.flags & ~(uint32_t)(SLB_FLAG_ABS | SLB_FLAG_NORM1 | SLB_FLAG_SCALE)) return false;
+    if (L.out_dim > 4) return false;
     return (L.flags & SLB_FLAG_NORM1) || L.out_dim == 1 || L.out_dim == D;
 }
 
@@ -851,7 +872,7 @@ int launch_filter(cudaStream_t st, const slb_sweep& cfg, const filter_args& a, s
     }
     SLB_LAUNCH_CHECK();
     if (!(g_filter_stages & 1)) return 0;
-    filter_head_kernel<DIN><<<HEAD_CTAS, HT, head_smem, st>>>(cfg, ah);
+    SLB_CUDA(slb_launch_dependent(filter_head_kernel<DIN>, dim3(HEAD_CTAS), dim3(HT), head_smem, st, cfg, ah));
     SLB_LAUNCH_CHECK();
     return 0;
 }

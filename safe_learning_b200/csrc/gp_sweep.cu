@@ -153,6 +153,33 @@ int slb_debug_refine_split(int64_t upto16, int64_t upto32) {
     return 0;
 }
 
+int slb_restore_tables(void* dst_dev, const void* src_host, int64_t split_bytes, int64_t total_bytes,
+                       void* stream, void* side_stream) {
+    SLB_CHECK(dst_dev != nullptr && src_host != nullptr, "slb_restore_tables: null buffer");
+    SLB_CHECK(split_bytes >= 0 && split_bytes <= total_bytes, "slb_restore_tables: split %lld outside [0, %lld]",
+              (long long)split_bytes, (long long)total_bytes);
+    cudaStream_t st = static_cast<cudaStream_t>(stream), side = static_cast<cudaStream_t>(side_stream);
+    char* dst = static_cast<char*>(dst_dev);
+    const char* src = static_cast<const char*>(src_host);
+    if (split_bytes > 0) SLB_CUDA(cudaMemcpyAsync(dst, src, (size_t)split_bytes, cudaMemcpyHostToDevice, st));
+    const int64_t rest = total_bytes - split_bytes;
+    if (rest <= 0) return 0;
+    if (side == nullptr || side == st) {
+        SLB_CUDA(cudaMemcpyAsync(dst + split_bytes, src + split_bytes, (size_t)rest, cudaMemcpyHostToDevice, st));
+        return 0;
+    }
+    // the second stream must not overtake earlier readers of the packed factors on `st`
+    int device = 0;
+    SLB_CUDA(cudaGetDevice(&device));
+    SLB_CHECK(device >= 0 && device < 64, "slb_restore_tables: device %d unsupported", device);
+    static cudaEvent_t order[64] = {};
+    if (order[device] == nullptr) SLB_CUDA(cudaEventCreateWithFlags(&order[device], cudaEventDisableTiming));
+    SLB_CUDA(cudaEventRecord(order[device], st));
+    SLB_CUDA(cudaStreamWaitEvent(side, order[device], 0));
+    SLB_CUDA(cudaMemcpyAsync(dst + split_bytes, src + split_bytes, (size_t)rest, cudaMemcpyHostToDevice, side));
+    return slb_record_factor_dependency(side);
+}
+
 int slb_record_factor_dependency(void* stream) {
     int device = 0;
     SLB_CUDA(cudaGetDevice(&device));

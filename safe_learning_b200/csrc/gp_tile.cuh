@@ -649,6 +649,11 @@ gp_tile_kernel(const __grid_constant__ slb_sweep cfg, const slb_gp_args a) {
     // kernel, its length lives in device memory; CTAs beyond it leave before the first barrier
     int64_t npts = a.n;
     if (a.count != nullptr) {
+        // the refine launches are programmatic dependents of the filter's head stage (and of each
+        // other): CTAs may be resident before the list exists
+        pdl_launch_dependents();
+        prefetch_descriptor_operands(cfg);
+        pdl_wait();
         npts = (int64_t)*a.count;
         // one launch per tile size; only the one whose range holds the list length does work
         if (npts <= a.count_min || npts > a.count_max) return;
@@ -704,7 +709,11 @@ int launch_gp_tile(cudaStream_t st, const slb_sweep& cfg, const slb_gp_args& a) 
     int64_t tiles = (a.n + TP - 1) / TP;
     // unsplit refine launches are persistent (see gp_tile_kernel): one CTA per SM
     if (a.count != nullptr && a.split_partial == nullptr && tiles > PREFETCH_CTAS) tiles = PREFETCH_CTAS;
-    gp_tile_kernel<DIN, TIMING, KEXPR, TP><<<(unsigned)tiles, NT, SMEM_TOTAL, st>>>(cfg, a);
+    if (a.count != nullptr)
+        SLB_CUDA(slb_launch_dependent(gp_tile_kernel<DIN, TIMING, KEXPR, TP>, dim3((unsigned)tiles), dim3(NT),
+                                      SMEM_TOTAL, st, cfg, a));
+    else
+        gp_tile_kernel<DIN, TIMING, KEXPR, TP><<<(unsigned)tiles, NT, SMEM_TOTAL, st>>>(cfg, a);
     SLB_LAUNCH_CHECK();
     return 0;
 }

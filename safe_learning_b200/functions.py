@@ -1637,6 +1637,7 @@ class PackedCache(object):
         self.nbytes = int(total) * 8
         self.token = tuple(id(gp._factor) for gp in self.gps)
         self._side = None
+        self._pinned = bool(self.host.is_pinned())
 
     def valid(self):
         return (self.token == tuple(id(gp._factor) for gp in self.gps)
@@ -1649,18 +1650,16 @@ class PackedCache(object):
         (``slb_record_factor_dependency``), so a sweep enqueued right after this call runs its filter
         stages while the factors are still arriving.  Returns the bytes copied."""
         total = self.arena.numel()
-        if not (overlap and self.host.is_pinned() and 0 < self.split < total):
-            self.arena.copy_(self.host, non_blocking=True)
+        lib = nat.load()
+        cur = torch.cuda.current_stream().cuda_stream
+        if not (overlap and self._pinned and 0 < self.split < total):
+            nat.check(lib.slb_restore_tables(self.arena.data_ptr(), self.host.data_ptr(), 8 * total, 8 * total,
+                                             cur, None), "slb_restore_tables")
             return self.nbytes
-        cur = torch.cuda.current_stream()
         if self._side is None:
             self._side = torch.cuda.Stream()
-        self.arena[:self.split].copy_(self.host[:self.split], non_blocking=True)
-        self._side.wait_stream(cur)            # earlier readers of the factors on `cur` are done
-        with torch.cuda.stream(self._side):
-            self.arena[self.split:].copy_(self.host[self.split:], non_blocking=True)
-        nat.check(nat.load().slb_record_factor_dependency(self._side.cuda_stream),
-                  "slb_record_factor_dependency")
+        nat.check(lib.slb_restore_tables(self.arena.data_ptr(), self.host.data_ptr(), 8 * self.split,
+                                         8 * total, cur, self._side.cuda_stream), "slb_restore_tables")
         dev.note_factor_dependency()
         return self.nbytes
 

@@ -6,6 +6,7 @@ import json
 import os
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+TAG = os.environ.get("SLB_TAG", "r02")      # r02: first half of round 2, r02b: second half
 P = os.path.join(ROOT, "profiles")
 
 
@@ -25,11 +26,11 @@ def jsonl(name):
 
 
 out = []
-b = last_json("r02_bench.json")
+b = last_json((TAG + "_bench.json"))
 if b:
     r, rf, f, e = b["roofline"], b["roofline_full_posterior"], b["filter"], b["e2e"]
     st = r.get("stage_ms", {})
-    out += ["| Quantity (N=1, `profiles/r02_bench.json`) | Value |", "|---|---|",
+    out += ["| Quantity (N=1, `profiles/%s_bench.json`) | Value |" % TAG, "|---|---|",
             "| `value` (device-resident, whole default step) | **%.3g points/s** (%.4f ms/step, spread %.4f–%.4f, %d launches/step) |"
             % (b["value"], b["ms_per_step"], b["ms_per_step_spread"]["min"], b["ms_per_step_spread"]["max"], b["gpu_launches"] // b["steps"]),
             "| `e2e` (host buffers in/out every step: %.2f MB H2D GP tables, %.1f KB D2H safe set + key/stats) | **%.3g points/s** (%.4f ms/step) |"
@@ -38,8 +39,11 @@ if b:
             % (100 * f["decided_by_mean_and_prior_bound"], 100 * f["decided_by_head_rank_bound"], 100 * f["refined_by_full_posterior"]),
             "| stage times, L2 flushed (mean / head / refine incl. its launches) | %.1f / %.1f / %.1f µs |"
             % (1e3 * st.get("mean", 0), 1e3 * st.get("head", 0), 1e3 * st.get("refine", 0)),
-            "| `roofline` = dominant kernel `filter_mean_kernel<3>` | %.2f TFLOP/s algorithmic (F_B = D·M·(3d_in+4+E_exp), E_exp=1) = **%.1f%% of the measured fp64 peak** (%.1f TF); %.3g exp/s = %.0f%% of the exp-only microbenchmark |"
-            % (r["achieved"], 100 * r["frac"], r["peak"], r["exp_per_s"], 100 * r["exp_frac"]),
+            "| `roofline` = %s (stage 1: %s) | %.2f TFLOP/s algorithmic (F_B = D·M·(3d_in+4+E_exp), E_exp=1) = **%.1f%% of %.1f TFLOP/s** (%s); %.3g exp/s = %.0f%% of the %s |"
+            % (r["kernel"].split(":")[0], r.get("stage1", "fp64 mean"), r["achieved"], 100 * r["frac"], r["peak"],
+               "fp32 FFMA peak 148 x 128 x 2 x 1.965 GHz" if r.get("stage1") == "fp32 screening" else "measured fp64 peak",
+               r.get("exp_per_s", 0), 100 * r.get("exp_frac", 0),
+               "SFU rate (16 ex2 per clock and SM)" if r.get("stage1") == "fp32 screening" else "exp-only microbenchmark"),
             "| `roofline_full_posterior` = `gp_tile_kernel<3,64>` over the whole grid (filter off) | %.3f ms → %.1f TFLOP/s algorithmic = **%.1f%% of the fp64 DMMA peak** |"
             % (rf["kernel_ms"], rf["achieved"], 100 * rf["frac"]),
             "| the same step with the filter off (round-1 path) | %.3g points/s (%.3f ms/step) |"
@@ -50,15 +54,15 @@ if b:
             % (b["cpu_baseline"]["cores"], b["cpu_baseline"]["value"]),
             "| clocks during the timed region | %s MHz of %s, reasons %s |"
             % (b["clocks"]["sm_mhz"], b["clocks"]["sm_max_mhz"], b["clocks"]["reasons"]), ""]
-ref = last_json("r02_bench_reference.json")
+ref = last_json((TAG + "_bench_reference.json"))
 if ref:
     out += ["`--impl reference` arm (same oracle, %d threads, %s steps): %.3g points/s." % (
         ref["cpu_baseline"]["cores"], ref["steps"], ref["value"]), ""]
 rows = []
-for name, label in (("r02_bench.json", "1, weak (256² per GPU)"), ("r02_bench_n2.json", "2, weak"),
-                    ("r02_bench_n4.json", "4, weak"), ("r02_bench_n8.json", "8, weak"),
-                    ("r02_bench_n1_strong.json", "1, strong (one 2048² grid)"),
-                    ("r02_bench_n2_strong.json", "2, strong"), ("r02_bench_n8_strong.json", "8, strong")):
+for name, label in (((TAG + "_bench.json"), "1, weak (256² per GPU)"), ((TAG + "_bench_n2.json"), "2, weak"),
+                    ((TAG + "_bench_n4.json"), "4, weak"), ((TAG + "_bench_n8.json"), "8, weak"),
+                    ((TAG + "_bench_n1_strong.json"), "1, strong (one 2048² grid)"),
+                    ((TAG + "_bench_n2_strong.json"), "2, strong"), ((TAG + "_bench_n8_strong.json"), "8, strong")):
     d = last_json(name)
     if d:
         par = d.get("parity")
@@ -69,9 +73,9 @@ for name, label in (("r02_bench.json", "1, weak (256² per GPU)"), ("r02_bench_n
 if rows:
     out += ["| GPUs, scaling | points/s (default step) | ms/step | e2e points/s | ms/step, filter off | parity vs oracle | key exchange |",
             "|---|---|---|---|---|---|---|"] + rows + [""]
-ex = jsonl("r02_bench_extra.jsonl")
+ex = jsonl((TAG + "_bench_extra.jsonl"))
 if ex:
-    out += ["Secondary measurements (`tools/bench_extra.py`, `profiles/r02_bench_extra.jsonl`, one B200):", ""]
+    out += ["Secondary measurements (`tools/bench_extra.py`, `profiles/" + TAG + "_bench_extra.jsonl`, one B200):", ""]
     for d in ex:
         k = d["bench"]
         if k == "c5_gp_sweep":
@@ -97,15 +101,15 @@ if ex:
         elif k == "notebook_pendulum_kernels":
             out.append("* the reference's 2001x1501 pendulum experiment, its own kernels, M=%d: update_safe_set %.2f ms = %.3g points/s" % (d["M"], d["update_safe_set_ms"], d["points_per_s"]))
     out.append("")
-dist = jsonl("r02_bench_extra_dist_n8.jsonl")
+dist = jsonl((TAG + "_bench_extra_dist_n8.jsonl"))
 if dist:
-    out += ["Stated-size configurations on 8 B200 (`tools/bench_extra_dist.py`, `profiles/r02_bench_extra_dist_n8.jsonl`; grid sharded by contiguous index range, peer-memory key exchange):", ""]
+    out += ["Stated-size configurations on 8 B200 (`tools/bench_extra_dist.py`, `profiles/" + TAG + "_bench_extra_dist_n8.jsonl`; grid sharded by contiguous index range, peer-memory key exchange):", ""]
     for d in dist:
         out.append("* %s (N=%d points, M=%d, %d factors): **%.2f ms** per update_safe_set = %.3g points/s; filter %.1f%% / %.1f%% / %.2f%% refined"
                    % (d["bench"], d["grid_points"], d["M"], d["factors"], d["ms_per_update_safe_set"], d["points_per_s"],
                       100 * d["filter"]["prior"], 100 * d["filter"]["head"], 100 * d["filter"]["refined"]))
     out.append("")
-for name in ("r02_filter_mean_kernel_ncu.json", "r02_filter_head_kernel_ncu.json", "r02_refine_tile_kernel_ncu.json", "r02_gp_tile_kernel_ncu.json"):
+for name in ((TAG + "_filter_mean_kernel_ncu.json"), (TAG + "_filter_head_kernel_ncu.json"), (TAG + "_refine_tile_kernel_ncu.json"), (TAG + "_gp_tile_kernel_ncu.json")):
     d = last_json(name) if False else (json.load(open(os.path.join(P, name))) if os.path.exists(os.path.join(P, name)) else None)
     if d:
         out.append("* ncu `%s`: %.1f µs, fp64 pipe %.0f%%, tensor pipe %.0f%%, issue slots %.0f%%, DRAM %.2f MB, %d registers, stalls %s"

@@ -11,6 +11,7 @@ import shutil
 import subprocess
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+TAG = os.environ.get("SLB_TAG", "r02")      # r02: first half of round 2, r02b: second half
 src, dst, tag = os.path.join(ROOT, "gpurun_out"), os.path.join(ROOT, "profiles"), "r02"
 
 
@@ -34,10 +35,13 @@ def launch_shares(path):
              "share": round(t / total, 4)} for k, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:12]]
 
 
-def ncu_summary(rep, label, extra=None):
+def ncu_summary(rep, label, extra=None, match=None):
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], stdout=subprocess.PIPE, text=True).stdout
     rr = list(csv.reader(io.StringIO(raw)))
     names, units, vals = rr[0], rr[1], rr[2]
+    if match is not None:          # a report holding several kernels: the first row whose name matches
+        ki = names.index("Kernel Name")
+        vals = next(r for r in rr[2:] if match in r[ki])
     m = {h: (v, u) for h, u, v in zip(names, units, vals)}
 
     def num(key, default=None):
@@ -83,29 +87,35 @@ def ncu_summary(rep, label, extra=None):
 
 
 done = []
-for rep, label, name in (
-        ("r02_filter_mean_kernel.ncu-rep", "filter stage 1 (mean, prior bound) on the C2 grid", "r02_filter_mean_kernel_ncu.json"),
-        ("r02_filter_head_kernel.ncu-rep", "filter stage 2 (head-subset variance bound) on list A of the C2 grid", "r02_filter_head_kernel_ncu.json"),
-        ("r02_gp_tile_kernel.ncu-rep", "refine pass (row-split 32-point tiles) on list B of the C2 grid", "r02_refine_tile_kernel_ncu.json"),
-        ("r02_gp_tile_full.ncu-rep", "full posterior for every point of the C2 grid (filter off): gp_tile_kernel<3, 64>", "r02_gp_tile_kernel_ncu.json")):
+STAGES = TAG + "_stages3.ncu-rep"          # one capture of the three stages of the default step (r02b)
+for rep, label, name, match in (
+        ((TAG + "_filter_mean_kernel.ncu-rep"), "filter stage 1 (fp32 screening mean where it applies, else the fp64 mean kernel) on the C2 grid", (TAG + "_filter_mean_kernel_ncu.json"), "filter_mean"),
+        ((TAG + "_filter_head_kernel.ncu-rep"), "filter stage 2 (head-subset variance bound, fp64 means of the entries the screened box leaves open) on list A of the C2 grid", (TAG + "_filter_head_kernel_ncu.json"), "filter_head"),
+        ((TAG + "_gp_tile_kernel.ncu-rep"), "refine pass (row- and factor-split 32-point tiles) on list B of the C2 grid", (TAG + "_refine_tile_kernel_ncu.json"), "gp_tile_kernel"),
+        ((TAG + "_gp_tile_full.ncu-rep"), "full posterior for every point of the C2 grid (filter off): gp_tile_kernel<3, 64>", (TAG + "_gp_tile_kernel_ncu.json"), None)):
     path = os.path.join(src, rep)
+    if not os.path.exists(path) and match is not None and os.path.exists(os.path.join(src, STAGES)):
+        path = os.path.join(src, STAGES)
+    else:
+        match = None
     if not os.path.exists(path):
         print("missing", rep)
         continue
-    json.dump(ncu_summary(path, label), open(os.path.join(dst, name), "w"), indent=1)
-    det = subprocess.run(["ncu", "-i", path, "--page", "details"], stdout=subprocess.PIPE, text=True).stdout
+    json.dump(ncu_summary(path, label, match=match), open(os.path.join(dst, name), "w"), indent=1)
+    cmd = ["ncu", "-i", path, "--page", "details"] + (["--kernel-name", "regex:" + match] if match else [])
+    det = subprocess.run(cmd, stdout=subprocess.PIPE, text=True).stdout
     open(os.path.join(dst, name.replace("_ncu.json", "_ncu_details.txt")), "w").write(det)
     done.append(name)
 
-if os.path.exists(os.path.join(src, "r02_launches.csv")):
-    json.dump(launch_shares(os.path.join(src, "r02_launches.csv")),
-              open(os.path.join(dst, "r02_launch_shares.json"), "w"), indent=1)
+if os.path.exists(os.path.join(src, (TAG + "_launches.csv"))):
+    json.dump(launch_shares(os.path.join(src, (TAG + "_launches.csv"))),
+              open(os.path.join(dst, (TAG + "_launch_shares.json")), "w"), indent=1)
 for name in os.listdir(src):
-    if name.startswith("r02_") and (name.endswith(".json") or name.endswith(".jsonl") or name.endswith("launches.csv")
+    if name.startswith(TAG + "_") and (name.endswith(".json") or name.endswith(".jsonl") or name.endswith("launches.csv")
                                     or name.endswith("racecheck.txt")) and "call" not in name:
         shutil.copy(os.path.join(src, name), os.path.join(dst, name))
 print("summaries:", done)
-for name in ("r02_bench.json", "r02_bench_n8.json"):
+for name in ((TAG + "_bench.json"), (TAG + "_bench_n8.json")):
     p = os.path.join(dst, name)
     if os.path.exists(p):
         b = json.loads(open(p).read().strip().splitlines()[-1])
