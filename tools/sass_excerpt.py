@@ -14,8 +14,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 tag = sys.argv[1] if len(sys.argv) > 1 else "r02"
 lib = os.path.join(ROOT, "safe_learning_b200", "libslb200.so")
 sass = subprocess.run(["cuobjdump", "-sass", lib], stdout=subprocess.PIPE, text=True).stdout
-WANT = ("DMMA", "UBLKCP", "SYNCS", "UTMALDG", "LDGSTS", "UTCHMMA", "UTCQMMA")
-KEEP = ("filter_mean_kernelILi3", "filter_head_kernelILi3", "gp_tile_kernelILi3ELb0ELb0ELi64",
+WANT = ("DMMA", "UBLKCP", "SYNCS", "UTMALDG", "LDGSTS", "UTCHMMA", "UTCQMMA", "MUFU.EX2", "FFMA", "ACQBULK", "PREEXIT")
+KEEP = ("filter_mean32_kernelILi3", "filter_mean_kernelILi3", "filter_head_kernelILi3", "gp_tile_kernelILi3ELb0ELb0ELi64",
         "gp_tile_kernelILi3ELb0ELb0ELi32", "gp_tile_kernelILi3ELb0ELb0ELi16",
         "bellman_argmax_tile_kernelILi2", "det_sweep_fast_kernel")
 
@@ -31,7 +31,7 @@ for line in sass.splitlines():
 
 out = ["# SASS evidence (%s) -- `cuobjdump -sass safe_learning_b200/libslb200.so`" % tag, "",
        "Instruction counts per kernel (d_in = 3 instantiations; the other dimensions are the same code):", "",
-       "| kernel | instructions | DMMA.8x8x4 | UBLKCP.S.G (TMA bulk copy) | SYNCS.* (mbarrier) |", "|---|---|---|---|---|"]
+       "| kernel | instructions | DMMA.8x8x4 | UBLKCP.S.G (TMA bulk copy) | SYNCS.* (mbarrier) | MUFU.EX2 | FFMA | ACQBULK / PREEXIT (PDL) |", "|---|---|---|---|---|---|---|---|"]
 details = []
 for fname, lines in funcs.items():
     key = next((k for k in KEEP if k in fname), None)
@@ -40,11 +40,16 @@ for fname, lines in funcs.items():
     cnt = collections.Counter()
     for ln in lines:
         for w in WANT:
-            if re.search(r"\b%s" % w, ln):
+            if re.search(r"\b%s" % re.escape(w), ln):
                 cnt[w] += 1
     short = subprocess.run(["c++filt", fname], stdout=subprocess.PIPE, text=True).stdout.strip()
     short = re.sub(r"\(anonymous namespace\)::", "", short).split("(")[0]
-    out.append("| `%s` | %d | %d | %d | %d |" % (short, len(lines), cnt["DMMA"], cnt["UBLKCP"], cnt["SYNCS"]))
+    out.append("| `%s` | %d | %d | %d | %d | %d | %d | %d / %d |" % (short, len(lines), cnt["DMMA"], cnt["UBLKCP"], cnt["SYNCS"],
+                                                          cnt["MUFU.EX2"], cnt["FFMA"], cnt["ACQBULK"], cnt["PREEXIT"]))
+    if cnt["MUFU.EX2"] > 8:
+        i = next(i for i, ln in enumerate(lines) if "MUFU.EX2" in ln)
+        details.append("`%s` (fp32 screening loop: FFMA exponent, MUFU.EX2, FFMA dot product):\n```\n%s\n```"
+                       % (short, "\n".join(lines[max(0, i - 6):i + 10])))
     shown = 0
     for i, ln in enumerate(lines):
         if re.search(r"\b(UBLKCP|SYNCS\.ARRIVE|SYNCS\.PHASECHK)", ln) and shown < 3:
