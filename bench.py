@@ -534,8 +534,10 @@ def run_ours(args, rank, world, local_rank):
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                 "d2h_bytes_per_step": int(d2h), "ms_per_step": e_total / args.steps,
                 "ms_per_step_spread": spread(e_per),
-                "api": "FunctionStack.import_cache(page-locked host mirror of the GP tables: one H2D "
-                       "copy), lyapunov.initial_safe_set = numpy mask (hashed, re-uploaded when it "
+                "api": "FunctionStack.import_cache(page-locked host mirror of the GP tables -> device "
+                       "arena in one library call: small tables on the sweep's stream, the packed "
+                       "factors on a second stream behind an event the factor-reading launches wait "
+                       "for), lyapunov.initial_safe_set = numpy mask (hashed, re-uploaded when it "
                        "changes), update_safe_set(), lyapunov.safe_set (numpy), feed_dict[c_max]"},
         "gpu_launches": int(launches),
         # `roofline`: the dominant kernel of the timed (default, filtered) step; the kernel that carries
