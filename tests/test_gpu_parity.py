@@ -1107,3 +1107,115 @@ def test_packed_restore_orders_the_factor_copy_behind_the_sweep(sl, filtered):
     cpu = W.build_oracle(par)
     cpu.update_safe_set()
     assert_array_equal(want, cpu.safe_set)
+
+
+@pytest.mark.parametrize("form", ["constant L_V", "1-norm L_V", "scaled abs L_V", "scaled V"])
+def test_screening_stage_other_lipschitz_forms(sl, form, mean_stage):
+    """The closed-form slack of the fp32 screening stage (filter.cu: screening_slack) has one branch per
+    accepted form of V / L_V: constant L_V, 1-norm of a linear map (one column for all outputs), scaled
+    abs-linear map, scaled quadratic V.  Flags must equal the full posterior's and the oracle's with
+    either first stage."""
+    import safe_learning_b200 as ns
+    import oracle as O
+    from safe_learning_b200 import _native as nat
+    par = W.make_pendulum(num_points=[53, 47], M=150, tau_scale=1 / 12., seed=21)
+    out = []
+    for mod, kind in ((ns, "product"), (O, "oracle")):
+        grid, dynamics = W._build(mod, par, kind)
+        policy = mod.Saturation(mod.LinearSystem(-par["K"]), -1., 1.)
+        lyap_fun = mod.QuadraticFunction(par["P"])
+        lin = mod.LinearSystem((2 * par["P"],))
+        if form == "constant L_V":
+            l_v = 0.25         # small enough that the decision depends on the GP (not a valid bound of V)
+        elif form == "1-norm L_V":
+            l_v = mod.Norm1Function(lin)
+        elif form == "scaled abs L_V":
+            l_v = mod.ScaledFunction(mod.AbsFunction(lin), 1.25)
+        else:
+            lyap_fun = mod.ScaledFunction(lyap_fun, 0.5)
+            l_v = mod.ScaledFunction(mod.AbsFunction(lin), 0.5)
+        out.append(mod.Lyapunov(grid, lyap_fun, dynamics, par["L_dyn"], l_v, par["tau"], policy,
+                                initial_set=par["initial"]))
+    gpu, cpu = out
+    desc = gpu.sweep_descriptor()
+    assert gpu._filter_enabled(desc)
+    lib = nat.load()
+    assert lib.slb_filter_stage1(desc) == (32 if mean_stage == "fp32 screening" else 64)
+    gpu.reset_filter_stats()
+    fast = gpu.compute_negative().cpu().numpy().copy()
+    st = gpu.filter_stats
+    assert st["prior"] > 0 and st["prior"] + st["head"] + st["refined"] == st["points"]
+    gpu.filter = False
+    full = gpu.compute_negative().cpu().numpy()
+    assert_array_equal(fast, full)
+    assert 0 < full.sum() < full.size, "trivial case: every point has the same flag"
+    assert_array_equal(full.astype(bool), cpu.full_grid_negative())
+
+
+def _linear_workload(d, num, M, seed, shared=False):
+    """Synthetic d-dimensional counterpart of the pendulum configuration (one action): noisy samples of a
+    stable linear map with a mild nonlinearity, a "wrong" linear prior mean, quadratic V."""
+    rng = np.random.default_rng(seed)
+    A = 0.85 * np.eye(d) + 0.05 * rng.standard_normal((d, d))
+    B = 0.1 * rng.standard_normal((d, 1))
+    X = rng.uniform(-1, 1, size=(M, d + 1))
+    Y = X[:, :d] @ A.T + X[:, d:] @ B.T + 0.02 * np.sin(3 * X[:, :d]) + 1e-3 * rng.standard_normal((M, d))
+    prior = np.hstack((A * 0.95, B * 1.1))
+    resid = Y - X @ prior.T
+    Q = rng.standard_normal((d, d))
+    P = Q @ Q.T + d * np.eye(d)
+    P = P / np.abs(P).max()
+    K = 0.3 * rng.standard_normal((1, d))
+    limits = np.array([[-1., 1.]] * d)
+    nump = np.asarray(num, dtype=int)
+    unit = (limits[:, 1] - limits[:, 0]) / (nump - 1)
+    axes = [np.arange(n) * u + lo for n, u, lo in zip(nump, unit, limits[:, 0])]
+    pts = np.column_stack([m.ravel() for m in np.meshgrid(*axes, indexing="ij")])
+    variances = [float(v) for v in resid.var(axis=0)]
+    lengthscales = [list(1.2 + 0.3 * rng.random(d + 1)) for _ in range(d)]
+    if shared:                                    # one Cholesky factor for all outputs
+        variances, lengthscales = [float(np.mean(variances))] * d, [lengthscales[0]] * d
+    return dict(name="linear%dd" % d, limits=limits, num_points=nump, tau=float(np.sum(unit) / 2) / 8,
+                X=X, Y=Y, variances=variances, lengthscales=lengthscales,
+                noise_variance=1e-6, beta=2.0, scale=1.0, prior_rows=prior, K=K, P=P,
+                L_dyn=float(np.linalg.norm(A, 1) + np.linalg.norm(B, 1) * np.linalg.norm(K, 1)),
+                initial=np.linalg.norm(pts, axis=1) <= 0.25)
+
+
+@pytest.mark.parametrize("d,num,M,tau_mult", [(1, [211], 60, 64.0), (3, [13, 11, 12], 90, 1.0),
+                                              (4, [7, 6, 7, 6], 70, 0.125)])
+def test_screening_stage_other_dimensions(sl, d, num, M, tau_mult, mean_stage):
+    """The fp32 screening kernel stores its centred rows as 2, 4 or 8 floats (d_in + 1 <= 2 / 4 / 8) and
+    unrolls the slack for up to four outputs: state dimensions 1, 3 and 4 with one action (d_in = 2, 4, 5)
+    next to the pendulum's d_in = 3, every first stage against the full posterior and the oracle."""
+    import safe_learning_b200 as ns
+    import oracle as O
+    from safe_learning_b200 import _native as nat
+    # d = 4: one shared factor (four 64 x 64 head factors + the screened tables do not fit the head
+    # stage's shared memory; such stacks keep the fp64 mean stage)
+    par = _linear_workload(d, num, M, seed=40 + d, shared=(d == 4))
+    par["tau"] *= tau_mult                        # mixed flags in every case (checked with the oracle)
+    out = []
+    for mod, kind in ((ns, "product"), (O, "oracle")):
+        grid, dynamics = W._build(mod, par, kind)
+        policy = mod.Saturation(mod.LinearSystem(-par["K"]), -1., 1.)
+        lyap_fun = mod.QuadraticFunction(par["P"])
+        l_v = mod.AbsFunction(mod.LinearSystem((2 * par["P"],)))
+        out.append(mod.Lyapunov(grid, lyap_fun, dynamics, par["L_dyn"], l_v, par["tau"], policy,
+                                initial_set=par["initial"]))
+    gpu, cpu = out
+    desc = gpu.sweep_descriptor()
+    assert gpu._filter_enabled(desc)
+    assert nat.load().slb_filter_stage1(desc) == (32 if mean_stage == "fp32 screening" else 64)
+    gpu.reset_filter_stats()
+    fast = gpu.compute_negative().cpu().numpy().copy()
+    st = gpu.filter_stats
+    assert st["prior"] > 0 and st["prior"] + st["head"] + st["refined"] == st["points"]
+    gpu.filter = False
+    full = gpu.compute_negative().cpu().numpy()
+    assert_array_equal(fast, full)
+    assert_array_equal(full.astype(bool), cpu.full_grid_negative())
+    gpu.filter = "auto"
+    gpu.update_safe_set()
+    cpu.update_safe_set()
+    assert_array_equal(gpu.safe_set, cpu.safe_set)
