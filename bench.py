@@ -415,7 +415,7 @@ def run_ours(args, rank, world, local_rank):
     except Exception:
         pass
     traffic = None
-    for name in ("r02_gp_tile_kernel_ncu.json", "r01_gp_tile_kernel_ncu.json"):
+    for name in ("r02b_gp_tile_kernel_ncu.json", "r02_gp_tile_kernel_ncu.json", "r01_gp_tile_kernel_ncu.json"):
         try:
             with open(os.path.join(ROOT, "profiles", name)) as fh:
                 traffic = json.load(fh).get("dram_bytes_per_launch")
@@ -453,6 +453,14 @@ def run_ours(args, rank, world, local_rank):
     stage_rooflines = None
     if mean_ms:
         stage1 = int(lib.slb_filter_stage1(cfg))
+
+        def ncu_traffic(name):
+            """dram__bytes_read.sum + dram__bytes_write.sum of one launch from the committed ncu summary"""
+            try:
+                with open(os.path.join(ROOT, "profiles", name)) as fh:
+                    return json.load(fh).get("dram_bytes_per_launch")
+            except Exception:
+                return None
         head_ms = stage_ms["mean_head"] - mean_ms
         refine_ms = filter_ms - stage_ms["mean_head"]
         flops_mean = 2 * M_TRAIN * (3 * 3 + 4 + 1)
@@ -471,7 +479,7 @@ def run_ours(args, rank, world, local_rank):
                 "achieved": ach, "peak": fp32_peak, "unit": "TFLOP/s", "frac": ach / fp32_peak,
                 "kernel_ms": mean_ms, "algorithmic_flops_per_point": flops_mean,
                 "exp_per_s": exp_rate1, "exp_peak_per_s": mufu_peak, "exp_frac": exp_rate1 / mufu_peak,
-                "traffic": None}
+                "traffic": ncu_traffic("r02b_filter_mean_kernel_ncu.json")}
         else:
             r_mean = {
                 "bound": "tensor", "kernel": "filter_mean_kernel<3> (fp64 pipe: DFMA, the pipe and peak "
@@ -487,7 +495,7 @@ def run_ours(args, rank, world, local_rank):
                                          "and factors of every 32-point tile split over spare CTAs)",
             "achieved": ach_ref, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach_ref / peak_tf,
             "kernel_ms": refine_ms, "points": fs["refined"], "algorithmic_flops_per_point": flops_pt,
-            "traffic": None,
+            "traffic": ncu_traffic("r02b_refine_tile_kernel_ncu.json"),
             "note": "a few hundred points cannot fill 148 SMs: the pass is bound by the latency of one "
                     "tile's serial chain (generation -> contraction -> reduction), not by the pipe"}
         r_head = {"kernel": "filter_head_kernel<3>", "kernel_ms": head_ms,
