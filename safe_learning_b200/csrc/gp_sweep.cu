@@ -133,7 +133,7 @@ int slb_launch_refine(cudaStream_t st, const slb_sweep& cfg, int64_t n_max, int6
                 a.split_max = split_max;
                 static const int split_factors = [] {      // SLB200_SPLIT_FACTORS=0: A/B timing knob
                     const char* e = getenv("SLB200_SPLIT_FACTORS");
-                    return e ? (atoi(e) != 0) : 1;
+                    return e ? atoi(e) : 1;
                 }();
                 a.split_factors = split_factors;
             }

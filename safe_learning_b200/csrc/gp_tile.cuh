@@ -665,7 +665,11 @@ gp_tile_kernel(const __grid_constant__ slb_sweep cfg, const slb_gp_args a) {
             // go to different CTAs first (half the generation phases and barriers in every CTA's
             // serial chain), the rest of the spare CTAs splits the rows
             const int nfac = cfg.gp.num_factors;
-            if (a.split_factors && nfac > 1 && spare >= 2 * nfac) { FS = nfac; spare /= nfac; }
+            // (split_factors 2: already with one CTA per factor and no row split -- A/B knob)
+            if (a.split_factors && nfac > 1 && spare >= (a.split_factors > 1 ? 1 : 2) * nfac) {
+                FS = nfac;
+                spare /= nfac;
+            }
             G = (int)(spare < 1 ? 1 : (spare > a.split_max ? a.split_max : spare));
             const int per_tile = G * FS;
             if ((int64_t)blockIdx.x >= ntiles * per_tile) return;
