@@ -409,3 +409,50 @@ def test_filter_bounds_are_certified_on_the_oracle():
         gamma = sla.solve_triangular(L.T, np.asarray(gp.alpha), lower=False)
         m_gamma = (Kx.T.dot(gamma) + s * gp._mean(z)) / s
         assert_allclose(m_gamma[:, 0], mean[:, j], rtol=1e-7, atol=1e-12)
+
+
+def test_filter_stage1_selection_is_host_logic():
+    """slb_filter_stage1 (which first stage the filtered sweep runs) is decided on the host from the
+    descriptor alone: the fp32 screening kernel needs plain RBF factors, V = QUADRATIC on at most four
+    outputs (optional scale), L_V constant or LINEAR with abs / 1-norm / scale, and room for every
+    factor's tables in the head stage's shared memory; everything else keeps the fp64 mean kernel."""
+    from safe_learning_b200 import _native as nat
+    lib = nat.load()
+
+    def sweep(D=2, M=500, factors=None, v_kind=nat.FN_QUADRATIC, v_flags=0, l_kind=nat.FN_LINEAR,
+              l_flags=nat.FLAG_ABS, l_out=None, prims=0):
+        cfg = nat.SlbSweep()
+        factors = D if factors is None else factors
+        cfg.gp.num_outputs, cfg.gp.num_factors, cfg.gp.input_dim = D, factors, D + 1
+        for f in range(factors):
+            cfg.gp.factors[f].M = M
+            cfg.gp.factors[f].kernel.num_prims = prims
+        for o in range(D):
+            cfg.gp.outputs[o].factor = min(o, factors - 1)
+        cfg.lyapunov.kind, cfg.lyapunov.in_dim, cfg.lyapunov.out_dim = v_kind, D, 1
+        cfg.lyapunov.flags = v_flags
+        cfg.lipschitz_v.kind, cfg.lipschitz_v.in_dim = l_kind, D
+        cfg.lipschitz_v.out_dim = D if l_out is None else l_out
+        cfg.lipschitz_v.flags = l_flags
+        return cfg
+
+    assert lib.slb_filter_stage1(sweep()) == 32                                   # the C2 composition
+    assert lib.slb_filter_stage1(sweep(l_kind=nat.FN_NONE)) == 32                 # constant L_V
+    assert lib.slb_filter_stage1(sweep(l_flags=nat.FLAG_NORM1, l_out=2)) == 32
+    assert lib.slb_filter_stage1(sweep(v_flags=nat.FLAG_SCALE, l_flags=nat.FLAG_ABS | nat.FLAG_SCALE)) == 32
+    assert lib.slb_filter_stage1(sweep(D=4, factors=1, M=100)) == 32
+    assert lib.slb_filter_stage1(sweep(v_kind=nat.FN_TRIANGULATION)) == 64        # no closed-form slack
+    assert lib.slb_filter_stage1(sweep(v_flags=nat.FLAG_ABS)) == 64
+    assert lib.slb_filter_stage1(sweep(l_flags=nat.FLAG_SATURATE)) == 64
+    assert lib.slb_filter_stage1(sweep(l_flags=nat.FLAG_MAXABS)) == 64
+    assert lib.slb_filter_stage1(sweep(prims=2)) == 64                            # covariance expression
+    assert lib.slb_filter_stage1(sweep(D=5, factors=1, M=100)) == 64              # slack written out for <= 4
+    assert lib.slb_filter_stage1(sweep(D=4, factors=4, M=100)) == 64              # four head factors fill the CTA
+    assert lib.slb_filter_stage1(sweep(M=5000)) == 64                             # tables do not fit
+    empty = nat.SlbSweep()
+    assert lib.slb_filter_stage1(empty) == 0                                      # no GP
+    try:
+        lib.slb_debug_filter_stages(7)
+        assert lib.slb_filter_stage1(sweep()) == 64                               # forced fp64 mean stage
+    finally:
+        lib.slb_debug_filter_stages(3)
