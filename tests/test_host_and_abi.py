@@ -456,3 +456,20 @@ def test_filter_stage1_selection_is_host_logic():
         assert lib.slb_filter_stage1(sweep()) == 64                               # forced fp64 mean stage
     finally:
         lib.slb_debug_filter_stages(3)
+
+
+def test_screening_bound_holds_in_a_c_restatement(tmp_path):
+    """tools/screening_bound_check.c restates the fp32 screening mean of gp_mean_staged.cuh with C floats
+    (worst-sign 2^-22 perturbation for ex2.approx) and holds it to the certified bound against long-double
+    sums over sixteen magnitude regimes (centre up to 300 length scales from the origin, |z - centre| up to
+    7): the derivation of the bound, checked without a GPU (the GPU test holds the kernel itself to it)."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    exe = str(tmp_path / "sbc")
+    subprocess.run(["gcc", "-O2", "-o", exe, os.path.join(ROOT, "tools", "screening_bound_check.c"), "-lm"],
+                   check=True)
+    proc = subprocess.run([exe], stdout=subprocess.PIPE, text=True, timeout=300)
+    assert proc.returncode == 0, proc.stdout[-2000:]
+    assert "ok: every mean inside its bound" in proc.stdout
