@@ -363,8 +363,9 @@ int slb_lyapunov_sweep(void* stream, const slb_sweep* cfg, int64_t idx_begin, in
  * points} accumulated over calls (the caller zeroes it). */
 int64_t slb_filter_workspace(int64_t n);
 /* which first stage slb_lyapunov_sweep_filtered runs for this configuration: 32 = the fp32 screening
- * kernel (plain RBF factors, quadratic V, constant / abs-linear L_V, tables fit the head stage's shared
- * memory) followed by an fp64 mean on the undecided points; 64 = the fp64 mean kernel; 0 = no GP */
+ * kernel (plain RBF factors, quadratic V on at most four outputs, constant / abs-linear L_V, tables fit
+ * the head stage's shared memory) with an fp64 mean only for the points its error box leaves open;
+ * 64 = the fp64 mean kernel; 0 = no GP */
 int slb_filter_stage1(const slb_sweep* cfg);
 int slb_lyapunov_sweep_filtered(void* stream, const slb_sweep* cfg, int64_t idx_begin,
                                 int64_t idx_end, uint8_t* negative_dev, double* values_dev,
