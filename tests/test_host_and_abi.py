@@ -473,3 +473,27 @@ def test_screening_bound_holds_in_a_c_restatement(tmp_path):
     proc = subprocess.run([exe], stdout=subprocess.PIPE, text=True, timeout=300)
     assert proc.returncode == 0, proc.stdout[-2000:]
     assert "ok: every mean inside its bound" in proc.stdout
+
+
+def test_screening_slack_inequalities():
+    """The closed-form slack of the screening stage (filter.cu: screening_slack) rests on two inequalities
+    over the box mu +- dm:  |V(mu + e) - V(mu)| <= sum_i |((P + P^T) mu)_i| dm_i + sum_ij |P_ij| dm_i dm_j
+    for V = x^T P x (P need not be symmetric), and | |A (mu + e)|_j - |A mu|_j | <= sum_i |A_ji| dm_i (summed
+    over j for the 1-norm form).  Checked at the corners and at random interior points of random boxes."""
+    rng = np.random.default_rng(17)
+    for n in (1, 2, 3, 4):
+        for _ in range(50):
+            P = rng.standard_normal((n, n))
+            A = rng.standard_normal((n, n))
+            mu = rng.standard_normal(n) * 10.0 ** rng.uniform(-3, 1)
+            dm = np.abs(rng.standard_normal(n)) * 10.0 ** rng.uniform(-8, 0)
+            dv = np.abs((P + P.T) @ mu) @ dm + dm @ np.abs(P) @ dm
+            rows = np.abs(A) @ dm
+            corners = np.array(np.meshgrid(*[[-1.0, 1.0]] * n)).reshape(n, -1).T
+            samples = np.vstack((corners, rng.uniform(-1, 1, size=(64, n)))) * dm
+            for e in samples:
+                x = mu + e
+                assert abs(x @ P @ x - mu @ P @ mu) <= dv * (1 + 1e-12) + 1e-300
+                diff = np.abs(np.abs(A @ x) - np.abs(A @ mu))
+                assert (diff <= rows * (1 + 1e-12) + 1e-300).all()
+                assert abs(np.abs(A @ x).sum() - np.abs(A @ mu).sum()) <= rows.sum() * (1 + 1e-12) + 1e-300
