@@ -493,7 +493,10 @@ def test_screening_slack_inequalities():
             samples = np.vstack((corners, rng.uniform(-1, 1, size=(64, n)))) * dm
             for e in samples:
                 x = mu + e
-                assert abs(x @ P @ x - mu @ P @ mu) <= dv * (1 + 1e-12) + 1e-300
+                # (the difference of two fp64 evaluations carries their rounding: a few ulps of |V|)
+                round_off = 8e-16 * n * (abs(x) @ abs(P) @ abs(x) + abs(mu) @ abs(P) @ abs(mu))
+                assert abs(x @ P @ x - mu @ P @ mu) <= dv * (1 + 1e-12) + round_off
                 diff = np.abs(np.abs(A @ x) - np.abs(A @ mu))
-                assert (diff <= rows * (1 + 1e-12) + 1e-300).all()
-                assert abs(np.abs(A @ x).sum() - np.abs(A @ mu).sum()) <= rows.sum() * (1 + 1e-12) + 1e-300
+                assert (diff <= rows * (1 + 1e-12) + 8e-16 * n * (abs(A) @ (abs(x) + abs(mu)))).all()
+                assert abs(np.abs(A @ x).sum() - np.abs(A @ mu).sum()) <= (
+                    rows.sum() * (1 + 1e-12) + 8e-16 * n * (abs(A) @ (abs(x) + abs(mu))).sum())
